@@ -1,0 +1,72 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) in this
+container through the dependency stubs in oracle/ref_stubs (test infrastructure only).
+
+    python oracle/make_golden.py [kmeans] [ops] [model] ...
+
+The fixtures travel to the GPU box; /root/reference does not. Each fixture stores the inputs
+(or the seed that regenerates them) and the reference's outputs.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+STUBS = os.path.join(ROOT, "oracle", "ref_stubs")
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+
+def _kmeans_child():
+    """Runs inside selective_labeling/ with USL_MODE set (the reference resolves its config from cwd)."""
+    sys.path.insert(0, STUBS)
+    sys.path.insert(0, ".")
+    import utils  # reference: shared/utils via the selective_labeling/utils symlink
+    from oracle.kmeans_oracle import make_mixture
+    cases = [
+        # name, N, D, K, Niter, modes, seed, spread (chosen so that no cluster empties: the
+        # reference's dense branch collapses through torch.argmin-of-NaN once one does)
+        ("kmeans_n2048_d128_k40", 2048, 128, 40, 6, 64, 3, 1.0),
+        ("kmeans_n4096_d384_k64", 4096, 384, 64, 5, 96, 0, 1.0),
+        ("kmeans_n3000_d64_k170", 3000, 64, 170, 4, 300, 1, 0.7),
+    ]
+    for name, N, D, K, Niter, modes, seed, spread in cases:
+        x16 = make_mixture(N, D, modes, seed=100 + seed, spread=spread)
+        x = x16.float()
+        cl, c = utils.KMeans(x, seed, K=K, Niter=Niter, verbose=False, force_no_lazy_tensor=True)
+        torch.manual_seed(seed)
+        r = torch.randperm(N)[:K]
+        out = dict(labels=cl.numpy().astype(np.int64), centroids=c.numpy(), init=r.numpy(),
+                   meta=np.array([N, D, K, Niter, modes, seed, int(spread * 1000)], dtype=np.int64))
+        if N * D <= 2048 * 128:
+            out["x16"] = x16.numpy()   # small case: store the inputs too
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+        assert int((torch.bincount(cl, minlength=K) == 0).sum()) == 0, "fixture must not contain empty clusters"
+        print("wrote", name)
+
+
+def gen_kmeans():
+    env = dict(os.environ, USL_MODE="USL", PYTHONPATH=ROOT)
+    cwd = os.path.join(REF, "u2seg", "Instance_Clustering", "selective_labeling")
+    subprocess.check_call([sys.executable, os.path.abspath(__file__), "_kmeans_child"], cwd=cwd, env=env)
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    what = sys.argv[1:] or ["kmeans", "ops", "model"]
+    if "_kmeans_child" in what:
+        _kmeans_child()
+        sys.exit(0)
+    if "kmeans" in what:
+        gen_kmeans()
+    if "ops" in what or "model" in what:
+        sys.path.insert(0, STUBS)
+        sys.path.insert(0, REF)
+        from oracle import make_golden_detector as mgd
+        if "ops" in what:
+            mgd.gen_ops(GOLD)
+        if "model" in what:
+            mgd.gen_model(GOLD)

@@ -1,0 +1,81 @@
+"""ctypes binding of libu2b200.so (the C ABI declared in include/u2b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, the
+product path raises. Build with `python -m u2seg_b200.build` (nvcc, sm_100a).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libu2b200.so")
+
+_lib = None
+
+c_void_p, c_int, c_int64, c_size_t, c_float = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float)
+
+# name -> (restype, argtypes); must list every symbol include/u2b200.h declares
+# (tests/test_abi.py parses the header and checks this table and the .so against it).
+SIGNATURES = {
+    "u2b_last_error": (ctypes.c_char_p, []),
+    "u2b_version": (c_int, []),
+    "u2b_sm_count": (c_int, []),
+    "u2b_kmeans_kpad": (c_int64, [c_int64]),
+    "u2b_kmeans_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "u2b_kmeans_xnorm_max": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "u2b_kmeans_prepare": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "u2b_kmeans_assign": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "u2b_kmeans_accumulate": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                                      c_size_t, c_void_p]),
+    "u2b_kmeans_finalize": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libu2b200.so not found at %s — build it with `python -m u2seg_b200.build` "
+                "(no CPU or PyTorch fallback exists for the B200 path)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class U2BError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().u2b_last_error()
+        raise U2BError("%s failed (code %d): %s" % (what or "libu2b200 call", rc,
+                                                    msg.decode() if msg else "?"))
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL). Tensors must be contiguous."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    assert t.is_contiguous(), "libu2b200 expects contiguous tensors"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+# number of kernels launched through the library since import (bench.py's `gpu_launches`)
+launch_count = 0
+
+
+def count_launches(n):
+    global launch_count
+    launch_count += n
