@@ -65,6 +65,60 @@ int u2b_kmeans_accumulate(const void* x16, const int32_t* labels, int64_t N, int
 /* M-step part 2, nn_utils.py:364: c32[k] = sums[k, 0:D] / sums[k, D] (NaN when empty). */
 int u2b_kmeans_finalize(const float* sums, int64_t K, int64_t D, float* c32, u2b_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Detector ops. Feature maps are NHWC ("channels_last"); dtype codes: 0 = fp32, 1 = fp16, 2 = bf16.
+ * rois5: (K, 5) fp32 rows (batch_index, x0, y0, x1, y1) — detectron2/modeling/poolers.py:72-98.
+ * ------------------------------------------------------------------------------------------ */
+
+/* poolers.py:23-59 assign_boxes_to_levels: levels[i] = clamp(floor(canonical_level +
+ * log2(sqrt(area)/canonical_size + 1e-8)), min_level, max_level) - min_level. */
+int u2b_assign_levels(const float* rois5, int64_t K, int min_level, int max_level,
+                      float canonical_size, int canonical_level, int32_t* levels,
+                      u2b_stream_t stream);
+
+/* poolers.py:206-263 ROIPooler.forward / layers/roi_align.py:49-65 ROIAlign.forward (ROIAlignV2:
+ * aligned=True, sampling_ratio=0). feats/hs/ws/scales are HOST arrays of num_levels (1..4) entries;
+ * feats[l] is a device pointer to (N, H_l, W_l, C). levels (device, K) may be NULL when num_levels==1.
+ * out: (K, P, P, C) of the same dtype. */
+int u2b_roi_align_fwd(int dtype, int num_levels, const void* const* feats, const int32_t* hs,
+                      const int32_t* ws, const float* scales, int64_t C, const float* rois5,
+                      const int32_t* levels, int64_t K, int P, void* out, u2b_stream_t stream);
+
+/* backward of the above: accumulates into grad_feats[l] (N, H_l, W_l, C) fp32, zeroed by the caller. */
+int u2b_roi_align_bwd(int dtype, int num_levels, float* const* grad_feats, const int32_t* hs,
+                      const int32_t* ws, const float* scales, int64_t C, const float* rois5,
+                      const int32_t* levels, int64_t K, int P, const void* grad_out,
+                      u2b_stream_t stream);
+
+/* layers/mask_ops.py:74-147 paste_masks_in_image: masks (N, M, M) fp32 probabilities, boxes (N, 4)
+ * fp32 -> out (N, H, W) bytes in {0,1} (= `img >= threshold`). */
+int u2b_paste_masks(const float* masks, const float* boxes, int64_t N, int M, int H, int W,
+                    float threshold, uint8_t* out, u2b_stream_t stream);
+
+/* structures/masks.py:191-222 BitMasks.crop_and_resize fused with the gt_masks[matched_idxs] gather
+ * of roi_heads.py:286-288. masks (G, H, W) bool bytes; gt_index (M) int64 or NULL (identity);
+ * boxes (M, 4). out_bool (M, P, P) bytes (value >= 0.5) and/or out_val (M, P, P) fp32; either may be NULL. */
+int u2b_crop_resize_masks(const uint8_t* masks, const int64_t* gt_index, const float* boxes,
+                          int64_t M, int H, int W, int P, uint8_t* out_bool, float* out_val,
+                          u2b_stream_t stream);
+
+/* structures/boxes.py:336-358 pairwise_iou + modeling/matcher.py:62-127 Matcher.__call__, fused:
+ * gt (G, 4), pred (A, 4) fp32 -> matches int64 (A) (first maximum), matched_vals fp32 (A),
+ * out_labels int8 (A). thresholds: nthr device floats [-inf, t.., +inf]; labels: nthr-1 device ints.
+ * allow_low_quality needs gt_max_scratch (G uint32). G must be in 1..1024. */
+int u2b_iou_match(const float* gt, int64_t G, const float* pred, int64_t A, const float* thresholds,
+                  const int32_t* labels, int nthr, int allow_low_quality, int64_t* matches,
+                  float* matched_vals, int8_t* out_labels, uint32_t* gt_max_scratch,
+                  u2b_stream_t stream);
+
+/* layers/nms.py:9-21 batched_nms (torchvision class-by-class semantics; IoU > threshold suppresses).
+ * order = indices of the boxes sorted by score, descending, stable. keep (n) int64 receives the kept
+ * original indices in score order, *num_keep (device) their number. No host synchronisation. */
+size_t u2b_nms_workspace_bytes(int64_t n);
+int u2b_batched_nms(const float* boxes, const int64_t* cats, const int64_t* order, int64_t n,
+                    float iou_threshold, int64_t* keep, int32_t* num_keep, void* workspace,
+                    size_t workspace_bytes, u2b_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

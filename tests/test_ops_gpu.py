@@ -1,0 +1,184 @@
+"""GPU parity of the detector ops (through the C ABI) vs reference goldens and the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import detector_oracle as do
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(golden_dir):
+    return np.load(os.path.join(golden_dir, "detector_ops.npz"))
+
+
+def T(a, dev="cuda"):
+    return torch.from_numpy(np.asarray(a)).to(dev)
+
+
+def cl(x):
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+def test_roialign_reference_known_answer():
+    # tests/layers/test_roi_align.py:14-47 (aligned=True expectation), channels padded to the vector width
+    from u2seg_b200.layers import ROIAlign
+    inp = torch.arange(25).reshape(1, 1, 5, 5).float().repeat(1, 4, 1, 1).cuda()
+    rois = torch.tensor([[0, 1, 1, 3, 3.0]]).cuda()
+    out = ROIAlign((4, 4), 1.0, 0, aligned=True)(cl(inp), rois)
+    want = torch.tensor([[4.5, 5.0, 5.5, 6.0], [7.0, 7.5, 8.0, 8.5], [9.5, 10.0, 10.5, 11.0], [12.0, 12.5, 13.0, 13.5]])
+    for c in range(4):
+        assert torch.allclose(out[0, c].cpu(), want)
+
+
+@pytest.mark.parametrize("P,key", [(7, "pool_out7"), (14, "pool_out14")])
+def test_pooler_matches_reference_golden(ops, P, key):
+    from u2seg_b200.layers import ROIPooler, assign_boxes_to_levels_rois, convert_boxes_to_pooler_format
+    feats = [cl(T(ops["pool_feat%d" % i])) for i in range(4)]
+    boxes = [T(ops["pool_boxes0"]), T(ops["pool_boxes1"])]
+    rois = convert_boxes_to_pooler_format(boxes)
+    lv = assign_boxes_to_levels_rois(rois.contiguous(), 2, 5, 224, 4)
+    assert np.array_equal(lv.cpu().numpy().astype(np.int64), ops["pool_levels"])             # INT: bit exact
+    out = ROIPooler(P, (0.25, 0.125, 0.0625, 0.03125), 0, "ROIAlignV2")(feats, boxes)
+    np.testing.assert_allclose(out.cpu().numpy(), ops[key], rtol=1e-4, atol=1e-5)
+
+
+def test_levels_at_power_of_two_boundaries():
+    from u2seg_b200.layers import assign_boxes_to_levels_rois
+    sizes = [224.0 * 2 ** k for k in (-3, -2, -1, 0, 1, 2)] + [111.99999, 112.00001, 223.9999, 224.0001, 448.0, 0.0, 1e-3]
+    rois = torch.tensor([[0, 3.0, 5.0, 3.0 + s, 5.0 + s] for s in sizes])
+    want = do.assign_levels(rois[:, 1:])
+    got = assign_boxes_to_levels_rois(rois.cuda(), 2, 5, 224, 4).cpu().long()
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.float16, 1e-3), (torch.bfloat16, 8e-3)])
+def test_pooler_hot_path_shapes_fwd_bwd(dtype, tol):
+    """(2,256,H,W) pyramid of a 512x512 image, K=256 rois, 7x7: forward and backward vs torchvision CPU."""
+    from u2seg_b200.layers import ROIPooler
+    g = torch.Generator().manual_seed(0)
+    feats = [torch.randn(2, 256, 512 // s, 512 // s, generator=g).to(dtype).float() for s in (4, 8, 16, 32)]
+    boxes = []
+    for _ in range(2):
+        c = torch.rand(128, 2, generator=g) * 512
+        wh = torch.exp(torch.rand(128, 2, generator=g) * 5 + 1.5)
+        b = torch.cat([c - wh / 2, c + wh / 2], 1).clamp(0, 512)
+        boxes.append(b)
+    fr = [f.clone().requires_grad_(True) for f in feats]
+    want = do.roi_pool(fr, boxes, 7)
+    gout = torch.randn(want.shape, generator=g).to(dtype).float()
+    want.backward(gout)
+    fg = [cl(f.to(dtype).cuda()).requires_grad_(True) for f in feats]
+    out = ROIPooler(7, (0.25, 0.125, 0.0625, 0.03125), 0, "ROIAlignV2")(fg, [b.cuda() for b in boxes])
+    assert out.dtype == dtype and out.shape == want.shape
+    np.testing.assert_allclose(out.float().cpu().numpy(), want.detach().numpy(), rtol=tol, atol=tol * 4)
+    out.backward(gout.to(dtype).cuda())
+    for a, b in zip(fg, fr):
+        scale = float(b.grad.abs().max())
+        assert float((a.grad.float().cpu() - b.grad).abs().max()) <= max(tol * 8 * scale, 1e-4)
+
+
+def test_roialign_empty_inputs():
+    # tests/layers/test_roi_align.py:111-128 (empty boxes)
+    from u2seg_b200.layers import ROIAlign
+    inp = cl(torch.randn(1, 8, 10, 10).cuda()).requires_grad_(True)
+    out = ROIAlign(7, 1.0, 0, aligned=True)(inp, torch.zeros(0, 5).cuda())
+    assert out.shape == (0, 8, 7, 7)
+    out.sum().backward()
+    assert float(inp.grad.abs().sum()) == 0.0
+
+
+def test_paste_masks_matches_reference(ops):
+    from u2seg_b200.layers import paste_masks_in_image
+    m, b = T(ops["paste_masks"]), T(ops["paste_boxes"])
+    got = paste_masks_in_image(m, b, (100, 150), 0.5).cpu()
+    want = torch.from_numpy(np.unpackbits(ops["paste_out"])[:9 * 100 * 150].reshape(9, 100, 150).astype(bool))
+    diff = (got != want)
+    if diff.any():   # FP->bool: exact except where |p - 0.5| < eps
+        soft = do.paste_masks_in_image(m.cpu(), b.cpu(), (100, 150), -1)  # uint8 soft values
+        assert diff.sum() <= 3 and bool(((soft[diff].int() - 127).abs() <= 1).all())
+
+
+def test_paste_masks_full_size_properties():
+    """config-5 size (N=100, 800x1333): pixels far outside every box are 0; a constant mask of ones fills
+    exactly the pixel centres inside the box."""
+    from u2seg_b200.layers import paste_masks_in_image
+    N, H, W = 100, 800, 1333
+    g = torch.Generator().manual_seed(1)
+    c = torch.rand(N, 2, generator=g) * torch.tensor([W, H])
+    wh = torch.rand(N, 2, generator=g) * 300 + 8
+    boxes = torch.cat([c - wh / 2, c + wh / 2], 1)
+    out = paste_masks_in_image(torch.ones(N, 28, 28).cuda(), boxes.cuda(), (H, W), 0.5).cpu()
+    ys = (torch.arange(H) + 0.5)[None, :, None]
+    xs = (torch.arange(W) + 0.5)[None, None, :]
+    b = boxes[:, :, None, None]
+    # bilinear with zero padding: value >= 0.5 iff the sample is at least half a mask-pixel inside the box
+    hw, hh = (b[:, 2] - b[:, 0]) / 56, (b[:, 3] - b[:, 1]) / 56
+    inside = (xs >= b[:, 0] + 1e-3) & (xs <= b[:, 2] - 1e-3) & (ys >= b[:, 1] + 1e-3) & (ys <= b[:, 3] - 1e-3)
+    far = (xs < b[:, 0] - hw - 1e-3) | (xs > b[:, 2] + hw + 1e-3) | (ys < b[:, 1] - hh - 1e-3) | (ys > b[:, 3] + hh + 1e-3)
+    assert bool(out[inside].all()) and not bool(out[far].any())
+
+
+def test_crop_and_resize_matches_reference(ops):
+    from u2seg_b200.layers import crop_and_resize_masks
+    gm = T(np.unpackbits(ops["crop_masks"])[:6 * 100 * 150].reshape(6, 100, 150).astype(bool))
+    got, val = crop_and_resize_masks(gm, T(ops["crop_boxes"]), 28, return_values=True)
+    want = np.unpackbits(ops["crop_out"])[:6 * 28 * 28].reshape(6, 28, 28).astype(bool)
+    diff = got.cpu().numpy() != want
+    assert diff.sum() <= 2 and bool((np.abs(val.cpu().numpy()[diff] - 0.5) < 1e-5).all())
+    # gather indirection == explicit gather
+    idx = torch.tensor([5, 0, 0, 3, 2, 1, 4, 4]).cuda()
+    bx = T(ops["crop_boxes"])[torch.tensor([0, 1, 2, 3, 4, 5, 0, 1])]
+    assert torch.equal(crop_and_resize_masks(gm, bx, 28, gt_index=idx), crop_and_resize_masks(gm[idx], bx, 28))
+
+
+def test_iou_matcher_matches_reference(ops):
+    from u2seg_b200.layers import Matcher
+    gt, an = T(ops["iou_gt"]), T(ops["iou_an"])
+    m, l = Matcher([0.3, 0.7], [0, -1, 1], allow_low_quality_matches=True).match_boxes(gt, an)
+    assert np.array_equal(m.cpu().numpy(), ops["match_rpn_idx"]) and np.array_equal(l.cpu().numpy(), ops["match_rpn_lab"])
+    m, l = Matcher([0.5], [0, 1], allow_low_quality_matches=False).match_boxes(gt, an)
+    assert np.array_equal(m.cpu().numpy(), ops["match_roi_idx"]) and np.array_equal(l.cpu().numpy(), ops["match_roi_lab"])
+
+
+def test_iou_matcher_full_anchor_set_vs_oracle():
+    from u2seg_b200.layers import Matcher
+    cfg = do.DetCfg()
+    anchors = torch.cat(do.make_anchors([(256 // s, 256 // s) for s in (1, 2, 4, 8, 16)], cfg))   # 1024^2 image: 261,888
+    assert anchors.shape[0] == 261888
+    _, boxes, _, _, _ = do.synthetic_batch(1, 64, 64, 800, 28, seed=3, G=20)
+    gt = boxes[0] * 16
+    iou = do.pairwise_iou(gt, anchors)
+    wm, wl = do.matcher(iou, (0.3, 0.7), (0, -1, 1), True)
+    m, l = Matcher([0.3, 0.7], [0, -1, 1], True).match_boxes(gt.cuda(), anchors.cuda())
+    assert torch.equal(m.cpu(), wm) and torch.equal(l.cpu(), wl)
+    # empty GT (matcher.py:80-88)
+    m, l = Matcher([0.3, 0.7], [0, -1, 1], True).match_boxes(torch.zeros(0, 4).cuda(), anchors[:100].cuda())
+    assert int(m.sum()) == 0 and bool((l == 0).all())
+
+
+@pytest.mark.parametrize("thr,key", [(0.65, "nms_keep_065"), (0.5, "nms_keep_050")])
+def test_batched_nms_matches_reference(ops, thr, key):
+    from u2seg_b200.layers import batched_nms
+    keep = batched_nms(T(ops["nms_boxes"]), T(ops["nms_scores"]), T(ops["nms_idxs"]), thr)
+    assert np.array_equal(keep.cpu().numpy(), ops[key])                        # INT: bit exact, same order
+
+
+def test_batched_nms_rpn_size_vs_oracle():
+    from u2seg_b200.layers import batched_nms
+    g = torch.Generator().manual_seed(4)
+    n = 9000
+    c = torch.rand(n, 2, generator=g) * 1024
+    wh = torch.exp(torch.rand(n, 2, generator=g) * 4 + 2)
+    b = torch.cat([c - wh / 2, c + wh / 2], 1).clamp(0, 1024)
+    s = torch.randn(n, generator=g)
+    s[100:200] = s[0]            # score ties: stable order
+    lv = torch.randint(0, 5, (n,), generator=g)
+    want = do.batched_nms(b, s, lv, 0.65)
+    got = batched_nms(b.cuda(), s.cuda(), lv.cuda(), 0.65).cpu()
+    assert set(got.tolist()) == set(want.tolist())
+    assert torch.equal(s[got], s[want])      # same score order (ties may permute among equal scores)
+    assert batched_nms(b[:0].cuda(), s[:0].cuda(), lv[:0].cuda(), 0.5).numel() == 0

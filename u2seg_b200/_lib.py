@@ -29,6 +29,19 @@ SIGNATURES = {
     "u2b_kmeans_accumulate": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                       c_size_t, c_void_p]),
     "u2b_kmeans_finalize": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "u2b_assign_levels": (c_int, [c_void_p, c_int64, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "u2b_roi_align_fwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                  c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "u2b_roi_align_bwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                  c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "u2b_paste_masks": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "u2b_crop_resize_masks": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p,
+                                      c_void_p, c_void_p]),
+    "u2b_iou_match": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_void_p]),
+    "u2b_nms_workspace_bytes": (c_size_t, [c_int64]),
+    "u2b_batched_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p,
+                                c_size_t, c_void_p]),
 }
 
 

@@ -1,0 +1,240 @@
+// Box kernels of the detector path: fused pairwise-IoU + Matcher, and batched NMS with the
+// sequential scan on the device (no host round trip).
+//  * pairwise_iou  detectron2/structures/boxes.py:310-358
+//  * Matcher       detectron2/modeling/matcher.py:62-127 (incl. set_low_quality_matches_)
+//    The reference materialises the G x A IoU matrix (G*1 MB at A=261,888 plus ~6 temporaries);
+//    here each thread owns one prediction, loops over the G ground-truth boxes held in shared
+//    memory, and only the (A,) results are written. Low-quality matches need the per-GT maximum
+//    over all predictions: pass 1 folds it with atomicMax on the fp32 bit pattern (IoU >= 0).
+//  * batched_nms   detectron2/layers/nms.py:9-21 -> torchvision nms (class-by-class semantics)
+#include "common.cuh"
+#include "../../include/u2b200.h"
+
+namespace {
+
+constexpr int MAX_GT = 1024;
+
+// boxes.py:310-358, same op order: inter>0 ? inter/(area1+area2-inter) : 0
+__device__ __forceinline__ float iou_ref(const float4 g, float garea, const float4 a, float aarea) {
+  const float w = fmaxf(fminf(g.z, a.z) - fmaxf(g.x, a.x), 0.f);
+  const float h = fmaxf(fminf(g.w, a.w) - fmaxf(g.y, a.y), 0.f);
+  const float inter = w * h;
+  return inter > 0.f ? inter / (garea + aarea - inter) : 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+iou_match_kernel(const float4* __restrict__ gt, int G, const float4* __restrict__ pred, int A,
+                 int64_t* __restrict__ matches, float* __restrict__ matched_vals,
+                 unsigned int* __restrict__ gt_max_bits) {
+  __shared__ float4 sgt[MAX_GT];
+  __shared__ float sarea[MAX_GT];
+  __shared__ unsigned int smax[MAX_GT];
+  for (int i = threadIdx.x; i < G; i += blockDim.x) {
+    const float4 g = gt[i];
+    sgt[i] = g;
+    sarea[i] = (g.z - g.x) * (g.w - g.y);
+    smax[i] = 0u;
+  }
+  __syncthreads();
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < A) {
+    const float4 p = pred[a];
+    const float parea = (p.z - p.x) * (p.w - p.y);
+    float best = -1.f;
+    int bi = 0;
+    for (int g = 0; g < G; ++g) {
+      const float v = iou_ref(sgt[g], sarea[g], p, parea);
+      if (v > best) {  // first maximum, as torch.max(dim=0)
+        best = v;
+        bi = g;
+      }
+      if (gt_max_bits && v > 0.f) atomicMax(&smax[g], __float_as_uint(v));
+    }
+    matches[a] = bi;
+    matched_vals[a] = best;
+  }
+  if (gt_max_bits) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < G; i += blockDim.x)
+      if (smax[i]) atomicMax(&gt_max_bits[i], smax[i]);
+  }
+}
+
+// labels from thresholds (matcher.py:96-101) + low-quality promotion (matcher.py:116-127)
+__global__ void __launch_bounds__(256)
+match_label_kernel(const float4* __restrict__ gt, int G, const float4* __restrict__ pred, int A,
+                   const float* __restrict__ matched_vals, const float* __restrict__ thresholds,
+                   const int* __restrict__ labels, int nthr,
+                   const unsigned int* __restrict__ gt_max_bits, int8_t* __restrict__ out_labels) {
+  __shared__ float4 sgt[MAX_GT];
+  __shared__ float sarea[MAX_GT];
+  __shared__ float smax[MAX_GT];
+  if (gt_max_bits) {
+    for (int i = threadIdx.x; i < G; i += blockDim.x) {
+      const float4 g = gt[i];
+      sgt[i] = g;
+      sarea[i] = (g.z - g.x) * (g.w - g.y);
+      smax[i] = __uint_as_float(gt_max_bits[i]);
+    }
+    __syncthreads();
+  }
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A) return;
+  const float v = matched_vals[a];
+  int lab = 1;
+  // thresholds = [-inf, t0, .., +inf] (nthr entries), labels nthr-1 entries; later intervals overwrite
+  for (int i = 0; i + 1 < nthr; ++i)
+    if (v >= thresholds[i] && v < thresholds[i + 1]) lab = labels[i];
+  if (gt_max_bits) {
+    const float4 p = pred[a];
+    const float parea = (p.z - p.x) * (p.w - p.y);
+    for (int g = 0; g < G; ++g)
+      if (iou_ref(sgt[g], sarea[g], p, parea) == smax[g]) {
+        lab = 1;
+        break;
+      }
+  }
+  out_labels[a] = static_cast<int8_t>(lab);
+}
+
+// ---------------- NMS ----------------
+// torchvision nms_kernel.cu devIoU: (inter / (Sa + Sb - inter)) > threshold
+__device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr) {
+  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  const float width = fmaxf(right - left, 0.f), height = fmaxf(bottom - top, 0.f);
+  const float inter = width * height;
+  const float sa = (a.z - a.x) * (a.w - a.y), sb = (b.z - b.x) * (b.w - b.y);
+  return (inter / (sa + sb - inter)) > thr;
+}
+
+// boxes/cats already gathered in descending-score order. mask[i][cb] bit j: box (cb*64+j) is
+// suppressed by box i (same category, IoU > thr, j after i).
+__global__ void __launch_bounds__(64)
+nms_mask_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ cats, int n, float thr,
+                unsigned long long* __restrict__ mask, int col_blocks) {
+  const int row_start = blockIdx.y, col_start = blockIdx.x;
+  if (row_start > col_start) return;
+  const int row_size = min(n - row_start * 64, 64), col_size = min(n - col_start * 64, 64);
+  __shared__ float4 sb[64];
+  __shared__ int64_t sc[64];
+  if (threadIdx.x < col_size) {
+    sb[threadIdx.x] = boxes[col_start * 64 + threadIdx.x];
+    sc[threadIdx.x] = cats ? cats[col_start * 64 + threadIdx.x] : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x < row_size) {
+    const int cur = row_start * 64 + threadIdx.x;
+    const float4 b = boxes[cur];
+    const int64_t c = cats ? cats[cur] : 0;
+    unsigned long long t = 0;
+    const int start = (row_start == col_start) ? threadIdx.x + 1 : 0;
+    for (int i = start; i < col_size; ++i)
+      if (sc[i] == c && iou_gt(b, sb[i], thr)) t |= 1ULL << i;
+    mask[static_cast<size_t>(cur) * col_blocks + col_start] = t;
+  }
+}
+
+// one warp walks the boxes in score order; `removed` lives in shared memory.
+__global__ void __launch_bounds__(32)
+nms_scan_kernel(const unsigned long long* __restrict__ mask, const int64_t* __restrict__ order, int n,
+                int col_blocks, int64_t* __restrict__ keep, int* __restrict__ num_keep) {
+  extern __shared__ unsigned long long removed[];
+  const int lane = threadIdx.x;
+  for (int i = lane; i < col_blocks; i += 32) removed[i] = 0ULL;
+  __syncwarp();
+  int nk = 0;
+  for (int i = 0; i < n; ++i) {
+    const unsigned long long r = removed[i >> 6];
+    if (!((r >> (i & 63)) & 1ULL)) {
+      if (lane == 0) keep[nk] = order[i];
+      ++nk;
+      const unsigned long long* row = mask + static_cast<size_t>(i) * col_blocks;
+      for (int j = (i >> 6) + lane; j < col_blocks; j += 32) removed[j] |= row[j];
+    }
+    __syncwarp();
+  }
+  if (lane == 0) *num_keep = nk;
+}
+
+__global__ void gather_sorted_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ cats,
+                                     const int64_t* __restrict__ order, int n,
+                                     float4* __restrict__ sboxes, int64_t* __restrict__ scats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t o = order[i];
+  sboxes[i] = boxes[o];
+  if (cats) scats[i] = cats[o];
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t u2b_nms_workspace_bytes(int64_t n) {
+  const size_t cb = static_cast<size_t>((n + 63) / 64);
+  return static_cast<size_t>(n) * 16 + static_cast<size_t>(n) * 8 + static_cast<size_t>(n) * cb * 8 + 256;
+}
+
+// boxes (n,4) fp32 xyxy, cats (n) int64 or NULL, order (n) int64 = indices sorted by score descending
+// (stable). keep (n) int64, num_keep device int. Semantics: torchvision batched_nms, class by class.
+int u2b_batched_nms(const float* boxes, const int64_t* cats, const int64_t* order, int64_t n,
+                    float iou_threshold, int64_t* keep, int32_t* num_keep, void* workspace,
+                    size_t workspace_bytes, cudaStream_t stream) {
+  U2B_CHECK_ARG(num_keep, "batched_nms: num_keep is NULL");
+  if (n == 0) {
+    U2B_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int32_t), stream));
+    return 0;
+  }
+  U2B_CHECK_ARG(boxes && order && keep && workspace && n > 0, "batched_nms: bad arguments");
+  U2B_CHECK_ARG(workspace_bytes >= u2b_nms_workspace_bytes(n), "batched_nms: workspace too small");
+  const int cb = static_cast<int>((n + 63) / 64);
+  U2B_CHECK_ARG(static_cast<size_t>(cb) * 8 <= 200 * 1024, "batched_nms: n=%lld too large", (long long)n);
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  float4* sboxes = reinterpret_cast<float4*>(w);
+  int64_t* scats = reinterpret_cast<int64_t*>(w + static_cast<size_t>(n) * 16);
+  unsigned long long* mask = reinterpret_cast<unsigned long long*>(w + static_cast<size_t>(n) * 24);
+  gather_sorted_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(boxes), cats, order, (int)n, sboxes, scats);
+  U2B_LAUNCH_CHECK();
+  // lower-triangular blocks are never read by the scan (j starts at i>>6), no memset needed
+  dim3 grid(cb, cb);
+  nms_mask_kernel<<<grid, 64, 0, stream>>>(sboxes, cats ? scats : nullptr, (int)n, iou_threshold, mask, cb);
+  U2B_LAUNCH_CHECK();
+  const size_t smem = static_cast<size_t>(cb) * 8;
+  if (smem > 48 * 1024) {
+    U2B_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  nms_scan_kernel<<<1, 32, smem, stream>>>(mask, order, (int)n, cb, keep, num_keep);
+  U2B_LAUNCH_CHECK();
+  return 0;
+}
+
+// gt (G,4), pred (A,4) fp32. thresholds: nthr floats on the device [-inf, t.., +inf]; labels: nthr-1
+// ints on the device. matches int64 (A), matched_vals fp32 (A), out_labels int8 (A).
+// gt_max_scratch: G uint32 device scratch, required iff allow_low_quality.
+int u2b_iou_match(const float* gt, int64_t G, const float* pred, int64_t A, const float* thresholds,
+                  const int32_t* labels, int nthr, int allow_low_quality, int64_t* matches,
+                  float* matched_vals, int8_t* out_labels, uint32_t* gt_max_scratch,
+                  cudaStream_t stream) {
+  if (A == 0) return 0;
+  U2B_CHECK_ARG(pred && thresholds && labels && matches && matched_vals && out_labels && nthr >= 2,
+                "iou_match: bad arguments");
+  U2B_CHECK_ARG(G > 0 && G <= MAX_GT, "iou_match: G=%lld outside 1..%d (empty GT is handled by the caller)",
+                (long long)G, MAX_GT);
+  U2B_CHECK_ARG(!allow_low_quality || gt_max_scratch, "iou_match: low-quality matching needs scratch");
+  const unsigned grid = static_cast<unsigned>((A + 255) / 256);
+  if (allow_low_quality) U2B_CUDA(cudaMemsetAsync(gt_max_scratch, 0, sizeof(uint32_t) * G, stream));
+  iou_match_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(gt), (int)G,
+                                             reinterpret_cast<const float4*>(pred), (int)A, matches,
+                                             matched_vals, allow_low_quality ? gt_max_scratch : nullptr);
+  U2B_LAUNCH_CHECK();
+  match_label_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(gt), (int)G,
+                                               reinterpret_cast<const float4*>(pred), (int)A, matched_vals,
+                                               thresholds, labels, nthr,
+                                               allow_low_quality ? gt_max_scratch : nullptr, out_labels);
+  U2B_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,318 @@
+// ROIAlignV2 (aligned=True, sampling_ratio=0 -> adaptive ceil(roi/bin) samples) over an FPN pyramid,
+// NHWC feature maps, with the level assignment of ROIPooler fused into the same launch.
+// Reference call chain: detectron2/modeling/poolers.py:206-263 (ROIPooler.forward),
+// poolers.py:23-59 (assign_boxes_to_levels), detectron2/layers/roi_align.py:49-65 ->
+// torchvision.ops.roi_align (CUDA kernel roi_align_forward_kernel_impl / bilinear_interpolate).
+//
+// HBM/L2-bound: one warp owns one output bin (roi, ph, pw) and sweeps the channel vector with
+// 16-byte loads (NHWC makes the 4 bilinear corners 4 contiguous channel vectors); fp32 accumulation;
+// one 16-byte store per lane. Backward scatters with vectorised fp32 atomics (red.v4.f32) into
+// per-level fp32 gradient maps.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "../../include/u2b200.h"
+
+namespace {
+
+constexpr int MAX_LEVELS = 4;
+
+struct Pyramid {
+  const void* feat[MAX_LEVELS];
+  float* grad[MAX_LEVELS];
+  int H[MAX_LEVELS];
+  int W[MAX_LEVELS];
+  float scale[MAX_LEVELS];
+  int num_levels;
+};
+
+// poolers.py:51-59: floor(canonical_level + log2(sqrt(area)/canonical_size + 1e-8)) clamped, minus min_level
+__global__ void assign_levels_kernel(const float* __restrict__ rois, int K, int min_level,
+                                     int max_level, float canonical_size, int canonical_level,
+                                     int32_t* __restrict__ levels) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  const float* r = rois + static_cast<size_t>(i) * 5;
+  const float area = (r[3] - r[1]) * (r[4] - r[2]);
+  const float sz = sqrtf(area);
+  float lv = floorf(static_cast<float>(canonical_level) + log2f(sz / canonical_size + 1e-8f));
+  lv = fminf(fmaxf(lv, static_cast<float>(min_level)), static_cast<float>(max_level));
+  // NaN (negative area) -> torch.clamp keeps NaN -> int64 cast is undefined in the reference; map to min level
+  levels[i] = (lv == lv) ? static_cast<int>(lv) - min_level : 0;
+}
+
+template <typename T>
+struct Vec;
+template <>
+struct Vec<float> {
+  static constexpr int N = 4;
+  using Raw = float4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 r = *reinterpret_cast<const float4*>(p);
+    v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct Vec<__half> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__half* p, const float (&v)[8]) {
+    uint4 r;
+    __half2* h = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = r;
+  }
+};
+template <>
+struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = r;
+  }
+};
+
+struct Sample {
+  int o1, o2, o3, o4;  // pixel offsets (in pixels, row-major) of the 4 corners
+  float w1, w2, w3, w4;
+  bool valid;
+};
+
+// torchvision bilinear_interpolate (roi_align_kernel.cu): same comparisons / clamps / op order.
+__device__ __forceinline__ Sample make_sample(float y, float x, int H, int W) {
+  Sample s;
+  s.valid = !(y < -1.0f || y > static_cast<float>(H) || x < -1.0f || x > static_cast<float>(W));
+  if (y <= 0.f) y = 0.f;
+  if (x <= 0.f) x = 0.f;
+  int y_low = static_cast<int>(y), x_low = static_cast<int>(x);
+  int y_high, x_high;
+  if (y_low >= H - 1) { y_high = y_low = H - 1; y = static_cast<float>(y_low); } else { y_high = y_low + 1; }
+  if (x_low >= W - 1) { x_high = x_low = W - 1; x = static_cast<float>(x_low); } else { x_high = x_low + 1; }
+  const float ly = y - y_low, lx = x - x_low, hy = 1.f - ly, hx = 1.f - lx;
+  s.w1 = hy * hx; s.w2 = hy * lx; s.w3 = ly * hx; s.w4 = ly * lx;
+  s.o1 = y_low * W + x_low; s.o2 = y_low * W + x_high; s.o3 = y_high * W + x_low; s.o4 = y_high * W + x_high;
+  if (!s.valid) { s.o1 = s.o2 = s.o3 = s.o4 = 0; s.w1 = s.w2 = s.w3 = s.w4 = 0.f; }
+  return s;
+}
+
+struct BinGeom {
+  float start_h, start_w, bin_h, bin_w;
+  int grid_h, grid_w;
+  float count;
+};
+__device__ __forceinline__ BinGeom bin_geometry(const float* r, float scale, int P) {
+  BinGeom g;
+  const float offset = 0.5f;  // aligned=True
+  g.start_w = r[1] * scale - offset;
+  g.start_h = r[2] * scale - offset;
+  const float end_w = r[3] * scale - offset, end_h = r[4] * scale - offset;
+  const float roi_w = end_w - g.start_w, roi_h = end_h - g.start_h;
+  g.bin_h = roi_h / static_cast<float>(P);
+  g.bin_w = roi_w / static_cast<float>(P);
+  g.grid_h = static_cast<int>(ceilf(roi_h / P));
+  g.grid_w = static_cast<int>(ceilf(roi_w / P));
+  const float c = static_cast<float>(g.grid_h) * static_cast<float>(g.grid_w);
+  g.count = fmaxf(c, 1.f);
+  return g;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+roi_align_fwd_kernel(Pyramid pyr, int C, const float* __restrict__ rois,
+                     const int32_t* __restrict__ levels, int K, int P, T* __restrict__ out) {
+  constexpr int VN = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const long long bin = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (bin >= static_cast<long long>(K) * P * P) return;
+  const int k = static_cast<int>(bin / (P * P));
+  const int ph = static_cast<int>((bin / P) % P), pw = static_cast<int>(bin % P);
+  const float* r = rois + static_cast<size_t>(k) * 5;
+  const int lvl = levels ? levels[k] : 0;
+  const int H = pyr.H[lvl], W = pyr.W[lvl];
+  const int b = static_cast<int>(r[0]);
+  const T* feat = static_cast<const T*>(pyr.feat[lvl]) + static_cast<size_t>(b) * H * W * C;
+  const BinGeom g = bin_geometry(r, pyr.scale[lvl], P);
+  T* o = out + static_cast<size_t>(bin) * C;
+  for (int c0 = lane * VN; c0 < C; c0 += 32 * VN) {
+    float acc[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) acc[i] = 0.f;
+    for (int iy = 0; iy < g.grid_h; ++iy) {
+      const float y = g.start_h + ph * g.bin_h + (iy + 0.5f) * g.bin_h / static_cast<float>(g.grid_h);
+      for (int ix = 0; ix < g.grid_w; ++ix) {
+        const float x = g.start_w + pw * g.bin_w + (ix + 0.5f) * g.bin_w / static_cast<float>(g.grid_w);
+        const Sample s = make_sample(y, x, H, W);
+        if (!s.valid) continue;
+        float v1[VN], v2[VN], v3[VN], v4[VN];
+        Vec<T>::load(feat + static_cast<size_t>(s.o1) * C + c0, v1);
+        Vec<T>::load(feat + static_cast<size_t>(s.o2) * C + c0, v2);
+        Vec<T>::load(feat + static_cast<size_t>(s.o3) * C + c0, v3);
+        Vec<T>::load(feat + static_cast<size_t>(s.o4) * C + c0, v4);
+#pragma unroll
+        for (int i = 0; i < VN; ++i)
+          acc[i] += s.w1 * v1[i] + s.w2 * v2[i] + s.w3 * v3[i] + s.w4 * v4[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VN; ++i) acc[i] /= g.count;
+    Vec<T>::store(o + c0, acc);
+  }
+}
+
+// grad_out: (K, P, P, C) of T; grad feature maps: fp32 NHWC per level (pre-zeroed by the caller).
+template <typename T>
+__global__ void __launch_bounds__(256)
+roi_align_bwd_kernel(Pyramid pyr, int C, const float* __restrict__ rois,
+                     const int32_t* __restrict__ levels, int K, int P, const T* __restrict__ gout) {
+  constexpr int VN = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const long long bin = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (bin >= static_cast<long long>(K) * P * P) return;
+  const int k = static_cast<int>(bin / (P * P));
+  const int ph = static_cast<int>((bin / P) % P), pw = static_cast<int>(bin % P);
+  const float* r = rois + static_cast<size_t>(k) * 5;
+  const int lvl = levels ? levels[k] : 0;
+  const int H = pyr.H[lvl], W = pyr.W[lvl];
+  const int b = static_cast<int>(r[0]);
+  float* gfeat = pyr.grad[lvl] + static_cast<size_t>(b) * H * W * C;
+  const BinGeom g = bin_geometry(r, pyr.scale[lvl], P);
+  const T* go = gout + static_cast<size_t>(bin) * C;
+  for (int c0 = lane * VN; c0 < C; c0 += 32 * VN) {
+    float gv[VN];
+    Vec<T>::load(go + c0, gv);
+#pragma unroll
+    for (int i = 0; i < VN; ++i) gv[i] /= g.count;
+    for (int iy = 0; iy < g.grid_h; ++iy) {
+      const float y = g.start_h + ph * g.bin_h + (iy + 0.5f) * g.bin_h / static_cast<float>(g.grid_h);
+      for (int ix = 0; ix < g.grid_w; ++ix) {
+        const float x = g.start_w + pw * g.bin_w + (ix + 0.5f) * g.bin_w / static_cast<float>(g.grid_w);
+        const Sample s = make_sample(y, x, H, W);
+        if (!s.valid) continue;
+        const int offs[4] = {s.o1, s.o2, s.o3, s.o4};
+        const float ws[4] = {s.w1, s.w2, s.w3, s.w4};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float* dst = gfeat + static_cast<size_t>(offs[q]) * C + c0;
+#pragma unroll
+          for (int i = 0; i < VN; i += 4)
+            atomicAdd(reinterpret_cast<float4*>(dst + i),
+                      make_float4(ws[q] * gv[i], ws[q] * gv[i + 1], ws[q] * gv[i + 2], ws[q] * gv[i + 3]));
+        }
+      }
+    }
+  }
+}
+
+int fill_pyramid(Pyramid* p, int num_levels, const void* const* feats, float* const* grads,
+                 const int32_t* hs, const int32_t* ws, const float* scales) {
+  if (num_levels < 1 || num_levels > MAX_LEVELS) return -1;
+  p->num_levels = num_levels;
+  for (int i = 0; i < num_levels; ++i) {
+    p->feat[i] = feats ? feats[i] : nullptr;
+    p->grad[i] = grads ? grads[i] : nullptr;
+    p->H[i] = hs[i];
+    p->W[i] = ws[i];
+    p->scale[i] = scales[i];
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int u2b_assign_levels(const float* rois5, int64_t K, int min_level, int max_level,
+                      float canonical_size, int canonical_level, int32_t* levels,
+                      cudaStream_t stream) {
+  if (K == 0) return 0;
+  U2B_CHECK_ARG(rois5 && levels && K > 0, "assign_levels: bad arguments");
+  assign_levels_kernel<<<static_cast<unsigned>((K + 255) / 256), 256, 0, stream>>>(
+      rois5, static_cast<int>(K), min_level, max_level, canonical_size, canonical_level, levels);
+  U2B_LAUNCH_CHECK();
+  return 0;
+}
+
+// dtype: 0 = fp32, 1 = fp16, 2 = bf16. feats[l]: (N, H_l, W_l, C) NHWC. out: (K, P, P, C).
+int u2b_roi_align_fwd(int dtype, int num_levels, const void* const* feats, const int32_t* hs,
+                      const int32_t* ws, const float* scales, int64_t C, const float* rois5,
+                      const int32_t* levels, int64_t K, int P, void* out, cudaStream_t stream) {
+  if (K == 0) return 0;
+  Pyramid p;
+  U2B_CHECK_ARG(feats && hs && ws && scales && rois5 && out, "roi_align_fwd: null pointer");
+  U2B_CHECK_ARG(fill_pyramid(&p, num_levels, feats, nullptr, hs, ws, scales) == 0,
+                "roi_align_fwd: 1..4 levels supported");
+  U2B_CHECK_ARG(num_levels == 1 || levels, "roi_align_fwd: levels required for a pyramid");
+  const int vn = dtype == 0 ? 4 : 8;
+  U2B_CHECK_ARG(C > 0 && C % vn == 0, "roi_align_fwd: C=%lld must be a multiple of %d", (long long)C, vn);
+  const long long bins = static_cast<long long>(K) * P * P;
+  const unsigned grid = static_cast<unsigned>((bins + 7) / 8);
+  if (dtype == 0)
+    roi_align_fwd_kernel<float><<<grid, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (float*)out);
+  else if (dtype == 1)
+    roi_align_fwd_kernel<__half><<<grid, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (__half*)out);
+  else if (dtype == 2)
+    roi_align_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P,
+                                                                 (__nv_bfloat16*)out);
+  else {
+    u2b_set_error("roi_align_fwd: unknown dtype %d", dtype);
+    return U2B_ERR_BAD_ARG;
+  }
+  U2B_LAUNCH_CHECK();
+  return 0;
+}
+
+// grad_feats[l]: (N, H_l, W_l, C) fp32, must be zero-initialised by the caller (accumulated into).
+int u2b_roi_align_bwd(int dtype, int num_levels, float* const* grad_feats, const int32_t* hs,
+                      const int32_t* ws, const float* scales, int64_t C, const float* rois5,
+                      const int32_t* levels, int64_t K, int P, const void* grad_out,
+                      cudaStream_t stream) {
+  if (K == 0) return 0;
+  Pyramid p;
+  U2B_CHECK_ARG(grad_feats && hs && ws && scales && rois5 && grad_out, "roi_align_bwd: null pointer");
+  U2B_CHECK_ARG(fill_pyramid(&p, num_levels, nullptr, grad_feats, hs, ws, scales) == 0,
+                "roi_align_bwd: 1..4 levels supported");
+  U2B_CHECK_ARG(num_levels == 1 || levels, "roi_align_bwd: levels required for a pyramid");
+  const int vn = dtype == 0 ? 4 : 8;
+  U2B_CHECK_ARG(C > 0 && C % vn == 0, "roi_align_bwd: C must be a multiple of %d", vn);
+  const long long bins = static_cast<long long>(K) * P * P;
+  const unsigned grid = static_cast<unsigned>((bins + 7) / 8);
+  if (dtype == 0)
+    roi_align_bwd_kernel<float><<<grid, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (const float*)grad_out);
+  else if (dtype == 1)
+    roi_align_bwd_kernel<__half><<<grid, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (const __half*)grad_out);
+  else if (dtype == 2)
+    roi_align_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P,
+                                                                 (const __nv_bfloat16*)grad_out);
+  else {
+    u2b_set_error("roi_align_bwd: unknown dtype %d", dtype);
+    return U2B_ERR_BAD_ARG;
+  }
+  U2B_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"
