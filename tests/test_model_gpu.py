@@ -1,0 +1,117 @@
+"""GPU parity of the whole detector step (product u2seg_b200 model, fp32, channels_last) against the
+reference's recorded outputs (tests/golden/detector_{train,infer}_*.npz) and the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import detector_oracle as do
+
+pytestmark = pytest.mark.gpu
+
+
+def _cpu_randperm(n, device=None):
+    return torch.randperm(n).to(device)     # CPU generator, the order the oracle/reference consume it in
+
+
+def _make_batch(data, train=True, out_sizes=None):
+    from u2seg_b200.structures import BitMasks, Boxes, Instances
+    images, boxes, classes, masks, sems = data
+    batch = []
+    for i, im in enumerate(images):
+        d = {"image": im}
+        if train:
+            inst = Instances((im.shape[1], im.shape[2]))
+            inst.gt_boxes = Boxes(boxes[i])
+            inst.gt_classes = classes[i]
+            inst.gt_masks = BitMasks(masks[i])
+            d["instances"] = inst
+            d["sem_seg"] = sems[i]
+        elif out_sizes is not None:
+            d["height"], d["width"] = out_sizes[i]
+        batch.append(d)
+    return batch
+
+
+def _build(K, params, training):
+    from u2seg_b200.config import get_u2seg_cfg
+    from u2seg_b200.modeling import build_model
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = get_u2seg_cfg(K)
+    model = build_model(cfg)
+    model.load_state_dict(params)
+    model = model.to(memory_format=torch.channels_last)
+    model.train(training)
+    return model
+
+
+def test_state_dict_names_and_shapes():
+    model = _build(800, do.init_params(do.DetCfg(800), 0), True)
+    sd = model.state_dict()
+    p = do.init_params(do.DetCfg(800), 0)
+    assert set(sd) == set(p) and len(sd) == 431 and len(list(model.parameters())) == 248
+
+
+def test_training_losses_match_reference(golden_dir, monkeypatch):
+    from u2seg_b200.modeling import rpn
+    g = np.load(os.path.join(golden_dir, "detector_train_256x320.npz"))
+    n, H, W, K, S, seed, G, lo, hi = [int(v) for v in g["meta"]]
+    model = _build(K, do.init_params(do.DetCfg(K, S), 0), True)
+    data = do.synthetic_batch(n, H, W, K, S, seed=seed, G=G, min_size=lo, max_size=hi)
+    monkeypatch.setattr(rpn, "_randperm", _cpu_randperm)
+    torch.manual_seed(seed)
+    losses = model(_make_batch(data))
+    assert list(losses.keys()) == [str(k) for k in g["keys"]]
+    for k, v in zip(g["keys"], g["values"]):
+        got = float(losses[str(k)])
+        assert abs(got - v) <= 1e-3 * max(1.0, abs(v)), (str(k), got, v)     # FP: within 1e-3 (fp32)
+    sum(losses.values()).backward()
+    grads = [p.grad for p in model.parameters()]
+    assert all(gr is not None and torch.isfinite(gr).all() for gr in grads)
+
+
+def test_training_gradients_match_oracle(monkeypatch):
+    """Backward parity: d(sum of losses)/d(params) vs autograd through the CPU oracle."""
+    from u2seg_b200.modeling import rpn
+    K, S, seed = 800, 28, 5
+    cfg = do.DetCfg(K, S)
+    params = do.init_params(cfg, 0)
+    data = do.synthetic_batch(1, 128, 160, K, S, seed=seed, G=4, min_size=16, max_size=80)
+    names = ["backbone.fpn_output2.weight", "backbone.bottom_up.res3.0.conv2.weight", "roi_heads.box_head.1.fc1.weight",
+             "roi_heads.mask_head.mask_fcn2.weight", "proposal_generator.rpn_head.conv.weight", "sem_seg_head.p4.2.weight",
+             "backbone.bottom_up.stem.conv1.norm.weight"]
+    op = {k: v.clone().requires_grad_(k in names) for k, v in params.items()}
+    torch.manual_seed(seed)
+    sum(do.forward_train(op, cfg, *data).values()).backward()
+    model = _build(K, params, True)
+    monkeypatch.setattr(rpn, "_randperm", _cpu_randperm)
+    torch.manual_seed(seed)
+    sum(model(_make_batch(data)).values()).backward()
+    named = dict(model.named_parameters())
+    for k in names:
+        a, b = named[k].grad.float().cpu(), op[k].grad
+        denom = float(b.abs().max()) + 1e-12
+        assert float((a - b).abs().max()) / denom <= 2e-3, (k, float((a - b).abs().max()), denom)
+
+
+def test_inference_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "detector_infer_200x304.npz"))
+    n, H, W, K, S, seed, G, lo, hi, oh, ow = [int(v) for v in g["meta"]]
+    cfg = do.DetCfg(K, S)
+    data = do.synthetic_batch(n, H, W, K, S, seed=seed, G=G, min_size=lo, max_size=hi)
+    model = _build(K, do.eval_fixture_params(cfg, data[0], seed=0), False)
+    out = model(_make_batch(data, train=False, out_sizes=[(oh, ow)]))[0]
+    inst = out["instances"]
+    assert np.array_equal(inst.pred_classes.cpu().numpy(), g["pred_classes"])                 # INT: bit exact
+    np.testing.assert_allclose(inst.pred_boxes.tensor.cpu().numpy(), g["pred_boxes"], rtol=1e-3, atol=1e-2)
+    np.testing.assert_allclose(inst.scores.cpu().numpy(), g["scores"], rtol=1e-3, atol=1e-5)
+    want_masks = np.unpackbits(g["pred_masks"])[:int(np.prod(g["mask_shape"]))].reshape(g["mask_shape"]).astype(bool)
+    got_masks = inst.pred_masks.cpu().numpy()
+    assert got_masks.shape == want_masks.shape
+    assert (got_masks != want_masks).mean() < 1e-4          # FP->bool: only pixels with |p-0.5| < eps may flip
+    sem = out["sem_seg"].argmax(0).cpu().numpy().astype(np.uint8)
+    assert (sem != g["sem_seg_argmax"]).mean() < 1e-3
+    pan, info = out["panoptic_seg"]
+    assert (pan.cpu().numpy() != g["panoptic"]).mean() < 2e-3 and len(info) == int(g["n_segments"][0])

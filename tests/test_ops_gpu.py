@@ -43,7 +43,7 @@ def test_pooler_matches_reference_golden(ops, P, key):
     lv = assign_boxes_to_levels_rois(rois.contiguous(), 2, 5, 224, 4)
     assert np.array_equal(lv.cpu().numpy().astype(np.int64), ops["pool_levels"])             # INT: bit exact
     out = ROIPooler(P, (0.25, 0.125, 0.0625, 0.03125), 0, "ROIAlignV2")(feats, boxes)
-    np.testing.assert_allclose(out.cpu().numpy(), ops[key], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out.cpu().numpy(), ops[key], rtol=1e-3, atol=1e-4)   # north_star: within 1e-3 fp32
 
 
 def test_levels_at_power_of_two_boundaries():

@@ -1,0 +1,58 @@
+"""Compute dispatch for the dense layers of the model (conv / norm / activation / residual).
+
+Round-1 state: convolutions and batch-norm statistics go through the library kernels of this image
+(cuDNN via F.conv2d, ATen batch_norm; counted as library calls, like cuBLAS), in channels_last;
+ops.USE_TCGEN05_CONV switches eligible convolutions to the hand-written tcgen05 implicit-GEMM kernel
+of libu2b200 (csrc/conv_tc.cu) as it comes online. ROI pooling, NMS, matching, mask ops and k-means
+always run in libu2b200.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch import nn
+
+USE_TCGEN05_CONV = False
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def batch_norm(x, bn, relu=False):
+    """nn.SyncBatchNorm semantics (layers/batch_norm.py:187): batch statistics over the whole
+    data-parallel group in training, running statistics in eval."""
+    if bn.training:
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        if _world() > 1:
+            from torch.nn.modules._functions import SyncBatchNorm as _SBN
+            y = _SBN.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum,
+                           dist.group.WORLD, _world())
+        else:
+            y = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, True, bn.momentum, bn.eps)
+    else:
+        y = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
+    return F.relu_(y) if relu else y
+
+
+def conv_norm_act(x, m, residual=None):
+    """y = act(norm(conv(x)) [+ residual]) for a backbone.Conv2d module `m`."""
+    if USE_TCGEN05_CONV:
+        from . import conv_tc
+        y = conv_tc.try_conv(x, m, residual)
+        if y is not None:
+            return y
+    y = F.conv2d(x, m.weight, m.bias, m.stride, m.padding, m.dilation, m.groups)
+    if m.norm is not None:
+        y = batch_norm(y, m.norm) if isinstance(m.norm, nn.BatchNorm2d) else m.norm(y)
+    if residual is not None:
+        y = y + residual
+    if m.activation is not None:
+        y = m.activation(y)
+    return y
+
+
+def lateral_add_upsample(lateral, feat, prev):
+    """fpn.py:153-156: lateral(feat) + F.interpolate(prev, scale_factor=2, mode='nearest')."""
+    td = F.interpolate(prev, scale_factor=2.0, mode="nearest")
+    return lateral(feat) + td
