@@ -119,6 +119,20 @@ int u2b_batched_nms(const float* boxes, const int64_t* cats, const int64_t* orde
                     float iou_threshold, int64_t* keep, int32_t* num_keep, void* workspace,
                     size_t workspace_bytes, u2b_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Convolution / Linear on tcgen05 tensor cores (implicit GEMM, TMA-fed, fp32 accumulation in TMEM).
+ * Replaces the F.conv2d call of detectron2/layers/wrappers.py:127 (and, as a 1x1 conv over a (1,1,M,K)
+ * image, nn.Linear of roi_heads/box_head.py:70 and fast_rcnn.py:236-239) for shapes with Cin % 64 == 0,
+ * Cout % 64 == 0, kernel 1x1 (pad 0) or 3x3 (pad 1), stride 1 or 2. dtype: 1 = fp16, 2 = bf16.
+ * ------------------------------------------------------------------------------------------ */
+int u2b_conv2d_supported(int Cin, int Cout, int R, int S, int stride, int pad);
+
+/* x (N,H,W,Cin) NHWC; w (Cout,R,S,Cin); out (N,OH,OW,Cout) NHWC, OH = (H + 2*pad - R)/stride + 1.
+ * Epilogue: out = [relu]( acc + bias[c] + residual ), bias (Cout fp32) / residual (as out) optional. */
+int u2b_conv2d_nhwc_fwd(int dtype, const void* x, int N, int H, int W, int Cin, const void* w, int Cout,
+                        int R, int S, int stride, int pad, const float* bias, const void* residual, int relu,
+                        void* out, u2b_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

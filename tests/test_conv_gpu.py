@@ -1,0 +1,79 @@
+"""GPU numerics of the tcgen05 implicit-GEMM convolution vs a plain PyTorch fp32 reference of the same
+op on identical (fp16/bf16-rounded) inputs. Tolerance: 1e-3 relative to the output scale (fp32 accumulate)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# (N, Cin, H, W, Cout, k, stride) — hot-path shapes of Appendix A at reduced spatial size + ragged edges
+SHAPES = [
+    (2, 256, 64, 64, 256, 3, 1),     # FPN output / RPN conv / mask_fcn class (BN=256, 4 stages)
+    (2, 256, 32, 48, 128, 3, 1),     # sem-seg head (BN=128)
+    (1, 64, 56, 56, 64, 3, 1),       # res2 conv2 (BN=64)
+    (2, 64, 40, 40, 256, 1, 1),      # res2 conv3 1x1
+    (2, 512, 16, 16, 2048, 1, 1),    # res5 conv3: 8 N-tiles
+    (2, 1024, 20, 28, 256, 1, 1),    # fpn lateral4, ragged 20x28
+    (2, 128, 33, 47, 128, 3, 2),     # stride-2 3x3 on odd sizes (res3.0.conv2)
+    (2, 256, 32, 32, 512, 1, 2),     # stride-2 shortcut
+    (3, 256, 14, 14, 256, 3, 1),     # mask head 14x14 ROIs (BW=16 tile with masked columns)
+    (1, 256, 200, 136, 256, 3, 1),   # inference-like ragged map
+]
+
+
+def _ref(x, w, b, stride, pad, res, relu):
+    torch.backends.cudnn.allow_tf32 = False
+    y = F.conv2d(x.float(), w.float(), b, stride, pad)
+    if res is not None:
+        y = y + res.float()
+    return F.relu(y) if relu else y
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_conv_forward_matches_fp32_reference(shape, dtype):
+    from u2seg_b200.modeling.conv_tc import conv2d_nhwc
+    N, Cin, H, W, Cout, k, stride = shape
+    g = torch.Generator(device="cuda").manual_seed(hash(shape) % 1000)
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g).to(dtype).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5).to(dtype)
+    b = torch.randn(Cout, device="cuda", generator=g)
+    pad = k // 2
+    for bias, res, relu in ((None, False, False), (b, False, True), (b, True, True)):
+        OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        r = torch.randn(N, Cout, OH, OW, device="cuda", generator=g).to(dtype).contiguous(memory_format=torch.channels_last) if res else None
+        y = conv2d_nhwc(x, w.permute(0, 2, 3, 1).contiguous(), stride, pad, bias, r, relu)
+        want = _ref(x, w, bias, stride, pad, r, relu)
+        assert y.shape == want.shape and y.dtype == dtype
+        err = (y.float() - want).abs().max().item()
+        scale = want.abs().max().item()
+        tol = (1e-3 if dtype == torch.float16 else 8e-3) * scale      # output rounding of the storage dtype
+        assert err <= tol, (shape, dtype, bias is not None, res, relu, err, scale)
+        # fp32-accumulate check independent of the output rounding: compare against the rounded reference
+        assert (y.float() - want.to(dtype).float()).abs().max().item() <= 2 * tol / 8 + 1e-6 * scale
+
+
+def test_conv_autograd_and_linear():
+    from u2seg_b200.modeling import conv_tc
+    from u2seg_b200.modeling.backbone import Conv2d
+    torch.manual_seed(0)
+    m = Conv2d(256, 256, 3, padding=1, bias=True, activation=F.relu_).cuda()
+    x = torch.randn(2, 256, 24, 40, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = conv_tc.try_conv(x, m)
+    assert y is not None
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    wr = m.weight.detach().bfloat16().float().requires_grad_(True)
+    yr = F.relu(F.conv2d(xr, wr, m.bias.detach(), 1, 1))
+    yr.backward(gy.float())
+    sc = lambda t: t.abs().max().item()
+    assert (y.float() - yr).abs().max().item() <= 8e-3 * sc(yr)
+    assert (x.grad.float() - xr.grad).abs().max().item() <= 2e-2 * sc(xr.grad)
+    assert (m.weight.grad.float() - wr.grad).abs().max().item() <= 2e-2 * sc(wr.grad)
+    # Linear via the same kernel (box head fc1: 12544 -> 1024)
+    lin = torch.nn.Linear(12544, 1024).cuda()
+    a = torch.randn(300, 12544, device="cuda").bfloat16()
+    got = conv_tc.linear(a, lin.weight, lin.bias, relu=True)
+    want = F.relu(F.linear(a.float(), lin.weight.bfloat16().float(), lin.bias))
+    assert (got.float() - want).abs().max().item() <= 8e-3 * sc(want)

@@ -74,7 +74,7 @@ def test_pooler_hot_path_shapes_fwd_bwd(dtype, tol):
     fg = [cl(f.to(dtype).cuda()).requires_grad_(True) for f in feats]
     out = ROIPooler(7, (0.25, 0.125, 0.0625, 0.03125), 0, "ROIAlignV2")(fg, [b.cuda() for b in boxes])
     assert out.dtype == dtype and out.shape == want.shape
-    np.testing.assert_allclose(out.float().cpu().numpy(), want.detach().numpy(), rtol=tol, atol=tol * 4)
+    np.testing.assert_allclose(out.detach().float().cpu().numpy(), want.detach().numpy(), rtol=tol, atol=tol * 4)
     out.backward(gout.to(dtype).cuda())
     for a, b in zip(fg, fr):
         scale = float(b.grad.abs().max())
@@ -115,9 +115,9 @@ def test_paste_masks_full_size_properties():
     ys = (torch.arange(H) + 0.5)[None, :, None]
     xs = (torch.arange(W) + 0.5)[None, None, :]
     b = boxes[:, :, None, None]
-    # bilinear with zero padding: value >= 0.5 iff the sample is at least half a mask-pixel inside the box
+    # bilinear with zero padding: 1 at least half a mask-pixel inside the box, 0 more than half a mask-pixel outside
     hw, hh = (b[:, 2] - b[:, 0]) / 56, (b[:, 3] - b[:, 1]) / 56
-    inside = (xs >= b[:, 0] + 1e-3) & (xs <= b[:, 2] - 1e-3) & (ys >= b[:, 1] + 1e-3) & (ys <= b[:, 3] - 1e-3)
+    inside = (xs >= b[:, 0] + hw + 1e-3) & (xs <= b[:, 2] - hw - 1e-3) & (ys >= b[:, 1] + hh + 1e-3) & (ys <= b[:, 3] - hh - 1e-3)
     far = (xs < b[:, 0] - hw - 1e-3) | (xs > b[:, 2] + hw + 1e-3) | (ys < b[:, 1] - hh - 1e-3) | (ys > b[:, 3] + hh + 1e-3)
     assert bool(out[inside].all()) and not bool(out[far].any())
 

@@ -1,0 +1,166 @@
+"""bench.py workload `train`: u2seg_R50_800 training step, batch 2 / GPU, synthetic 1024x1024
+COCO-panoptic-shaped inputs (BASELINE.json configs[1]; configs[2] under torchrun)."""
+import json
+import os
+import time
+
+import torch
+import torch.distributed as dist
+
+IMS_PER_GPU, H, W, NUM_CLASSES, SEM_CLASSES = 2, 1024, 1024, 800, 28
+# analytic conv/GEMM work of one step (2 images): 673.8 GMAC fwd -> x2 flop x3 (fwd+dgrad+wgrad)
+FLOP_PER_IMAGE = 2.021e12
+
+
+def _to_device(batch, dev):
+    out = []
+    for d in batch:
+        out.append({"image": d["image"].to(dev, non_blocking=True), "instances": d["instances"].to(dev, non_blocking=True),
+                    "sem_seg": d["sem_seg"].to(dev, non_blocking=True), "height": d["height"], "width": d["width"]})
+    return out
+
+
+def _batch_bytes(batch):
+    n = 0
+    for d in batch:
+        n += d["image"].numel() * d["image"].element_size() + d["sem_seg"].numel() * d["sem_seg"].element_size()
+        i = d["instances"]
+        n += i.gt_boxes.tensor.numel() * 4 + i.gt_classes.numel() * 8 + i.gt_masks.tensor.numel()
+    return n
+
+
+def run_train(args, ClockSampler, load_peaks, dist_info):
+    from . import _lib
+    from .config import get_u2seg_cfg
+    from .data_synth import synthetic_batch
+    from .engine import Trainer
+
+    rank, world, local = dist_info()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    torch.backends.cudnn.benchmark = True
+    cfg = get_u2seg_cfg(NUM_CLASSES)
+    torch.manual_seed(0)
+    trainer = Trainer(cfg, amp_dtype=torch.bfloat16, device=dev)
+    if world > 1:   # identical initial weights on every rank (DDP broadcasts rank 0's)
+        for t in list(trainer.model.parameters()) + list(trainer.model.buffers()):
+            dist.broadcast(t.data, 0)
+
+    pool_n = 4
+    host_pool = [synthetic_batch(IMS_PER_GPU, H, W, NUM_CLASSES, SEM_CLASSES, seed=1234 + 97 * rank + i, pin=True)
+                 for i in range(pool_n)]
+    dev_pool = [_to_device(b, dev) for b in host_pool]
+    warm = max(3, args.warmup)
+    for i in range(warm):
+        trainer.run_step(dev_pool[i % pool_n])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+
+    # ---- value: inputs resident in HBM ----
+    sampler = ClockSampler(local)
+    l0 = _lib.launch_count
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    last = None
+    for i in range(args.steps):
+        last = trainer.run_step(dev_pool[i % pool_n])
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = _lib.launch_count - l0
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t) / args.steps
+    value = IMS_PER_GPU * world / (ms_step * 1e-3)
+    loss_total = float(sum(last.values()))
+
+    # ---- e2e: public API with HOST (pinned) inputs; H2D every step, loss read back every step ----
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    d2h = 0
+    for i in range(e2e_steps):
+        losses = trainer.run_step(_to_device(host_pool[i % pool_n], dev))
+        host_losses = torch.stack(list(losses.values())).float().cpu()    # D2H of the step's result
+        d2h = host_losses.numel() * 4
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / e2e_steps
+    tt = torch.tensor([dt], device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_value = IMS_PER_GPU * world / float(tt)
+
+    achieved = FLOP_PER_IMAGE * (value / world) / 1e12
+    line = {
+        "metric": "u2seg_R50_800_train_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "u2seg_R50_800.yaml training step (PanopticFPN R50-FPN, SyncBN, CascadeROIHeads, "
+                               "800 classes), batch 2/GPU, synthetic 1024x1024 COCO-panoptic-shaped inputs, "
+                               "fwd+bwd+allreduce+clip+SGD", "global_batch": IMS_PER_GPU * world,
+                   "image_size": [H, W], "parallelism": "dp%d" % world,
+                   "l2_note": "activations per step (>1.8 GB) exceed the 126 MB L2; a pool of %d distinct batches is cycled" % pool_n},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": _batch_bytes(host_pool[0]),
+                "d2h_bytes_per_step": d2h,
+                "what": "Trainer.run_step(batch) with pinned host inputs (uint8 images, bit masks, sem_seg) copied H2D "
+                        "and the 10 losses read back every step"},
+        "roofline": {"bound": "tensor", "kernel": "whole training step: conv/GEMM flop of SURVEY §8(d) "
+                                                  "(2.021 TFLOP/image fwd+bwd); round-1 convolutions run in cuDNN",
+                     "achieved": achieved, "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sus"],
+                     "peak_source": peaks["src"] + " bf16 sustained", "traffic": None},
+        "final_loss": loss_total,
+    }
+    if rank == 0 and world == 1 and not os.environ.get("U2B_BENCH_SKIP_CPU"):
+        line["cpu_baseline"] = cpu_train_sample(1)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_train_sample(steps, n_images=1):
+    """The oracle port of the reference step (fp32, torch CPU ops, all host threads) on a bounded sample:
+    `n_images` 1024x1024 images per step, forward + backward."""
+    import torch
+    from oracle import detector_oracle as do
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = do.DetCfg(NUM_CLASSES, SEM_CLASSES)
+    params = {k: (v.clone().requires_grad_(v.is_floating_point() and "running" not in k)) for k, v in
+              do.init_params(cfg, 0).items()}
+    data = do.synthetic_batch(n_images, H, W, NUM_CLASSES, SEM_CLASSES, seed=1234)
+    ts = []
+    for i in range(steps + 1):
+        t0 = time.perf_counter()
+        torch.manual_seed(i)
+        loss = sum(do.forward_train(params, cfg, *data).values())
+        loss.backward()
+        for p in params.values():
+            p.grad = None
+        if i > 0:
+            ts.append(time.perf_counter() - t0)
+    t = sum(ts) / len(ts)
+    return {"value": n_images / t, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d x 1024x1024 image(s) per step, fwd+bwd of the oracle port of PanopticFPN (fp32), %d timed step(s)"
+                      % (n_images, steps), "s_per_step": t}
+
+
+def reference_line(args):
+    r = cpu_train_sample(max(1, min(args.steps, 3)), n_images=1)
+    return {"impl": "reference", "metric": "u2seg_R50_800_train_images_per_sec", "value": r["value"], "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["s_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "u2seg_R50_800.yaml training step, synthetic 1024x1024 (oracle port of the reference "
+                                   "CPU path; 1 image per step sample)"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -1,0 +1,116 @@
+"""Training / inference engine for the detector path — the B200-side counterpart of
+detectron2/engine/{train_loop.py:479-521 AMPTrainer.run_step, defaults.py:60-79 create_ddp_model,
+defaults.py:253-321 DefaultPredictor} and detectron2/solver/build.py:63-139 (SGD momentum 0.9 +
+per-parameter gradient-norm clipping + WarmupMultiStepLR).
+
+Data parallelism (one process per GPU): every parameter's .grad is a view into ONE flat fp32 buffer, so
+the DDP-equivalent is a single NCCL all-reduce of that buffer per step (SUM / world), issued after
+backward; SyncBN statistics are exchanged inside the model. Loss scalars stay on the device.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from .modeling import build_model
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class WarmupMultiStepLR:
+    """solver/build.py:283-323 + lr_scheduler.py (linear warmup, multi-step decay)."""
+
+    def __init__(self, cfg):
+        s = cfg.SOLVER
+        self.base_lr, self.steps, self.gamma = s.BASE_LR, [x for x in s.STEPS if x <= s.MAX_ITER], s.GAMMA
+        self.warmup_factor, self.warmup_iters = s.WARMUP_FACTOR, s.WARMUP_ITERS
+
+    def lr(self, it):
+        f = self.gamma ** sum(1 for s in self.steps if it >= s)
+        if it < self.warmup_iters:
+            alpha = it / self.warmup_iters
+            f *= self.warmup_factor * (1 - alpha) + alpha
+        return self.base_lr * f
+
+
+class Trainer:
+    def __init__(self, cfg, model=None, amp_dtype=torch.bfloat16, device=None):
+        self.cfg = cfg
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.model = model if model is not None else build_model(cfg)
+        self.model = self.model.to(self.device).to(memory_format=torch.channels_last)
+        self.model.train()
+        self.amp_dtype = amp_dtype if cfg.SOLVER.AMP.ENABLED else None
+        self.params = [p for p in self.model.parameters() if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        # solver/build.py:119-139 get_default_optimizer_params: norm layers get WEIGHT_DECAY_NORM
+        s = cfg.SOLVER
+        norm_ids = set()
+        for m in self.model.modules():
+            if isinstance(m, (torch.nn.modules.batchnorm._BatchNorm, torch.nn.GroupNorm)):
+                norm_ids.update(id(p) for p in m.parameters(recurse=False))
+        groups = [{"params": [p], "weight_decay": s.WEIGHT_DECAY_NORM if id(p) in norm_ids else s.WEIGHT_DECAY}
+                  for p in self.params]
+        self.optimizer = torch.optim.SGD(groups, lr=s.BASE_LR, momentum=s.MOMENTUM, nesterov=s.NESTEROV, foreach=True)
+        self.clip = s.CLIP_GRADIENTS if s.CLIP_GRADIENTS.ENABLED else None
+        self.sched = WarmupMultiStepLR(cfg)
+        self.iter = 0
+        self.scaler = torch.amp.GradScaler("cuda") if self.amp_dtype == torch.float16 else None
+
+    def run_step(self, batched_inputs):
+        """train_loop.py:479-521. Returns the dict of (detached, device-resident) losses."""
+        lr = self.sched.lr(self.iter)
+        for g in self.optimizer.param_groups:
+            g["lr"] = lr
+        self.flat_grad.zero_()
+        if self.amp_dtype is not None:
+            with torch.autocast("cuda", dtype=self.amp_dtype):
+                loss_dict = self.model(batched_inputs)
+        else:
+            loss_dict = self.model(batched_inputs)
+        losses = sum(loss_dict.values())
+        if self.scaler is not None:
+            self.scaler.scale(losses).backward()
+        else:
+            losses.backward()
+        if _world() > 1:   # the single gradient all-reduce (DDP: SUM / world)
+            dist.all_reduce(self.flat_grad)
+            self.flat_grad.div_(_world())
+        if self.scaler is not None:
+            self.scaler.unscale_(self.optimizer)
+        if self.clip is not None:   # solver/build.py:63-73: clip_grad_norm_ per parameter tensor
+            assert self.clip.CLIP_TYPE == "norm"
+            grads = [p.grad for p in self.params]
+            norms = torch._foreach_norm(grads, self.clip.NORM_TYPE)
+            coef = torch.clamp(self.clip.CLIP_VALUE / (torch.stack(norms) + 1e-6), max=1.0)
+            torch._foreach_mul_(grads, list(coef.unbind(0)))
+        if self.scaler is not None:
+            self.scaler.step(self.optimizer)
+            self.scaler.update()
+        else:
+            self.optimizer.step()
+        self.iter += 1
+        return {k: v.detach() for k, v in loss_dict.items()}
+
+
+class DefaultPredictor:
+    """engine/defaults.py:253-321 (single image in, post-processed dict out)."""
+
+    def __init__(self, cfg, model=None):
+        self.cfg = cfg
+        self.model = (model if model is not None else build_model(cfg)).to(memory_format=torch.channels_last)
+        self.model.eval()
+
+    @torch.no_grad()
+    def __call__(self, image_chw, height=None, width=None):
+        d = {"image": image_chw}
+        if height is not None:
+            d["height"], d["width"] = height, width
+        return self.model([d])[0]
