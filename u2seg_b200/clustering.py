@@ -84,6 +84,31 @@ def to_device_fp16(x, device=None):
     return x.to(device=device, dtype=torch.float16, non_blocking=True).contiguous()
 
 
+def init_centroids_sharded(x_local, r, row_offset, group=None):
+    """c = x[r].clone() (nn_utils.py:338) when the rows of x are sharded over ranks: every rank contributes the
+    rows it owns, one all-reduce(SUM) assembles the (K, D) fp32 centroids on all ranks."""
+    N, D = x_local.shape
+    r_dev = r.to(x_local.device)
+    local = (r_dev >= row_offset) & (r_dev < row_offset + N)
+    c = torch.zeros((r.shape[0], D), dtype=torch.float32, device=x_local.device)
+    c[local] = x_local[(r_dev[local] - row_offset)].float()
+    if group is not None:
+        torch.distributed.all_reduce(c, group=group)
+    return c
+
+
+def lloyd_loop(state, c, Niter, group=None):
+    """Niter x (E-step, local M-step sums, all-reduce of the (K, D+1) sums, centroid update). `state` provides
+    assign(c) / accumulate() -> sums / finalize(c) (KMeansState on the GPU)."""
+    for _ in range(Niter):
+        state.assign(c)
+        sums = state.accumulate()
+        if group is not None:
+            torch.distributed.all_reduce(sums, group=group)
+        state.finalize(c)
+    return c
+
+
 def KMeans(x, seed, K=10, Niter=10, init_inds=None, verbose=True, force_no_lazy_tensor=False,
            group=None, row_offset=0, n_global=None):
     """Lloyd's algorithm, Euclidean metric. Mirrors nn_utils.py:304 `KMeans`.
@@ -111,17 +136,10 @@ def KMeans(x, seed, K=10, Niter=10, init_inds=None, verbose=True, force_no_lazy_
         print("Init indices {}".format(r.numpy()))
 
     st = KMeansState(x16, K)
-    # c = x[r].clone() — rows may live on other ranks when sharded
-    r_dev = r.to(x16.device)
-    local = (r_dev >= row_offset) & (r_dev < row_offset + N)
-    c = torch.zeros((K, D), dtype=torch.float32, device=x16.device)
-    c[local] = x16[(r_dev[local] - row_offset)].float()
+    c = init_centroids_sharded(x16, r, row_offset, group)     # c = x[r].clone(); rows may live on other ranks
     if group is not None:
-        torch.distributed.all_reduce(c, group=group)
         torch.distributed.all_reduce(st.scal[0:1], op=torch.distributed.ReduceOp.MAX, group=group)
-
-    for _ in range(Niter):
-        st.lloyd_iteration(c, group=group)
+    lloyd_loop(st, c, Niter, group)
 
     cl = st.labels.long()
     if verbose:

@@ -35,6 +35,27 @@ class WarmupMultiStepLR:
         return self.base_lr * f
 
 
+class FlatGradients:
+    """All gradients as views into one flat fp32 buffer -> the DDP-equivalent is ONE all-reduce per step."""
+
+    def __init__(self, params, device):
+        self.params = list(params)
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self, group=None):
+        if _world() > 1:
+            dist.all_reduce(self.flat, group=group)
+            self.flat.div_(_world())
+
+
 class Trainer:
     def __init__(self, cfg, model=None, amp_dtype=torch.bfloat16, device=None):
         self.cfg = cfg
@@ -44,12 +65,7 @@ class Trainer:
         self.model.train()
         self.amp_dtype = amp_dtype if cfg.SOLVER.AMP.ENABLED else None
         self.params = [p for p in self.model.parameters() if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
-        off = 0
-        for p in self.params:
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        self.grads = FlatGradients(self.params, self.device)
         # solver/build.py:119-139 get_default_optimizer_params: norm layers get WEIGHT_DECAY_NORM
         s = cfg.SOLVER
         norm_ids = set()
@@ -69,7 +85,7 @@ class Trainer:
         lr = self.sched.lr(self.iter)
         for g in self.optimizer.param_groups:
             g["lr"] = lr
-        self.flat_grad.zero_()
+        self.grads.zero_()
         if self.amp_dtype is not None:
             with torch.autocast("cuda", dtype=self.amp_dtype):
                 loss_dict = self.model(batched_inputs)
@@ -80,9 +96,7 @@ class Trainer:
             self.scaler.scale(losses).backward()
         else:
             losses.backward()
-        if _world() > 1:   # the single gradient all-reduce (DDP: SUM / world)
-            dist.all_reduce(self.flat_grad)
-            self.flat_grad.div_(_world())
+        self.grads.all_reduce_mean()   # the single gradient all-reduce (DDP: SUM / world)
         if self.scaler is not None:
             self.scaler.unscale_(self.optimizer)
         if self.clip is not None:   # solver/build.py:63-73: clip_grad_norm_ per parameter tensor
