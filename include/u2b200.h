@@ -113,10 +113,11 @@ int u2b_iou_match(const float* gt, int64_t G, const float* pred, int64_t A, cons
 
 /* layers/nms.py:9-21 batched_nms (torchvision class-by-class semantics; IoU > threshold suppresses).
  * order = indices of the boxes sorted by score, descending, stable. keep (n) int64 receives the kept
- * original indices in score order, *num_keep (device) their number. No host synchronisation. */
+ * original indices in score order, *num_keep (device) their number; the scan stops after max_keep kept boxes
+ * (max_keep < 0: keep all). No host synchronisation. */
 size_t u2b_nms_workspace_bytes(int64_t n);
 int u2b_batched_nms(const float* boxes, const int64_t* cats, const int64_t* order, int64_t n,
-                    float iou_threshold, int64_t* keep, int32_t* num_keep, void* workspace,
+                    float iou_threshold, int64_t max_keep, int64_t* keep, int32_t* num_keep, void* workspace,
                     size_t workspace_bytes, u2b_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

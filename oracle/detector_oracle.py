@@ -440,6 +440,19 @@ def sample_proposals_for_roi_heads(cfg: DetCfg, proposals, gt_boxes_list, gt_cla
     return out
 
 
+class _ScaleGradient(torch.autograd.Function):
+    """roi_heads/cascade_rcnn.py:20-28: identity in forward, gradient x scale in backward."""
+
+    @staticmethod
+    def forward(ctx, input, scale):
+        ctx.scale = scale
+        return input
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output * ctx.scale, None
+
+
 def l1_box_loss(cfg, proposal_boxes, gt_boxes, pred_deltas, gt_classes, weights):
     """roi_heads/fast_rcnn.py:424-463 (cls-agnostic) with smooth_l1_beta 0."""
     fg = torch.nonzero((gt_classes >= 0) & (gt_classes < cfg.num_classes), as_tuple=True)[0]
@@ -475,6 +488,7 @@ def roi_heads_train(net: Net, feats, image_sizes, proposals, gt_boxes_list, gt_c
                     nxt.append({"proposal_boxes": b, "gt_classes": cls, "gt_boxes": g})
                 cur = nxt
         x = roi_pool(flist, [c["proposal_boxes"] for c in cur], cfg.box_pool)
+        x = _ScaleGradient.apply(x, 1.0 / 3)                     # cascade_rcnn.py:271-272 (training only)
         scores, deltas = net.box_stage(x, k)
         pb = torch.cat([c["proposal_boxes"] for c in cur])
         gcls = torch.cat([c["gt_classes"] for c in cur])

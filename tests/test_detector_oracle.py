@@ -91,6 +91,25 @@ def test_training_losses_match_reference(golden_dir):
         assert abs(float(losses[str(k)]) - v) <= 1e-6 * max(1.0, abs(v)), (k, float(losses[str(k)]), v)
 
 
+def test_training_gradients_match_reference(golden_dir):
+    """backward parity of the oracle: per-parameter gradient norms of the summed loss vs the reference's
+    (catches forward-neutral pieces such as cascade_rcnn._ScaleGradient)."""
+    g = np.load(os.path.join(golden_dir, "detector_train_256x320.npz"))
+    n, H, W, K, S, seed, G, lo, hi = [int(v) for v in g["meta"]]
+    cfg = do.DetCfg(num_classes=K, sem_classes=S)
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k)
+              for k, v in do.init_params(cfg, seed=0).items()}
+    data = do.synthetic_batch(n, H, W, K, S, seed=seed, G=G, min_size=lo, max_size=hi)
+    torch.manual_seed(seed)
+    sum(do.forward_train(params, cfg, *data).values()).backward()
+    assert len(g["grad_names"]) == 248
+    for name, want in zip(g["grad_names"], g["grad_norms"]):
+        got = float(params[str(name)].grad.norm())
+        assert abs(got - want) <= 1e-4 * max(want, 1e-6), (str(name), got, want)
+    np.testing.assert_allclose(params["backbone.fpn_output3.weight"].grad[:8].numpy(), g["grad_fpn_output3_first8"],
+                               rtol=1e-4, atol=1e-7)
+
+
 def test_inference_matches_reference(golden_dir):
     g = np.load(os.path.join(golden_dir, "detector_infer_200x304.npz"))
     n, H, W, K, S, seed, G, lo, hi, oh, ow = [int(v) for v in g["meta"]]

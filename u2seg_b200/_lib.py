@@ -43,7 +43,7 @@ SIGNATURES = {
     "u2b_conv2d_nhwc_fwd": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                     c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "u2b_nms_workspace_bytes": (c_size_t, [c_int64]),
-    "u2b_batched_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p,
+    "u2b_batched_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int64, c_void_p, c_void_p, c_void_p,
                                 c_size_t, c_void_p]),
 }
 

@@ -135,26 +135,54 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ ca
   }
 }
 
-// one warp walks the boxes in score order; `removed` lives in shared memory.
-__global__ void __launch_bounds__(32)
+// Sequential part of greedy NMS, on the device. One CTA walks the sorted boxes in blocks of 64: thread 0 resolves
+// the 64 intra-block decisions from the diagonal mask words (registers + shared memory only), then all threads OR
+// the kept rows into the `removed` bitmap of the later blocks (coalesced: thread j owns column word j).
+// Stops as soon as max_keep boxes are kept (proposal_utils.py:122 `keep[:post_nms_topk]`).
+__global__ void __launch_bounds__(256)
 nms_scan_kernel(const unsigned long long* __restrict__ mask, const int64_t* __restrict__ order, int n,
-                int col_blocks, int64_t* __restrict__ keep, int* __restrict__ num_keep) {
+                int col_blocks, int max_keep, int64_t* __restrict__ keep, int* __restrict__ num_keep) {
   extern __shared__ unsigned long long removed[];
-  const int lane = threadIdx.x;
-  for (int i = lane; i < col_blocks; i += 32) removed[i] = 0ULL;
-  __syncwarp();
-  int nk = 0;
-  for (int i = 0; i < n; ++i) {
-    const unsigned long long r = removed[i >> 6];
-    if (!((r >> (i & 63)) & 1ULL)) {
-      if (lane == 0) keep[nk] = order[i];
-      ++nk;
-      const unsigned long long* row = mask + static_cast<size_t>(i) * col_blocks;
-      for (int j = (i >> 6) + lane; j < col_blocks; j += 32) removed[j] |= row[j];
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long s_kept;
+  __shared__ int s_nk, s_stop;
+  const int t = threadIdx.x;
+  for (int i = t; i < col_blocks; i += blockDim.x) removed[i] = 0ULL;
+  if (t == 0) { s_nk = 0; s_stop = 0; }
+  __syncthreads();
+  for (int b = 0; b < col_blocks; ++b) {
+    const int rows = min(64, n - b * 64);
+    if (t < rows) diag[t] = mask[static_cast<size_t>(b * 64 + t) * col_blocks + b];
+    __syncthreads();
+    if (t == 0) {
+      unsigned long long rem = removed[b], kw = 0ULL;
+      int cnt = s_nk;
+      for (int i = 0; i < rows; ++i) {
+        if (!((rem >> i) & 1ULL)) {
+          keep[cnt++] = order[b * 64 + i];
+          kw |= 1ULL << i;
+          rem |= diag[i];
+          if (cnt >= max_keep) { s_stop = 1; break; }
+        }
+      }
+      s_kept = kw;
+      s_nk = cnt;
     }
-    __syncwarp();
+    __syncthreads();
+    if (s_stop) break;
+    const unsigned long long kw = s_kept;
+    for (int j = b + 1 + t; j < col_blocks; j += blockDim.x) {
+      unsigned long long acc = 0ULL, bits = kw;
+      while (bits) {
+        const int i = __ffsll(static_cast<long long>(bits)) - 1;
+        bits &= bits - 1;
+        acc |= mask[static_cast<size_t>(b * 64 + i) * col_blocks + j];
+      }
+      removed[j] |= acc;
+    }
+    __syncthreads();
   }
-  if (lane == 0) *num_keep = nk;
+  if (t == 0) *num_keep = s_nk;
 }
 
 __global__ void gather_sorted_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ cats,
@@ -179,7 +207,7 @@ size_t u2b_nms_workspace_bytes(int64_t n) {
 // boxes (n,4) fp32 xyxy, cats (n) int64 or NULL, order (n) int64 = indices sorted by score descending
 // (stable). keep (n) int64, num_keep device int. Semantics: torchvision batched_nms, class by class.
 int u2b_batched_nms(const float* boxes, const int64_t* cats, const int64_t* order, int64_t n,
-                    float iou_threshold, int64_t* keep, int32_t* num_keep, void* workspace,
+                    float iou_threshold, int64_t max_keep, int64_t* keep, int32_t* num_keep, void* workspace,
                     size_t workspace_bytes, cudaStream_t stream) {
   U2B_CHECK_ARG(num_keep, "batched_nms: num_keep is NULL");
   if (n == 0) {
@@ -205,7 +233,12 @@ int u2b_batched_nms(const float* boxes, const int64_t* cats, const int64_t* orde
   if (smem > 48 * 1024) {
     U2B_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  nms_scan_kernel<<<1, 32, smem, stream>>>(mask, order, (int)n, cb, keep, num_keep);
+  const int mk = (max_keep < 0 || max_keep > n) ? (int)n : (int)max_keep;
+  if (mk == 0) {
+    U2B_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int32_t), stream));
+    return 0;
+  }
+  nms_scan_kernel<<<1, 256, smem, stream>>>(mask, order, (int)n, cb, mk, keep, num_keep);
   U2B_LAUNCH_CHECK();
   return 0;
 }

@@ -56,8 +56,18 @@ class FlatGradients:
             self.flat.div_(_world())
 
 
+class _BackboneTuple(torch.nn.Module):
+    def __init__(self, backbone, keys):
+        super().__init__()
+        self.backbone, self.keys = backbone, keys
+
+    def forward(self, x):
+        out = self.backbone(x)
+        return tuple(out[k] for k in self.keys)
+
+
 class Trainer:
-    def __init__(self, cfg, model=None, amp_dtype=torch.bfloat16, device=None):
+    def __init__(self, cfg, model=None, amp_dtype=torch.bfloat16, device=None, graph_backbone=False):
         self.cfg = cfg
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.model = model if model is not None else build_model(cfg)
@@ -72,22 +82,42 @@ class Trainer:
         for m in self.model.modules():
             if isinstance(m, (torch.nn.modules.batchnorm._BatchNorm, torch.nn.GroupNorm)):
                 norm_ids.update(id(p) for p in m.parameters(recurse=False))
-        groups = [{"params": [p], "weight_decay": s.WEIGHT_DECAY_NORM if id(p) in norm_ids else s.WEIGHT_DECAY}
-                  for p in self.params]
+        groups = [{"params": [p for p in self.params if id(p) in norm_ids], "weight_decay": s.WEIGHT_DECAY_NORM},
+                  {"params": [p for p in self.params if id(p) not in norm_ids], "weight_decay": s.WEIGHT_DECAY}]
         self.optimizer = torch.optim.SGD(groups, lr=s.BASE_LR, momentum=s.MOMENTUM, nesterov=s.NESTEROV, foreach=True)
         self.clip = s.CLIP_GRADIENTS if s.CLIP_GRADIENTS.ENABLED else None
         self.sched = WarmupMultiStepLR(cfg)
         self.iter = 0
         self.scaler = torch.amp.GradScaler("cuda") if self.amp_dtype == torch.float16 else None
+        self.graph_backbone = graph_backbone and _world() == 1
+        self._graph_tried = False
+
+    def _maybe_capture_backbone(self, batched_inputs):
+        """CUDA-graph the forward+backward of the static-shape backbone (launch-bound inner loop of the step)."""
+        if not self.graph_backbone or self._graph_tried:
+            return
+        self._graph_tried = True
+        with torch.no_grad():
+            x = self.model.preprocess_image(batched_inputs).tensor
+        keys = list(self.model.backbone._out_features)
+        wrapper = _BackboneTuple(self.model.backbone, keys)
+        sample = torch.zeros_like(x)
+        if self.amp_dtype is not None:
+            with torch.autocast("cuda", dtype=self.amp_dtype, cache_enabled=False):
+                graphed = torch.cuda.make_graphed_callables(wrapper, (sample,))
+        else:
+            graphed = torch.cuda.make_graphed_callables(wrapper, (sample,))
+        self.model._graphed_backbone = (graphed, keys, tuple(x.shape))
 
     def run_step(self, batched_inputs):
         """train_loop.py:479-521. Returns the dict of (detached, device-resident) losses."""
         lr = self.sched.lr(self.iter)
         for g in self.optimizer.param_groups:
             g["lr"] = lr
+        self._maybe_capture_backbone(batched_inputs)
         self.grads.zero_()
         if self.amp_dtype is not None:
-            with torch.autocast("cuda", dtype=self.amp_dtype):
+            with torch.autocast("cuda", dtype=self.amp_dtype, cache_enabled=not self.graph_backbone):
                 loss_dict = self.model(batched_inputs)
         else:
             loss_dict = self.model(batched_inputs)

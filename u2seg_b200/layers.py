@@ -265,13 +265,11 @@ def batched_nms(boxes, scores, idxs, iou_threshold, max_keep=None):
     ws_bytes = int(L.u2b_nms_workspace_bytes(n))
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=boxes.device)
     cats = idxs.to(torch.int64).contiguous() if idxs is not None else None
-    _lib.check(L.u2b_batched_nms(_lib.ptr(b), _lib.ptr(cats), _lib.ptr(order), n, float(iou_threshold), _lib.ptr(keep),
-                                 _lib.ptr(cnt), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()), "u2b_batched_nms")
+    _lib.check(L.u2b_batched_nms(_lib.ptr(b), _lib.ptr(cats), _lib.ptr(order), n, float(iou_threshold),
+                                 -1 if max_keep is None else int(max_keep), _lib.ptr(keep), _lib.ptr(cnt), _lib.ptr(ws),
+                                 ws_bytes, _lib.stream_ptr()), "u2b_batched_nms")
     _lib.count_launches(3)
-    k = int(cnt.item())
-    if max_keep is not None:
-        k = min(k, max_keep)
-    return keep[:k]
+    return keep[:int(cnt.item())]
 
 
 def nms(boxes, scores, iou_threshold):
