@@ -154,23 +154,26 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int64_t* __re
     const int rows = min(64, n - b * 64);
     if (t < rows) diag[t] = mask[static_cast<size_t>(b * 64 + t) * col_blocks + b];
     __syncthreads();
-    if (t == 0) {
+    const int base = s_nk;
+    if (t == 0) {  // registers + shared memory only: no global access on the serial chain
       unsigned long long rem = removed[b], kw = 0ULL;
-      int cnt = s_nk;
+      int cnt = base;
       for (int i = 0; i < rows; ++i) {
         if (!((rem >> i) & 1ULL)) {
-          keep[cnt++] = order[b * 64 + i];
+          ++cnt;
           kw |= 1ULL << i;
           rem |= diag[i];
           if (cnt >= max_keep) { s_stop = 1; break; }
         }
       }
       s_kept = kw;
-      s_nk = cnt;
     }
     __syncthreads();
-    if (s_stop) break;
     const unsigned long long kw = s_kept;
+    if (t < rows && ((kw >> t) & 1ULL))   // kept boxes of this block written in parallel, in order
+      keep[base + __popcll(kw & ((1ULL << t) - 1ULL))] = order[b * 64 + t];
+    if (t == 0) s_nk = base + __popcll(kw);
+    if (s_stop) break;
     for (int j = b + 1 + t; j < col_blocks; j += blockDim.x) {
       unsigned long long acc = 0ULL, bits = kw;
       while (bits) {

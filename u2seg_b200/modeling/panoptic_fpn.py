@@ -32,6 +32,7 @@ class PanopticFPN(nn.Module):
         self.combine_instances_score_thresh = c.INSTANCES_CONFIDENCE_THRESH
         assert cfg.MODEL.PANOPTIC_FPN.INSTANCE_LOSS_WEIGHT == 1.0
         self.input_format = cfg.INPUT.FORMAT
+        self._side_stream = None
 
     @property
     def device(self):
@@ -64,10 +65,18 @@ class PanopticFPN(nn.Module):
         gt_sem_seg = [x["sem_seg"].to(self.device, non_blocking=True) for x in batched_inputs]
         gt_sem_seg = ImageList.from_tensors(gt_sem_seg, self.backbone.size_divisibility,
                                             self.sem_seg_head.ignore_value).tensor
-        _, sem_seg_losses = self.sem_seg_head(features, gt_sem_seg)
+        # The semantic head has no host synchronisation; the proposal / ROI-sampling path below has ~30
+        # (data-dependent shapes). Run the former on a side stream so the GPU stays busy across those bubbles.
+        main = torch.cuda.current_stream()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream()
+        self._side_stream.wait_stream(main)
+        with torch.cuda.stream(self._side_stream):
+            _, sem_seg_losses = self.sem_seg_head(features, gt_sem_seg)
         gt_instances = [x["instances"].to(self.device) for x in batched_inputs]
         proposals, proposal_losses = self.proposal_generator(images, features, gt_instances)
         _, detector_losses = self.roi_heads(images, features, proposals, gt_instances)
+        main.wait_stream(self._side_stream)
         losses = sem_seg_losses
         losses.update(proposal_losses)
         losses.update(detector_losses)
