@@ -56,6 +56,9 @@ int u2b_kmeans_assign(const void* x16, int64_t N, int64_t D, int64_t K, const vo
                       int32_t* labels, int32_t* amb_count_out, void* workspace,
                       size_t workspace_bytes, u2b_stream_t stream);
 
+/* thread-block cluster size of the E-step kernel (1, 2 or 4): centroid tiles are TMA-multicast across the cluster */
+int u2b_kmeans_set_cluster(int cluster);
+
 /* M-step part 1, nn_utils.py:359-363: sums[k, 0:D] = sum of rows with label k, sums[k, D] =
  * count (fp32). (K, D+1) fp32 — the buffer a row-sharded job all-reduces across ranks. */
 int u2b_kmeans_accumulate(const void* x16, const int32_t* labels, int64_t N, int64_t D, int64_t K,
@@ -127,6 +130,8 @@ int u2b_batched_nms(const float* boxes, const int64_t* cats, const int64_t* orde
  * Cout % 64 == 0, kernel 1x1 (pad 0) or 3x3 (pad 1), stride 1 or 2. dtype: 1 = fp16, 2 = bf16.
  * ------------------------------------------------------------------------------------------ */
 int u2b_conv2d_supported(int Cin, int Cout, int R, int S, int stride, int pad);
+/* thread-block cluster size of the kernel (1, 2 or 4): with >1 the filter tile is TMA-multicast across the cluster */
+int u2b_conv2d_set_cluster(int cluster);
 
 /* x (N,H,W,Cin) NHWC; w (Cout,R,S,Cin); out (N,OH,OW,Cout) NHWC, OH = (H + 2*pad - R)/stride + 1.
  * Epilogue: out = [relu]( acc + bias[c] + residual ), bias (Cout fp32) / residual (as out) optional. */

@@ -29,10 +29,12 @@ def _ref(x, w, b, stride, pad, res, relu):
     return F.relu(y) if relu else y
 
 
+@pytest.mark.parametrize("cluster", [1, 2, 4])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("shape", SHAPES)
-def test_conv_forward_matches_fp32_reference(shape, dtype):
-    from u2seg_b200.modeling.conv_tc import conv2d_nhwc
+def test_conv_forward_matches_fp32_reference(shape, dtype, cluster):
+    from u2seg_b200.modeling.conv_tc import conv2d_nhwc, set_cluster
+    set_cluster(cluster)
     N, Cin, H, W, Cout, k, stride = shape
     g = torch.Generator(device="cuda").manual_seed(hash(shape) % 1000)
     x = torch.randn(N, Cin, H, W, device="cuda", generator=g).to(dtype).contiguous(memory_format=torch.channels_last)

@@ -29,10 +29,12 @@ def test_kmeans_matches_reference_golden(golden_dir, idx):
     np.testing.assert_allclose(c.cpu().numpy(), g["centroids"], rtol=1e-3, atol=1e-5)  # FP: 1e-3
 
 
+@pytest.mark.parametrize("cluster", [1, 2, 4])
 @pytest.mark.parametrize("N,D,K", [(1, 64, 1), (127, 64, 3), (129, 128, 160), (5000, 384, 161), (20000, 384, 800),
-                                    (4097, 256, 300)])
-def test_assign_bit_exact_vs_oracle(N, D, K):
-    from u2seg_b200.clustering import KMeansState
+                                    (4097, 256, 300), (40000, 384, 800)])
+def test_assign_bit_exact_vs_oracle(N, D, K, cluster):
+    from u2seg_b200.clustering import KMeansState, set_cluster
+    set_cluster(cluster)
     x16 = make_mixture(N, D, max(2, K + 7), seed=N + K, spread=1.0)
     g = torch.Generator().manual_seed(5)
     c = x16.float()[torch.randint(0, N, (K,), generator=g)] + 0.01 * torch.randn(K, D, generator=g)

@@ -81,6 +81,28 @@ def test_pooler_hot_path_shapes_fwd_bwd(dtype, tol):
         assert float((a.grad.float().cpu() - b.grad).abs().max()) <= max(tol * 8 * scale, 1e-4)
 
 
+def test_feature_tap_shared_backward_equals_separate_calls():
+    """4 pooling calls through one FeatureTap (one zero-fill + one cast per step) == 4 independent calls."""
+    from u2seg_b200.layers import FeatureTap, ROIPooler
+    g = torch.Generator().manual_seed(3)
+    feats = [cl(torch.randn(2, 64, 128 // s, 128 // s, generator=g).cuda()) for s in (4, 8, 16, 32)]
+    boxes = [[(torch.rand(20, 2, generator=g) * 100).repeat(1, 2).add(torch.tensor([0, 0, 20.0, 28.0])).cuda() for _ in range(2)]
+             for _ in range(4)]
+    pool = [ROIPooler(7, (0.25, 0.125, 0.0625, 0.03125)), ROIPooler(14, (0.25, 0.125, 0.0625, 0.03125))]
+    gouts = None
+    res = []
+    for shared in (False, True):
+        fs = [f.clone().requires_grad_(True) for f in feats]
+        tap = FeatureTap(fs) if shared else None
+        outs = [pool[i % 2](fs, boxes[i], tap=tap) for i in range(4)]
+        if gouts is None:
+            gouts = [torch.randn_like(o) for o in outs]
+        torch.autograd.backward(outs, gouts)
+        res.append([f.grad.clone() for f in fs])
+    for a, b in zip(*res):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+
+
 def test_roialign_empty_inputs():
     # tests/layers/test_roi_align.py:111-128 (empty boxes)
     from u2seg_b200.layers import ROIAlign

@@ -2,7 +2,7 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.nn.functional as F
-from u2seg_b200.modeling.conv_tc import conv2d_nhwc
+from u2seg_b200.modeling.conv_tc import conv2d_nhwc, set_cluster
 
 SHAPES = [  # name, N, Cin, H, W, Cout, k, stride  (Appendix A, training)
     ("fpn_output2/rpn_p2", 2, 256, 256, 256, 256, 3, 1), ("fpn_output3", 2, 256, 128, 128, 256, 3, 1),
@@ -22,7 +22,6 @@ def timeit(fn, n=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 torch.backends.cudnn.benchmark = True
-print("%-22s %10s %10s %10s %10s" % ("shape", "GFLOP", "tc_ms", "tc_TF/s", "cudnn_ms"))
 for name, N, Cin, H, W, Cout, k, s in SHAPES:
     x = torch.randn(N, Cin, H, W, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
     if H == 1:
@@ -32,6 +31,10 @@ for name, N, Cin, H, W, Cout, k, s in SHAPES:
     pad = k // 2
     OH, OW = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
     fl = 2.0 * N * OH * OW * Cout * Cin * k * k
-    t1 = timeit(lambda: conv2d_nhwc(x, wo, s, pad))
+    ts = []
+    for cl in (1, 2, 4):
+        set_cluster(cl)
+        ts.append(timeit(lambda: conv2d_nhwc(x, wo, s, pad)))
     t2 = timeit(lambda: F.conv2d(x, w, None, s, pad))
-    print("%-22s %10.1f %10.3f %10.1f %10.3f  (cudnn %.1f TF/s)" % (name, fl / 1e9, t1, fl / t1 / 1e9, t2, fl / t2 / 1e9))
+    print("%-22s %8.1f GF | tc cl1 %.3f ms %6.1f TF/s | cl2 %.3f ms %6.1f | cl4 %.3f ms %6.1f | cudnn %.3f ms %6.1f TF/s"
+          % (name, fl / 1e9, ts[0], fl / ts[0] / 1e9, ts[1], fl / ts[1] / 1e9, ts[2], fl / ts[2] / 1e9, t2, fl / t2 / 1e9))

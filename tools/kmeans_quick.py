@@ -3,7 +3,7 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from oracle.kmeans_oracle import make_mixture
-from u2seg_b200.clustering import KMeansState
+from u2seg_b200.clustering import KMeansState, set_cluster
 
 N, D, K = int(sys.argv[1]) if len(sys.argv) > 1 else 1280000, 384, 800
 x16 = make_mixture(N, D, 1000, seed=0, spread=1.0).cuda()
@@ -18,6 +18,12 @@ def timeit(fn, n=10):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
+for cl in (1, 2, 4):
+    set_cluster(cl)
+    tcl = timeit(lambda: st.assign(c))
+    print(f"cluster {cl}: assign {tcl:.3f} ms = {2*N*K*D/tcl/1e9:.1f} TFLOP/s")
+if len(sys.argv) > 2:
+    set_cluster(int(sys.argv[2]))
 ta = timeit(lambda: st.assign(c))
 tm = timeit(lambda: st.accumulate())
 tf = timeit(lambda: st.finalize(c))

@@ -26,6 +26,7 @@ SIGNATURES = {
     "u2b_kmeans_prepare": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "u2b_kmeans_assign": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "u2b_kmeans_set_cluster": (c_int, [c_int]),
     "u2b_kmeans_accumulate": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                       c_size_t, c_void_p]),
     "u2b_kmeans_finalize": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
@@ -40,6 +41,7 @@ SIGNATURES = {
     "u2b_iou_match": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_void_p]),
     "u2b_conv2d_supported": (c_int, [c_int] * 6),
+    "u2b_conv2d_set_cluster": (c_int, [c_int]),
     "u2b_conv2d_nhwc_fwd": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                     c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "u2b_nms_workspace_bytes": (c_size_t, [c_int64]),

@@ -13,6 +13,11 @@ import torch
 from . import _lib
 
 
+def set_cluster(cl):
+    """thread-block cluster size of the E-step kernel (1 = no multicast, 2, 4)."""
+    _lib.check(_lib.lib().u2b_kmeans_set_cluster(int(cl)), "u2b_kmeans_set_cluster")
+
+
 class KMeansState:
     """Device buffers for one (N, D, K) problem; reused across iterations."""
 

@@ -174,14 +174,25 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int64_t* __re
       keep[base + __popcll(kw & ((1ULL << t) - 1ULL))] = order[b * 64 + t];
     if (t == 0) s_nk = base + __popcll(kw);
     if (s_stop) break;
-    for (int j = b + 1 + t; j < col_blocks; j += blockDim.x) {
-      unsigned long long acc = 0ULL, bits = kw;
-      while (bits) {
-        const int i = __ffsll(static_cast<long long>(bits)) - 1;
-        bits &= bits - 1;
-        acc |= mask[static_cast<size_t>(b * 64 + i) * col_blocks + j];
+    // OR the kept rows into `removed` for the later blocks. Warp w owns rows w, w+8, ..; lanes own column words
+    // (coalesced 256 B row segments). The 8 loads of a warp are unconditional and independent (one L2 latency per
+    // column chunk instead of one per kept row), then folded into shared memory with 64-bit atomicOr.
+    {
+      const int w = t >> 5, lane = t & 31;
+      for (int j0 = b + 1; j0 < col_blocks; j0 += 32) {
+        const int j = j0 + lane;
+        unsigned long long v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int i = w + 8 * r;
+          const bool on = (j < col_blocks) && i < rows && ((kw >> i) & 1ULL);
+          v[r] = on ? mask[static_cast<size_t>(b * 64 + i) * col_blocks + j] : 0ULL;
+        }
+        unsigned long long acc = 0ULL;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc |= v[r];
+        if (acc) atomicOr(&removed[j], acc);
       }
-      removed[j] |= acc;
     }
     __syncthreads();
   }

@@ -28,6 +28,7 @@ constexpr int CONV_THREADS = 256;
 struct ConvParams {
   int N, H, W, Cin, Cout, R, S, stride, pad, OH, OW;
   int BW, BH, tiles_w, tiles_h, tiles_m, tiles_n, num_tiles, kblocks_c;
+  int m_groups, num_work;  // cluster scheduling: work = (m_group, n_tile), a CTA owns m_tile = m_group*CL + rank
   int relu, is_bf16;
   const float* bias;
   const void* residual;
@@ -63,7 +64,11 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) {
   }
 }
 
-template <int BN, bool BF16>
+// CL = cluster size (1, 2, 4). With CL > 1 the CTAs of a cluster work on CL neighbouring M tiles with the same
+// filter tile sequence: each loads 1/CL of every B tile and TMA-multicasts it to all of them, so the filter is read
+// from L2 once per cluster; a smem stage is reusable only when every CTA of the cluster has consumed it
+// (tcgen05.commit multicast onto all `empty` barriers, which count CL arrivals).
+template <int BN, bool BF16, int CL>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const ConvParams p) {
@@ -86,7 +91,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
       ptx::mbar_init(&full[i], 1);
-      ptx::mbar_init(&empty[i], 1);
+      ptx::mbar_init(&empty[i], CL);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&T_full[i], 1);
@@ -100,15 +105,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();  // peers' barriers must be initialised before any remote arrive / multicast
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int kblocks = p.R * p.S * p.kblocks_c;
+  const int rank = CL > 1 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
+  constexpr int PART_ROWS = BN / CL;
 
   if (warp == 0) {
     if (ptx::elect_one()) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
+      for (int work = cluster_id; work < p.num_work; work += num_clusters) {
+        const int tn = work % p.tiles_n;
+        int tm = (work / p.tiles_n) * CL + rank;
+        if (tm >= p.tiles_m) tm = p.tiles_m - 1;  // padding CTA of the last group: loads valid data, stores nothing
         const int owb = tm % p.tiles_w, ohb = (tm / p.tiles_w) % p.tiles_h, n = tm / (p.tiles_w * p.tiles_h);
         const int x_base = owb * p.BW * p.stride - p.pad, y_base = ohb * p.BH * p.stride - p.pad;
         for (int r = 0; r < p.R; ++r)
@@ -118,8 +130,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
               ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
               ptx::tma_load_4d(sa, &tmap_x, &full[stage], cb * BK, x_base + s, y_base + r, n);
-              ptx::tma_load_2d(sa + A_BYTES, &tmap_w, &full[stage], ((r * p.S + s) * p.kblocks_c + cb) * BK,
-                               tn * BN);
+              const int kcol = ((r * p.S + s) * p.kblocks_c + cb) * BK;
+              if (CL == 1)
+                ptx::tma_load_2d(sa + A_BYTES, &tmap_w, &full[stage], kcol, tn * BN);
+              else
+                ptx::tma_load_2d_mc(sa + A_BYTES + rank * (PART_ROWS * BK * 2), &tmap_w, &full[stage], kcol,
+                                    tn * BN + rank * PART_ROWS, kMask);
               if (++stage == Cfg::STAGES) {
                 stage = 0;
                 phase ^= 1;
@@ -132,7 +148,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const uint32_t idesc = ptx::umma_idesc_f16(BM, BN, BF16 ? 1u : 0u);
       const uint32_t sbase = ptx::smem_u32(smem);
       uint32_t stage = 0, phase = 0, acc_it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++acc_it) {
+      for (int work = cluster_id; work < p.num_work; work += num_clusters, ++acc_it) {
         const uint32_t buf = acc_it & 1, tphase = (acc_it >> 1) & 1;
         ptx::mbar_wait(&T_empty[buf], tphase ^ 1);
         ptx::tc_fence_after();
@@ -145,7 +161,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             ptx::umma_f16(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-          ptx::umma_commit(&empty[stage]);
+          if (CL == 1)
+            ptx::umma_commit(&empty[stage]);
+          else
+            ptx::umma_commit_mc(&empty[stage], kMask);
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -159,11 +178,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int row = q * 32 + lane;
     const int bh = row / p.BW, bw = row % p.BW;
     uint32_t acc_it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++acc_it) {
-      const int tn = tile % p.tiles_n, tm = tile / p.tiles_n;
+    for (int work = cluster_id; work < p.num_work; work += num_clusters, ++acc_it) {
+      const int tn = work % p.tiles_n, tm_raw = (work / p.tiles_n) * CL + rank;
+      const int tm = tm_raw < p.tiles_m ? tm_raw : p.tiles_m - 1;
       const int owb = tm % p.tiles_w, ohb = (tm / p.tiles_w) % p.tiles_h, n = tm / (p.tiles_w * p.tiles_h);
       const int oh = ohb * p.BH + bh, ow = owb * p.BW + bw;
-      const bool valid = oh < p.OH && ow < p.OW;
+      const bool valid = oh < p.OH && ow < p.OW && tm_raw < p.tiles_m;
       const size_t pix = (static_cast<size_t>(n) * p.OH + oh) * p.OW + ow;
       uint16_t* orow = static_cast<uint16_t*>(p.out) + pix * p.Cout + tn * BN;
       const uint16_t* rrow =
@@ -224,23 +244,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();  // no CTA may exit while a peer can still multicast into / arrive on its smem
   if (warp == 2) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN, bool BF16>
+template <int BN, bool BF16, int CL>
 int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN>;
   static bool attr = false;
   if (!attr) {
-    U2B_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    U2B_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, BF16, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::SMEM_BYTES));
     attr = true;
   }
-  const int grid = p.num_tiles < u2b_num_sms() ? p.num_tiles : u2b_num_sms();
-  conv_tc_kernel<BN, BF16><<<grid, CONV_THREADS, Cfg::SMEM_BYTES, stream>>>(tx, tw, p);
-  U2B_LAUNCH_CHECK();
+  int clusters = u2b_num_sms() / CL;
+  if (clusters > p.num_work) clusters = p.num_work;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(CONV_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  U2B_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, BF16, CL>, tx, tw, p));
   return 0;
 }
+
+int g_conv_cluster = 2;  // default cluster size (u2b_conv2d_set_cluster)
 
 }  // namespace
 
@@ -288,6 +323,10 @@ int u2b_conv2d_nhwc_fwd(int dtype, const void* x, int N, int H, int W, int Cin, 
   p.tiles_n = Cout / BN;
   p.num_tiles = p.tiles_m * p.tiles_n;
   p.kblocks_c = Cin / BK;
+  int CL = g_conv_cluster;
+  if (p.tiles_m < CL) CL = 1;
+  p.m_groups = (p.tiles_m + CL - 1) / CL;
+  p.num_work = p.m_groups * p.tiles_n;
   p.relu = relu; p.is_bf16 = dtype == 2;
   p.bias = bias; p.residual = residual; p.out = out;
   const CUtensorMapDataType tdt = dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -304,15 +343,30 @@ int u2b_conv2d_nhwc_fwd(int dtype, const void* x, int N, int H, int W, int Cin, 
   {
     uint64_t dims[2] = {(uint64_t)R * S * Cin, (uint64_t)Cout};
     uint64_t strides[1] = {(uint64_t)R * S * Cin * 2};
-    uint32_t box[2] = {BK, (uint32_t)BN};
+    uint32_t box[2] = {BK, (uint32_t)(BN / CL)};
     int rc = u2b_encode_tmap(&tw, tdt, 2, w, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc) return rc;
   }
   const bool bf = dtype == 2;
-  if (BN == 256) return bf ? launch_conv<256, true>(tx, tw, p, stream) : launch_conv<256, false>(tx, tw, p, stream);
-  if (BN == 128) return bf ? launch_conv<128, true>(tx, tw, p, stream) : launch_conv<128, false>(tx, tw, p, stream);
-  return bf ? launch_conv<64, true>(tx, tw, p, stream) : launch_conv<64, false>(tx, tw, p, stream);
+#define U2B_DISPATCH(BN_)                                                                              \
+  if (BN == BN_) {                                                                                     \
+    if (CL == 4) return bf ? launch_conv<BN_, true, 4>(tx, tw, p, stream) : launch_conv<BN_, false, 4>(tx, tw, p, stream); \
+    if (CL == 2) return bf ? launch_conv<BN_, true, 2>(tx, tw, p, stream) : launch_conv<BN_, false, 2>(tx, tw, p, stream); \
+    return bf ? launch_conv<BN_, true, 1>(tx, tw, p, stream) : launch_conv<BN_, false, 1>(tx, tw, p, stream);             \
+  }
+  U2B_DISPATCH(256)
+  U2B_DISPATCH(128)
+  U2B_DISPATCH(64)
+#undef U2B_DISPATCH
+  return U2B_ERR_UNSUPPORTED;
+}
+
+// cluster size used by the convolution kernel: 1 (no multicast), 2 or 4
+int u2b_conv2d_set_cluster(int cluster) {
+  U2B_CHECK_ARG(cluster == 1 || cluster == 2 || cluster == 4, "conv2d_set_cluster: 1, 2 or 4");
+  g_conv_cluster = cluster;
+  return 0;
 }
 
 }  // extern "C"

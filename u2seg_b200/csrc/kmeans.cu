@@ -62,6 +62,10 @@ struct Top3 {
   }
 };
 
+// CL = thread-block cluster size: the CL CTAs of a cluster work on CL neighbouring row tiles and walk the same
+// centroid-tile sequence; each loads NT/CL rows of every centroid tile and TMA-multicasts them to the whole cluster,
+// so the (K x D) centroid matrix is read from L2 once per cluster instead of once per CTA.
+template <int CL>
 __global__ void __launch_bounds__(ASSIGN_THREADS, 1)
 kmeans_assign_kernel(const __grid_constant__ CUtensorMap tmap_x,
                      const __grid_constant__ CUtensorMap tmap_c, const float* __restrict__ cnorm,
@@ -100,7 +104,7 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap tmap_x,
     }
     for (int i = 0; i < BSTAGES; ++i) {
       ptx::mbar_init(&B_full[i], 1);
-      ptx::mbar_init(&B_empty[i], 1);
+      ptx::mbar_init(&B_empty[i], CL);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&T_full[i], 1);
@@ -115,15 +119,23 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap tmap_x,
   for (int i = threadIdx.x; i < kpad; i += blockDim.x) sCnorm[i] = cnorm[i];
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const int rank = CL > 1 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
+  const int num_groups = (num_tiles + CL - 1) / CL;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
+  constexpr int PART_ROWS = NT / CL;
 
   if (warp == 0) {
     // ===================== TMA producer (one thread) =====================
     if (ptx::elect_one()) {
       uint32_t bstage = 0, bphase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int grp = cluster_id; grp < num_groups; grp += num_clusters, ++it) {
+        int tile = grp * CL + rank;
+        if (tile >= num_tiles) tile = num_tiles - 1;  // padding CTA of the last group (results discarded)
         for (int n = 0; n < ntiles_n; ++n) {
           for (int kb = 0; kb < kblocks; ++kb) {
             if (n == 0) {
@@ -133,8 +145,11 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap tmap_x,
             }
             ptx::mbar_wait(&B_empty[bstage], bphase ^ 1);
             ptx::mbar_arrive_expect_tx(&B_full[bstage], B_STAGE_BYTES);
-            ptx::tma_load_2d(sB + bstage * B_STAGE_BYTES, &tmap_c, &B_full[bstage], kb * BK,
-                             n * NT);
+            if (CL == 1)
+              ptx::tma_load_2d(sB + bstage * B_STAGE_BYTES, &tmap_c, &B_full[bstage], kb * BK, n * NT);
+            else
+              ptx::tma_load_2d_mc(sB + bstage * B_STAGE_BYTES + rank * (PART_ROWS * BK * 2), &tmap_c,
+                                  &B_full[bstage], kb * BK, n * NT + rank * PART_ROWS, kMask);
             if (++bstage == BSTAGES) {
               bstage = 0;
               bphase ^= 1;
@@ -151,7 +166,7 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap tmap_x,
       const uint32_t b_addr = ptx::smem_u32(sB);
       uint32_t bstage = 0, bphase = 0, acc_it = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int grp = cluster_id; grp < num_groups; grp += num_clusters, ++it) {
         for (int n = 0; n < ntiles_n; ++n, ++acc_it) {
           const uint32_t buf = acc_it & 1, tphase = (acc_it >> 1) & 1;
           ptx::mbar_wait(&T_empty[buf], tphase ^ 1);
@@ -166,7 +181,10 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap tmap_x,
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
               ptx::umma_f16(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-            ptx::umma_commit(&B_empty[bstage]);
+            if (CL == 1)
+              ptx::umma_commit(&B_empty[bstage]);
+            else
+              ptx::umma_commit_mc(&B_empty[bstage], kMask);
             if (n == ntiles_n - 1) ptx::umma_commit(&A_empty[kb]);
             if (++bstage == BSTAGES) {
               bstage = 0;
@@ -188,7 +206,8 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap tmap_x,
     const float margin = 1.25f * 0.001953125f * xm * sqrtf(cm2) + 1e-30f;
     uint32_t acc_it = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int grp = cluster_id; grp < num_groups; grp += num_clusters, ++it) {
+      const int tile = grp * CL + rank;   // >= num_tiles for the padding CTA: row >= N below, nothing is written
       Top3 t;
       t.init();
       for (int n = 0; n < ntiles_n; ++n, ++acc_it) {
@@ -248,55 +267,116 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap tmap_x,
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();
   if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+int g_kmeans_cluster = 2;
+
+template <int CL>
+int launch_assign(const CUtensorMap& tx, const CUtensorMap& tc, const float* cnorm, const float* xmax,
+                  const float* cmax2, int32_t* labels, int4* amb, int* amb_count, int N, int kpad, int kblocks,
+                  int num_tiles, int smem, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    U2B_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  227 * 1024));
+    attr_set = true;
+  }
+  const int groups = (num_tiles + CL - 1) / CL;
+  int clusters = u2b_num_sms() / CL;
+  if (clusters > groups) clusters = groups;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(ASSIGN_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  U2B_CUDA(cudaLaunchKernelEx(&cfg, kmeans_assign_kernel<CL>, tx, tc, cnorm, xmax, cmax2, labels, amb, amb_count, N,
+                              N, kpad, kblocks, num_tiles));
+  return 0;
+}
+
 // Exact fp32 decision (reference formula sum_d (x-c)^2) for rows the fp16 tensor pass could not
-// decide. One warp per entry. entry = {row, i1, i2, full}: full==0 -> only {i1,i2} can be the
-// argmin (third-best was outside the bound); full==1 -> scan every centroid.
-__global__ void kmeans_refine_kernel(const __half* __restrict__ x, const float* __restrict__ c32,
-                                     const int4* __restrict__ amb, const int* __restrict__ amb_count,
-                                     int amb_capacity, int32_t* __restrict__ labels, int D, int K) {
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  const int total_warps = gridDim.x * warps_per_block;
+// decide. entry = {row, i1, i2, full}: full==0 -> only {i1,i2} can be the argmin (third-best was outside the
+// bound): one warp per entry. full==1 -> every centroid is scanned: one CTA per entry, warps stride over the
+// centroids, lanes over D (coalesced fp32 rows), (distance, index) pairs min-reduced through shared memory.
+__device__ __forceinline__ float warp_dist(const float* __restrict__ xs, const float* __restrict__ cr, int D,
+                                           int lane) {
+  float s = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float df = xs[d] - cr[d];
+    s = fmaf(df, df, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+__global__ void __launch_bounds__(256)
+kmeans_refine_kernel(const __half* __restrict__ x, const float* __restrict__ c32,
+                     const int4* __restrict__ amb, const int* __restrict__ amb_count,
+                     int amb_capacity, int32_t* __restrict__ labels, int D, int K) {
+  extern __shared__ float rs[];   // [8 warps][D] x rows (pair pass) / [D] x row + reduction scratch (full pass)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int cnt = *amb_count;
   if (cnt > amb_capacity) cnt = amb_capacity;
-  for (int e = gwarp; e < cnt; e += total_warps) {
+  // ---- pass 1: two-candidate entries, one warp each ----
+  float* xs = rs + warp * D;
+  for (int e = blockIdx.x * 8 + warp; e < cnt; e += gridDim.x * 8) {
     const int4 ent = amb[e];
+    if (ent.w) continue;
     const __half* xr = x + static_cast<size_t>(ent.x) * D;
-    auto dist = [&](int k) -> float {
-      const float* cr = c32 + static_cast<size_t>(k) * D;
-      float s = 0.f;
-      for (int d = lane; d < D; d += 32) {
-        const float df = __half2float(xr[d]) - cr[d];
-        s = fmaf(df, df, s);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      return s;
-    };
-    int best;
-    if (!ent.w) {
-      const float d1 = dist(ent.y), d2 = dist(ent.z);
-      // first-minimum semantics: on an exact tie the lower index wins; NaN never wins
-      const bool take2 = (d2 < d1) || (d2 == d1 && ent.z < ent.y) || (d1 != d1 && d2 == d2);
-      best = take2 ? ent.z : ent.y;
-    } else {
-      float bv = __int_as_float(0x7f800000);
-      best = ent.y;
-      bool any = false;
-      for (int k = 0; k < K; ++k) {
-        const float d = dist(k);
-        if (d < bv || (!any && d == d)) {
-          bv = d;
-          best = k;
-          any = true;
-        }
+    for (int d = lane; d < D; d += 32) xs[d] = __half2float(xr[d]);
+    __syncwarp();
+    const float d1 = warp_dist(xs, c32 + static_cast<size_t>(ent.y) * D, D, lane);
+    const float d2 = warp_dist(xs, c32 + static_cast<size_t>(ent.z) * D, D, lane);
+    // first-minimum semantics: on an exact tie the lower index wins; NaN never wins
+    const bool take2 = (d2 < d1) || (d2 == d1 && ent.z < ent.y) || (d1 != d1 && d2 == d2);
+    if (lane == 0) labels[ent.x] = take2 ? ent.z : ent.y;
+    __syncwarp();
+  }
+  __syncthreads();
+  // ---- pass 2: full scans, one CTA each ----
+  __shared__ float s_best[8];
+  __shared__ int s_idx[8];
+  for (int e = blockIdx.x; e < cnt; e += gridDim.x) {
+    const int4 ent = amb[e];
+    if (!ent.w) continue;     // uniform across the CTA
+    const __half* xr = x + static_cast<size_t>(ent.x) * D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) rs[d] = __half2float(xr[d]);
+    __syncthreads();
+    float bv = __int_as_float(0x7f800000);
+    int bi = 0x7fffffff;
+    for (int k = warp; k < K; k += 8) {
+      const float d = warp_dist(rs, c32 + static_cast<size_t>(k) * D, D, lane);
+      if (d < bv || (d == bv && k < bi)) {   // NaN compares false: never selected
+        bv = d;
+        bi = k;
       }
     }
-    if (lane == 0) labels[ent.x] = best;
+    if (lane == 0) {
+      s_best[warp] = bv;
+      s_idx[warp] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float v = s_best[0];
+      int i = s_idx[0];
+      for (int w = 1; w < 8; ++w)
+        if (s_best[w] < v || (s_best[w] == v && s_idx[w] < i)) {
+          v = s_best[w];
+          i = s_idx[w];
+        }
+      labels[ent.x] = (i == 0x7fffffff) ? ent.y : i;   // every distance NaN/inf: keep the tensor pass's label
+    }
+    __syncthreads();
   }
 }
 
@@ -515,6 +595,9 @@ int u2b_kmeans_assign(const void* x16, int64_t N, int64_t D, int64_t K, const vo
   int4* amb = reinterpret_cast<int4*>(static_cast<uint8_t*>(workspace) + 256);
   U2B_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int), stream));
 
+  const int num_tiles = static_cast<int>(ceil_div64(N, BM));
+  int CL = g_kmeans_cluster;
+  if (num_tiles < CL) CL = 1;
   CUtensorMap tx, tc;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(D), static_cast<uint64_t>(N)};
@@ -528,33 +611,35 @@ int u2b_kmeans_assign(const void* x16, int64_t N, int64_t D, int64_t K, const vo
   {
     uint64_t dims[2] = {static_cast<uint64_t>(D), static_cast<uint64_t>(kpad)};
     uint64_t strides[1] = {static_cast<uint64_t>(D) * 2};
-    uint32_t box[2] = {BK, NT};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(NT / CL)};
     int rc = u2b_encode_tmap(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c16, dims, strides, box,
                              nullptr, CU_TENSOR_MAP_SWIZZLE_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc) return rc;
   }
-  const int num_tiles = static_cast<int>(ceil_div64(N, BM));
   const int smem = AssignSmem::bytes(kpad);
-  static bool attr_set = false;
-  if (!attr_set) {
-    U2B_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   U2B_CHECK_ARG(smem <= 227 * 1024, "kmeans_assign: shared memory budget exceeded");
-  const int grid = num_tiles < u2b_num_sms() ? num_tiles : u2b_num_sms();
-  kmeans_assign_kernel<<<grid, ASSIGN_THREADS, smem, stream>>>(
-      tx, tc, cnorm, xmax, cmax2, labels, amb, amb_count, static_cast<int>(N), static_cast<int>(N),
-      kpad, static_cast<int>(D / BK), num_tiles);
-  U2B_LAUNCH_CHECK();
-  kmeans_refine_kernel<<<u2b_num_sms() * 2, 256, 0, stream>>>(
+  int rc;
+  if (CL == 4)
+    rc = launch_assign<4>(tx, tc, cnorm, xmax, cmax2, labels, amb, amb_count, (int)N, kpad, (int)(D / BK), num_tiles, smem, stream);
+  else if (CL == 2)
+    rc = launch_assign<2>(tx, tc, cnorm, xmax, cmax2, labels, amb, amb_count, (int)N, kpad, (int)(D / BK), num_tiles, smem, stream);
+  else
+    rc = launch_assign<1>(tx, tc, cnorm, xmax, cmax2, labels, amb, amb_count, (int)N, kpad, (int)(D / BK), num_tiles, smem, stream);
+  if (rc) return rc;
+  kmeans_refine_kernel<<<u2b_num_sms() * 2, 256, static_cast<size_t>(8) * D * sizeof(float), stream>>>(
       static_cast<const __half*>(x16), c32, amb, amb_count, static_cast<int>(N), labels,
       static_cast<int>(D), static_cast<int>(K));
   U2B_LAUNCH_CHECK();
   if (amb_count_out)
     U2B_CUDA(cudaMemcpyAsync(amb_count_out, amb_count, sizeof(int), cudaMemcpyDeviceToDevice,
                              stream));
+  return 0;
+}
+
+int u2b_kmeans_set_cluster(int cluster) {
+  U2B_CHECK_ARG(cluster == 1 || cluster == 2 || cluster == 4, "kmeans_set_cluster: 1, 2 or 4");
+  g_kmeans_cluster = cluster;
   return 0;
 }
 

@@ -43,6 +43,24 @@ paste_masks_kernel(const float* __restrict__ masks, const float* __restrict__ bo
     const float wy1 = iy - iy_nw, wy0 = (iy_nw + 1.f) - iy;
     const bool y0ok = yi0 >= 0 && yi0 < M, y1ok = yi1 >= 0 && yi1 < M;
     uint8_t res[16];
+    uint8_t* o = out + (static_cast<size_t>(n) * H + y) * W + xg;
+    {
+      // Fast path: the 16-pixel group (or the whole row) lies outside the mask's support, where every bilinear
+      // corner is out of bounds and grid_sample yields exactly 0. ix is monotone in x when x1 > x0.
+      const float gxa = ((static_cast<float>(xg) + 0.5f) - x0) / (x1 - x0) * 2.f - 1.f;
+      const float gxb = ((static_cast<float>(xg + 15) + 0.5f) - x0) / (x1 - x0) * 2.f - 1.f;
+      const float ixa = ((gxa + 1.f) * fM - 1.f) / 2.f, ixb = ((gxb + 1.f) * fM - 1.f) / 2.f;
+      const bool row_out = !(y0ok || y1ok) && (iy == iy);
+      const bool grp_out = (x1 > x0) && (ixb < -1.f || ixa > fM);
+      if ((row_out || grp_out) && 0.f < threshold) {
+        if (xg + 16 <= W && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+          *reinterpret_cast<uint4*>(o) = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+          for (int j = 0; j < 16 && xg + j < W; ++j) o[j] = 0;
+        }
+        continue;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int x = xg + j;
@@ -61,7 +79,6 @@ paste_masks_kernel(const float* __restrict__ masks, const float* __restrict__ bo
       // NaN (degenerate box: 0/0) compares false, as `img >= threshold` does in the reference
       res[j] = (v >= threshold) ? 1 : 0;
     }
-    uint8_t* o = out + (static_cast<size_t>(n) * H + y) * W + xg;
     if (xg + 16 <= W && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
       *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(res);
     } else {

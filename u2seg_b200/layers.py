@@ -53,11 +53,54 @@ def assign_boxes_to_levels_rois(rois5, min_level, max_level, canonical_box_size,
     return levels
 
 
+class _GradHolder:
+    """fp32 NHWC gradient maps shared by every pooling call of one forward pass (see FeatureTap)."""
+
+    def __init__(self):
+        self.bufs = None
+
+    def get(self, shapes, device):
+        if self.bufs is None:
+            self.bufs = [torch.zeros((s[0], s[2], s[3], s[1]), dtype=torch.float32, device=device) for s in shapes]
+        return self.bufs
+
+
+class _PoolTap(torch.autograd.Function):
+    """Identity 'tap' on the pyramid: returns a scalar token every pooling call of the step depends on. The
+    pooling backward passes scatter into the shared fp32 maps of `holder` and send only a scalar gradient to the
+    token; autograd therefore runs this node's backward after ALL of them, where the maps are cast once and
+    handed to the feature maps. (The reference zero-fills, scatters and casts a full pyramid per call: 4x/step.)"""
+
+    @staticmethod
+    def forward(ctx, holder, *feats):
+        ctx.holder = holder
+        ctx.meta = [(tuple(f.shape), f.dtype) for f in feats]
+        return feats[0].new_zeros(())
+
+    @staticmethod
+    def backward(ctx, gtoken):
+        bufs = ctx.holder.bufs
+        ctx.holder.bufs = None
+        if bufs is None:
+            return (None,) + tuple(None for _ in ctx.meta)
+        return (None,) + tuple(b.permute(0, 3, 1, 2).to(dt) for b, (_, dt) in zip(bufs, ctx.meta))
+
+
+class FeatureTap:
+    """Create once per forward pass over the list of pyramid levels, pass as `tap=` to every ROIPooler call."""
+
+    def __init__(self, feats):
+        self.holder = _GradHolder()
+        self.feats = [f.detach() for f in feats]
+        self.token = _PoolTap.apply(self.holder, *feats) if any(f.requires_grad for f in feats) else None
+
+
 class _MultiLevelROIAlign(torch.autograd.Function):
     """out[K, C, P, P] (channels_last) = ROIAlignV2 of rois on their assigned pyramid level."""
 
     @staticmethod
-    def forward(ctx, rois5, levels, P, scales, *feats):
+    def forward(ctx, rois5, levels, P, scales, token, holder, *feats):
+        ctx.holder = holder
         L = _lib.lib()
         f0 = feats[0]
         _need_cuda(f0, "roi_align")
@@ -65,7 +108,7 @@ class _MultiLevelROIAlign(torch.autograd.Function):
         feats_cl = [to_nhwc(f) for f in feats]
         C = f0.shape[1]
         K = rois5.shape[0]
-        out = torch.empty((K, C, P, P), dtype=dt, device=f0.device).contiguous(memory_format=torch.channels_last)
+        out = torch.empty((K, P, P, C), dtype=dt, device=f0.device).permute(0, 3, 1, 2)   # (K,C,P,P), NHWC storage
         if K > 0:
             ptrs = _arr(ctypes.c_void_p, [f.data_ptr() for f in feats_cl])
             hs = _arr(ctypes.c_int32, [f.shape[2] for f in feats_cl])
@@ -87,7 +130,11 @@ class _MultiLevelROIAlign(torch.autograd.Function):
         P, scales, shapes, dt = ctx.meta
         K = rois5.shape[0]
         C = shapes[0][1]
-        grads = [torch.zeros((s[0], s[2], s[3], s[1]), dtype=torch.float32, device=gout.device) for s in shapes]
+        shared = ctx.holder is not None
+        if shared:
+            grads = ctx.holder.get(shapes, gout.device)
+        else:
+            grads = [torch.zeros((s[0], s[2], s[3], s[1]), dtype=torch.float32, device=gout.device) for s in shapes]
         if K > 0:
             g = to_nhwc(gout.to(dt))
             ptrs = _arr(ctypes.c_void_p, [t.data_ptr() for t in grads])
@@ -98,8 +145,10 @@ class _MultiLevelROIAlign(torch.autograd.Function):
                                            _lib.ptr(levels) if ctx.has_levels else None, K, P,
                                            ctypes.c_void_p(g.data_ptr()), _lib.stream_ptr()), "u2b_roi_align_bwd")
             _lib.count_launches(1)
+        if shared:   # gradients reach the features through _PoolTap; the token only orders the backward passes
+            return (None, None, None, None, gout.new_zeros(()), None) + tuple(None for _ in shapes)
         outs = [t.permute(0, 3, 1, 2).to(dt) for t in grads]   # logical NCHW views of the NHWC grads
-        return (None, None, None, None) + tuple(outs)
+        return (None, None, None, None, None, None) + tuple(outs)
 
 
 class ROIAlign(nn.Module):
@@ -119,7 +168,7 @@ class ROIAlign(nn.Module):
     def forward(self, input, rois):
         assert rois.dim() == 2 and rois.size(1) == 5
         rois = _aligned(rois, torch.float32)
-        return _MultiLevelROIAlign.apply(rois, None, self.output_size, (self.spatial_scale,), input)
+        return _MultiLevelROIAlign.apply(rois, None, self.output_size, (self.spatial_scale,), None, None, input)
 
 
 def convert_boxes_to_pooler_format(box_tensors):
@@ -148,8 +197,9 @@ class ROIPooler(nn.Module):
         assert len(scales) == self.max_level - self.min_level + 1
         self.canonical_level, self.canonical_box_size = canonical_level, canonical_box_size
 
-    def forward(self, x, box_lists):
-        """x: list of (N,C,Hl,Wl); box_lists: list (per image) of (Ni,4) tensors (or objects with .tensor)."""
+    def forward(self, x, box_lists, tap=None):
+        """x: list of (N,C,Hl,Wl); box_lists: list (per image) of (Ni,4) tensors (or objects with .tensor).
+        tap: optional FeatureTap over the same `x` shared by all pooling calls of the step."""
         boxes = [b.tensor if hasattr(b, "tensor") else b for b in box_lists]
         assert len(x) == len(self.scales) and len(boxes) == x[0].size(0)
         rois = _aligned(convert_boxes_to_pooler_format(boxes).float())
@@ -157,7 +207,9 @@ class ROIPooler(nn.Module):
         if len(x) > 1:
             levels = assign_boxes_to_levels_rois(rois, self.min_level, self.max_level, self.canonical_box_size,
                                                  self.canonical_level)
-        return _MultiLevelROIAlign.apply(rois, levels, self.output_size, self.scales, *x)
+        if tap is not None and tap.token is not None:
+            return _MultiLevelROIAlign.apply(rois, levels, self.output_size, self.scales, tap.token, tap.holder, *tap.feats)
+        return _MultiLevelROIAlign.apply(rois, levels, self.output_size, self.scales, None, None, *x)
 
 
 # --------------------------------------------------------------------------------------

@@ -17,7 +17,7 @@ def conv2d_nhwc(x, w_ohwi, stride, pad, bias=None, residual=None, relu=False):
     N, Cin, H, W = x.shape
     Cout, R, S, _ = w_ohwi.shape
     OH, OW = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
-    out = torch.empty((N, Cout, OH, OW), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
+    out = torch.empty((N, OH, OW, Cout), dtype=x.dtype, device=x.device).permute(0, 3, 1, 2)   # NHWC storage
     if out.numel() == 0:
         return out
     _lib.check(L.u2b_conv2d_nhwc_fwd(_CODE[x.dtype], ctypes.c_void_p(x.data_ptr()), N, H, W, Cin,
@@ -26,6 +26,11 @@ def conv2d_nhwc(x, w_ohwi, stride, pad, bias=None, residual=None, relu=False):
                                      int(relu), ctypes.c_void_p(out.data_ptr()), _lib.stream_ptr()), "u2b_conv2d_nhwc_fwd")
     _lib.count_launches(1)
     return out
+
+
+def set_cluster(cl):
+    """thread-block cluster size of the conv kernel (1 = no multicast, 2, 4)."""
+    _lib.check(_lib.lib().u2b_conv2d_set_cluster(int(cl)), "u2b_conv2d_set_cluster")
 
 
 def _nhwc(x):

@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from ..layers import Matcher, ROIPooler, batched_nms, crop_and_resize_masks
+from ..layers import FeatureTap, Matcher, ROIPooler, batched_nms, crop_and_resize_masks
 from ..registry import ROI_BOX_HEAD_REGISTRY, ROI_HEADS_REGISTRY, ROI_MASK_HEAD_REGISTRY
 from ..structures import Boxes, Instances
 from .backbone import Conv2d, ShapeSpec, c2_msra_fill, c2_xavier_fill
@@ -304,6 +304,7 @@ class CascadeROIHeads(nn.Module):
 
     # ---- cascade_rcnn.py ----
     def forward(self, images, features, proposals, targets=None):
+        self._tap = FeatureTap([features[f] for f in self.box_in_features]) if self.training else None
         if self.training:
             proposals = self.label_and_sample_proposals(proposals, targets)
             losses = self._forward_box(features, proposals, targets)
@@ -356,7 +357,7 @@ class CascadeROIHeads(nn.Module):
         return proposals
 
     def _run_stage(self, feats, proposals, stage):
-        x = self.box_pooler(feats, [p.proposal_boxes for p in proposals])
+        x = self.box_pooler(feats, [p.proposal_boxes for p in proposals], tap=self._tap)
         if self.training:
             x = _ScaleGradient.apply(x, 1.0 / self.num_cascade_stages)
         return self.box_predictor[stage](self.box_head[stage](x))
@@ -389,7 +390,7 @@ class CascadeROIHeads(nn.Module):
             sel = (inst.gt_classes != -1) & (inst.gt_classes != self.num_classes)
             fg.append(inst[sel.nonzero().squeeze(1)])
         feats = [features[f] for f in self.mask_in_features]
-        x = self.mask_pooler(feats, [i.proposal_boxes for i in fg])
+        x = self.mask_pooler(feats, [i.proposal_boxes for i in fg], tap=self._tap)
         logits = self.mask_head(x)
         masks = [t.gt_masks.tensor if len(t) else None for t in targets]
         return {"loss_mask": mask_rcnn_loss(logits, fg, masks)}
