@@ -143,7 +143,7 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------
 # B200 arm, k-means
 # --------------------------------------------------------------------------------------
-def run_kmeans(args):
+def run_kmeans(args, emit=True):
     import torch
     import torch.distributed as dist
     from u2seg_b200 import _lib
@@ -154,7 +154,8 @@ def run_kmeans(args):
     dev = torch.device("cuda", local)
     group = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     peaks = load_peaks()
 
@@ -252,12 +253,16 @@ def run_kmeans(args):
                        "h2d_bytes_per_step": int(xh.numel() * 2), "d2h_bytes_per_step": int(n_loc * 8 + KM_K * KM_D * 4),
                        "what": "KMeans(x_host_pinned_fp16, seed, K=800, Niter=%d) incl. H2D of X, D2H of labels+centroids; "
                                "value = N*Niter/time" % niter}
+    if rank == 0 and world == 1 and not os.environ.get("U2B_BENCH_SKIP_CPU"):
+        rows = 16384
+        v, tcpu, cores = kmeans_cpu_sample(rows, 2, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "embeddings/s", "cores": cores, "kind": "port",
+                                "sample": "%d rows x K=800 x D=384, one E+M step (oracle port of nn_utils.KMeans)" % rows}
+    del st, x16
+    torch.cuda.empty_cache()
+    if not emit:
+        return line
     if rank == 0:
-        if world == 1:
-            rows = 16384
-            v, tcpu, cores = kmeans_cpu_sample(rows, 2, 1)
-            line["cpu_baseline"] = {"value": v, "unit": "embeddings/s", "cores": cores, "kind": "port",
-                                    "sample": "%d rows x K=800 x D=384, one E+M step (oracle port of nn_utils.KMeans)" % rows}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -278,7 +283,7 @@ def main():
     if args.workload == "kmeans":
         return run_kmeans(args)
     from u2seg_b200.bench_train import run_train
-    return run_train(args, ClockSampler, load_peaks, dist_info)
+    return run_train(args, ClockSampler, load_peaks, dist_info, run_kmeans)
 
 
 if __name__ == "__main__":

@@ -29,7 +29,7 @@ def _batch_bytes(batch):
     return n
 
 
-def run_train(args, ClockSampler, load_peaks, dist_info):
+def run_train(args, ClockSampler, load_peaks, dist_info, run_kmeans=None):
     from . import _lib
     from .config import get_u2seg_cfg
     from .data_synth import synthetic_batch
@@ -101,6 +101,7 @@ def run_train(args, ClockSampler, load_peaks, dist_info):
     e2e_value = IMS_PER_GPU * world / float(tt)
 
     achieved = FLOP_PER_IMAGE * (value / world) / 1e12
+    conv_roof = conv_tc_roofline(peaks)
     line = {
         "metric": "u2seg_R50_800_train_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -127,6 +128,33 @@ def run_train(args, ClockSampler, load_peaks, dist_info):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def conv_tc_roofline(peaks):
+    """Dominant hand-written kernel of the step: conv_tc_kernel on the FPN-output / RPN-head 3x3 (256->256 on
+    2x256x256 px, 154.6 GFLOP per launch = 2*M*Cout*9*Cin). Timed live with CUDA events on the launch stream,
+    back-to-back launches on distinct buffers larger than L2 in aggregate."""
+    from .modeling.conv_tc import conv2d_nhwc
+    N, C, Hh, Ww = 2, 256, 256, 256
+    xs = [torch.randn(N, C, Hh, Ww, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last) for _ in range(4)]
+    w = (torch.randn(C, 3, 3, C, device="cuda") * 0.02).bfloat16()
+    for i in range(4):
+        conv2d_nhwc(xs[i], w, 1, 1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 40
+    e0.record()
+    for i in range(reps):
+        conv2d_nhwc(xs[i % 4], w, 1, 1)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * N * Hh * Ww * C * C * 9
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "conv_tc_kernel<256,bf16> (tcgen05 implicit GEMM), FPN output2 / RPN p2 shape",
+            "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": ach / peaks["tf_burst"],
+            "peak_source": peaks["src"] + " bf16 burst (kernel timed alone)", "traffic": None,
+            "algorithmic_flops_per_launch": flops, "ms_per_launch": ms}
 
 
 def cpu_train_sample(steps, n_images=1):

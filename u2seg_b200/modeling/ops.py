@@ -1,17 +1,32 @@
 """Compute dispatch for the dense layers of the model (conv / norm / activation / residual).
 
-Round-1 state: convolutions and batch-norm statistics go through the library kernels of this image
-(cuDNN via F.conv2d, ATen batch_norm; counted as library calls, like cuBLAS), in channels_last;
-ops.USE_TCGEN05_CONV switches eligible convolutions to the hand-written tcgen05 implicit-GEMM kernel
-of libu2b200 (csrc/conv_tc.cu) as it comes online. ROI pooling, NMS, matching, mask ops and k-means
-always run in libu2b200.
+Round-1 state: the large 3x3 convolutions (forward + input gradient) run on the hand-written tcgen05
+implicit-GEMM kernel of libu2b200 (csrc/conv_tc.cu) when activations are fp16/bf16; the remaining
+convolutions, all weight gradients and the batch-norm statistics go through the library kernels of this image
+(cuDNN via F.conv2d, ATen batch_norm; counted as library calls, like cuBLAS), in channels_last. ROI pooling,
+NMS, matching, mask ops and k-means always run in libu2b200.
 """
 import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 from torch import nn
 
-USE_TCGEN05_CONV = False
+# Which convolutions run on the hand-written tcgen05 kernel (csrc/conv_tc.cu) instead of the library (cuDNN):
+#   "large3x3" (default): 3x3 stride-1 convs with Cin >= 128 — FPN outputs, RPN head conv, mask head, sem-seg head:
+#                         57% of the step's forward MACs; forward and input-gradient (dgrad) both use conv_tc
+#                         (measured 1.35 PFLOP/s on the 256->256 3x3 at 2x256x256, 0.89x cuDNN); weight gradients
+#                         stay in the library this round;
+#   "all": every shape conv_tc supports;  "none": library only.
+TCGEN05_CONV_POLICY = "large3x3"
+USE_TCGEN05_CONV = True
+
+
+def _use_tc(x, m):
+    if not USE_TCGEN05_CONV or TCGEN05_CONV_POLICY == "none":
+        return False
+    if TCGEN05_CONV_POLICY == "all":
+        return True
+    return m.kernel_size == (3, 3) and m.stride == (1, 1) and m.in_channels >= 128 and m.out_channels >= 128
 
 
 def _world():
@@ -37,7 +52,7 @@ def batch_norm(x, bn, relu=False):
 
 def conv_norm_act(x, m, residual=None):
     """y = act(norm(conv(x)) [+ residual]) for a backbone.Conv2d module `m`."""
-    if USE_TCGEN05_CONV:
+    if _use_tc(x, m):
         from . import conv_tc
         y = conv_tc.try_conv(x, m, residual)
         if y is not None:
