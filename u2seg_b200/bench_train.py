@@ -116,12 +116,20 @@ def run_train(args, ClockSampler, load_peaks, dist_info, run_kmeans=None):
                 "d2h_bytes_per_step": d2h,
                 "what": "Trainer.run_step(batch) with pinned host inputs (uint8 images, bit masks, sem_seg) copied H2D "
                         "and the 10 losses read back every step"},
-        "roofline": {"bound": "tensor", "kernel": "whole training step: conv/GEMM flop of SURVEY §8(d) "
-                                                  "(2.021 TFLOP/image fwd+bwd); round-1 convolutions run in cuDNN",
-                     "achieved": achieved, "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sus"],
-                     "peak_source": peaks["src"] + " bf16 sustained", "traffic": None},
+        "roofline": conv_roof,
+        "step_roofline": {"bound": "tensor", "what": "whole training step: conv/GEMM flop of SURVEY 8(d) "
+                                                     "(2.021 TFLOP/image fwd+bwd) / step time",
+                          "achieved": achieved, "peak": peaks["tf_sus"], "unit": "TFLOP/s",
+                          "frac": achieved / peaks["tf_sus"], "peak_source": peaks["src"] + " bf16 sustained"},
+        "conv_policy": "tcgen05 conv_tc for 3x3 stride-1 convs with Cin,Cout>=128 (fwd+dgrad); cuDNN elsewhere and for wgrad",
         "final_loss": loss_total,
     }
+    if run_kmeans is not None and not os.environ.get("U2B_BENCH_SKIP_KMEANS"):
+        del trainer, dev_pool
+        torch.cuda.empty_cache()
+        km = run_kmeans(args, emit=False)     # second half of BASELINE.json's metric: k-means embeddings/s
+        line["kmeans"] = {k: km[k] for k in ("metric", "value", "unit", "ms_per_step", "roofline", "e2e", "gpu_launches",
+                                             "config", "scaling") if k in km}
     if rank == 0 and world == 1 and not os.environ.get("U2B_BENCH_SKIP_CPU"):
         line["cpu_baseline"] = cpu_train_sample(1)
     if rank == 0:
