@@ -139,6 +139,25 @@ int u2b_conv2d_nhwc_fwd(int dtype, const void* x, int N, int H, int W, int Cin, 
                         int R, int S, int stride, int pad, const float* bias, const void* residual, int relu,
                         void* out, u2b_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training-mode (Sync)BatchNorm on NHWC activations (P = N*H*W pixels, C % 8 == 0 channels), fused with the
+ * residual add and ReLU that follow it. Replaces nn.SyncBatchNorm (detectron2/layers/batch_norm.py:187) inside
+ * Conv2d.forward (layers/wrappers.py:87-134) and the `out += shortcut; relu` of backbone/resnet.py:194-210.
+ * dtype: 0 fp32, 1 fp16, 2 bf16. `sums` is a (2C) fp32 scratch that must be zero on entry to stats / bwd_reduce;
+ * a data-parallel job all-reduces it between the reduce and the finalize / apply step.
+ * ------------------------------------------------------------------------------------------ */
+int u2b_bn_stats(int dtype, const void* x, int64_t P, int C, float* sums, u2b_stream_t stream);
+int u2b_bn_finalize(float* sums, double n_total, const float* w, const float* b, float eps, float momentum,
+                    float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
+                    float* shift, int C, u2b_stream_t stream);
+int u2b_bn_apply(int dtype, const void* x, const float* scale, const float* shift, const void* residual, int relu,
+                 void* y, int64_t P, int C, u2b_stream_t stream);
+int u2b_bn_bwd_reduce(int dtype, const void* dy, const void* x, const void* y, const float* mean,
+                      const float* invstd, int64_t P, int C, float* sums, u2b_stream_t stream);
+int u2b_bn_bwd_apply(int dtype, const void* dy, const void* x, const void* y, const float* mean,
+                     const float* invstd, const float* w, const float* sums, double n_total, void* dx,
+                     void* dres, int64_t P, int C, u2b_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

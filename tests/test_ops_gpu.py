@@ -204,3 +204,46 @@ def test_batched_nms_rpn_size_vs_oracle():
     assert set(got.tolist()) == set(want.tolist())
     assert torch.equal(s[got], s[want])      # same score order (ties may permute among equal scores)
     assert batched_nms(b[:0].cuda(), s[:0].cuda(), lv[:0].cuda(), 0.5).numel() == 0
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("C,HW,res,relu", [(64, (33, 47), False, True), (256, (16, 16), True, True), (2048, (4, 6), True, False),
+                                           (512, (20, 12), False, False)])
+def test_fused_bn_act_matches_torch(dtype, tol, C, HW, res, relu):
+    """u2b_bn_* (stats, finalize, apply, bwd_reduce, bwd_apply) vs F.batch_norm(training) + add + relu in fp32."""
+    import torch.nn.functional as F
+    from u2seg_b200.modeling.backbone import SyncBatchNorm
+    from u2seg_b200.modeling.fused_bn import bn_act
+    g = torch.Generator().manual_seed(C + HW[0])
+    N = 2
+    x = (torch.randn(N, C, *HW, generator=g) * 2 + 0.5).to(dtype)
+    r = torch.randn(N, C, *HW, generator=g).to(dtype) if res else None
+    gy = torch.randn(N, C, *HW, generator=g).to(dtype)
+    bn = SyncBatchNorm(C).cuda().train()
+    with torch.no_grad():
+        bn.weight.copy_(1 + 0.2 * torch.randn(C, generator=g))
+        bn.bias.copy_(0.2 * torch.randn(C, generator=g))
+    rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
+    xg = cl(x.cuda()).requires_grad_(True)
+    rg = cl(r.cuda()).requires_grad_(True) if res else None
+    y = bn_act(xg, bn, rg, relu)
+    y.backward(cl(gy.cuda()))
+    # fp32 reference on the same (rounded) inputs
+    xr = x.float().cuda().requires_grad_(True)
+    rr = r.float().cuda().requires_grad_(True) if res else None
+    w, b = bn.weight.detach().clone().requires_grad_(True), bn.bias.detach().clone().requires_grad_(True)
+    rm, rv = rm0.clone(), rv0.clone()
+    yr = F.batch_norm(xr, rm, rv, w, b, True, 0.1, bn.eps)
+    if res:
+        yr = yr + rr
+    if relu:
+        yr = F.relu(yr)
+    yr.backward(gy.float().cuda())
+    sc = lambda t: float(t.abs().max()) + 1e-12
+    assert float((y.float() - yr).abs().max()) <= tol * sc(yr)
+    assert float((xg.grad.float() - xr.grad).abs().max()) <= tol * 2 * sc(xr.grad)
+    if res:
+        assert float((rg.grad.float() - rr.grad).abs().max()) <= tol * sc(rr.grad)
+    assert float((bn.weight.grad - w.grad).abs().max()) <= tol * 2 * sc(w.grad)
+    assert float((bn.bias.grad - b.grad).abs().max()) <= tol * 2 * sc(b.grad)
+    assert torch.allclose(bn.running_mean, rm, rtol=1e-4, atol=1e-5) and torch.allclose(bn.running_var, rv, rtol=1e-4, atol=1e-5)

@@ -15,69 +15,85 @@ namespace {
 
 constexpr int PASTE_MAX_M = 56;  // mask side staged in smem (28 in the reference configs)
 
-// one block = one instance x PASTE_ROWS output rows; thread = 16 consecutive x pixels
-constexpr int PASTE_ROWS = 8;
+// One block = one instance x PASTE_ROWS output rows. The x-dependent part of the bilinear sample (source column,
+// the two column weights) is identical for every row, so it is computed once per block into a shared-memory column
+// table; each thread then produces 16 consecutive pixels of a row (one 16-byte store) from the table, the mask in
+// shared memory and the row's two y weights. Groups / rows outside the mask's support are written as zeros without
+// touching the table (there every bilinear corner is out of bounds and grid_sample yields exactly 0).
+constexpr int PASTE_ROWS = 32;
+constexpr int PASTE_MAX_W = 4096;
+
+struct ColEntry {
+  float wx0, wx1;
+  int xi0;
+};
 
 __global__ void __launch_bounds__(256)
 paste_masks_kernel(const float* __restrict__ masks, const float* __restrict__ boxes, int N, int M,
                    int H, int W, float threshold, uint8_t* __restrict__ out) {
   __shared__ float sm[PASTE_MAX_M * PASTE_MAX_M];
+  extern __shared__ ColEntry cols[];  // [W]
   const int n = blockIdx.y;
   const float* mk = masks + static_cast<size_t>(n) * M * M;
   for (int i = threadIdx.x; i < M * M; i += blockDim.x) sm[i] = mk[i];
-  __syncthreads();
   const float x0 = boxes[n * 4 + 0], y0 = boxes[n * 4 + 1], x1 = boxes[n * 4 + 2], y1 = boxes[n * 4 + 3];
+  const float fM = static_cast<float>(M);
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    // mask_ops.py:51-54: img_x = (arange + 0.5 - x0) / (x1 - x0) * 2 - 1; grid_sample unnormalize
+    // (align_corners=False): ((g + 1) * size - 1) / 2
+    const float gx = ((static_cast<float>(x) + 0.5f) - x0) / (x1 - x0) * 2.f - 1.f;
+    const float ix = ((gx + 1.f) * fM - 1.f) / 2.f;
+    const float ix_nw = floorf(ix);
+    ColEntry e;
+    // out-of-range coordinates are clamped to sentinels whose two corners are both invalid:
+    // left of the mask -> -2, right of it -> M + 1, NaN (degenerate box) -> -3
+    e.xi0 = (ix_nw != ix_nw) ? -3 : (ix_nw < -1.f ? -2 : (ix_nw > fM ? M + 1 : static_cast<int>(ix_nw)));
+    e.wx1 = ix - ix_nw;
+    e.wx0 = (ix_nw + 1.f) - ix;
+    cols[x] = e;
+  }
+  __syncthreads();
   const int groups_per_row = (W + 15) / 16;
   const int row0 = blockIdx.x * PASTE_ROWS;
-  const float fM = static_cast<float>(M);
   for (int t = threadIdx.x; t < PASTE_ROWS * groups_per_row; t += blockDim.x) {
     const int y = row0 + t / groups_per_row;
     if (y >= H) break;
     const int xg = (t % groups_per_row) * 16;
-    // mask_ops.py:51-54: img_y = (arange + 0.5 - y0) / (y1 - y0) * 2 - 1
     const float gy = ((static_cast<float>(y) + 0.5f) - y0) / (y1 - y0) * 2.f - 1.f;
-    // grid_sample unnormalize, align_corners=False: ((g + 1) * size - 1) / 2
     const float iy = ((gy + 1.f) * fM - 1.f) / 2.f;
     const float iy_nw = floorf(iy);
-    const int yi0 = static_cast<int>(iy_nw), yi1 = yi0 + 1;
+    const int yi0 = (iy_nw != iy_nw) ? -3 : (iy_nw < -1.f ? -2 : (iy_nw > fM ? M + 1 : static_cast<int>(iy_nw)));
+    const int yi1 = yi0 + 1;
     const float wy1 = iy - iy_nw, wy0 = (iy_nw + 1.f) - iy;
     const bool y0ok = yi0 >= 0 && yi0 < M, y1ok = yi1 >= 0 && yi1 < M;
-    uint8_t res[16];
     uint8_t* o = out + (static_cast<size_t>(n) * H + y) * W + xg;
-    {
-      // Fast path: the 16-pixel group (or the whole row) lies outside the mask's support, where every bilinear
-      // corner is out of bounds and grid_sample yields exactly 0. ix is monotone in x when x1 > x0.
-      const float gxa = ((static_cast<float>(xg) + 0.5f) - x0) / (x1 - x0) * 2.f - 1.f;
-      const float gxb = ((static_cast<float>(xg + 15) + 0.5f) - x0) / (x1 - x0) * 2.f - 1.f;
-      const float ixa = ((gxa + 1.f) * fM - 1.f) / 2.f, ixb = ((gxb + 1.f) * fM - 1.f) / 2.f;
-      const bool row_out = !(y0ok || y1ok) && (iy == iy);
-      const bool grp_out = (x1 > x0) && (ixb < -1.f || ixa > fM);
-      if ((row_out || grp_out) && 0.f < threshold) {
-        if (xg + 16 <= W && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-          *reinterpret_cast<uint4*>(o) = make_uint4(0u, 0u, 0u, 0u);
-        } else {
-          for (int j = 0; j < 16 && xg + j < W; ++j) o[j] = 0;
-        }
-        continue;
-      }
-    }
+    const int xlast = (xg + 15 < W) ? xg + 15 : W - 1;
+    const int ca = cols[xg].xi0, cb = cols[xlast].xi0;
+    // ix is monotone in x for x1 > x0: if the first column is already right of the mask, or the last one still left
+    // of it, every column of the group has both corners outside [0, M) -> exact zeros
+    const bool grp_out = (x1 > x0) && (ca >= M || cb <= -2);
+    uint8_t res[16];
+    if ((!(y0ok || y1ok) || grp_out) && 0.f < threshold) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int x = xg + j;
-      const float gx = ((static_cast<float>(x) + 0.5f) - x0) / (x1 - x0) * 2.f - 1.f;
-      const float ix = ((gx + 1.f) * fM - 1.f) / 2.f;
-      const float ix_nw = floorf(ix);
-      const int xi0 = static_cast<int>(ix_nw), xi1 = xi0 + 1;
-      const float wx1 = ix - ix_nw, wx0 = (ix_nw + 1.f) - ix;
-      const bool x0ok = xi0 >= 0 && xi0 < M, x1ok = xi1 >= 0 && xi1 < M;
-      float v = 0.f;
-      // ATen grid_sampler_2d bilinear: nw*(ix_se-ix)*(iy_se-iy) + ne*(ix-ix_sw)*(iy_sw-iy) + sw*... + se*...
-      if (y0ok && x0ok) v += sm[yi0 * M + xi0] * (wx0 * wy0);
-      if (y0ok && x1ok) v += sm[yi0 * M + xi1] * (wx1 * wy0);
-      if (y1ok && x0ok) v += sm[yi1 * M + xi0] * (wx0 * wy1);
-      if (y1ok && x1ok) v += sm[yi1 * M + xi1] * (wx1 * wy1);
-      // NaN (degenerate box: 0/0) compares false, as `img >= threshold` does in the reference
-      res[j] = (v >= threshold) ? 1 : 0;
+      for (int j = 0; j < 16; ++j) res[j] = 0;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int x = xg + j;
+        float v = 0.f;
+        if (x < W) {
+          const ColEntry e = cols[x];
+          const int xi0 = e.xi0, xi1 = e.xi0 + 1;
+          const bool x0ok = xi0 >= 0 && xi0 < M, x1ok = xi1 >= 0 && xi1 < M;
+          // ATen grid_sampler_2d bilinear: nw*(ix_se-ix)*(iy_se-iy) + ne*(ix-ix_sw)*(iy_sw-iy) + sw*... + se*...
+          if (y0ok && x0ok) v += sm[yi0 * M + xi0] * (e.wx0 * wy0);
+          if (y0ok && x1ok) v += sm[yi0 * M + xi1] * (e.wx1 * wy0);
+          if (y1ok && x0ok) v += sm[yi1 * M + xi0] * (e.wx0 * wy1);
+          if (y1ok && x1ok) v += sm[yi1 * M + xi1] * (e.wx1 * wy1);
+        }
+        // NaN (degenerate box: 0/0) compares false, as `img >= threshold` does in the reference
+        res[j] = (v >= threshold) ? 1 : 0;
+      }
     }
     if (xg + 16 <= W && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
       *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(res);
@@ -143,8 +159,16 @@ int u2b_paste_masks(const float* masks, const float* boxes, int64_t N, int M, in
   U2B_CHECK_ARG(masks && boxes && out && N > 0 && H > 0 && W > 0, "paste_masks: bad arguments");
   U2B_CHECK_ARG(M > 0 && M <= PASTE_MAX_M, "paste_masks: mask side %d unsupported (<= %d)", M, PASTE_MAX_M);
   U2B_CHECK_ARG(N <= 65535, "paste_masks: N too large for one launch");
+  U2B_CHECK_ARG(W <= PASTE_MAX_W, "paste_masks: W=%d too wide (<= %d)", W, PASTE_MAX_W);
   dim3 grid((H + PASTE_ROWS - 1) / PASTE_ROWS, static_cast<unsigned>(N));
-  paste_masks_kernel<<<grid, 256, 0, stream>>>(masks, boxes, (int)N, M, H, W, threshold, out);
+  const size_t smem = static_cast<size_t>(W) * sizeof(ColEntry);
+  static bool attr = false;
+  if (!attr) {
+    U2B_CUDA(cudaFuncSetAttribute(paste_masks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(PASTE_MAX_W * sizeof(ColEntry))));
+    attr = true;
+  }
+  paste_masks_kernel<<<grid, 256, smem, stream>>>(masks, boxes, (int)N, M, H, W, threshold, out);
   U2B_LAUNCH_CHECK();
   return 0;
 }

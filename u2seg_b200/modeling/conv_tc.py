@@ -99,13 +99,9 @@ def try_conv(x, m, residual=None):
     is_relu = m.activation in (F.relu, F.relu_)
     fuse_relu = m.norm is None and residual is None and is_relu
     y = _ConvTC.apply(x, m.weight, m.bias, m.stride[0], m.padding[0], fuse_relu)
-    if m.norm is not None:
-        y = ops.batch_norm(y, m.norm) if isinstance(m.norm, torch.nn.BatchNorm2d) else m.norm(y)
-    if residual is not None:
-        y = y + residual
-    if m.activation is not None and not fuse_relu:
-        y = m.activation(y)
-    return y
+    if fuse_relu:
+        return y
+    return ops._norm_act(y, m, residual)
 
 
 def linear(x, weight, bias, relu=False):

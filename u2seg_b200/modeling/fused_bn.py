@@ -1,0 +1,97 @@
+"""Training-mode SyncBatchNorm + residual add + ReLU as ONE autograd node over libu2b200's NHWC kernels
+(csrc/batchnorm.cu). Semantics of nn.SyncBatchNorm (detectron2/layers/batch_norm.py:187): batch statistics over
+the whole data-parallel group, running statistics updated with momentum (unbiased variance)."""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from .. import _lib
+
+_CODE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+_scratch = {}
+
+
+def _zeros2c(C, device):
+    """(2C,) fp32 scratch, zero on entry; u2b_bn_finalize hands it back zeroed, backward zeroes it explicitly."""
+    key = (device, C)
+    if key not in _scratch:
+        _scratch[key] = torch.zeros((2 * C,), dtype=torch.float32, device=device)
+    return _scratch[key]
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def _nhwc(x):
+    if x.is_contiguous(memory_format=torch.channels_last) and x.stride(1) == 1:
+        return x
+    return x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class _BNAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, eps, momentum, relu):
+        L = _lib.lib()
+        s = _lib.stream_ptr()
+        xc = _nhwc(x)
+        N, C, H, W = xc.shape
+        P = N * H * W
+        dt = _CODE[xc.dtype]
+        dev = xc.device
+        world = _world()
+        sums = _zeros2c(C, dev)
+        _lib.check(L.u2b_bn_stats(dt, _p(xc), P, C, _p(sums), s), "u2b_bn_stats")
+        if world > 1:
+            dist.all_reduce(sums)
+        stats = torch.empty((4, C), dtype=torch.float32, device=dev)   # mean, invstd, scale, shift
+        n_total = float(P) * world
+        _lib.check(L.u2b_bn_finalize(_p(sums), n_total, _p(weight), _p(bias), float(eps), float(momentum),
+                                     _p(running_mean), _p(running_var), _p(stats[0]), _p(stats[1]), _p(stats[2]),
+                                     _p(stats[3]), C, s), "u2b_bn_finalize")
+        res = _nhwc(residual.to(xc.dtype)) if residual is not None else None
+        y = torch.empty((N, H, W, C), dtype=xc.dtype, device=dev).permute(0, 3, 1, 2)
+        _lib.check(L.u2b_bn_apply(dt, _p(xc), _p(stats[2]), _p(stats[3]), _p(res), int(relu), _p(y), P, C, s), "u2b_bn_apply")
+        _lib.count_launches(3)
+        ctx.save_for_backward(xc, y if relu else torch.empty(0), weight, stats)
+        ctx.meta = (relu, residual is not None, n_total, world)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        L = _lib.lib()
+        s = _lib.stream_ptr()
+        xc, y, weight, stats = ctx.saved_tensors
+        relu, has_res, n_total, world = ctx.meta
+        N, C, H, W = xc.shape
+        P = N * H * W
+        dt = _CODE[xc.dtype]
+        g = _nhwc(gy.to(xc.dtype))
+        sums = torch.zeros((2 * C,), dtype=torch.float32, device=xc.device)
+        yy = y if relu else None
+        _lib.check(L.u2b_bn_bwd_reduce(dt, _p(g), _p(xc), _p(yy), _p(stats[0]), _p(stats[1]), P, C, _p(sums), s),
+                   "u2b_bn_bwd_reduce")
+        gb, gw = sums[:C].clone(), sums[C:].clone()          # parameter gradients are the LOCAL sums (DDP reduces them)
+        if world > 1:
+            dist.all_reduce(sums)
+        dx = torch.empty((N, H, W, C), dtype=xc.dtype, device=xc.device).permute(0, 3, 1, 2)
+        dres = torch.empty((N, H, W, C), dtype=xc.dtype, device=xc.device).permute(0, 3, 1, 2) if has_res else None
+        _lib.check(L.u2b_bn_bwd_apply(dt, _p(g), _p(xc), _p(yy), _p(stats[0]), _p(stats[1]), _p(weight), _p(sums), n_total,
+                                      _p(dx), _p(dres), P, C, s), "u2b_bn_bwd_apply")
+        _lib.count_launches(2)
+        return dx, gw.to(weight.dtype), gb.to(weight.dtype), dres, None, None, None, None, None
+
+
+def bn_act(x, bn, residual=None, relu=False):
+    """relu(SyncBN_train(x) + residual) for a BatchNorm2d-like module `bn` in training mode."""
+    return _BNAct.apply(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, bn.eps,
+                        0.1 if bn.momentum is None else bn.momentum, relu)
+
+
+def supported(x, bn):
+    return x.is_cuda and x.dtype in _CODE and x.dim() == 4 and x.shape[1] % 8 == 0 and bn.training and bn.affine

@@ -37,7 +37,7 @@ def batch_norm(x, bn, relu=False):
     """nn.SyncBatchNorm semantics (layers/batch_norm.py:187): batch statistics over the whole
     data-parallel group in training, running statistics in eval."""
     if bn.training:
-        if bn.num_batches_tracked is not None:
+        if bn.num_batches_tracked is not None and not getattr(bn, "_counter_batched", False):
             bn.num_batches_tracked.add_(1)
         if _world() > 1:
             from torch.nn.modules._functions import SyncBatchNorm as _SBN
@@ -50,6 +50,30 @@ def batch_norm(x, bn, relu=False):
     return F.relu_(y) if relu else y
 
 
+FUSED_BN = True     # SyncBN + residual + ReLU through libu2b200 (csrc/batchnorm.cu) in training mode
+
+
+def _norm_act(y, m, residual):
+    """act(norm(y) [+ residual])"""
+    if m.norm is not None:
+        if isinstance(m.norm, nn.BatchNorm2d):
+            if FUSED_BN:
+                from . import fused_bn
+                is_relu = m.activation in (F.relu, F.relu_)
+                if fused_bn.supported(y, m.norm) and (m.activation is None or is_relu):
+                    if m.norm.num_batches_tracked is not None and not getattr(m.norm, "_counter_batched", False):
+                        m.norm.num_batches_tracked.add_(1)
+                    return fused_bn.bn_act(y, m.norm, residual, is_relu)
+            y = batch_norm(y, m.norm)
+        else:
+            y = m.norm(y)
+    if residual is not None:
+        y = y + residual
+    if m.activation is not None:
+        y = m.activation(y)
+    return y
+
+
 def conv_norm_act(x, m, residual=None):
     """y = act(norm(conv(x)) [+ residual]) for a backbone.Conv2d module `m`."""
     if _use_tc(x, m):
@@ -58,13 +82,7 @@ def conv_norm_act(x, m, residual=None):
         if y is not None:
             return y
     y = F.conv2d(x, m.weight, m.bias, m.stride, m.padding, m.dilation, m.groups)
-    if m.norm is not None:
-        y = batch_norm(y, m.norm) if isinstance(m.norm, nn.BatchNorm2d) else m.norm(y)
-    if residual is not None:
-        y = y + residual
-    if m.activation is not None:
-        y = m.activation(y)
-    return y
+    return _norm_act(y, m, residual)
 
 
 def lateral_add_upsample(lateral, feat, prev):

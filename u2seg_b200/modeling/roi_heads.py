@@ -147,18 +147,18 @@ class FastRCNNOutputLayers(nn.Module):
     def box_reg_loss(self, proposal_boxes, gt_boxes, pred_deltas, gt_classes):
         """fast_rcnn.py:424-463."""
         box_dim = proposal_boxes.shape[1]
-        fg_inds = torch.nonzero((gt_classes >= 0) & (gt_classes < self.num_classes), as_tuple=True)[0]
+        fg = (gt_classes >= 0) & (gt_classes < self.num_classes)
         if pred_deltas.shape[1] == box_dim:
-            fg_pred = pred_deltas[fg_inds]
+            pred = pred_deltas
         else:
-            fg_pred = pred_deltas.view(-1, self.num_classes, box_dim)[fg_inds, gt_classes[fg_inds]]
-        tgt = self.box2box_transform.get_deltas(proposal_boxes[fg_inds], gt_boxes[fg_inds])
-        diff = fg_pred.float() - tgt
-        if self.smooth_l1_beta < 1e-5:
-            loss = diff.abs().sum()
-        else:
-            n = diff.abs()
-            loss = torch.where(n < self.smooth_l1_beta, 0.5 * n ** 2 / self.smooth_l1_beta, n - 0.5 * self.smooth_l1_beta).sum()
+            idx = gt_classes.clamp(0, self.num_classes - 1)
+            pred = pred_deltas.view(-1, self.num_classes, box_dim)[torch.arange(len(idx), device=idx.device), idx]
+        # masked sum over the foreground rows instead of nonzero() + gather (no host sync); background rows may hold
+        # inf/NaN targets (degenerate or absent GT) and are replaced, not multiplied, by zero
+        n = (pred.float() - self.box2box_transform.get_deltas(proposal_boxes, gt_boxes)).abs()
+        if self.smooth_l1_beta >= 1e-5:
+            n = torch.where(n < self.smooth_l1_beta, 0.5 * n ** 2 / self.smooth_l1_beta, n - 0.5 * self.smooth_l1_beta)
+        loss = torch.where(fg[:, None], n, torch.zeros((), dtype=n.dtype, device=n.device)).sum()
         return loss / max(gt_classes.numel(), 1.0)
 
     def predict_boxes(self, predictions, proposals):

@@ -223,15 +223,15 @@ class RPN(nn.Module):
         pos_mask = gt_labels == 1
         anchors_t = Boxes.cat(anchors).tensor
         gt_anchor_deltas = torch.stack([self.box2box_transform.get_deltas(anchors_t, k) for k in gt_boxes])
-        diff = torch.cat(pred_anchor_deltas, dim=1)[pos_mask] - gt_anchor_deltas[pos_mask]
-        if self.smooth_l1_beta < 1e-5:
-            loc = diff.abs().sum()
-        else:
-            n = diff.abs()
-            loc = torch.where(n < self.smooth_l1_beta, 0.5 * n ** 2 / self.smooth_l1_beta, n - 0.5 * self.smooth_l1_beta).sum()
+        # masked sums instead of boolean-mask gathers (rpn.py:405-418): same terms, no data-dependent shapes / host syncs
+        n = (torch.cat(pred_anchor_deltas, dim=1).float() - gt_anchor_deltas).abs()
+        if self.smooth_l1_beta >= 1e-5:
+            n = torch.where(n < self.smooth_l1_beta, 0.5 * n ** 2 / self.smooth_l1_beta, n - 0.5 * self.smooth_l1_beta)
+        loc = torch.where(pos_mask[..., None], n, torch.zeros((), dtype=n.dtype, device=n.device)).sum()
         valid = gt_labels >= 0
-        obj = F.binary_cross_entropy_with_logits(torch.cat(pred_objectness_logits, dim=1)[valid].float(),
-                                                 gt_labels[valid].to(torch.float32), reduction="sum")
+        obj = F.binary_cross_entropy_with_logits(torch.cat(pred_objectness_logits, dim=1).float(),
+                                                 gt_labels.to(torch.float32), weight=valid.to(torch.float32),
+                                                 reduction="sum")
         normalizer = self.batch_size_per_image * num_images
         losses = {"loss_rpn_cls": obj / normalizer, "loss_rpn_loc": loc / normalizer}
         return {k: v * self.loss_weight.get(k, 1.0) for k, v in losses.items()}
