@@ -101,7 +101,7 @@ def dist_info():
 def kmeans_cpu_sample(rows, steps, warmup):
     import torch
     from oracle.kmeans_oracle import assign_oracle, make_mixture, update_oracle
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(max(1, min(os.cpu_count() or 1, 32)))
     x = make_mixture(rows, KM_D, 1000, seed=0, spread=1.0).float()
     g = torch.Generator().manual_seed(0)
     c = x[torch.randperm(rows, generator=g)[:KM_K]].clone()

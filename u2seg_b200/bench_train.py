@@ -41,7 +41,7 @@ def run_train(args, ClockSampler, load_peaks, dist_info, run_kmeans=None):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = False   # ROI counts vary per step: autotuning every new shape costs far more than it saves
     cfg = get_u2seg_cfg(NUM_CLASSES)
     torch.manual_seed(0)
     trainer = Trainer(cfg, amp_dtype=torch.bfloat16, device=dev)
@@ -165,12 +165,18 @@ def conv_tc_roofline(peaks):
             "algorithmic_flops_per_launch": flops, "ms_per_launch": ms}
 
 
+def cpu_threads():
+    """torch CPU threads for the reference arm: all cores up to 32 (beyond that the reference's many small ATen ops
+    get slower, not faster: measured 125 s/step at 128 threads vs ~12 s at 8 on the same code)."""
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
 def cpu_train_sample(steps, n_images=1):
     """The oracle port of the reference step (fp32, torch CPU ops, all host threads) on a bounded sample:
     `n_images` 1024x1024 images per step, forward + backward."""
     import torch
     from oracle import detector_oracle as do
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads())
     cfg = do.DetCfg(NUM_CLASSES, SEM_CLASSES)
     params = {k: (v.clone().requires_grad_(v.is_floating_point() and "running" not in k)) for k, v in
               do.init_params(cfg, 0).items()}

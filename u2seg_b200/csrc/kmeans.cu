@@ -38,7 +38,7 @@ struct AssignSmem {
   static constexpr int BAR_OFF = MERGE_OFF + MERGE_BYTES;
   static constexpr int NBARS = 2 * MAXKB + 2 * BSTAGES + 4;  // 24
   static constexpr int TMEMPTR_OFF = BAR_OFF + NBARS * 8;
-  static constexpr int CNORM_OFF = TMEMPTR_OFF + 16;
+  static constexpr int CNORM_OFF = (TMEMPTR_OFF + 16 + 15) / 16 * 16;
   static int bytes(int kpad) { return CNORM_OFF + kpad * 4 + 1024; }
 };
 
@@ -227,10 +227,16 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap tmap_x,
 #pragma unroll
         for (int c = 0; c < HALF_N / 16; ++c) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = jbase + c * 16 + j;
-            const float d = fmaf(-2.0f, __uint_as_float(r[c][j]), sCnorm[col]);
-            t.push(d, col);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            // |c|^2 for 4 consecutive centroids in one 16-byte shared-memory load (broadcast to the warp)
+            const float4 cn = *reinterpret_cast<const float4*>(sCnorm + jbase + c * 16 + j4 * 4);
+            const float cnv[4] = {cn.x, cn.y, cn.z, cn.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int col = jbase + c * 16 + j4 * 4 + jj;
+              const float d = fmaf(-2.0f, __uint_as_float(r[c][j4 * 4 + jj]), cnv[jj]);
+              t.push(d, col);
+            }
           }
         }
       }
@@ -449,7 +455,7 @@ kmeans_accum_kernel(const __half* __restrict__ x, const int32_t* __restrict__ la
   const long long r1 = (r0 + rows_per < N) ? (r0 + rows_per) : N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int col0 = slice * W;
-  constexpr int UNROLL = 4;
+  constexpr int UNROLL = 8;
   for (long long base = r0 + static_cast<long long>(warp) * UNROLL; base < r1;
        base += static_cast<long long>(nwarps) * UNROLL) {
     int lab[UNROLL];
