@@ -143,19 +143,32 @@ int u2b_conv2d_nhwc_fwd(int dtype, const void* x, int N, int H, int W, int Cin, 
  * Training-mode (Sync)BatchNorm on NHWC activations (P = N*H*W pixels, C % 8 == 0 channels), fused with the
  * residual add and ReLU that follow it. Replaces nn.SyncBatchNorm (detectron2/layers/batch_norm.py:187) inside
  * Conv2d.forward (layers/wrappers.py:87-134) and the `out += shortcut; relu` of backbone/resnet.py:194-210.
- * dtype: 0 fp32, 1 fp16, 2 bf16. `sums` is a (2C) fp32 scratch that must be zero on entry to stats / bwd_reduce;
- * a data-parallel job all-reduces it between the reduce and the finalize / apply step.
+ * dtype: 0 fp32, 1 fp16, 2 bf16. Reductions write per-strip partial rows (no atomics, deterministic); a
+ * data-parallel job sums them (u2b_bn_sum_partials), all-reduces the (2C) sums and passes them on with S = 1.
  * ------------------------------------------------------------------------------------------ */
-int u2b_bn_stats(int dtype, const void* x, int64_t P, int C, float* sums, u2b_stream_t stream);
-int u2b_bn_finalize(float* sums, double n_total, const float* w, const float* b, float eps, float momentum,
-                    float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
-                    float* shift, int C, u2b_stream_t stream);
-int u2b_bn_apply(int dtype, const void* x, const float* scale, const float* shift, const void* residual, int relu,
-                 void* y, int64_t P, int C, u2b_stream_t stream);
-int u2b_bn_bwd_reduce(int dtype, const void* dy, const void* x, const void* y, const float* mean,
-                      const float* invstd, int64_t P, int C, float* sums, u2b_stream_t stream);
-int u2b_bn_bwd_apply(int dtype, const void* dy, const void* x, const void* y, const float* mean,
-                     const float* invstd, const float* w, const float* sums, double n_total, void* dx,
+int u2b_bn_supported(int C);
+/* rows of the partial-sum buffer the reduce kernels write: partials is (num_strips, 2C) fp32 */
+int u2b_bn_num_strips(int64_t P, int C);
+/* partials[s] = (sum x | sum x^2) over pixel strip s */
+int u2b_bn_stats(int dtype, const void* x, int64_t P, int C, float* partials, u2b_stream_t stream);
+/* sums[0:C2] = sum of the S partial rows (for the all-reduce of a data-parallel job) */
+int u2b_bn_sum_partials(const float* partials, int S, int C2, float* sums, u2b_stream_t stream);
+/* stats (4C): mean | invstd | scale = w*invstd | shift = b - mean*scale, from S partial rows (S = 1: summed /
+ * all-reduced) over n_total pixels; running statistics updated with momentum (unbiased variance) */
+int u2b_bn_finalize(const float* partials, int S, double n_total, const float* w, const float* b, float eps,
+                    float momentum, float* running_mean, float* running_var, float* stats, int C,
+                    u2b_stream_t stream);
+/* y = [relu](x * scale[c] + shift[c] [+ residual]) */
+int u2b_bn_apply(int dtype, const void* x, const float* stats, const void* residual, int relu, void* y, int64_t P,
+                 int C, u2b_stream_t stream);
+/* partials[s] = (sum dz | sum dz*xhat), dz = dy * (y > 0) when y != NULL (fused ReLU backward) */
+int u2b_bn_bwd_reduce(int dtype, const void* dy, const void* x, const void* y, const float* stats, int64_t P, int C,
+                      float* partials, u2b_stream_t stream);
+/* coeff (3C): dx = A*dz + B*x + K; gw_gb (2C, nullable) = dgamma | dbeta (the local sums) */
+int u2b_bn_bwd_coeff(const float* partials, int S, double n_total, const float* stats, const float* w, float* coeff,
+                     float* gw_gb, int C, u2b_stream_t stream);
+/* dx = A*dz + B*x + K; dres = dz when dres != NULL */
+int u2b_bn_bwd_apply(int dtype, const void* dy, const void* x, const void* y, const float* coeff, void* dx,
                      void* dres, int64_t P, int C, u2b_stream_t stream);
 
 #ifdef __cplusplus

@@ -44,14 +44,18 @@ SIGNATURES = {
     "u2b_conv2d_set_cluster": (c_int, [c_int]),
     "u2b_conv2d_nhwc_fwd": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                     c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "u2b_bn_supported": (c_int, [c_int]),
+    "u2b_bn_num_strips": (c_int, [c_int64, c_int]),
     "u2b_bn_stats": (c_int, [c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
-    "u2b_bn_finalize": (c_int, [c_void_p, ctypes.c_double, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
-                                c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
-    "u2b_bn_apply": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p]),
-    "u2b_bn_bwd_reduce": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p,
-                                  c_void_p]),
-    "u2b_bn_bwd_apply": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                 ctypes.c_double, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "u2b_bn_sum_partials": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "u2b_bn_finalize": (c_int, [c_void_p, c_int, ctypes.c_double, c_void_p, c_void_p, c_float, c_float, c_void_p,
+                                c_void_p, c_void_p, c_int, c_void_p]),
+    "u2b_bn_apply": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p]),
+    "u2b_bn_bwd_reduce": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "u2b_bn_bwd_coeff": (c_int, [c_void_p, c_int, ctypes.c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_void_p]),
+    "u2b_bn_bwd_apply": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                 c_void_p]),
     "u2b_nms_workspace_bytes": (c_size_t, [c_int64]),
     "u2b_batched_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int64, c_void_p, c_void_p, c_void_p,
                                 c_size_t, c_void_p]),

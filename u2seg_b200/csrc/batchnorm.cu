@@ -4,14 +4,17 @@
 // (out += shortcut; relu).
 //
 // HBM-bound. Forward = 2 reads + 1 write of the activation (library path: 2 reads + 1 write for BN, then 1 read +
-// 1 write each for the add and the ReLU); backward = 3 reads + 1-2 writes.
-//   stats      : per-channel sum / sum of squares (fp32), register accumulation over a pixel strip, block reduction
-//                in shared memory, one fp32 atomicAdd per channel per block
-//   finalize   : mean / invstd / scale / shift, running statistics (momentum, unbiased variance); re-zeroes scratch
-//   apply      : y = relu(x * scale[c] + shift[c] + residual)
-//   bwd_reduce : sum(dz), sum(dz * xhat) with dz = dy * (y > 0)
-//   bwd_apply  : dx = scale * (dz - sum_dy/n - xhat * sum_dy_xhat/n); dres = dz
-// With data parallelism the (2C) scratch sums are all-reduced between stats/bwd_reduce and finalize/bwd_apply.
+// 1 write each for the add and the ReLU); backward = 5 reads + 1-2 writes, no separate ReLU/add backward kernels.
+//   reduce (MODE 0: sum x, sum x^2; MODE 1: sum dz, sum dz*xhat with dz = dy*(y>0)):
+//       grid = (pixel strips, channel groups of 256); a thread owns 8 channels (one 16-byte vector) and a pixel
+//       lane, keeps 4 independent loads in flight, block-reduces through shared memory and writes ONE partial row
+//       per strip - no atomics, deterministic. Partials are summed by the finalize / coefficient kernels (or by
+//       sum_partials when a data-parallel job has to all-reduce the (2C) sums in between).
+//   finalize  : mean / invstd / scale / shift, running statistics (momentum, unbiased variance)
+//   apply     : y = relu(x * scale[c] + shift[c] + residual); per-thread channel coefficients live in registers
+//   bwd_coeff : dx = A[c]*dz + B[c]*x + K[c] with A = w*invstd, B = -A*invstd*S2/n, K = -A*S1/n - B*mean;
+//               also emits dgamma = S2, dbeta = S1 (local sums)
+//   bwd_apply : dx (and dres = dz), coefficients in registers
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -72,131 +75,182 @@ struct V8<__nv_bfloat16> {
 };
 
 constexpr int BN_THREADS = 256;
+constexpr int BN_VPB = 32;  // channel vectors (of 8) per block -> 256 channels per channel group
 
-// Two per-channel sums over pixels. MODE 0: (x, x^2). MODE 1: (dz, dz*xhat), dz = dy * (y>0 if y given).
-// Thread t owns channel vector (t % vecs) and pixels (t / vecs) + k * (BN_THREADS / vecs) of the block's strip.
+inline int vecs_per_block(int C) { return (C / 8 < BN_VPB) ? C / 8 : BN_VPB; }
+inline int channel_groups(int C) { return (C / 8 + BN_VPB - 1) / BN_VPB; }
+inline int num_strips(long long P, int C) {
+  const int lanes = BN_THREADS / vecs_per_block(C);
+  long long s = P / (static_cast<long long>(lanes) * 8);
+  const long long cap = static_cast<long long>(u2b_num_sms()) * 4 / channel_groups(C);
+  if (s > cap) s = cap;
+  if (s < 1) s = 1;
+  return static_cast<int>(s);
+}
+
 template <typename T, int MODE>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ x, const T* __restrict__ y,
                  const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int C,
-                 float* __restrict__ sums) {
-  extern __shared__ float red[];  // [BN_THREADS][16]
-  const int vecs = C / 8;
-  float s0[8], s1[8];
+                 int vpb, float* __restrict__ partials) {
+  __shared__ float red[BN_THREADS * 16];
+  const int lanes = BN_THREADS / vpb;
+  const int tv = threadIdx.x % vpb, tp = threadIdx.x / vpb;
+  const int vec = blockIdx.y * vpb + tv;
+  const bool active = vec * 8 < C && tp < lanes;
+  const int c0 = vec * 8;
+  float s0[8], s1[8], m[8], is[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s0[i] = s1[i] = 0.f;
+  if (MODE == 1 && active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      m[i] = mean[c0 + i];
+      is[i] = invstd[c0 + i];
+    }
+  }
   const long long strip = (P + gridDim.x - 1) / gridDim.x;
   const long long p0 = blockIdx.x * strip;
   const long long p1 = (p0 + strip < P) ? p0 + strip : P;
-  for (int v0 = 0; v0 < vecs; v0 += BN_THREADS) {  // C > 2048: several passes over the channel vectors
-    const int pv = (vecs - v0 < BN_THREADS) ? (vecs - v0) : BN_THREADS;  // vectors handled in this pass
-    const int ppi = BN_THREADS / pv;                                     // pixels per iteration
-    const int tv = threadIdx.x % pv, tp = threadIdx.x / pv;
-    const int c0 = (v0 + tv) * 8;
-    float m[8], is[8];
-    if (MODE == 1) {
+  if (active) {
+    constexpr int U = 4;
+    for (long long pb = p0 + tp; pb < p1; pb += static_cast<long long>(lanes) * U) {
+      float va[U][8], vx[U][8], vy[U][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        m[i] = mean[c0 + i];
-        is[i] = invstd[c0 + i];
-      }
-    }
-    if (tp < ppi) {
-      for (long long p = p0 + tp; p < p1; p += ppi) {
-        float va[8];
-        V8<T>::load(a + p * C + c0, va);
-        if (MODE == 0) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            s0[i] += va[i];
-            s1[i] = fmaf(va[i], va[i], s1[i]);
+      for (int u = 0; u < U; ++u) {
+        const long long p = pb + static_cast<long long>(u) * lanes;
+        if (p < p1) {
+          V8<T>::load(a + p * C + c0, va[u]);
+          if (MODE == 1) {
+            V8<T>::load(x + p * C + c0, vx[u]);
+            if (y) V8<T>::load(y + p * C + c0, vy[u]);
           }
         } else {
-          float vx[8];
-          V8<T>::load(x + p * C + c0, vx);
-          if (y) {
-            float vy[8];
-            V8<T>::load(y + p * C + c0, vy);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) va[i] = vy[i] > 0.f ? va[i] : 0.f;
-          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            s0[i] += va[i];
-            s1[i] = fmaf(va[i], (vx[i] - m[i]) * is[i], s1[i]);
+            va[u][i] = 0.f;
+            if (MODE == 1) { vx[u][i] = 0.f; vy[u][i] = 1.f; }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (MODE == 0) {
+            s0[i] += va[u][i];
+            s1[i] = fmaf(va[u][i], va[u][i], s1[i]);
+          } else {
+            const float g = (y && !(vy[u][i] > 0.f)) ? 0.f : va[u][i];
+            s0[i] += g;
+            s1[i] = fmaf(g, (vx[u][i] - m[i]) * is[i], s1[i]);
           }
         }
       }
     }
-    // block reduction over the ppi pixel lanes of each channel vector
+  }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      red[threadIdx.x * 16 + i] = s0[i];
-      red[threadIdx.x * 16 + 8 + i] = s1[i];
-      s0[i] = s1[i] = 0.f;
-    }
-    __syncthreads();
-    if (threadIdx.x < pv) {
-      float t0[8], t1[8];
+  for (int i = 0; i < 8; ++i) {
+    red[threadIdx.x * 16 + i] = s0[i];
+    red[threadIdx.x * 16 + 8 + i] = s1[i];
+  }
+  __syncthreads();
+  if (tp == 0 && vec * 8 < C) {
+    float t0[8], t1[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) t0[i] = t1[i] = 0.f;
-      for (int q = 0; q < ppi; ++q) {
-        const float* r = red + (q * pv + threadIdx.x) * 16;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          t0[i] += r[i];
-          t1[i] += r[8 + i];
-        }
-      }
-      const int cc = (v0 + threadIdx.x) * 8;
+    for (int i = 0; i < 8; ++i) t0[i] = t1[i] = 0.f;
+    for (int q = 0; q < lanes; ++q) {
+      const float* r = red + (q * vpb + tv) * 16;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        atomicAdd(sums + cc + i, t0[i]);
-        atomicAdd(sums + C + cc + i, t1[i]);
+        t0[i] += r[i];
+        t1[i] += r[8 + i];
       }
     }
-    __syncthreads();
+    float* out = partials + static_cast<size_t>(blockIdx.x) * 2 * C;
+    V8<float>::store(out + c0, t0);
+    V8<float>::store(out + C + c0, t1);
   }
 }
 
-__global__ void bn_finalize_kernel(float* __restrict__ sums, double n_total, const float* __restrict__ w,
-                                   const float* __restrict__ b, float eps, float momentum,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   float* __restrict__ mean, float* __restrict__ invstd,
-                                   float* __restrict__ scale, float* __restrict__ shift, int C) {
+__global__ void bn_sum_partials_kernel(const float* __restrict__ partials, int S, int C2, float* __restrict__ sums) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C2) return;
+  float s = 0.f;
+  for (int i = 0; i < S; ++i) s += partials[static_cast<size_t>(i) * C2 + c];
+  sums[c] = s;
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int S, double n_total,
+                                   const float* __restrict__ w, const float* __restrict__ b, float eps,
+                                   float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ stats, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double s = sums[c], ss = sums[C + c];
+  double s = 0.0, ss = 0.0;
+  for (int i = 0; i < S; ++i) {
+    s += partials[static_cast<size_t>(i) * 2 * C + c];
+    ss += partials[static_cast<size_t>(i) * 2 * C + C + c];
+  }
   const double mu = s / n_total;
   double var = ss / n_total - mu * mu;
   if (var < 0.0) var = 0.0;
   const float is = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  mean[c] = static_cast<float>(mu);
-  invstd[c] = is;
   const float sc = (w ? w[c] : 1.f) * is;
-  scale[c] = sc;
-  shift[c] = (b ? b[c] : 0.f) - static_cast<float>(mu) * sc;
+  stats[c] = static_cast<float>(mu);
+  stats[C + c] = is;
+  stats[2 * C + c] = sc;
+  stats[3 * C + c] = (b ? b[c] : 0.f) - static_cast<float>(mu) * sc;
   if (running_mean) {
     const double unbiased = n_total > 1.0 ? var * n_total / (n_total - 1.0) : var;
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mu);
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
   }
-  sums[c] = 0.f;  // scratch is handed back zeroed
-  sums[C + c] = 0.f;
 }
 
+__global__ void bn_bwd_coeff_kernel(const float* __restrict__ partials, int S, double n_total,
+                                    const float* __restrict__ stats, const float* __restrict__ w,
+                                    float* __restrict__ coeff, float* __restrict__ gw_gb, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = 0; i < S; ++i) {
+    s1 += partials[static_cast<size_t>(i) * 2 * C + c];
+    s2 += partials[static_cast<size_t>(i) * 2 * C + C + c];
+  }
+  if (gw_gb) {
+    gw_gb[c] = s2;      // dgamma = sum dz * xhat
+    gw_gb[C + c] = s1;  // dbeta  = sum dz
+  }
+  const float mu = stats[c], is = stats[C + c];
+  const float inv_n = static_cast<float>(1.0 / n_total);
+  const float A = (w ? w[c] : 1.f) * is;
+  const float B = -A * is * s2 * inv_n;
+  coeff[c] = A;
+  coeff[C + c] = B;
+  coeff[2 * C + c] = -A * s1 * inv_n - B * mu;
+}
+
+// total_vec vectors of 8 channels; (blockDim*gridDim) % (C/8) == 0 so a thread's channels never change
 template <typename T>
 __global__ void __launch_bounds__(256)
-bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
-                const T* __restrict__ residual, int relu, T* __restrict__ y, long long total_vec, int C) {
+bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats, const T* __restrict__ residual, int relu,
+                T* __restrict__ y, long long total_vec, int C) {
   const int vecs = C / 8;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>(i % vecs) * 8;
+  const long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int c0 = static_cast<int>(i0 % vecs) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = stats[2 * C + c0 + k];
+    sh[k] = stats[3 * C + c0 + k];
+  }
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = i0; i < total_vec; i += stride) {
     float v[8];
     V8<T>::load(x + i * 8, v);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], scale[c0 + k], shift[c0 + k]);
+    for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
     if (residual) {
       float r[8];
       V8<T>::load(residual + i * 8, r);
@@ -214,13 +268,20 @@ bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ scale, const 
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
-                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                    const float* __restrict__ w, const float* __restrict__ sums, float inv_n,
-                    T* __restrict__ dx, T* __restrict__ dres, long long total_vec, int C) {
+                    const float* __restrict__ coeff, T* __restrict__ dx, T* __restrict__ dres,
+                    long long total_vec, int C) {
   const int vecs = C / 8;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_vec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>(i % vecs) * 8;
+  const long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int c0 = static_cast<int>(i0 % vecs) * 8;
+  float A[8], B[8], K[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    A[k] = coeff[c0 + k];
+    B[k] = coeff[C + c0 + k];
+    K[k] = coeff[2 * C + c0 + k];
+  }
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = i0; i < total_vec; i += stride) {
     float g[8], vx[8];
     V8<T>::load(dy + i * 8, g);
     V8<T>::load(x + i * 8, vx);
@@ -233,32 +294,26 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
     if (dres) V8<T>::store(dres + i * 8, g);
     float o[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = c0 + k;
-      const float is = invstd[c];
-      const float xh = (vx[k] - mean[c]) * is;
-      o[k] = (w ? w[c] : 1.f) * is * (g[k] - sums[c] * inv_n - xh * sums[C + c] * inv_n);
-    }
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], g[k], fmaf(B[k], vx[k], K[k]));
     V8<T>::store(dx + i * 8, o);
   }
 }
 
 template <typename T, int MODE>
 int launch_reduce(const void* a, const void* x, const void* y, const float* mean, const float* invstd,
-                  long long P, int C, float* sums, cudaStream_t stream) {
-  long long blocks = (P + 63) / 64;
-  const long long cap = static_cast<long long>(u2b_num_sms()) * 8;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  bn_reduce_kernel<T, MODE><<<static_cast<unsigned>(blocks), BN_THREADS, BN_THREADS * 16 * sizeof(float), stream>>>(
-      static_cast<const T*>(a), static_cast<const T*>(x), static_cast<const T*>(y), mean, invstd, P, C, sums);
+                  long long P, int C, float* partials, cudaStream_t stream) {
+  dim3 grid(num_strips(P, C), channel_groups(C));
+  bn_reduce_kernel<T, MODE><<<grid, BN_THREADS, 0, stream>>>(static_cast<const T*>(a), static_cast<const T*>(x),
+                                                             static_cast<const T*>(y), mean, invstd, P, C,
+                                                             vecs_per_block(C), partials);
   U2B_LAUNCH_CHECK();
   return 0;
 }
 
+// grid*256 must be a multiple of C/8 (a power of two <= 256 here): any grid works when 256 % (C/8) == 0
 inline unsigned ew_grid(long long total_vec) {
   long long b = (total_vec + 255) / 256;
-  const long long cap = static_cast<long long>(u2b_num_sms()) * 16;
+  const long long cap = static_cast<long long>(u2b_num_sms()) * 8;
   return static_cast<unsigned>(b > cap ? cap : (b < 1 ? 1 : b));
 }
 
@@ -270,63 +325,83 @@ inline unsigned ew_grid(long long total_vec) {
 
 extern "C" {
 
-// sums (2C fp32) += per-channel (sum x, sum x^2) over the P pixels of x (P, C) NHWC. C % 8 == 0.
-int u2b_bn_stats(int dtype, const void* x, int64_t P, int C, float* sums, cudaStream_t stream) {
-  if (P == 0) return 0;
-  U2B_CHECK_ARG(x && sums && C > 0 && C % 8 == 0, "bn_stats: bad arguments (C %% 8 == 0 required)");
-  U2B_BN_DISPATCH(return (launch_reduce<float, 0>(x, nullptr, nullptr, nullptr, nullptr, P, C, sums, stream)),
-                  return (launch_reduce<__half, 0>(x, nullptr, nullptr, nullptr, nullptr, P, C, sums, stream)),
-                  return (launch_reduce<__nv_bfloat16, 0>(x, nullptr, nullptr, nullptr, nullptr, P, C, sums, stream)))
+// channel counts handled: multiples of 8 whose vector count C/8 divides 256 (64, 128, 256, 512, 1024, 2048, ...)
+int u2b_bn_supported(int C) { return C >= 8 && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0; }
+
+// number of partial rows (strips) the reduce kernels write for a (P, C) activation
+int u2b_bn_num_strips(int64_t P, int C) { return num_strips(P, C); }
+
+// partials[s][0:C] = sum x, partials[s][C:2C] = sum x^2 over strip s of the P pixels of x (P, C) NHWC
+int u2b_bn_stats(int dtype, const void* x, int64_t P, int C, float* partials, cudaStream_t stream) {
+  U2B_CHECK_ARG(x && partials && P > 0 && u2b_bn_supported(C), "bn_stats: bad arguments");
+  U2B_BN_DISPATCH(return (launch_reduce<float, 0>(x, nullptr, nullptr, nullptr, nullptr, P, C, partials, stream)),
+                  return (launch_reduce<__half, 0>(x, nullptr, nullptr, nullptr, nullptr, P, C, partials, stream)),
+                  return (launch_reduce<__nv_bfloat16, 0>(x, nullptr, nullptr, nullptr, nullptr, P, C, partials, stream)))
 }
 
-// From the (all-reduced) sums over n_total pixels: mean, invstd, scale = w*invstd, shift = b - mean*scale; running
-// statistics updated with `momentum` (unbiased variance) when given; sums is zeroed for the next use.
-int u2b_bn_finalize(float* sums, double n_total, const float* w, const float* b, float eps, float momentum,
-                    float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
-                    float* shift, int C, cudaStream_t stream) {
-  U2B_CHECK_ARG(sums && mean && invstd && scale && shift && C > 0 && n_total > 0, "bn_finalize: bad arguments");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sums, n_total, w, b, eps, momentum, running_mean,
-                                                          running_var, mean, invstd, scale, shift, C);
+// sums[0:C2] = sum over the S partial rows (used when the sums are all-reduced across ranks before finalize/coeff)
+int u2b_bn_sum_partials(const float* partials, int S, int C2, float* sums, cudaStream_t stream) {
+  U2B_CHECK_ARG(partials && sums && S > 0 && C2 > 0, "bn_sum_partials: bad arguments");
+  bn_sum_partials_kernel<<<(C2 + 127) / 128, 128, 0, stream>>>(partials, S, C2, sums);
   U2B_LAUNCH_CHECK();
   return 0;
 }
 
-// y = [relu](x * scale[c] + shift[c] [+ residual])
-int u2b_bn_apply(int dtype, const void* x, const float* scale, const float* shift, const void* residual, int relu,
-                 void* y, int64_t P, int C, cudaStream_t stream) {
+// From S partial rows (S = 1: already summed / all-reduced) over n_total pixels: stats[0:C] mean, [C:2C] invstd,
+// [2C:3C] scale = w*invstd, [3C:4C] shift = b - mean*scale; running statistics updated (unbiased variance).
+int u2b_bn_finalize(const float* partials, int S, double n_total, const float* w, const float* b, float eps,
+                    float momentum, float* running_mean, float* running_var, float* stats, int C,
+                    cudaStream_t stream) {
+  U2B_CHECK_ARG(partials && stats && S > 0 && C > 0 && n_total > 0, "bn_finalize: bad arguments");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partials, S, n_total, w, b, eps, momentum, running_mean,
+                                                          running_var, stats, C);
+  U2B_LAUNCH_CHECK();
+  return 0;
+}
+
+// y = [relu](x * scale[c] + shift[c] [+ residual]); stats from u2b_bn_finalize
+int u2b_bn_apply(int dtype, const void* x, const float* stats, const void* residual, int relu, void* y, int64_t P,
+                 int C, cudaStream_t stream) {
   if (P == 0) return 0;
-  U2B_CHECK_ARG(x && y && scale && shift && C % 8 == 0, "bn_apply: bad arguments");
+  U2B_CHECK_ARG(x && y && stats && u2b_bn_supported(C), "bn_apply: bad arguments");
   const long long tv = static_cast<long long>(P) * C / 8;
   U2B_BN_DISPATCH(
-      (bn_apply_kernel<float><<<ew_grid(tv), 256, 0, stream>>>((const float*)x, scale, shift, (const float*)residual, relu, (float*)y, tv, C)),
-      (bn_apply_kernel<__half><<<ew_grid(tv), 256, 0, stream>>>((const __half*)x, scale, shift, (const __half*)residual, relu, (__half*)y, tv, C)),
-      (bn_apply_kernel<__nv_bfloat16><<<ew_grid(tv), 256, 0, stream>>>((const __nv_bfloat16*)x, scale, shift, (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)y, tv, C)))
+      (bn_apply_kernel<float><<<ew_grid(tv), 256, 0, stream>>>((const float*)x, stats, (const float*)residual, relu, (float*)y, tv, C)),
+      (bn_apply_kernel<__half><<<ew_grid(tv), 256, 0, stream>>>((const __half*)x, stats, (const __half*)residual, relu, (__half*)y, tv, C)),
+      (bn_apply_kernel<__nv_bfloat16><<<ew_grid(tv), 256, 0, stream>>>((const __nv_bfloat16*)x, stats, (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)y, tv, C)))
   U2B_LAUNCH_CHECK();
   return 0;
 }
 
-// sums (2C) += (sum dz, sum dz*xhat), dz = dy * (y > 0) when y != NULL (fused ReLU backward)
-int u2b_bn_bwd_reduce(int dtype, const void* dy, const void* x, const void* y, const float* mean,
-                      const float* invstd, int64_t P, int C, float* sums, cudaStream_t stream) {
-  if (P == 0) return 0;
-  U2B_CHECK_ARG(dy && x && mean && invstd && sums && C % 8 == 0, "bn_bwd_reduce: bad arguments");
-  U2B_BN_DISPATCH(return (launch_reduce<float, 1>(dy, x, y, mean, invstd, P, C, sums, stream)),
-                  return (launch_reduce<__half, 1>(dy, x, y, mean, invstd, P, C, sums, stream)),
-                  return (launch_reduce<__nv_bfloat16, 1>(dy, x, y, mean, invstd, P, C, sums, stream)))
+// partials[s] = (sum dz, sum dz*xhat) per strip, dz = dy * (y > 0) when y != NULL (fused ReLU backward)
+int u2b_bn_bwd_reduce(int dtype, const void* dy, const void* x, const void* y, const float* stats, int64_t P, int C,
+                      float* partials, cudaStream_t stream) {
+  U2B_CHECK_ARG(dy && x && stats && partials && P > 0 && u2b_bn_supported(C), "bn_bwd_reduce: bad arguments");
+  U2B_BN_DISPATCH(return (launch_reduce<float, 1>(dy, x, y, stats, stats + C, P, C, partials, stream)),
+                  return (launch_reduce<__half, 1>(dy, x, y, stats, stats + C, P, C, partials, stream)),
+                  return (launch_reduce<__nv_bfloat16, 1>(dy, x, y, stats, stats + C, P, C, partials, stream)))
 }
 
-// dx = w*invstd*(dz - sums[c]/n - xhat*sums[C+c]/n); dres = dz when dres != NULL. sums = all-reduced bwd sums.
-int u2b_bn_bwd_apply(int dtype, const void* dy, const void* x, const void* y, const float* mean,
-                     const float* invstd, const float* w, const float* sums, double n_total, void* dx,
+// coefficients of dx = A*dz + B*x + K from S partial rows (S = 1: all-reduced sums); gw_gb (2C, nullable) receives
+// dgamma | dbeta = the sums themselves (meaningful when the rows are this rank's local sums)
+int u2b_bn_bwd_coeff(const float* partials, int S, double n_total, const float* stats, const float* w, float* coeff,
+                     float* gw_gb, int C, cudaStream_t stream) {
+  U2B_CHECK_ARG(partials && stats && coeff && S > 0 && C > 0 && n_total > 0, "bn_bwd_coeff: bad arguments");
+  bn_bwd_coeff_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partials, S, n_total, stats, w, coeff, gw_gb, C);
+  U2B_LAUNCH_CHECK();
+  return 0;
+}
+
+// dx = A*dz + B*x + K; dres = dz when dres != NULL
+int u2b_bn_bwd_apply(int dtype, const void* dy, const void* x, const void* y, const float* coeff, void* dx,
                      void* dres, int64_t P, int C, cudaStream_t stream) {
   if (P == 0) return 0;
-  U2B_CHECK_ARG(dy && x && dx && mean && invstd && sums && C % 8 == 0 && n_total > 0, "bn_bwd_apply: bad arguments");
+  U2B_CHECK_ARG(dy && x && dx && coeff && u2b_bn_supported(C), "bn_bwd_apply: bad arguments");
   const long long tv = static_cast<long long>(P) * C / 8;
-  const float inv_n = static_cast<float>(1.0 / n_total);
   U2B_BN_DISPATCH(
-      (bn_bwd_apply_kernel<float><<<ew_grid(tv), 256, 0, stream>>>((const float*)dy, (const float*)x, (const float*)y, mean, invstd, w, sums, inv_n, (float*)dx, (float*)dres, tv, C)),
-      (bn_bwd_apply_kernel<__half><<<ew_grid(tv), 256, 0, stream>>>((const __half*)dy, (const __half*)x, (const __half*)y, mean, invstd, w, sums, inv_n, (__half*)dx, (__half*)dres, tv, C)),
-      (bn_bwd_apply_kernel<__nv_bfloat16><<<ew_grid(tv), 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, mean, invstd, w, sums, inv_n, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, tv, C)))
+      (bn_bwd_apply_kernel<float><<<ew_grid(tv), 256, 0, stream>>>((const float*)dy, (const float*)x, (const float*)y, coeff, (float*)dx, (float*)dres, tv, C)),
+      (bn_bwd_apply_kernel<__half><<<ew_grid(tv), 256, 0, stream>>>((const __half*)dy, (const __half*)x, (const __half*)y, coeff, (__half*)dx, (__half*)dres, tv, C)),
+      (bn_bwd_apply_kernel<__nv_bfloat16><<<ew_grid(tv), 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, coeff, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, tv, C)))
   U2B_LAUNCH_CHECK();
   return 0;
 }

@@ -16,49 +16,46 @@ namespace {
 constexpr int PASTE_MAX_M = 56;  // mask side staged in smem (28 in the reference configs)
 
 // One block = one instance x PASTE_ROWS output rows. The x-dependent part of the bilinear sample (source column,
-// the two column weights) is identical for every row, so it is computed once per block into a shared-memory column
-// table; each thread then produces 16 consecutive pixels of a row (one 16-byte store) from the table, the mask in
-// shared memory and the row's two y weights. Groups / rows outside the mask's support are written as zeros without
-// touching the table (there every bilinear corner is out of bounds and grid_sample yields exactly 0).
+// the two column weights) is identical for every row, so it is computed once per block into shared-memory column
+// tables (structure of arrays: conflict-free 16-byte reads); each thread then produces 4 consecutive pixels of a
+// row (a warp writes 128 contiguous bytes) from the tables, the mask in shared memory and the row's two y weights.
+// Rows / groups outside the mask's support are written as zeros directly (there every bilinear corner is out of
+// bounds and grid_sample yields exactly 0).
 constexpr int PASTE_ROWS = 32;
 constexpr int PASTE_MAX_W = 4096;
 
-struct ColEntry {
-  float wx0, wx1;
-  int xi0;
-};
-
 __global__ void __launch_bounds__(256)
 paste_masks_kernel(const float* __restrict__ masks, const float* __restrict__ boxes, int N, int M,
-                   int H, int W, float threshold, uint8_t* __restrict__ out) {
+                   int H, int W, int Wpad, float threshold, uint8_t* __restrict__ out) {
   __shared__ float sm[PASTE_MAX_M * PASTE_MAX_M];
-  extern __shared__ ColEntry cols[];  // [W]
+  extern __shared__ __align__(16) uint8_t col_raw[];
+  float* cwx0 = reinterpret_cast<float*>(col_raw);  // [Wpad]
+  float* cwx1 = cwx0 + Wpad;                        // [Wpad]
+  int* cxi0 = reinterpret_cast<int*>(cwx1 + Wpad);  // [Wpad]
   const int n = blockIdx.y;
   const float* mk = masks + static_cast<size_t>(n) * M * M;
   for (int i = threadIdx.x; i < M * M; i += blockDim.x) sm[i] = mk[i];
   const float x0 = boxes[n * 4 + 0], y0 = boxes[n * 4 + 1], x1 = boxes[n * 4 + 2], y1 = boxes[n * 4 + 3];
   const float fM = static_cast<float>(M);
-  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+  for (int x = threadIdx.x; x < Wpad; x += blockDim.x) {
     // mask_ops.py:51-54: img_x = (arange + 0.5 - x0) / (x1 - x0) * 2 - 1; grid_sample unnormalize
     // (align_corners=False): ((g + 1) * size - 1) / 2
     const float gx = ((static_cast<float>(x) + 0.5f) - x0) / (x1 - x0) * 2.f - 1.f;
     const float ix = ((gx + 1.f) * fM - 1.f) / 2.f;
     const float ix_nw = floorf(ix);
-    ColEntry e;
     // out-of-range coordinates are clamped to sentinels whose two corners are both invalid:
     // left of the mask -> -2, right of it -> M + 1, NaN (degenerate box) -> -3
-    e.xi0 = (ix_nw != ix_nw) ? -3 : (ix_nw < -1.f ? -2 : (ix_nw > fM ? M + 1 : static_cast<int>(ix_nw)));
-    e.wx1 = ix - ix_nw;
-    e.wx0 = (ix_nw + 1.f) - ix;
-    cols[x] = e;
+    cxi0[x] = (ix_nw != ix_nw) ? -3 : (ix_nw < -1.f ? -2 : (ix_nw > fM ? M + 1 : static_cast<int>(ix_nw)));
+    cwx1[x] = ix - ix_nw;
+    cwx0[x] = (ix_nw + 1.f) - ix;
   }
   __syncthreads();
-  const int groups_per_row = (W + 15) / 16;
+  const int groups_per_row = Wpad / 4;
   const int row0 = blockIdx.x * PASTE_ROWS;
   for (int t = threadIdx.x; t < PASTE_ROWS * groups_per_row; t += blockDim.x) {
     const int y = row0 + t / groups_per_row;
     if (y >= H) break;
-    const int xg = (t % groups_per_row) * 16;
+    const int xg = (t % groups_per_row) * 4;
     const float gy = ((static_cast<float>(y) + 0.5f) - y0) / (y1 - y0) * 2.f - 1.f;
     const float iy = ((gy + 1.f) * fM - 1.f) / 2.f;
     const float iy_nw = floorf(iy);
@@ -66,39 +63,34 @@ paste_masks_kernel(const float* __restrict__ masks, const float* __restrict__ bo
     const int yi1 = yi0 + 1;
     const float wy1 = iy - iy_nw, wy0 = (iy_nw + 1.f) - iy;
     const bool y0ok = yi0 >= 0 && yi0 < M, y1ok = yi1 >= 0 && yi1 < M;
-    uint8_t* o = out + (static_cast<size_t>(n) * H + y) * W + xg;
-    const int xlast = (xg + 15 < W) ? xg + 15 : W - 1;
-    const int ca = cols[xg].xi0, cb = cols[xlast].xi0;
-    // ix is monotone in x for x1 > x0: if the first column is already right of the mask, or the last one still left
-    // of it, every column of the group has both corners outside [0, M) -> exact zeros
-    const bool grp_out = (x1 > x0) && (ca >= M || cb <= -2);
-    uint8_t res[16];
-    if ((!(y0ok || y1ok) || grp_out) && 0.f < threshold) {
+    const int4 xi = *reinterpret_cast<const int4*>(cxi0 + xg);
+    // ix is monotone in x for x1 > x0: first column already right of the mask, or last one still left of it
+    const bool grp_out = (x1 > x0) && (xi.x >= M || xi.w <= -2);
+    uint8_t res[4] = {0, 0, 0, 0};
+    if (!((!(y0ok || y1ok) || grp_out) && 0.f < threshold)) {
+      const float4 w0 = *reinterpret_cast<const float4*>(cwx0 + xg);
+      const float4 w1 = *reinterpret_cast<const float4*>(cwx1 + xg);
+      const int xis[4] = {xi.x, xi.y, xi.z, xi.w};
+      const float w0s[4] = {w0.x, w0.y, w0.z, w0.w}, w1s[4] = {w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-      for (int j = 0; j < 16; ++j) res[j] = 0;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int x = xg + j;
+      for (int j = 0; j < 4; ++j) {
+        const int xi0 = xis[j], xi1 = xis[j] + 1;
+        const bool x0ok = xi0 >= 0 && xi0 < M, x1ok = xi1 >= 0 && xi1 < M;
         float v = 0.f;
-        if (x < W) {
-          const ColEntry e = cols[x];
-          const int xi0 = e.xi0, xi1 = e.xi0 + 1;
-          const bool x0ok = xi0 >= 0 && xi0 < M, x1ok = xi1 >= 0 && xi1 < M;
-          // ATen grid_sampler_2d bilinear: nw*(ix_se-ix)*(iy_se-iy) + ne*(ix-ix_sw)*(iy_sw-iy) + sw*... + se*...
-          if (y0ok && x0ok) v += sm[yi0 * M + xi0] * (e.wx0 * wy0);
-          if (y0ok && x1ok) v += sm[yi0 * M + xi1] * (e.wx1 * wy0);
-          if (y1ok && x0ok) v += sm[yi1 * M + xi0] * (e.wx0 * wy1);
-          if (y1ok && x1ok) v += sm[yi1 * M + xi1] * (e.wx1 * wy1);
-        }
+        // ATen grid_sampler_2d bilinear: nw*(ix_se-ix)*(iy_se-iy) + ne*(ix-ix_sw)*(iy_sw-iy) + sw*... + se*...
+        if (y0ok && x0ok) v += sm[yi0 * M + xi0] * (w0s[j] * wy0);
+        if (y0ok && x1ok) v += sm[yi0 * M + xi1] * (w1s[j] * wy0);
+        if (y1ok && x0ok) v += sm[yi1 * M + xi0] * (w0s[j] * wy1);
+        if (y1ok && x1ok) v += sm[yi1 * M + xi1] * (w1s[j] * wy1);
         // NaN (degenerate box: 0/0) compares false, as `img >= threshold` does in the reference
         res[j] = (v >= threshold) ? 1 : 0;
       }
     }
-    if (xg + 16 <= W && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-      *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(res);
+    uint8_t* o = out + (static_cast<size_t>(n) * H + y) * W + xg;
+    if (xg + 4 <= W && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+      *reinterpret_cast<uchar4*>(o) = make_uchar4(res[0], res[1], res[2], res[3]);
     } else {
-      for (int j = 0; j < 16 && xg + j < W; ++j) o[j] = res[j];
+      for (int j = 0; j < 4 && xg + j < W; ++j) o[j] = res[j];
     }
   }
 }
@@ -161,14 +153,15 @@ int u2b_paste_masks(const float* masks, const float* boxes, int64_t N, int M, in
   U2B_CHECK_ARG(N <= 65535, "paste_masks: N too large for one launch");
   U2B_CHECK_ARG(W <= PASTE_MAX_W, "paste_masks: W=%d too wide (<= %d)", W, PASTE_MAX_W);
   dim3 grid((H + PASTE_ROWS - 1) / PASTE_ROWS, static_cast<unsigned>(N));
-  const size_t smem = static_cast<size_t>(W) * sizeof(ColEntry);
+  const int Wpad = (W + 3) / 4 * 4;
+  const size_t smem = static_cast<size_t>(Wpad) * 12;
   static bool attr = false;
   if (!attr) {
     U2B_CUDA(cudaFuncSetAttribute(paste_masks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(PASTE_MAX_W * sizeof(ColEntry))));
+                                  PASTE_MAX_W * 12));
     attr = true;
   }
-  paste_masks_kernel<<<grid, 256, smem, stream>>>(masks, boxes, (int)N, M, H, W, threshold, out);
+  paste_masks_kernel<<<grid, 256, smem, stream>>>(masks, boxes, (int)N, M, H, W, Wpad, threshold, out);
   U2B_LAUNCH_CHECK();
   return 0;
 }

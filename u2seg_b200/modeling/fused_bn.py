@@ -9,15 +9,18 @@ import torch.distributed as dist
 from .. import _lib
 
 _CODE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
-_scratch = {}
+_ws = {}
 
 
-def _zeros2c(C, device):
-    """(2C,) fp32 scratch, zero on entry; u2b_bn_finalize hands it back zeroed, backward zeroes it explicitly."""
-    key = (device, C)
-    if key not in _scratch:
-        _scratch[key] = torch.zeros((2 * C,), dtype=torch.float32, device=device)
-    return _scratch[key]
+def _partials(S, C, device):
+    """(S, 2C) fp32 workspace; one growing buffer per device (kernels are stream-ordered, each use is consumed by
+    the finalize / coefficient kernel enqueued right after it)."""
+    need = S * 2 * C
+    buf = _ws.get(device)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty((max(need, 1 << 20),), dtype=torch.float32, device=device)
+        _ws[device] = buf
+    return buf
 
 
 def _world():
@@ -45,18 +48,21 @@ class _BNAct(torch.autograd.Function):
         dt = _CODE[xc.dtype]
         dev = xc.device
         world = _world()
-        sums = _zeros2c(C, dev)
-        _lib.check(L.u2b_bn_stats(dt, _p(xc), P, C, _p(sums), s), "u2b_bn_stats")
-        if world > 1:
-            dist.all_reduce(sums)
-        stats = torch.empty((4, C), dtype=torch.float32, device=dev)   # mean, invstd, scale, shift
+        S = int(L.u2b_bn_num_strips(P, C))
+        part = _partials(S, C, dev)
+        _lib.check(L.u2b_bn_stats(dt, _p(xc), P, C, _p(part), s), "u2b_bn_stats")
+        stats = torch.empty((4 * C,), dtype=torch.float32, device=dev)   # mean | invstd | scale | shift
         n_total = float(P) * world
-        _lib.check(L.u2b_bn_finalize(_p(sums), n_total, _p(weight), _p(bias), float(eps), float(momentum),
-                                     _p(running_mean), _p(running_var), _p(stats[0]), _p(stats[1]), _p(stats[2]),
-                                     _p(stats[3]), C, s), "u2b_bn_finalize")
+        if world > 1:
+            sums = torch.empty((2 * C,), dtype=torch.float32, device=dev)
+            _lib.check(L.u2b_bn_sum_partials(_p(part), S, 2 * C, _p(sums), s), "u2b_bn_sum_partials")
+            dist.all_reduce(sums)
+            part, S = sums, 1
+        _lib.check(L.u2b_bn_finalize(_p(part), S, n_total, _p(weight), _p(bias), float(eps), float(momentum),
+                                     _p(running_mean), _p(running_var), _p(stats), C, s), "u2b_bn_finalize")
         res = _nhwc(residual.to(xc.dtype)) if residual is not None else None
         y = torch.empty((N, H, W, C), dtype=xc.dtype, device=dev).permute(0, 3, 1, 2)
-        _lib.check(L.u2b_bn_apply(dt, _p(xc), _p(stats[2]), _p(stats[3]), _p(res), int(relu), _p(y), P, C, s), "u2b_bn_apply")
+        _lib.check(L.u2b_bn_apply(dt, _p(xc), _p(stats), _p(res), int(relu), _p(y), P, C, s), "u2b_bn_apply")
         _lib.count_launches(3)
         ctx.save_for_backward(xc, y if relu else torch.empty(0), weight, stats)
         ctx.meta = (relu, residual is not None, n_total, world)
@@ -71,20 +77,28 @@ class _BNAct(torch.autograd.Function):
         N, C, H, W = xc.shape
         P = N * H * W
         dt = _CODE[xc.dtype]
+        dev = xc.device
         g = _nhwc(gy.to(xc.dtype))
-        sums = torch.zeros((2 * C,), dtype=torch.float32, device=xc.device)
         yy = y if relu else None
-        _lib.check(L.u2b_bn_bwd_reduce(dt, _p(g), _p(xc), _p(yy), _p(stats[0]), _p(stats[1]), P, C, _p(sums), s),
-                   "u2b_bn_bwd_reduce")
-        gb, gw = sums[:C].clone(), sums[C:].clone()          # parameter gradients are the LOCAL sums (DDP reduces them)
+        S = int(L.u2b_bn_num_strips(P, C))
+        part = _partials(S, C, dev)
+        _lib.check(L.u2b_bn_bwd_reduce(dt, _p(g), _p(xc), _p(yy), _p(stats), P, C, _p(part), s), "u2b_bn_bwd_reduce")
+        coeff = torch.empty((3 * C,), dtype=torch.float32, device=dev)
+        gwb = torch.empty((2 * C,), dtype=torch.float32, device=dev)      # dgamma | dbeta (LOCAL sums: DDP reduces them)
         if world > 1:
+            sums = torch.empty((2 * C,), dtype=torch.float32, device=dev)
+            _lib.check(L.u2b_bn_sum_partials(_p(part), S, 2 * C, _p(sums), s), "u2b_bn_sum_partials")
+            gwb[:C].copy_(sums[C:])
+            gwb[C:].copy_(sums[:C])
             dist.all_reduce(sums)
-        dx = torch.empty((N, H, W, C), dtype=xc.dtype, device=xc.device).permute(0, 3, 1, 2)
-        dres = torch.empty((N, H, W, C), dtype=xc.dtype, device=xc.device).permute(0, 3, 1, 2) if has_res else None
-        _lib.check(L.u2b_bn_bwd_apply(dt, _p(g), _p(xc), _p(yy), _p(stats[0]), _p(stats[1]), _p(weight), _p(sums), n_total,
-                                      _p(dx), _p(dres), P, C, s), "u2b_bn_bwd_apply")
-        _lib.count_launches(2)
-        return dx, gw.to(weight.dtype), gb.to(weight.dtype), dres, None, None, None, None, None
+            _lib.check(L.u2b_bn_bwd_coeff(_p(sums), 1, n_total, _p(stats), _p(weight), _p(coeff), None, C, s), "u2b_bn_bwd_coeff")
+        else:
+            _lib.check(L.u2b_bn_bwd_coeff(_p(part), S, n_total, _p(stats), _p(weight), _p(coeff), _p(gwb), C, s), "u2b_bn_bwd_coeff")
+        dx = torch.empty((N, H, W, C), dtype=xc.dtype, device=dev).permute(0, 3, 1, 2)
+        dres = torch.empty((N, H, W, C), dtype=xc.dtype, device=dev).permute(0, 3, 1, 2) if has_res else None
+        _lib.check(L.u2b_bn_bwd_apply(dt, _p(g), _p(xc), _p(yy), _p(coeff), _p(dx), _p(dres), P, C, s), "u2b_bn_bwd_apply")
+        _lib.count_launches(3)
+        return dx, gwb[:C].to(weight.dtype), gwb[C:].to(weight.dtype), dres, None, None, None, None, None
 
 
 def bn_act(x, bn, residual=None, relu=False):
@@ -94,4 +108,5 @@ def bn_act(x, bn, residual=None, relu=False):
 
 
 def supported(x, bn):
-    return x.is_cuda and x.dtype in _CODE and x.dim() == 4 and x.shape[1] % 8 == 0 and bn.training and bn.affine
+    return (x.is_cuda and x.dtype in _CODE and x.dim() == 4 and bn.training and bn.affine
+            and bool(_lib.lib().u2b_bn_supported(int(x.shape[1]))))
