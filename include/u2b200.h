@@ -167,6 +167,17 @@ int u2b_bn_bwd_reduce(int dtype, const void* dy, const void* x, const void* y, c
 /* coeff (3C): dx = A*dz + B*x + K; gw_gb (2C, nullable) = dgamma | dbeta (the local sums) */
 int u2b_bn_bwd_coeff(const float* partials, int S, double n_total, const float* stats, const float* w, float* coeff,
                      float* gw_gb, int C, u2b_stream_t stream);
+/* Data-parallel (SyncBN) variants with the cross-GPU reduction fused into the kernel: `sums` (2C, this rank's summed
+ * partials) is stored into every peer's symmetric buffer over NVLink, published with release/acquire flags, and
+ * reduced locally - no NCCL call. peers: device array of `world` device pointers (every rank's buffer of
+ * u2b_bn_xchg_buffer_bytes, zero-initialised once); epoch = 1, 2, 3, ... one per exchange, identical on all ranks. */
+size_t u2b_bn_xchg_buffer_bytes(int world, int slot_floats);
+int u2b_bn_xchg_finalize(const float* sums, const void* peers, int world, int rank, uint32_t epoch, int slot_floats,
+                         double n_total, const float* w, const float* b, float eps, float momentum,
+                         float* running_mean, float* running_var, float* stats, int C, u2b_stream_t stream);
+int u2b_bn_xchg_bwd_coeff(const float* sums, const void* peers, int world, int rank, uint32_t epoch, int slot_floats,
+                          double n_total, const float* stats, const float* w, float* coeff, float* gw_gb, int C,
+                          u2b_stream_t stream);
 /* dx = A*dz + B*x + K; dres = dz when dres != NULL */
 int u2b_bn_bwd_apply(int dtype, const void* dy, const void* x, const void* y, const float* coeff, void* dx,
                      void* dres, int64_t P, int C, u2b_stream_t stream);

@@ -1,0 +1,56 @@
+"""2-GPU test (run under torchrun by tools/run_multigpu_tests.sh; skipped in the single-process pytest runs):
+fused SyncBN with the in-kernel NVLink peer exchange == NCCL all-reduce path == single-process BN over the
+concatenated batch."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+
+pytestmark = pytest.mark.gpu
+
+_MULTI = int(os.environ.get("WORLD_SIZE", "1")) > 1
+
+
+@pytest.mark.skipif(not _MULTI, reason="needs torchrun with WORLD_SIZE > 1")
+def test_syncbn_peer_exchange_matches_reference():
+    import torch.nn.functional as F
+    from u2seg_b200.modeling import fused_bn
+    from u2seg_b200.modeling.backbone import SyncBatchNorm
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    for it, (C, HW) in enumerate([(64, (24, 40)), (256, (16, 16)), (2048, (4, 4)), (512, (8, 12))] * 3):
+        g = torch.Generator().manual_seed(100 + it)
+        xs = [torch.randn(2, C, *HW, generator=g) * 2 + 0.3 for _ in range(world)]
+        gys = [torch.randn(2, C, *HW, generator=g) for _ in range(world)]
+        w, b = 1 + 0.2 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+        # reference: one process, whole batch
+        xr = torch.cat(xs).cuda().requires_grad_(True)
+        wr, br = w.clone().cuda().requires_grad_(True), b.clone().cuda().requires_grad_(True)
+        rm, rv = torch.zeros(C).cuda(), torch.ones(C).cuda()
+        yr = F.relu(F.batch_norm(xr, rm, rv, wr, br, True, 0.1, 1e-5))
+        yr.backward(torch.cat(gys).cuda())
+        outs = {}
+        for mode in ("1", "0"):       # peer exchange, then NCCL
+            os.environ["U2B_SYNCBN_XCHG"] = mode
+            bn = SyncBatchNorm(C).cuda().train()
+            with torch.no_grad():
+                bn.weight.copy_(w)
+                bn.bias.copy_(b)
+            x = xs[rank].cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+            y = fused_bn.bn_act(x, bn, None, True)
+            y.backward(gys[rank].cuda().contiguous(memory_format=torch.channels_last))
+            outs[mode] = (y.detach(), x.grad.clone(), bn.weight.grad.clone(), bn.running_var.clone())
+            sl = slice(2 * rank, 2 * rank + 2)
+            assert torch.allclose(y, yr[sl], rtol=1e-4, atol=1e-4)
+            assert torch.allclose(x.grad, xr.grad[sl], rtol=1e-3, atol=1e-5)
+            assert torch.allclose(bn.running_mean, rm, rtol=1e-4, atol=1e-5) and torch.allclose(bn.running_var, rv, rtol=1e-4, atol=1e-5)
+            gw = bn.weight.grad.clone()
+            dist.all_reduce(gw)
+            assert torch.allclose(gw, wr.grad, rtol=1e-3, atol=1e-4)
+        for a, c in zip(outs["1"], outs["0"]):
+            assert torch.allclose(a, c, rtol=1e-5, atol=1e-6)
+    os.environ["U2B_SYNCBN_XCHG"] = "1"
+    dist.barrier()

@@ -26,6 +26,16 @@ template <typename T>
 struct V8;  // 8 channels per thread
 template <>
 struct V8<float> {
+  struct Raw { float4 a, b; };
+  static __device__ __forceinline__ Raw ldraw(const float* p) {
+    Raw r;
+    r.a = reinterpret_cast<const float4*>(p)[0];
+    r.b = reinterpret_cast<const float4*>(p)[1];
+    return r;
+  }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[8]) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+  }
   static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
     const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -37,6 +47,16 @@ struct V8<float> {
 };
 template <>
 struct V8<__half> {
+  using Raw = uint4;
+  static __device__ __forceinline__ Raw ldraw(const __half* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
   static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
     const uint4 r = *reinterpret_cast<const uint4*>(p);
     const __half2* h = reinterpret_cast<const __half2*>(&r);
@@ -56,6 +76,16 @@ struct V8<__half> {
 };
 template <>
 struct V8<__nv_bfloat16> {
+  using Raw = uint4;
+  static __device__ __forceinline__ Raw ldraw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
     const uint4 r = *reinterpret_cast<const uint4*>(p);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
@@ -82,7 +112,7 @@ inline int channel_groups(int C) { return (C / 8 + BN_VPB - 1) / BN_VPB; }
 inline int num_strips(long long P, int C) {
   const int lanes = BN_THREADS / vecs_per_block(C);
   long long s = P / (static_cast<long long>(lanes) * 8);
-  const long long cap = static_cast<long long>(u2b_num_sms()) * 4 / channel_groups(C);
+  const long long cap = static_cast<long long>(u2b_num_sms()) * 2 / channel_groups(C);
   if (s > cap) s = cap;
   if (s < 1) s = 1;
   return static_cast<int>(s);
@@ -114,36 +144,46 @@ bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ x, const T* __re
   const long long p1 = (p0 + strip < P) ? p0 + strip : P;
   if (active) {
     constexpr int U = 4;
+    using Raw = typename V8<T>::Raw;
     for (long long pb = p0 + tp; pb < p1; pb += static_cast<long long>(lanes) * U) {
-      float va[U][8], vx[U][8], vy[U][8];
+      Raw ra[U], rx[U], ry[U];   // packed loads stay in flight; unpacked one at a time below
+      bool ok[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long p = pb + static_cast<long long>(u) * lanes;
-        if (p < p1) {
-          V8<T>::load(a + p * C + c0, va[u]);
+        ok[u] = p < p1;
+        if (ok[u]) {
+          ra[u] = V8<T>::ldraw(a + p * C + c0);
           if (MODE == 1) {
-            V8<T>::load(x + p * C + c0, vx[u]);
-            if (y) V8<T>::load(y + p * C + c0, vy[u]);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            va[u][i] = 0.f;
-            if (MODE == 1) { vx[u][i] = 0.f; vy[u][i] = 1.f; }
+            rx[u] = V8<T>::ldraw(x + p * C + c0);
+            if (y) ry[u] = V8<T>::ldraw(y + p * C + c0);
           }
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        float va[8];
+        V8<T>::unpack(ra[u], va);
+        if (MODE == 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (MODE == 0) {
-            s0[i] += va[u][i];
-            s1[i] = fmaf(va[u][i], va[u][i], s1[i]);
-          } else {
-            const float g = (y && !(vy[u][i] > 0.f)) ? 0.f : va[u][i];
-            s0[i] += g;
-            s1[i] = fmaf(g, (vx[u][i] - m[i]) * is[i], s1[i]);
+          for (int i = 0; i < 8; ++i) {
+            s0[i] += va[i];
+            s1[i] = fmaf(va[i], va[i], s1[i]);
+          }
+        } else {
+          float vx[8];
+          V8<T>::unpack(rx[u], vx);
+          if (y) {
+            float vy[8];
+            V8<T>::unpack(ry[u], vy);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) va[i] = vy[i] > 0.f ? va[i] : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            s0[i] += va[i];
+            s1[i] = fmaf(va[i], (vx[i] - m[i]) * is[i], s1[i]);
           }
         }
       }
@@ -185,12 +225,23 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int S, do
                                    const float* __restrict__ w, const float* __restrict__ b, float eps,
                                    float momentum, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float* __restrict__ stats, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  // block = 32 channels x 8 strip lanes; lanes sum strided partial rows, then combine through shared memory
+  __shared__ double sh[2][8][32];
+  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double s = 0.0, ss = 0.0;
-  for (int i = 0; i < S; ++i) {
-    s += partials[static_cast<size_t>(i) * 2 * C + c];
-    ss += partials[static_cast<size_t>(i) * 2 * C + C + c];
+  if (c < C)
+    for (int i = sl; i < S; i += 8) {
+      s += partials[static_cast<size_t>(i) * 2 * C + c];
+      ss += partials[static_cast<size_t>(i) * 2 * C + C + c];
+    }
+  sh[0][sl][cl] = s;
+  sh[1][sl][cl] = ss;
+  __syncthreads();
+  if (sl != 0 || c >= C) return;
+  for (int q = 1; q < 8; ++q) {
+    s += sh[0][q][cl];
+    ss += sh[1][q][cl];
   }
   const double mu = s / n_total;
   double var = ss / n_total - mu * mu;
@@ -211,12 +262,22 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int S, do
 __global__ void bn_bwd_coeff_kernel(const float* __restrict__ partials, int S, double n_total,
                                     const float* __restrict__ stats, const float* __restrict__ w,
                                     float* __restrict__ coeff, float* __restrict__ gw_gb, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ float sh[2][8][32];
+  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float s1 = 0.f, s2 = 0.f;
-  for (int i = 0; i < S; ++i) {
-    s1 += partials[static_cast<size_t>(i) * 2 * C + c];
-    s2 += partials[static_cast<size_t>(i) * 2 * C + C + c];
+  if (c < C)
+    for (int i = sl; i < S; i += 8) {
+      s1 += partials[static_cast<size_t>(i) * 2 * C + c];
+      s2 += partials[static_cast<size_t>(i) * 2 * C + C + c];
+    }
+  sh[0][sl][cl] = s1;
+  sh[1][sl][cl] = s2;
+  __syncthreads();
+  if (sl != 0 || c >= C) return;
+  for (int q = 1; q < 8; ++q) {
+    s1 += sh[0][q][cl];
+    s2 += sh[1][q][cl];
   }
   if (gw_gb) {
     gw_gb[c] = s2;      // dgamma = sum dz * xhat
@@ -299,6 +360,113 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
   }
 }
 
+// ---------------- cross-GPU exchange over NVLink peer memory (SyncBN without NCCL launches) ----------------
+// Symmetric buffer of every rank (same layout, allocated once through torch symmetric memory):
+//   float data[2][world][slot_floats];  uint32 flags[world]   (flags at byte offset 2*world*slot_floats*4)
+// Call `epoch` (1, 2, 3, ... identical on all ranks, one per exchange) uses data slot epoch & 1. Rank r stores its
+// sums into data[slot][r] of EVERY rank (remote stores over NVLink), fences, then publishes `epoch` in flags[r] of
+// every rank; it then waits until its own flags[q] >= epoch for all q and reduces data[slot][0..world) locally in a
+// fixed order (all ranks get bit-identical sums). A rank can be at most one call ahead of a peer (it needs the
+// peer's flag of the previous call to proceed), so two slots are enough.
+#ifndef U2B_XCHG_TIMEOUT_CYCLES
+#define U2B_XCHG_TIMEOUT_CYCLES (6000000000LL)
+#endif
+
+__device__ __forceinline__ void xchg_all_reduce(float* __restrict__ vals /*smem [n]*/, int n,
+                                                const unsigned long long* __restrict__ peers, int world, int rank,
+                                                unsigned int epoch, int slot_floats) {
+  const int slot = epoch & 1;
+  const size_t flag_off = static_cast<size_t>(2) * world * slot_floats * sizeof(float);
+  for (int p = 0; p < world; ++p) {
+    float* dst = reinterpret_cast<float*>(peers[p]) + (static_cast<size_t>(slot) * world + rank) * slot_floats;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = vals[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < world) {
+    unsigned int* f = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(peers[threadIdx.x]) + flag_off) + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+  }
+  if (threadIdx.x < world) {
+    const unsigned int* f =
+        reinterpret_cast<const unsigned int*>(reinterpret_cast<const char*>(peers[rank]) + flag_off) + threadIdx.x;
+    const long long t0 = clock64();
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (static_cast<int>(v - epoch) >= 0) break;
+      if (clock64() - t0 > U2B_XCHG_TIMEOUT_CYCLES) {
+        printf("u2b: SyncBN peer exchange timeout rank %d waiting for rank %d epoch %u (have %u)\n", rank,
+               threadIdx.x, epoch, v);
+        __trap();
+      }
+    } while (true);
+  }
+  __syncthreads();
+  __threadfence_system();
+  const float* mine = reinterpret_cast<const float*>(peers[rank]) + static_cast<size_t>(slot) * world * slot_floats;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float acc = 0.f;
+    for (int q = 0; q < world; ++q) acc += __ldcv(mine + static_cast<size_t>(q) * slot_floats + i);
+    vals[i] = acc;
+  }
+  __syncthreads();
+}
+
+// one CTA: local (2C) sums -> exchange -> mean/invstd/scale/shift + running statistics
+__global__ void __launch_bounds__(1024)
+bn_xchg_finalize_kernel(const float* __restrict__ sums, const unsigned long long* __restrict__ peers, int world,
+                        int rank, unsigned int epoch, int slot_floats, double n_total, const float* __restrict__ w,
+                        const float* __restrict__ b, float eps, float momentum, float* __restrict__ running_mean,
+                        float* __restrict__ running_var, float* __restrict__ stats, int C) {
+  extern __shared__ float xv[];  // [2C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) xv[i] = sums[i];
+  __syncthreads();
+  xchg_all_reduce(xv, 2 * C, peers, world, rank, epoch, slot_floats);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double mu = static_cast<double>(xv[c]) / n_total;
+    double var = static_cast<double>(xv[C + c]) / n_total - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float is = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = (w ? w[c] : 1.f) * is;
+    stats[c] = static_cast<float>(mu);
+    stats[C + c] = is;
+    stats[2 * C + c] = sc;
+    stats[3 * C + c] = (b ? b[c] : 0.f) - static_cast<float>(mu) * sc;
+    if (running_mean) {
+      const double unbiased = n_total > 1.0 ? var * n_total / (n_total - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mu);
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+    }
+  }
+}
+
+// one CTA: local (2C) backward sums -> dgamma/dbeta (local) -> exchange -> dx coefficients
+__global__ void __launch_bounds__(1024)
+bn_xchg_bwd_coeff_kernel(const float* __restrict__ sums, const unsigned long long* __restrict__ peers, int world,
+                         int rank, unsigned int epoch, int slot_floats, double n_total,
+                         const float* __restrict__ stats, const float* __restrict__ w, float* __restrict__ coeff,
+                         float* __restrict__ gw_gb, int C) {
+  extern __shared__ float xv[];  // [2C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) xv[i] = sums[i];
+  __syncthreads();
+  if (gw_gb)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      gw_gb[c] = xv[C + c];
+      gw_gb[C + c] = xv[c];
+    }
+  xchg_all_reduce(xv, 2 * C, peers, world, rank, epoch, slot_floats);
+  const float inv_n = static_cast<float>(1.0 / n_total);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mu = stats[c], is = stats[C + c];
+    const float A = (w ? w[c] : 1.f) * is;
+    const float B = -A * is * xv[C + c] * inv_n;
+    coeff[c] = A;
+    coeff[C + c] = B;
+    coeff[2 * C + c] = -A * xv[c] * inv_n - B * mu;
+  }
+}
+
 template <typename T, int MODE>
 int launch_reduce(const void* a, const void* x, const void* y, const float* mean, const float* invstd,
                   long long P, int C, float* partials, cudaStream_t stream) {
@@ -353,7 +521,7 @@ int u2b_bn_finalize(const float* partials, int S, double n_total, const float* w
                     float momentum, float* running_mean, float* running_var, float* stats, int C,
                     cudaStream_t stream) {
   U2B_CHECK_ARG(partials && stats && S > 0 && C > 0 && n_total > 0, "bn_finalize: bad arguments");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partials, S, n_total, w, b, eps, momentum, running_mean,
+  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, stream>>>(partials, S, n_total, w, b, eps, momentum, running_mean,
                                                           running_var, stats, C);
   U2B_LAUNCH_CHECK();
   return 0;
@@ -387,7 +555,39 @@ int u2b_bn_bwd_reduce(int dtype, const void* dy, const void* x, const void* y, c
 int u2b_bn_bwd_coeff(const float* partials, int S, double n_total, const float* stats, const float* w, float* coeff,
                      float* gw_gb, int C, cudaStream_t stream) {
   U2B_CHECK_ARG(partials && stats && coeff && S > 0 && C > 0 && n_total > 0, "bn_bwd_coeff: bad arguments");
-  bn_bwd_coeff_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partials, S, n_total, stats, w, coeff, gw_gb, C);
+  bn_bwd_coeff_kernel<<<(C + 31) / 32, 256, 0, stream>>>(partials, S, n_total, stats, w, coeff, gw_gb, C);
+  U2B_LAUNCH_CHECK();
+  return 0;
+}
+
+// Data-parallel variants: `sums` (2C, this rank's summed partials) are exchanged with all peers through the
+// symmetric buffers `peers[world]` (device array of device pointers to every rank's buffer) inside the kernel.
+// epoch: 1, 2, 3, ... advancing by one per exchange, identical on every rank. slot_floats >= 2C.
+size_t u2b_bn_xchg_buffer_bytes(int world, int slot_floats) {
+  return static_cast<size_t>(2) * world * slot_floats * sizeof(float) + static_cast<size_t>(world) * 4 + 64;
+}
+
+int u2b_bn_xchg_finalize(const float* sums, const void* peers, int world, int rank, uint32_t epoch, int slot_floats,
+                         double n_total, const float* w, const float* b, float eps, float momentum,
+                         float* running_mean, float* running_var, float* stats, int C, cudaStream_t stream) {
+  U2B_CHECK_ARG(sums && peers && stats && world > 0 && world <= 32 && rank >= 0 && rank < world && 2 * C <= slot_floats,
+                "bn_xchg_finalize: bad arguments");
+  bn_xchg_finalize_kernel<<<1, 1024, static_cast<size_t>(2) * C * sizeof(float), stream>>>(
+      sums, static_cast<const unsigned long long*>(peers), world, rank, epoch, slot_floats, n_total, w, b, eps,
+      momentum, running_mean, running_var, stats, C);
+  U2B_LAUNCH_CHECK();
+  return 0;
+}
+
+int u2b_bn_xchg_bwd_coeff(const float* sums, const void* peers, int world, int rank, uint32_t epoch, int slot_floats,
+                          double n_total, const float* stats, const float* w, float* coeff, float* gw_gb, int C,
+                          cudaStream_t stream) {
+  U2B_CHECK_ARG(sums && peers && stats && coeff && world > 0 && world <= 32 && rank >= 0 && rank < world &&
+                    2 * C <= slot_floats,
+                "bn_xchg_bwd_coeff: bad arguments");
+  bn_xchg_bwd_coeff_kernel<<<1, 1024, static_cast<size_t>(2) * C * sizeof(float), stream>>>(
+      sums, static_cast<const unsigned long long*>(peers), world, rank, epoch, slot_floats, n_total, stats, w, coeff,
+      gw_gb, C);
   U2B_LAUNCH_CHECK();
   return 0;
 }

@@ -27,6 +27,49 @@ def _world():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
+class _PeerExchange:
+    """Symmetric (peer-mapped) buffers for the in-kernel SyncBN reduction over NVLink (csrc/batchnorm.cu
+    xchg_all_reduce). Allocated once per process through torch's symmetric-memory allocator; every BN forward /
+    backward of the step consumes one `epoch`, in the same order on every rank."""
+    SLOT_FLOATS = 4096   # 2C for C <= 2048
+
+    def __init__(self, device):
+        import torch.distributed._symmetric_memory as symm
+        L = _lib.lib()
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        nbytes = int(L.u2b_bn_xchg_buffer_bytes(self.world, self.SLOT_FLOATS))
+        self.buf = symm.empty(nbytes // 4 + 16, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD.group_name)
+        self.peers = torch.tensor([int(p) for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=device)
+        self.epoch = 0
+        dist.barrier()
+
+    def next_epoch(self):
+        self.epoch = (self.epoch + 1) & 0x7fffffff
+        return self.epoch
+
+
+_xchg = {"obj": None, "failed": False}
+
+
+def peer_exchange(device):
+    """The process-wide exchange object, or None (NCCL all-reduce path) when disabled / unavailable."""
+    import os
+    if _xchg["failed"] or os.environ.get("U2B_SYNCBN_XCHG", "1") == "0":
+        return None
+    if _xchg["obj"] is None:
+        try:
+            _xchg["obj"] = _PeerExchange(device)
+        except Exception as e:   # no P2P / symmetric memory: keep NCCL
+            import warnings
+            warnings.warn("u2seg_b200: NVLink peer exchange for SyncBN unavailable (%r); using NCCL all-reduce" % (e,))
+            _xchg["failed"] = True
+            return None
+    return _xchg["obj"]
+
+
 def _nhwc(x):
     if x.is_contiguous(memory_format=torch.channels_last) and x.stride(1) == 1:
         return x
@@ -53,13 +96,23 @@ class _BNAct(torch.autograd.Function):
         _lib.check(L.u2b_bn_stats(dt, _p(xc), P, C, _p(part), s), "u2b_bn_stats")
         stats = torch.empty((4 * C,), dtype=torch.float32, device=dev)   # mean | invstd | scale | shift
         n_total = float(P) * world
+        done = False
         if world > 1:
             sums = torch.empty((2 * C,), dtype=torch.float32, device=dev)
             _lib.check(L.u2b_bn_sum_partials(_p(part), S, 2 * C, _p(sums), s), "u2b_bn_sum_partials")
-            dist.all_reduce(sums)
-            part, S = sums, 1
-        _lib.check(L.u2b_bn_finalize(_p(part), S, n_total, _p(weight), _p(bias), float(eps), float(momentum),
-                                     _p(running_mean), _p(running_var), _p(stats), C, s), "u2b_bn_finalize")
+            px = peer_exchange(dev)
+            if px is not None and 2 * C <= px.SLOT_FLOATS:
+                _lib.check(L.u2b_bn_xchg_finalize(_p(sums), _p(px.peers), px.world, px.rank, px.next_epoch(),
+                                                  px.SLOT_FLOATS, n_total, _p(weight), _p(bias), float(eps),
+                                                  float(momentum), _p(running_mean), _p(running_var), _p(stats), C, s),
+                           "u2b_bn_xchg_finalize")
+                done = True
+            else:
+                dist.all_reduce(sums)
+                part, S = sums, 1
+        if not done:
+            _lib.check(L.u2b_bn_finalize(_p(part), S, n_total, _p(weight), _p(bias), float(eps), float(momentum),
+                                         _p(running_mean), _p(running_var), _p(stats), C, s), "u2b_bn_finalize")
         res = _nhwc(residual.to(xc.dtype)) if residual is not None else None
         y = torch.empty((N, H, W, C), dtype=xc.dtype, device=dev).permute(0, 3, 1, 2)
         _lib.check(L.u2b_bn_apply(dt, _p(xc), _p(stats), _p(res), int(relu), _p(y), P, C, s), "u2b_bn_apply")
@@ -88,10 +141,17 @@ class _BNAct(torch.autograd.Function):
         if world > 1:
             sums = torch.empty((2 * C,), dtype=torch.float32, device=dev)
             _lib.check(L.u2b_bn_sum_partials(_p(part), S, 2 * C, _p(sums), s), "u2b_bn_sum_partials")
-            gwb[:C].copy_(sums[C:])
-            gwb[C:].copy_(sums[:C])
-            dist.all_reduce(sums)
-            _lib.check(L.u2b_bn_bwd_coeff(_p(sums), 1, n_total, _p(stats), _p(weight), _p(coeff), None, C, s), "u2b_bn_bwd_coeff")
+            px = peer_exchange(dev)
+            if px is not None and 2 * C <= px.SLOT_FLOATS:
+                _lib.check(L.u2b_bn_xchg_bwd_coeff(_p(sums), _p(px.peers), px.world, px.rank, px.next_epoch(),
+                                                   px.SLOT_FLOATS, n_total, _p(stats), _p(weight), _p(coeff), _p(gwb),
+                                                   C, s), "u2b_bn_xchg_bwd_coeff")
+            else:
+                gwb[:C].copy_(sums[C:])
+                gwb[C:].copy_(sums[:C])
+                dist.all_reduce(sums)
+                _lib.check(L.u2b_bn_bwd_coeff(_p(sums), 1, n_total, _p(stats), _p(weight), _p(coeff), None, C, s),
+                           "u2b_bn_bwd_coeff")
         else:
             _lib.check(L.u2b_bn_bwd_coeff(_p(part), S, n_total, _p(stats), _p(weight), _p(coeff), _p(gwb), C, s), "u2b_bn_bwd_coeff")
         dx = torch.empty((N, H, W, C), dtype=xc.dtype, device=dev).permute(0, 3, 1, 2)
