@@ -381,8 +381,7 @@ __device__ __forceinline__ void xchg_all_reduce(float* __restrict__ vals /*smem 
     float* dst = reinterpret_cast<float*>(peers[p]) + (static_cast<size_t>(slot) * world + rank) * slot_floats;
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = vals[i];
   }
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();  // the release store below is cumulative over the block's writes observed through this barrier
   if (threadIdx.x < world) {
     unsigned int* f = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(peers[threadIdx.x]) + flag_off) + rank;
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
@@ -403,7 +402,6 @@ __device__ __forceinline__ void xchg_all_reduce(float* __restrict__ vals /*smem 
     } while (true);
   }
   __syncthreads();
-  __threadfence_system();
   const float* mine = reinterpret_cast<const float*>(peers[rank]) + static_cast<size_t>(slot) * world * slot_floats;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     float acc = 0.f;
@@ -414,7 +412,7 @@ __device__ __forceinline__ void xchg_all_reduce(float* __restrict__ vals /*smem 
 }
 
 // one CTA: local (2C) sums -> exchange -> mean/invstd/scale/shift + running statistics
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512)
 bn_xchg_finalize_kernel(const float* __restrict__ sums, const unsigned long long* __restrict__ peers, int world,
                         int rank, unsigned int epoch, int slot_floats, double n_total, const float* __restrict__ w,
                         const float* __restrict__ b, float eps, float momentum, float* __restrict__ running_mean,
@@ -442,7 +440,7 @@ bn_xchg_finalize_kernel(const float* __restrict__ sums, const unsigned long long
 }
 
 // one CTA: local (2C) backward sums -> dgamma/dbeta (local) -> exchange -> dx coefficients
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512)
 bn_xchg_bwd_coeff_kernel(const float* __restrict__ sums, const unsigned long long* __restrict__ peers, int world,
                          int rank, unsigned int epoch, int slot_floats, double n_total,
                          const float* __restrict__ stats, const float* __restrict__ w, float* __restrict__ coeff,
@@ -572,7 +570,7 @@ int u2b_bn_xchg_finalize(const float* sums, const void* peers, int world, int ra
                          float* running_mean, float* running_var, float* stats, int C, cudaStream_t stream) {
   U2B_CHECK_ARG(sums && peers && stats && world > 0 && world <= 32 && rank >= 0 && rank < world && 2 * C <= slot_floats,
                 "bn_xchg_finalize: bad arguments");
-  bn_xchg_finalize_kernel<<<1, 1024, static_cast<size_t>(2) * C * sizeof(float), stream>>>(
+  bn_xchg_finalize_kernel<<<1, 512, static_cast<size_t>(2) * C * sizeof(float), stream>>>(
       sums, static_cast<const unsigned long long*>(peers), world, rank, epoch, slot_floats, n_total, w, b, eps,
       momentum, running_mean, running_var, stats, C);
   U2B_LAUNCH_CHECK();
@@ -585,7 +583,7 @@ int u2b_bn_xchg_bwd_coeff(const float* sums, const void* peers, int world, int r
   U2B_CHECK_ARG(sums && peers && stats && coeff && world > 0 && world <= 32 && rank >= 0 && rank < world &&
                     2 * C <= slot_floats,
                 "bn_xchg_bwd_coeff: bad arguments");
-  bn_xchg_bwd_coeff_kernel<<<1, 1024, static_cast<size_t>(2) * C * sizeof(float), stream>>>(
+  bn_xchg_bwd_coeff_kernel<<<1, 512, static_cast<size_t>(2) * C * sizeof(float), stream>>>(
       sums, static_cast<const unsigned long long*>(peers), world, rank, epoch, slot_floats, n_total, stats, w, coeff,
       gw_gb, C);
   U2B_LAUNCH_CHECK();
