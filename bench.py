@@ -7,6 +7,7 @@ Workloads (BASELINE.json `metric`: "u2seg_R50_800 train images/sec ...; k-means 
   train   u2seg_R50_800 training step, batch 2 / GPU, synthetic 1024x1024 (configs[1]) — default
           once the detector step is available in this build, else kmeans
   kmeans  Lloyd iterations, N=1.28M, D=384, K=800 (configs[3]); rows sharded over ranks
+  infer   u2seg_R50_300 panoptic inference, synthetic 800x1333, batch 1 (configs[4])
 
 One JSON line on rank 0. `value` = device-resident throughput (CUDA events, max over ranks);
 `e2e` = same metric through the public API with host buffers (H2D/D2H inside the timed region);
@@ -274,7 +275,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=None, choices=["train", "kmeans"])
+    ap.add_argument("--workload", default=None, choices=["train", "kmeans", "infer"])
     args = ap.parse_args()
     if args.workload is None:
         args.workload = "train" if os.path.exists(os.path.join(ROOT, "u2seg_b200", "bench_train.py")) else "kmeans"
@@ -282,6 +283,9 @@ def main():
         return run_reference(args)
     if args.workload == "kmeans":
         return run_kmeans(args)
+    if args.workload == "infer":
+        from u2seg_b200.bench_infer import run_infer
+        return run_infer(args, ClockSampler, load_peaks, dist_info)
     from u2seg_b200.bench_train import run_train
     return run_train(args, ClockSampler, load_peaks, dist_info, run_kmeans)
 
