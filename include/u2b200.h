@@ -108,18 +108,20 @@ int u2b_crop_resize_masks(const uint8_t* masks, const int64_t* gt_index, const f
 /* structures/boxes.py:336-358 pairwise_iou + modeling/matcher.py:62-127 Matcher.__call__, fused:
  * gt (G, 4), pred (A, 4) fp32 -> matches int64 (A) (first maximum), matched_vals fp32 (A),
  * out_labels int8 (A). thresholds: nthr device floats [-inf, t.., +inf]; labels: nthr-1 device ints.
- * allow_low_quality needs gt_max_scratch (G uint32). G must be in 1..1024. */
-int u2b_iou_match(const float* gt, int64_t G, const float* pred, int64_t A, const float* thresholds,
-                  const int32_t* labels, int nthr, int allow_low_quality, int64_t* matches,
-                  float* matched_vals, int8_t* out_labels, uint32_t* gt_max_scratch,
+ * allow_low_quality needs gt_max_scratch (G uint32). G must be in 1..1024. gt_valid (G bytes, nullable) marks the
+ * live rows of a fixed-capacity GT buffer; padded rows are never matched. */
+int u2b_iou_match(const float* gt, int64_t G, const uint8_t* gt_valid, const float* pred, int64_t A,
+                  const float* thresholds, const int32_t* labels, int nthr, int allow_low_quality,
+                  int64_t* matches, float* matched_vals, int8_t* out_labels, uint32_t* gt_max_scratch,
                   u2b_stream_t stream);
 
 /* layers/nms.py:9-21 batched_nms (torchvision class-by-class semantics; IoU > threshold suppresses).
  * order = indices of the boxes sorted by score, descending, stable. keep (n) int64 receives the kept
  * original indices in score order, *num_keep (device) their number; the scan stops after max_keep kept boxes
- * (max_keep < 0: keep all). No host synchronisation. */
+ * (max_keep < 0: keep all). valid (n bytes in the ORIGINAL box order, nullable): boxes with valid[i] == 0 are
+ * neither kept nor suppress anything (fixed-capacity buffers). No host synchronisation. */
 size_t u2b_nms_workspace_bytes(int64_t n);
-int u2b_batched_nms(const float* boxes, const int64_t* cats, const int64_t* order, int64_t n,
+int u2b_batched_nms(const float* boxes, const int64_t* cats, const int64_t* order, const uint8_t* valid, int64_t n,
                     float iou_threshold, int64_t max_keep, int64_t* keep, int32_t* num_keep, void* workspace,
                     size_t workspace_bytes, u2b_stream_t stream);
 

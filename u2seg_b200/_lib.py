@@ -38,7 +38,7 @@ SIGNATURES = {
     "u2b_paste_masks": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "u2b_crop_resize_masks": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p,
                                       c_void_p, c_void_p]),
-    "u2b_iou_match": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p,
+    "u2b_iou_match": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_void_p]),
     "u2b_conv2d_supported": (c_int, [c_int] * 6),
     "u2b_conv2d_set_cluster": (c_int, [c_int]),
@@ -62,8 +62,8 @@ SIGNATURES = {
     "u2b_bn_bwd_apply": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                  c_void_p]),
     "u2b_nms_workspace_bytes": (c_size_t, [c_int64]),
-    "u2b_batched_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int64, c_void_p, c_void_p, c_void_p,
-                                c_size_t, c_void_p]),
+    "u2b_batched_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int64, c_void_p, c_void_p,
+                                c_void_p, c_size_t, c_void_p]),
 }
 
 

@@ -23,17 +23,19 @@ __device__ __forceinline__ float iou_ref(const float4 g, float garea, const floa
 }
 
 __global__ void __launch_bounds__(256)
-iou_match_kernel(const float4* __restrict__ gt, int G, const float4* __restrict__ pred, int A,
-                 int64_t* __restrict__ matches, float* __restrict__ matched_vals,
-                 unsigned int* __restrict__ gt_max_bits) {
+iou_match_kernel(const float4* __restrict__ gt, int G, const uint8_t* __restrict__ gt_valid,
+                 const float4* __restrict__ pred, int A, int64_t* __restrict__ matches,
+                 float* __restrict__ matched_vals, unsigned int* __restrict__ gt_max_bits) {
   __shared__ float4 sgt[MAX_GT];
   __shared__ float sarea[MAX_GT];
   __shared__ unsigned int smax[MAX_GT];
+  __shared__ uint8_t sval[MAX_GT];
   for (int i = threadIdx.x; i < G; i += blockDim.x) {
     const float4 g = gt[i];
     sgt[i] = g;
     sarea[i] = (g.z - g.x) * (g.w - g.y);
     smax[i] = 0u;
+    sval[i] = gt_valid ? gt_valid[i] : 1;
   }
   __syncthreads();
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -43,6 +45,7 @@ iou_match_kernel(const float4* __restrict__ gt, int G, const float4* __restrict_
     float best = -1.f;
     int bi = 0;
     for (int g = 0; g < G; ++g) {
+      if (!sval[g]) continue;  // padded GT slot (fixed-capacity buffers): not a candidate
       const float v = iou_ref(sgt[g], sarea[g], p, parea);
       if (v > best) {  // first maximum, as torch.max(dim=0)
         best = v;
@@ -51,7 +54,7 @@ iou_match_kernel(const float4* __restrict__ gt, int G, const float4* __restrict_
       if (gt_max_bits && v > 0.f) atomicMax(&smax[g], __float_as_uint(v));
     }
     matches[a] = bi;
-    matched_vals[a] = best;
+    matched_vals[a] = best < 0.f ? 0.f : best;  // no valid GT at all: quality 0 (matcher.py:80-88 labels it background)
   }
   if (gt_max_bits) {
     __syncthreads();
@@ -62,8 +65,8 @@ iou_match_kernel(const float4* __restrict__ gt, int G, const float4* __restrict_
 
 // labels from thresholds (matcher.py:96-101) + low-quality promotion (matcher.py:116-127)
 __global__ void __launch_bounds__(256)
-match_label_kernel(const float4* __restrict__ gt, int G, const float4* __restrict__ pred, int A,
-                   const float* __restrict__ matched_vals, const float* __restrict__ thresholds,
+match_label_kernel(const float4* __restrict__ gt, int G, const uint8_t* __restrict__ gt_valid,
+                   const float4* __restrict__ pred, int A, const float* __restrict__ matched_vals, const float* __restrict__ thresholds,
                    const int* __restrict__ labels, int nthr,
                    const unsigned int* __restrict__ gt_max_bits, int8_t* __restrict__ out_labels) {
   __shared__ float4 sgt[MAX_GT];
@@ -74,7 +77,8 @@ match_label_kernel(const float4* __restrict__ gt, int G, const float4* __restric
       const float4 g = gt[i];
       sgt[i] = g;
       sarea[i] = (g.z - g.x) * (g.w - g.y);
-      smax[i] = __uint_as_float(gt_max_bits[i]);
+      // padded GT slots never promote anything: an unreachable maximum
+      smax[i] = (gt_valid && !gt_valid[i]) ? -1.f : __uint_as_float(gt_max_bits[i]);
     }
     __syncthreads();
   }
@@ -140,14 +144,21 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ ca
 // the kept rows into the `removed` bitmap of the later blocks (coalesced: thread j owns column word j).
 // Stops as soon as max_keep boxes are kept (proposal_utils.py:122 `keep[:post_nms_topk]`).
 __global__ void __launch_bounds__(256)
-nms_scan_kernel(const unsigned long long* __restrict__ mask, const int64_t* __restrict__ order, int n,
-                int col_blocks, int max_keep, int64_t* __restrict__ keep, int* __restrict__ num_keep) {
+nms_scan_kernel(const unsigned long long* __restrict__ mask, const int64_t* __restrict__ order,
+                const uint8_t* __restrict__ valid, int n, int col_blocks, int max_keep,
+                int64_t* __restrict__ keep, int* __restrict__ num_keep) {
   extern __shared__ unsigned long long removed[];
   __shared__ unsigned long long diag[64];
   __shared__ unsigned long long s_kept;
   __shared__ int s_nk, s_stop;
   const int t = threadIdx.x;
-  for (int i = t; i < col_blocks; i += blockDim.x) removed[i] = 0ULL;
+  for (int i = t; i < col_blocks; i += blockDim.x) {
+    unsigned long long r = 0ULL;
+    if (valid)  // boxes flagged invalid (fixed-capacity buffers) start out removed
+      for (int j = 0; j < 64 && i * 64 + j < n; ++j)
+        if (!valid[order[i * 64 + j]]) r |= 1ULL << j;
+    removed[i] = r;
+  }
   if (t == 0) { s_nk = 0; s_stop = 0; }
   __syncthreads();
   for (int b = 0; b < col_blocks; ++b) {
@@ -220,7 +231,7 @@ size_t u2b_nms_workspace_bytes(int64_t n) {
 
 // boxes (n,4) fp32 xyxy, cats (n) int64 or NULL, order (n) int64 = indices sorted by score descending
 // (stable). keep (n) int64, num_keep device int. Semantics: torchvision batched_nms, class by class.
-int u2b_batched_nms(const float* boxes, const int64_t* cats, const int64_t* order, int64_t n,
+int u2b_batched_nms(const float* boxes, const int64_t* cats, const int64_t* order, const uint8_t* valid, int64_t n,
                     float iou_threshold, int64_t max_keep, int64_t* keep, int32_t* num_keep, void* workspace,
                     size_t workspace_bytes, cudaStream_t stream) {
   U2B_CHECK_ARG(num_keep, "batched_nms: num_keep is NULL");
@@ -252,7 +263,7 @@ int u2b_batched_nms(const float* boxes, const int64_t* cats, const int64_t* orde
     U2B_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int32_t), stream));
     return 0;
   }
-  nms_scan_kernel<<<1, 256, smem, stream>>>(mask, order, (int)n, cb, mk, keep, num_keep);
+  nms_scan_kernel<<<1, 256, smem, stream>>>(mask, order, valid, (int)n, cb, mk, keep, num_keep);
   U2B_LAUNCH_CHECK();
   return 0;
 }
@@ -260,9 +271,9 @@ int u2b_batched_nms(const float* boxes, const int64_t* cats, const int64_t* orde
 // gt (G,4), pred (A,4) fp32. thresholds: nthr floats on the device [-inf, t.., +inf]; labels: nthr-1
 // ints on the device. matches int64 (A), matched_vals fp32 (A), out_labels int8 (A).
 // gt_max_scratch: G uint32 device scratch, required iff allow_low_quality.
-int u2b_iou_match(const float* gt, int64_t G, const float* pred, int64_t A, const float* thresholds,
-                  const int32_t* labels, int nthr, int allow_low_quality, int64_t* matches,
-                  float* matched_vals, int8_t* out_labels, uint32_t* gt_max_scratch,
+int u2b_iou_match(const float* gt, int64_t G, const uint8_t* gt_valid, const float* pred, int64_t A,
+                  const float* thresholds, const int32_t* labels, int nthr, int allow_low_quality,
+                  int64_t* matches, float* matched_vals, int8_t* out_labels, uint32_t* gt_max_scratch,
                   cudaStream_t stream) {
   if (A == 0) return 0;
   U2B_CHECK_ARG(pred && thresholds && labels && matches && matched_vals && out_labels && nthr >= 2,
@@ -272,11 +283,11 @@ int u2b_iou_match(const float* gt, int64_t G, const float* pred, int64_t A, cons
   U2B_CHECK_ARG(!allow_low_quality || gt_max_scratch, "iou_match: low-quality matching needs scratch");
   const unsigned grid = static_cast<unsigned>((A + 255) / 256);
   if (allow_low_quality) U2B_CUDA(cudaMemsetAsync(gt_max_scratch, 0, sizeof(uint32_t) * G, stream));
-  iou_match_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(gt), (int)G,
+  iou_match_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(gt), (int)G, gt_valid,
                                              reinterpret_cast<const float4*>(pred), (int)A, matches,
                                              matched_vals, allow_low_quality ? gt_max_scratch : nullptr);
   U2B_LAUNCH_CHECK();
-  match_label_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(gt), (int)G,
+  match_label_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(gt), (int)G, gt_valid,
                                                reinterpret_cast<const float4*>(pred), (int)A, matched_vals,
                                                thresholds, labels, nthr,
                                                allow_low_quality ? gt_max_scratch : nullptr, out_labels);

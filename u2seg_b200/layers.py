@@ -278,8 +278,9 @@ class Matcher:
                                  torch.tensor(self.labels, dtype=torch.int32, device=device))
         return self._dev[device]
 
-    def match_boxes(self, gt_boxes, pred_boxes):
-        """-> (matches int64 (A,), match_labels int8 (A,)) == Matcher()(pairwise_iou(gt, pred))."""
+    def match_boxes(self, gt_boxes, pred_boxes, gt_valid=None):
+        """-> (matches int64 (A,), match_labels int8 (A,)) == Matcher()(pairwise_iou(gt, pred)).
+        gt_valid: optional bool (G,) for fixed-capacity GT buffers (padded rows are never matched)."""
         L = _lib.lib()
         _need_cuda(pred_boxes, "Matcher")
         G, A = gt_boxes.shape[0], pred_boxes.shape[0]
@@ -294,12 +295,40 @@ class Matcher:
         scratch = torch.empty((G,), dtype=torch.int32, device=dev) if self.allow_low_quality_matches else None
         if A > 0:
             g, p = _aligned(gt_boxes, torch.float32), _aligned(pred_boxes, torch.float32)
-            _lib.check(L.u2b_iou_match(_lib.ptr(g), G, _lib.ptr(p), A, _lib.ptr(thr), _lib.ptr(lab),
+            gv = gt_valid.to(torch.uint8).contiguous() if gt_valid is not None else None
+            _lib.check(L.u2b_iou_match(_lib.ptr(g), G, _lib.ptr(gv), _lib.ptr(p), A, _lib.ptr(thr), _lib.ptr(lab),
                                        len(self.thresholds), int(self.allow_low_quality_matches), _lib.ptr(matches),
                                        _lib.ptr(vals), _lib.ptr(out), _lib.ptr(scratch), _lib.stream_ptr()),
                        "u2b_iou_match")
             _lib.count_launches(2)
         return matches, out
+
+
+def batched_nms_static(boxes, scores, idxs, iou_threshold, max_keep, valid=None):
+    """batched_nms with fixed-capacity outputs and NO host synchronisation: returns (keep int64 (max_keep,) — rows
+    beyond the count are 0 — and count int32 (1,) on the device). valid: optional bool (n,)."""
+    L = _lib.lib()
+    _need_cuda(boxes, "batched_nms")
+    n = boxes.shape[0]
+    dev = boxes.device
+    keep = torch.zeros((max(n, max_keep),), dtype=torch.int64, device=dev)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+    if n == 0:
+        return keep[:max_keep], cnt
+    b = _aligned(boxes, torch.float32)
+    sc = scores.float()
+    if valid is not None:
+        sc = torch.where(valid, sc, torch.full_like(sc, float("-inf")))
+    order = torch.sort(sc, descending=True, stable=True)[1]
+    ws_bytes = int(L.u2b_nms_workspace_bytes(n))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    cats = idxs.to(torch.int64).contiguous() if idxs is not None else None
+    vv = valid.to(torch.uint8).contiguous() if valid is not None else None
+    _lib.check(L.u2b_batched_nms(_lib.ptr(b), _lib.ptr(cats), _lib.ptr(order), _lib.ptr(vv), n, float(iou_threshold),
+                                 int(max_keep), _lib.ptr(keep), _lib.ptr(cnt), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
+               "u2b_batched_nms")
+    _lib.count_launches(3)
+    return keep[:max_keep], cnt
 
 
 def batched_nms(boxes, scores, idxs, iou_threshold, max_keep=None):
@@ -317,7 +346,7 @@ def batched_nms(boxes, scores, idxs, iou_threshold, max_keep=None):
     ws_bytes = int(L.u2b_nms_workspace_bytes(n))
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=boxes.device)
     cats = idxs.to(torch.int64).contiguous() if idxs is not None else None
-    _lib.check(L.u2b_batched_nms(_lib.ptr(b), _lib.ptr(cats), _lib.ptr(order), n, float(iou_threshold),
+    _lib.check(L.u2b_batched_nms(_lib.ptr(b), _lib.ptr(cats), _lib.ptr(order), None, n, float(iou_threshold),
                                  -1 if max_keep is None else int(max_keep), _lib.ptr(keep), _lib.ptr(cnt), _lib.ptr(ws),
                                  ws_bytes, _lib.stream_ptr()), "u2b_batched_nms")
     _lib.count_launches(3)
