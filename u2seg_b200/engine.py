@@ -67,7 +67,12 @@ class _BackboneTuple(torch.nn.Module):
 
 
 class Trainer:
-    def __init__(self, cfg, model=None, amp_dtype=torch.bfloat16, device=None, graph_backbone=False):
+    """static_graph=True: the step runs through modeling/static_train.py (fixed-capacity device buffers, no host
+    synchronisation) and forward + backward + clip + SGD are captured in ONE CUDA graph that is replayed every step;
+    inputs are copied into static buffers. Requires same-size images and at most `g_max` instances per image."""
+
+    def __init__(self, cfg, model=None, amp_dtype=torch.bfloat16, device=None, graph_backbone=False,
+                 static_graph=False, g_max=None):
         self.cfg = cfg
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.model = model if model is not None else build_model(cfg)
@@ -91,6 +96,86 @@ class Trainer:
         self.scaler = torch.amp.GradScaler("cuda") if self.amp_dtype == torch.float16 else None
         self.graph_backbone = graph_backbone and _world() == 1
         self._graph_tried = False
+        self.static_graph = static_graph and _world() == 1
+        self.g_max = g_max
+        self._graph = None
+        self._lr_t = torch.zeros((), dtype=torch.float32, device=self.device)
+        self._mom_bufs = None
+        self.nonfinite_flag = None
+
+    # ---------------- static-shape, whole-step CUDA graph ----------------
+    def _sgd_foreach(self):
+        """solver/build.py:119-139 SGD(momentum, weight decay) with the learning rate read from a device scalar, so
+        that the captured graph follows the LR schedule."""
+        s = self.cfg.SOLVER
+        if self._mom_bufs is None:
+            self._mom_bufs = [[torch.zeros_like(p) for p in g["params"]] for g in self.optimizer.param_groups]
+        for g, bufs in zip(self.optimizer.param_groups, self._mom_bufs):
+            params = g["params"]
+            if not params:
+                continue
+            grads = [p.grad for p in params]
+            if g["weight_decay"] != 0:
+                torch._foreach_add_(grads, params, alpha=g["weight_decay"])
+            torch._foreach_mul_(bufs, s.MOMENTUM)
+            torch._foreach_add_(bufs, grads)
+            upd = torch._foreach_mul(bufs, self._lr_t)
+            torch._foreach_sub_(params, upd)
+
+    def _clip_foreach(self):
+        if self.clip is None:
+            return
+        grads = [p.grad for p in self.params]
+        norms = torch._foreach_norm(grads, self.clip.NORM_TYPE)
+        coef = torch.clamp(self.clip.CLIP_VALUE / (torch.stack(norms) + 1e-6), max=1.0)
+        torch._foreach_mul_(grads, list(coef.unbind(0)))
+
+    def _static_step(self):
+        from .modeling.static_train import forward_train_static
+        self.grads.zero_()
+        with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
+            loss_dict, flag = forward_train_static(self.model, *self._static_in)
+        sum(loss_dict.values()).backward()
+        self._clip_foreach()
+        self._sgd_foreach()
+        return {k: v.detach() for k, v in loss_dict.items()}, flag
+
+    def _load_static_inputs(self, batched_inputs):
+        from .modeling.static_train import pack_batch
+        g_max = self.g_max or max(1, max(len(d["instances"]) for d in batched_inputs))
+        packed = pack_batch(batched_inputs, self.device, g_max)
+        if getattr(self, "_static_in", None) is None:
+            self.g_max = g_max
+            self._static_in = [t.clone() for t in packed]
+        else:
+            for dst, src in zip(self._static_in, packed):
+                assert dst.shape == src.shape, "static_graph needs constant input shapes (%s vs %s)" % (dst.shape, src.shape)
+                dst.copy_(src, non_blocking=True)
+
+    def _run_step_static(self, batched_inputs):
+        self._lr_t.fill_(self.sched.lr(self.iter))
+        self._load_static_inputs(batched_inputs)
+        if self._graph is None:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):     # warm-up outside capture: lazy initialisations, autotuning, workspaces
+                for _ in range(3):
+                    self._static_step()
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._static_out = self._static_step()
+        self._graph.replay()
+        self.iter += 1
+        losses, self.nonfinite_flag = self._static_out
+        return losses
+
+    def check_finite(self):
+        """proposal_utils.py:105-110 divergence guard, read off the critical path (costs one host sync)."""
+        if self.nonfinite_flag is not None and bool(self.nonfinite_flag):
+            raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")
 
     def _maybe_capture_backbone(self, batched_inputs):
         """CUDA-graph the forward+backward of the static-shape backbone (launch-bound inner loop of the step)."""
@@ -111,6 +196,8 @@ class Trainer:
 
     def run_step(self, batched_inputs):
         """train_loop.py:479-521. Returns the dict of (detached, device-resident) losses."""
+        if self.static_graph:
+            return self._run_step_static(batched_inputs)
         lr = self.sched.lr(self.iter)
         for g in self.optimizer.param_groups:
             g["lr"] = lr

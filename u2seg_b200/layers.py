@@ -173,11 +173,10 @@ class ROIAlign(nn.Module):
 
 def convert_boxes_to_pooler_format(box_tensors):
     """poolers.py:72-98: list of (Ni,4) -> (sum Ni, 5) with the batch index in column 0."""
-    sizes = [len(b) for b in box_tensors]
     boxes = torch.cat(box_tensors, dim=0)
-    idx = torch.repeat_interleave(torch.arange(len(box_tensors), dtype=boxes.dtype, device=boxes.device),
-                                  torch.tensor(sizes, device=boxes.device), output_size=sum(sizes))
-    return torch.cat([idx[:, None], boxes], dim=1)
+    idx = torch.cat([torch.full((len(b), 1), float(i), dtype=boxes.dtype, device=boxes.device)
+                     for i, b in enumerate(box_tensors)], dim=0)     # device fills only: CUDA-graph capturable
+    return torch.cat([idx, boxes], dim=1)
 
 
 class ROIPooler(nn.Module):

@@ -1,0 +1,259 @@
+"""Static-shape training forward of PanopticFPN: the same computation as panoptic_fpn.PanopticFPN.forward
+(reference: detectron2/modeling/meta_arch/panoptic_fpn.py:90-138 and everything it calls), restructured around
+fixed-capacity device buffers so that it contains NO host synchronisation and NO data-dependent shape:
+
+  * proposals: per image 4000 slots + a device-side count (NMS runs with validity masks, proposal_utils.py:103-122);
+  * anchor / proposal sampling (sampling.py:9-54): random keys + top-k instead of nonzero + randperm — the same
+    uniform-random-subset semantics, with counts kept on the device;
+  * sampled ROIs: 512 slots per image (foreground first), mask branch: 128 slots per image, each with a validity
+    mask; losses are masked sums divided by device-side counts (identical values to the reference's means);
+  * cascade stages keep all rows and carry the `nonempty` filter (cascade_rcnn.py:292-295) as a mask.
+
+This is what lets engine.Trainer capture forward + backward + optimizer in ONE CUDA graph (the reference's step has
+>= 25 device->host syncs). GT is passed as padded tensors: gt_boxes (N,G,4), gt_classes (N,G),
+gt_valid (N,G) bool, gt_masks (N,G,H,W) bool, sem_seg (N,H,W); all images of a batch share one size.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from ..layers import FeatureTap, batched_nms_static, crop_and_resize_masks
+from ..structures import Boxes
+
+# sampling keys: uniform random numbers by default; tests swap in a deterministic key function
+_rand_keys = lambda mask: torch.rand(mask.shape, dtype=torch.float32, device=mask.device)  # noqa: E731
+
+
+def _topk_select(mask, k):
+    """indices (k,) of up to k True entries of `mask` chosen uniformly at random, and a bool (k,) telling which of the
+    k slots are real (sampling.py:49-53 `randperm(n)[:k]`)."""
+    key = torch.where(mask, _rand_keys(mask), torch.full((), 2.0, dtype=torch.float32, device=mask.device))
+    vals, idx = torch.topk(key, min(k, key.numel()), largest=False, sorted=True)
+    return idx, vals < 2.0
+
+
+def subsample_static(is_pos, is_neg, num_samples, positive_fraction):
+    """sampling.py:9-54 with fixed shapes: returns idx (num_samples,), ok (num_samples,) bool, is_fg (num_samples,)
+    bool; positives first. num_pos = min(#pos, int(num_samples*fraction)), num_neg = min(#neg, num_samples-num_pos)."""
+    max_pos = int(num_samples * positive_fraction)
+    pidx, pok = _topk_select(is_pos, max_pos)
+    num_pos = pok.sum()
+    nidx, nok = _topk_select(is_neg, num_samples)
+    nok = nok & (torch.arange(nidx.numel(), device=nidx.device) < (num_samples - num_pos))
+    idx = torch.cat([pidx, nidx])
+    ok = torch.cat([pok, nok])
+    fg = torch.cat([torch.ones_like(pok), torch.zeros_like(nok)])
+    order = torch.sort((~ok).to(torch.int8), stable=True)[1][:num_samples]     # compact: real slots first, order kept
+    return idx[order], ok[order], (fg & ok)[order]
+
+
+def _masked_l1(pred, target, mask):
+    n = (pred.float() - target).abs()
+    return torch.where(mask[..., None], n, torch.zeros((), dtype=n.dtype, device=n.device)).sum()
+
+
+def _nonempty(b):
+    return ((b[:, 2] - b[:, 0]) > 0) & ((b[:, 3] - b[:, 1]) > 0)
+
+
+def _clip(b, size):
+    h, w = size
+    return torch.stack((b[:, 0].clamp(0, w), b[:, 1].clamp(0, h), b[:, 2].clamp(0, w), b[:, 3].clamp(0, h)), dim=-1)
+
+
+def rpn_static(rpn, images_size, features, gt_boxes, gt_valid, flags):
+    """proposal_generator/rpn.py:431-533 -> (proposals (N,P,4), prop_valid (N,P) bool, losses)."""
+    feats = [features[f] for f in rpn.in_features]
+    anchors = rpn.anchor_generator(feats)
+    logits, deltas = rpn.rpn_head(feats)
+    N = logits[0].shape[0]
+    logits = [s.permute(0, 2, 3, 1).flatten(1) for s in logits]
+    deltas = [x.view(N, -1, 4, x.shape[-2], x.shape[-1]).permute(0, 3, 4, 1, 2).flatten(1, -2) for x in deltas]
+    anchors_t = Boxes.cat(anchors).tensor
+    A = anchors_t.shape[0]
+    # ---- label_and_sample_anchors (rpn.py:307-363) ----
+    with torch.no_grad():
+        labels_all, matched_all = [], []
+        for n in range(N):
+            midx, lab = rpn.anchor_matcher.match_boxes(gt_boxes[n], anchors_t, gt_valid=gt_valid[n])
+            idx, ok, fg = subsample_static(lab == 1, lab == 0, rpn.batch_size_per_image, rpn.positive_fraction)
+            out = torch.full((A + 1,), -1, dtype=torch.int8, device=lab.device)
+            # unselected slots are redirected to a scratch element (index A) so they can never collide with a selected anchor
+            out.scatter_(0, torch.where(ok, idx, torch.full_like(idx, A)), fg.to(torch.int8))
+            labels_all.append(out[:A])
+            matched_all.append(gt_boxes[n][midx])
+        gt_labels = torch.stack(labels_all)
+        gt_anchor_deltas = torch.stack([rpn.box2box_transform.get_deltas(anchors_t, k) for k in matched_all])
+    pos_mask = gt_labels == 1
+    loc = _masked_l1(torch.cat(deltas, dim=1), gt_anchor_deltas, pos_mask)
+    valid = gt_labels >= 0
+    obj = F.binary_cross_entropy_with_logits(torch.cat(logits, dim=1).float(), gt_labels.to(torch.float32),
+                                             weight=valid.to(torch.float32), reduction="sum")
+    normalizer = rpn.batch_size_per_image * N
+    losses = {"loss_rpn_cls": obj / normalizer * rpn.loss_weight["loss_rpn_cls"],
+              "loss_rpn_loc": loc / normalizer * rpn.loss_weight["loss_rpn_loc"]}
+    # ---- predict_proposals + find_top_rpn_proposals (rpn.py:482-533, proposal_utils.py:22-135) ----
+    with torch.no_grad():
+        pre, post = rpn.pre_nms_topk[True], rpn.post_nms_topk[True]
+        tk_scores, tk_boxes, lvl_ids = [], [], []
+        bidx = torch.arange(N, device=anchors_t.device)
+        for lid, (a, lg, dl) in enumerate(zip(anchors, logits, deltas)):
+            props = rpn.box2box_transform.apply_deltas(dl.reshape(-1, 4), a.tensor.unsqueeze(0).expand(N, -1, -1).reshape(-1, 4)).view(N, -1, 4)
+            k = min(lg.shape[1], pre)
+            sc, idx = lg.float().topk(k, dim=1)
+            tk_scores.append(sc)
+            tk_boxes.append(props[bidx[:, None], idx])
+            lvl_ids.append(torch.full((k,), lid, dtype=torch.int64, device=anchors_t.device))
+        tk_scores, tk_boxes, lvl_ids = torch.cat(tk_scores, 1), torch.cat(tk_boxes, 1), torch.cat(lvl_ids)
+        finite = torch.isfinite(tk_boxes).all(dim=2) & torch.isfinite(tk_scores)
+        flags.append(~finite.all())      # proposal_utils.py:105-110 FloatingPointError, checked off the critical path
+        out_boxes, out_valid = [], []
+        for n in range(N):
+            b = _clip(tk_boxes[n], images_size)
+            v = finite[n] & ((b[:, 2] - b[:, 0]) > rpn.min_box_size) & ((b[:, 3] - b[:, 1]) > rpn.min_box_size)
+            keep, cnt = batched_nms_static(b, tk_scores[n], lvl_ids, rpn.nms_thresh, post, valid=v)
+            out_boxes.append(b[keep])
+            out_valid.append(torch.arange(post, device=b.device) < cnt)
+    return torch.stack(out_boxes), torch.stack(out_valid), losses
+
+
+def roi_heads_static(rh, images_size, features, proposals, prop_valid, gt_boxes, gt_classes, gt_valid, gt_masks):
+    """roi_heads/cascade_rcnn.py:137-299 + roi_heads.py:220-302,818-846 + mask_head.py:33-112, fixed shapes."""
+    N, K = proposals.shape[0], rh.num_classes
+    dev = proposals.device
+    R = rh.batch_size_per_image
+    feats = [features[f] for f in rh.box_in_features]
+    tap = FeatureTap(feats)
+    dummy = torch.cat([torch.zeros(2, device=dev), torch.ones(2, device=dev)])     # placeholder box of dead slots
+    # ---- label_and_sample_proposals ----
+    with torch.no_grad():
+        boxes0, cls0, ok0, fg0, gidx0, gtb0 = [], [], [], [], [], []
+        for n in range(N):
+            cand = torch.cat([proposals[n], gt_boxes[n]])                       # proposals first, then GT
+            cv = torch.cat([prop_valid[n], gt_valid[n]])
+            midx, mlab = rh.proposal_matcher.match_boxes(gt_boxes[n], cand, gt_valid=gt_valid[n])
+            cls = gt_classes[n][midx]
+            cls = torch.where(mlab == 0, torch.full_like(cls, K), cls)
+            has_gt = gt_valid[n].any()
+            cls = torch.where(has_gt, cls, torch.full_like(cls, K))
+            idx, ok, fg = subsample_static(cv & (cls < K), cv & (cls == K), R, rh.positive_fraction)
+            b = torch.where(ok[:, None], cand[idx], dummy)
+            boxes0.append(b)
+            cls0.append(torch.where(ok, cls[idx], torch.full_like(idx, -100)))
+            ok0.append(ok)
+            fg0.append(fg)
+            gidx0.append(midx[idx])
+            gtb0.append(gt_boxes[n][midx[idx]])
+    losses = {}
+    cur_boxes, cur_cls, cur_ok, cur_gtb = boxes0, cls0, ok0, gtb0
+    for k in range(rh.num_cascade_stages):
+        if k > 0:
+            with torch.no_grad():
+                nb, nc, nok, ngb = [], [], [], []
+                for n in range(N):
+                    b = _clip(prev_boxes[n].detach(), images_size)
+                    ok = cur_ok[n] & _nonempty(b)                                # cascade_rcnn.py:292-295
+                    b = torch.where(ok[:, None], b, dummy)
+                    midx, lab = rh.proposal_matchers[k].match_boxes(gt_boxes[n], b, gt_valid=gt_valid[n])
+                    cls = gt_classes[n][midx]
+                    cls = torch.where(lab == 0, torch.full_like(cls, K), cls)
+                    cls = torch.where(gt_valid[n].any(), cls, torch.full_like(cls, K))
+                    nb.append(b)
+                    nc.append(torch.where(ok, cls, torch.full_like(cls, -100)))
+                    nok.append(ok)
+                    ngb.append(gt_boxes[n][midx])
+                cur_boxes, cur_cls, cur_ok, cur_gtb = nb, nc, nok, ngb
+        x = rh.box_pooler(feats, cur_boxes, tap=tap)
+        x = _ScaleGrad.apply(x, 1.0 / rh.num_cascade_stages)
+        scores, deltas = rh.box_predictor[k](rh.box_head[k](x))
+        cls_all, ok_all = torch.cat(cur_cls), torch.cat(cur_ok)
+        pb, gb = torch.cat(cur_boxes), torch.cat(cur_gtb)
+        count = ok_all.sum().clamp(min=1).to(torch.float32)
+        # fast_rcnn.py:307-352: mean CE over the sampled rows; L1 over the foreground rows / #rows
+        ce = F.cross_entropy(scores.float(), cls_all, reduction="sum", ignore_index=-100)
+        losses["loss_cls_stage%d" % k] = ce / count
+        fg = ok_all & (cls_all >= 0) & (cls_all < K)
+        tgt = rh.box_predictor[k].box2box_transform.get_deltas(pb, gb)
+        losses["loss_box_reg_stage%d" % k] = _masked_l1(deltas, tgt, fg) / count * rh.box_predictor[k].loss_weight["loss_box_reg"]
+        prev_boxes = rh.box_predictor[k].box2box_transform.apply_deltas(deltas, pb).split(R)
+    # ---- mask branch on the stage-0 foreground slots (first quarter of every image's slots) ----
+    M = int(R * rh.positive_fraction)
+    mb = [b[:M] for b in boxes0]
+    mok = torch.cat([f[:M] for f in fg0])
+    mcls = torch.cat([c[:M] for c in cls0]).clamp(0, K - 1)
+    xm = rh.mask_pooler(feats, mb, tap=tap)
+    logits = rh.mask_head(xm)
+    side = logits.shape[-1]
+    with torch.no_grad():
+        tgt = torch.cat([crop_and_resize_masks(gt_masks[n], mb[n], side, gt_index=gidx0[n][:M]) for n in range(N)])
+    sel = logits[torch.arange(logits.shape[0], device=dev), mcls].float()
+    bce = F.binary_cross_entropy_with_logits(sel, tgt.to(torch.float32), reduction="none")
+    denom = (mok.sum() * side * side).clamp(min=1).to(torch.float32)
+    losses["loss_mask"] = (bce * mok[:, None, None].to(bce.dtype)).sum() / denom
+    return losses
+
+
+class _ScaleGrad(torch.autograd.Function):
+    """cascade_rcnn.py:20-28."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.scale = scale
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.scale, None
+
+
+def forward_train_static(model, images_u8, gt_boxes, gt_classes, gt_valid, gt_masks, sem_seg):
+    """PanopticFPN.forward (training) on padded tensors. images_u8: (N,3,H,W) uint8 on the device. Returns
+    (dict of the 10 losses in the reference's key order, nonfinite flag tensor)."""
+    N, _, H, W = images_u8.shape
+    x = ((images_u8.float() - model.pixel_mean) / model.pixel_std)
+    s = model.backbone.size_divisibility
+    Hp, Wp = (H + s - 1) // s * s, (W + s - 1) // s * s
+    if (Hp, Wp) != (H, W):
+        x = F.pad(x, (0, Wp - W, 0, Hp - H))
+        sem_seg = F.pad(sem_seg, (0, Wp - W, 0, Hp - H), value=model.sem_seg_head.ignore_value)
+    x = x.contiguous(memory_format=torch.channels_last)
+    if model._bn_counters:
+        torch._foreach_add_(model._bn_counters, 1)
+    features = model.backbone(x)
+    main = torch.cuda.current_stream()
+    if model._side_stream is None:
+        model._side_stream = torch.cuda.Stream()
+    model._side_stream.wait_stream(main)
+    with torch.cuda.stream(model._side_stream):
+        _, sem_losses = model.sem_seg_head(features, sem_seg)
+    flags = []
+    proposals, prop_valid, rpn_losses = rpn_static(model.proposal_generator, (H, W), features, gt_boxes, gt_valid, flags)
+    det_losses = roi_heads_static(model.roi_heads, (H, W), features, proposals, prop_valid, gt_boxes, gt_classes,
+                                  gt_valid, gt_masks)
+    main.wait_stream(model._side_stream)
+    losses = dict(sem_losses)
+    losses.update(rpn_losses)
+    losses.update(det_losses)
+    return losses, torch.stack(flags).any()
+
+
+def pack_batch(batched_inputs, device, g_max=None):
+    """list[dict] (reference input format, same-size images) -> the padded tensors forward_train_static takes."""
+    imgs = torch.stack([d["image"] for d in batched_inputs]).to(device, non_blocking=True)
+    G = g_max or max(1, max(len(d["instances"]) for d in batched_inputs))
+    N, H, W = len(batched_inputs), imgs.shape[-2], imgs.shape[-1]
+    gb = torch.zeros((N, G, 4), dtype=torch.float32, device=device)
+    gc = torch.zeros((N, G), dtype=torch.int64, device=device)
+    gv = torch.zeros((N, G), dtype=torch.bool, device=device)
+    gm = torch.zeros((N, G, H, W), dtype=torch.bool, device=device)
+    for n, d in enumerate(batched_inputs):
+        inst = d["instances"]
+        g = len(inst)
+        if g:
+            gb[n, :g] = inst.gt_boxes.tensor.to(device, non_blocking=True)
+            gc[n, :g] = inst.gt_classes.to(device, non_blocking=True)
+            gv[n, :g] = True
+            gm[n, :g] = inst.gt_masks.tensor.to(device, non_blocking=True)
+    sem = torch.stack([d["sem_seg"] for d in batched_inputs]).to(device, non_blocking=True)
+    return imgs, gb, gc, gv, gm, sem
