@@ -172,12 +172,13 @@ int u2b_bn_bwd_coeff(const float* partials, int S, double n_total, const float* 
 /* Data-parallel (SyncBN) variants with the cross-GPU reduction fused into the kernel: `sums` (2C, this rank's summed
  * partials) is stored into every peer's symmetric buffer over NVLink, published with release/acquire flags, and
  * reduced locally - no NCCL call. peers: device array of `world` device pointers (every rank's buffer of
- * u2b_bn_xchg_buffer_bytes, zero-initialised once); epoch = 1, 2, 3, ... one per exchange, identical on all ranks. */
+ * u2b_bn_xchg_buffer_bytes, zero-initialised once); epoch_ctr: device uint32 (start 0) advanced inside the kernel,
+ * one per exchange, so every rank sees the same sequence and CUDA-graph replays stay valid. */
 size_t u2b_bn_xchg_buffer_bytes(int world, int slot_floats);
-int u2b_bn_xchg_finalize(const float* sums, const void* peers, int world, int rank, uint32_t epoch, int slot_floats,
+int u2b_bn_xchg_finalize(const float* sums, const void* peers, int world, int rank, uint32_t* epoch_ctr, int slot_floats,
                          double n_total, const float* w, const float* b, float eps, float momentum,
                          float* running_mean, float* running_var, float* stats, int C, u2b_stream_t stream);
-int u2b_bn_xchg_bwd_coeff(const float* sums, const void* peers, int world, int rank, uint32_t epoch, int slot_floats,
+int u2b_bn_xchg_bwd_coeff(const float* sums, const void* peers, int world, int rank, uint32_t* epoch_ctr, int slot_floats,
                           double n_total, const float* stats, const float* w, float* coeff, float* gw_gb, int C,
                           u2b_stream_t stream);
 /* dx = A*dz + B*x + K; dres = dz when dres != NULL */

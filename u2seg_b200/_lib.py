@@ -55,9 +55,9 @@ SIGNATURES = {
     "u2b_bn_bwd_coeff": (c_int, [c_void_p, c_int, ctypes.c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p]),
     "u2b_bn_xchg_buffer_bytes": (c_size_t, [c_int, c_int]),
-    "u2b_bn_xchg_finalize": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_uint32, c_int, ctypes.c_double, c_void_p,
+    "u2b_bn_xchg_finalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, ctypes.c_double, c_void_p,
                                      c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
-    "u2b_bn_xchg_bwd_coeff": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_uint32, c_int, ctypes.c_double, c_void_p,
+    "u2b_bn_xchg_bwd_coeff": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, ctypes.c_double, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "u2b_bn_bwd_apply": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                  c_void_p]),

@@ -44,7 +44,8 @@ def run_train(args, ClockSampler, load_peaks, dist_info, run_kmeans=None):
     torch.backends.cudnn.benchmark = False   # ROI counts vary per step: autotuning every new shape costs far more than it saves
     cfg = get_u2seg_cfg(NUM_CLASSES)
     torch.manual_seed(0)
-    trainer = Trainer(cfg, amp_dtype=torch.bfloat16, device=dev)
+    static = os.environ.get("U2B_STATIC_GRAPH", "1") != "0"
+    trainer = Trainer(cfg, amp_dtype=torch.bfloat16, device=dev, static_graph=static, g_max=20)
     if world > 1:   # identical initial weights on every rank (DDP broadcasts rank 0's)
         for t in list(trainer.model.parameters()) + list(trainer.model.buffers()):
             dist.broadcast(t.data, 0)
@@ -122,6 +123,8 @@ def run_train(args, ClockSampler, load_peaks, dist_info, run_kmeans=None):
                           "achieved": achieved, "peak": peaks["tf_sus"], "unit": "TFLOP/s",
                           "frac": achieved / peaks["tf_sus"], "peak_source": peaks["src"] + " bf16 sustained"},
         "conv_policy": "tcgen05 conv_tc for 3x3 stride-1 convs with Cin,Cout>=128 (fwd+dgrad); cuDNN elsewhere and for wgrad",
+        "step_mode": ("static shapes (fixed-capacity device buffers, no host sync), forward+backward+all-reduce+clip+SGD "
+                      "replayed from one CUDA graph") if static else "dynamic shapes (reference-shaped), eager",
         "final_loss": loss_total,
     }
     if run_kmeans is not None and not os.environ.get("U2B_BENCH_SKIP_KMEANS"):

@@ -414,12 +414,16 @@ __device__ __forceinline__ void xchg_all_reduce(float* __restrict__ vals /*smem 
 // one CTA: local (2C) sums -> exchange -> mean/invstd/scale/shift + running statistics
 __global__ void __launch_bounds__(512)
 bn_xchg_finalize_kernel(const float* __restrict__ sums, const unsigned long long* __restrict__ peers, int world,
-                        int rank, unsigned int epoch, int slot_floats, double n_total, const float* __restrict__ w,
+                        int rank, unsigned int* __restrict__ epoch_ctr, int slot_floats, double n_total,
+                        const float* __restrict__ w,
                         const float* __restrict__ b, float eps, float momentum, float* __restrict__ running_mean,
                         float* __restrict__ running_var, float* __restrict__ stats, int C) {
   extern __shared__ float xv[];  // [2C]
+  // the exchange number lives in device memory (advanced here), so a CUDA-graph replay uses fresh epochs
+  const unsigned int epoch = *epoch_ctr + 1u;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) xv[i] = sums[i];
   __syncthreads();
+  if (threadIdx.x == 0) *epoch_ctr = epoch;
   xchg_all_reduce(xv, 2 * C, peers, world, rank, epoch, slot_floats);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const double mu = static_cast<double>(xv[c]) / n_total;
@@ -442,12 +446,14 @@ bn_xchg_finalize_kernel(const float* __restrict__ sums, const unsigned long long
 // one CTA: local (2C) backward sums -> dgamma/dbeta (local) -> exchange -> dx coefficients
 __global__ void __launch_bounds__(512)
 bn_xchg_bwd_coeff_kernel(const float* __restrict__ sums, const unsigned long long* __restrict__ peers, int world,
-                         int rank, unsigned int epoch, int slot_floats, double n_total,
+                         int rank, unsigned int* __restrict__ epoch_ctr, int slot_floats, double n_total,
                          const float* __restrict__ stats, const float* __restrict__ w, float* __restrict__ coeff,
                          float* __restrict__ gw_gb, int C) {
   extern __shared__ float xv[];  // [2C]
+  const unsigned int epoch = *epoch_ctr + 1u;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) xv[i] = sums[i];
   __syncthreads();
+  if (threadIdx.x == 0) *epoch_ctr = epoch;
   if (gw_gb)
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       gw_gb[c] = xv[C + c];
@@ -560,31 +566,33 @@ int u2b_bn_bwd_coeff(const float* partials, int S, double n_total, const float* 
 
 // Data-parallel variants: `sums` (2C, this rank's summed partials) are exchanged with all peers through the
 // symmetric buffers `peers[world]` (device array of device pointers to every rank's buffer) inside the kernel.
-// epoch: 1, 2, 3, ... advancing by one per exchange, identical on every rank. slot_floats >= 2C.
+// epoch_ctr: device uint32 (start 0), advanced by one per exchange inside the kernel; every rank performs the same
+// sequence of exchanges, so the counters stay identical (and a CUDA-graph replay keeps working). slot_floats >= 2C.
 size_t u2b_bn_xchg_buffer_bytes(int world, int slot_floats) {
   return static_cast<size_t>(2) * world * slot_floats * sizeof(float) + static_cast<size_t>(world) * 4 + 64;
 }
 
-int u2b_bn_xchg_finalize(const float* sums, const void* peers, int world, int rank, uint32_t epoch, int slot_floats,
+int u2b_bn_xchg_finalize(const float* sums, const void* peers, int world, int rank, uint32_t* epoch_ctr, int slot_floats,
                          double n_total, const float* w, const float* b, float eps, float momentum,
                          float* running_mean, float* running_var, float* stats, int C, cudaStream_t stream) {
-  U2B_CHECK_ARG(sums && peers && stats && world > 0 && world <= 32 && rank >= 0 && rank < world && 2 * C <= slot_floats,
+  U2B_CHECK_ARG(sums && peers && stats && epoch_ctr && world > 0 && world <= 32 && rank >= 0 && rank < world &&
+                    2 * C <= slot_floats,
                 "bn_xchg_finalize: bad arguments");
   bn_xchg_finalize_kernel<<<1, 512, static_cast<size_t>(2) * C * sizeof(float), stream>>>(
-      sums, static_cast<const unsigned long long*>(peers), world, rank, epoch, slot_floats, n_total, w, b, eps,
+      sums, static_cast<const unsigned long long*>(peers), world, rank, epoch_ctr, slot_floats, n_total, w, b, eps,
       momentum, running_mean, running_var, stats, C);
   U2B_LAUNCH_CHECK();
   return 0;
 }
 
-int u2b_bn_xchg_bwd_coeff(const float* sums, const void* peers, int world, int rank, uint32_t epoch, int slot_floats,
+int u2b_bn_xchg_bwd_coeff(const float* sums, const void* peers, int world, int rank, uint32_t* epoch_ctr, int slot_floats,
                           double n_total, const float* stats, const float* w, float* coeff, float* gw_gb, int C,
                           cudaStream_t stream) {
-  U2B_CHECK_ARG(sums && peers && stats && coeff && world > 0 && world <= 32 && rank >= 0 && rank < world &&
+  U2B_CHECK_ARG(sums && peers && stats && coeff && epoch_ctr && world > 0 && world <= 32 && rank >= 0 && rank < world &&
                     2 * C <= slot_floats,
                 "bn_xchg_bwd_coeff: bad arguments");
   bn_xchg_bwd_coeff_kernel<<<1, 512, static_cast<size_t>(2) * C * sizeof(float), stream>>>(
-      sums, static_cast<const unsigned long long*>(peers), world, rank, epoch, slot_floats, n_total, stats, w, coeff,
+      sums, static_cast<const unsigned long long*>(peers), world, rank, epoch_ctr, slot_floats, n_total, stats, w, coeff,
       gw_gb, C);
   U2B_LAUNCH_CHECK();
   return 0;

@@ -96,7 +96,7 @@ class Trainer:
         self.scaler = torch.amp.GradScaler("cuda") if self.amp_dtype == torch.float16 else None
         self.graph_backbone = graph_backbone and _world() == 1
         self._graph_tried = False
-        self.static_graph = static_graph and _world() == 1
+        self.static_graph = static_graph
         self.g_max = g_max
         self._graph = None
         self._lr_t = torch.zeros((), dtype=torch.float32, device=self.device)
@@ -136,6 +136,7 @@ class Trainer:
         with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
             loss_dict, flag = forward_train_static(self.model, *self._static_in)
         sum(loss_dict.values()).backward()
+        self.grads.all_reduce_mean()          # one NCCL all-reduce of the flat gradient buffer (captured with the graph)
         self._clip_foreach()
         self._sgd_foreach()
         return {k: v.detach() for k, v in loss_dict.items()}, flag

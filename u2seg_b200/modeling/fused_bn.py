@@ -43,12 +43,8 @@ class _PeerExchange:
         torch.cuda.synchronize(device)
         self.hdl = symm.rendezvous(self.buf, dist.group.WORLD.group_name)
         self.peers = torch.tensor([int(p) for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=device)
-        self.epoch = 0
+        self.epoch_ctr = torch.zeros((1,), dtype=torch.int32, device=device)   # advanced inside the kernels
         dist.barrier()
-
-    def next_epoch(self):
-        self.epoch = (self.epoch + 1) & 0x7fffffff
-        return self.epoch
 
 
 _xchg = {"obj": None, "failed": False}
@@ -102,7 +98,7 @@ class _BNAct(torch.autograd.Function):
             _lib.check(L.u2b_bn_sum_partials(_p(part), S, 2 * C, _p(sums), s), "u2b_bn_sum_partials")
             px = peer_exchange(dev)
             if px is not None and 2 * C <= px.SLOT_FLOATS:
-                _lib.check(L.u2b_bn_xchg_finalize(_p(sums), _p(px.peers), px.world, px.rank, px.next_epoch(),
+                _lib.check(L.u2b_bn_xchg_finalize(_p(sums), _p(px.peers), px.world, px.rank, _p(px.epoch_ctr),
                                                   px.SLOT_FLOATS, n_total, _p(weight), _p(bias), float(eps),
                                                   float(momentum), _p(running_mean), _p(running_var), _p(stats), C, s),
                            "u2b_bn_xchg_finalize")
@@ -143,7 +139,7 @@ class _BNAct(torch.autograd.Function):
             _lib.check(L.u2b_bn_sum_partials(_p(part), S, 2 * C, _p(sums), s), "u2b_bn_sum_partials")
             px = peer_exchange(dev)
             if px is not None and 2 * C <= px.SLOT_FLOATS:
-                _lib.check(L.u2b_bn_xchg_bwd_coeff(_p(sums), _p(px.peers), px.world, px.rank, px.next_epoch(),
+                _lib.check(L.u2b_bn_xchg_bwd_coeff(_p(sums), _p(px.peers), px.world, px.rank, _p(px.epoch_ctr),
                                                    px.SLOT_FLOATS, n_total, _p(stats), _p(weight), _p(coeff), _p(gwb),
                                                    C, s), "u2b_bn_xchg_bwd_coeff")
             else:
