@@ -349,22 +349,42 @@ kmeans_refine_kernel(const __half* __restrict__ x, const float* __restrict__ c32
     __syncwarp();
   }
   __syncthreads();
-  // ---- pass 2: full scans, one CTA each ----
+  // ---- pass 2: full scans, one CTA each; every lane owns one centroid (float4 reads of its fp32 row, x broadcast
+  //      from shared memory), sequential fp32 accumulation over D as a plain sum of squares ----
   __shared__ float s_best[8];
   __shared__ int s_idx[8];
   for (int e = blockIdx.x; e < cnt; e += gridDim.x) {
     const int4 ent = amb[e];
     if (!ent.w) continue;     // uniform across the CTA
     const __half* xr = x + static_cast<size_t>(ent.x) * D;
+    __syncthreads();
     for (int d = threadIdx.x; d < D; d += blockDim.x) rs[d] = __half2float(xr[d]);
     __syncthreads();
     float bv = __int_as_float(0x7f800000);
     int bi = 0x7fffffff;
-    for (int k = warp; k < K; k += 8) {
-      const float d = warp_dist(rs, c32 + static_cast<size_t>(k) * D, D, lane);
-      if (d < bv || (d == bv && k < bi)) {   // NaN compares false: never selected
-        bv = d;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      const float4* cr = reinterpret_cast<const float4*>(c32 + static_cast<size_t>(k) * D);
+      float acc = 0.f;
+      for (int d4 = 0; d4 < D / 4; ++d4) {
+        const float4 c = cr[d4];
+        const float a0 = rs[4 * d4] - c.x, a1 = rs[4 * d4 + 1] - c.y, a2 = rs[4 * d4 + 2] - c.z, a3 = rs[4 * d4 + 3] - c.w;
+        acc = fmaf(a0, a0, acc);
+        acc = fmaf(a1, a1, acc);
+        acc = fmaf(a2, a2, acc);
+        acc = fmaf(a3, a3, acc);
+      }
+      if (acc < bv) {   // ascending k per thread: first minimum kept; NaN compares false
+        bv = acc;
         bi = k;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov < bv || (ov == bv && oi < bi)) {
+        bv = ov;
+        bi = oi;
       }
     }
     if (lane == 0) {
@@ -382,7 +402,6 @@ kmeans_refine_kernel(const __half* __restrict__ x, const float* __restrict__ c32
         }
       labels[ent.x] = (i == 0x7fffffff) ? ent.y : i;   // every distance NaN/inf: keep the tensor pass's label
     }
-    __syncthreads();
   }
 }
 
