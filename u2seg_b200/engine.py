@@ -104,6 +104,7 @@ class Trainer:
         self.nonfinite_flag = None
 
     # ---------------- static-shape, whole-step CUDA graph ----------------
+    @torch.no_grad()
     def _sgd_foreach(self):
         """solver/build.py:119-139 SGD(momentum, weight decay) with the learning rate read from a device scalar, so
         that the captured graph follows the LR schedule."""
@@ -122,6 +123,7 @@ class Trainer:
             upd = torch._foreach_mul(bufs, self._lr_t)
             torch._foreach_sub_(params, upd)
 
+    @torch.no_grad()
     def _clip_foreach(self):
         if self.clip is None:
             return
