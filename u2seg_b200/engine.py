@@ -167,10 +167,15 @@ class Trainer:
                     self._static_step()
             cur.wait_stream(side)
             torch.cuda.synchronize()
+            from . import _lib
             self._graph = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count
             with torch.cuda.graph(self._graph):
                 self._static_out = self._static_step()
+            self.graph_own_launches = _lib.launch_count - l0      # libu2b200 kernels replayed per step
         self._graph.replay()
+        from . import _lib
+        _lib.count_launches(self.graph_own_launches)
         self.iter += 1
         losses, self.nonfinite_flag = self._static_out
         return losses
