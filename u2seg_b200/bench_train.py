@@ -136,9 +136,16 @@ def run_train(args, ClockSampler, load_peaks, dist_info, run_kmeans=None):
     if rank == 0 and world == 1 and not os.environ.get("U2B_BENCH_SKIP_CPU"):
         line["cpu_baseline"] = cpu_train_sample(1)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # A process group whose collectives were captured in a CUDA graph can block in its destructor; everything
+        # is measured and printed, so leave without running destructors (all ranks, after a final barrier).
+        dist.barrier()
+        torch.cuda.synchronize()
+        import sys
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def conv_tc_roofline(peaks):
