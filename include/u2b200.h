@@ -105,6 +105,18 @@ int u2b_crop_resize_masks(const uint8_t* masks, const int64_t* gt_index, const f
                           int64_t M, int H, int W, int P, uint8_t* out_bool, float* out_val,
                           u2b_stream_t stream);
 
+/* modeling/meta_arch/semantic_seg.py:255-267 SemSegFPNHead.losses: bilinear upsampling by `scale`
+ * (F.interpolate, align_corners=False) of the stride-`scale` logits fused with F.cross_entropy(ignore_index) and
+ * with the backward of both. logits (N, h, w, C) NHWC of dtype 0 = fp32 / 1 = fp16 / 2 = bf16; targets
+ * (N, h*scale, w*scale) int64. partials (u2b_upsample_ce_num_partials(N, H, W) x 2 fp32) receives per-tile
+ * [sum of pixel losses, number of non-ignored pixels]: loss = sum(partials[:,0]) / sum(partials[:,1]).
+ * grad_logits (N, h, w, C) fp32, ZEROED by the caller, nullable: receives d(sum of pixel losses)/d(logits); the
+ * gradient of the mean loss is grad_logits * grad_out / count. */
+int64_t u2b_upsample_ce_num_partials(int64_t N, int H, int W);
+int u2b_upsample_ce_supported(int C, int scale);
+int u2b_upsample_ce(int dtype, const void* logits, const int64_t* targets, int64_t N, int h, int w, int C,
+                    int scale, int64_t ignore_index, float* grad_logits, float* partials, u2b_stream_t stream);
+
 /* structures/boxes.py:336-358 pairwise_iou + modeling/matcher.py:62-127 Matcher.__call__, fused:
  * gt (G, 4), pred (A, 4) fp32 -> matches int64 (A) (first maximum), matched_vals fp32 (A),
  * out_labels int8 (A). thresholds: nthr device floats [-inf, t.., +inf]; labels: nthr-1 device ints.

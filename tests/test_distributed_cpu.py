@@ -89,8 +89,9 @@ def _grad_worker(rank, world, port, q):
     model(x).square().sum().backward()
     assert all(p.grad.data_ptr() >= fg.flat.data_ptr() for p in model.parameters())   # still views of the flat buffer
     fg.all_reduce_mean()
-    if rank == 0:
-        q.put(fg.flat.clone())
+    if rank == 0:   # gradients in parameter order (each starts on a 64-element boundary of the flat buffer)
+        assert fg.flat.numel() % 64 == 0 and all((p.grad.data_ptr() - fg.flat.data_ptr()) % 256 == 0 for p in model.parameters())
+        q.put(torch.cat([p.grad.flatten() for p in model.parameters()]).clone())
     dist.destroy_process_group()
 
 

@@ -4,6 +4,7 @@ import os
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from oracle import detector_oracle as do
 
@@ -247,3 +248,36 @@ def test_fused_bn_act_matches_torch(dtype, tol, C, HW, res, relu):
     assert float((bn.weight.grad - w.grad).abs().max()) <= tol * 2 * sc(w.grad)
     assert float((bn.bias.grad - b.grad).abs().max()) <= tol * 2 * sc(b.grad)
     assert torch.allclose(bn.running_mean, rm, rtol=1e-4, atol=1e-5) and torch.allclose(bn.running_var, rv, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("N,C,h,w,scale,dtype", [(2, 28, 37, 50, 4, torch.float32), (1, 28, 64, 64, 4, torch.bfloat16),
+                                                 (2, 5, 33, 17, 2, torch.float32), (1, 40, 8, 8, 8, torch.float32)])
+def test_upsample_cross_entropy_matches_interpolate_plus_cross_entropy(N, C, h, w, scale, dtype):
+    """semantic_seg.py:255-267 fused: loss and d(loss)/d(logits) against F.interpolate + F.cross_entropy (fp32)."""
+    from u2seg_b200.layers import upsample_cross_entropy
+    g = torch.Generator().manual_seed(7)
+    z = (torch.randn(N, C, h, w, generator=g) * 3).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    t = torch.randint(0, C, (N, h * scale, w * scale), generator=g)
+    t[torch.rand(t.shape, generator=g) < 0.2] = 255          # ignored pixels
+    t = t.cuda()
+    za = z.clone().requires_grad_(True)
+    zb = z.clone().requires_grad_(True)
+    got = upsample_cross_entropy(za, t, scale, 255)
+    up = F.interpolate(zb.float(), scale_factor=scale, mode="bilinear", align_corners=False)
+    want = F.cross_entropy(up, t, reduction="mean", ignore_index=255)
+    assert abs(float(got) - float(want)) <= 1e-5 * abs(float(want)) + 1e-6           # FLOAT: 1e-5 relative
+    (got * 0.5).backward()
+    (want * 0.5).backward()
+    tol = 1e-5 if dtype == torch.float32 else 1e-2         # bf16 gradient is rounded to bf16 on both sides
+    d = float((za.grad.float() - zb.grad.float()).abs().max())
+    assert d <= tol * float(zb.grad.float().abs().max()) + 1e-9, d
+    assert za.grad.shape == z.shape and za.grad.dtype == dtype
+
+
+def test_upsample_cross_entropy_all_ignored_is_nan_like_reference():
+    from u2seg_b200.layers import upsample_cross_entropy
+    z = torch.randn(1, 4, 8, 8).cuda().contiguous(memory_format=torch.channels_last)
+    t = torch.full((1, 32, 32), 255, dtype=torch.int64).cuda()
+    got = upsample_cross_entropy(z, t, 4, 255)
+    want = F.cross_entropy(F.interpolate(z, scale_factor=4, mode="bilinear", align_corners=False), t, ignore_index=255)
+    assert torch.isnan(got) and torch.isnan(want)

@@ -38,6 +38,10 @@ SIGNATURES = {
     "u2b_paste_masks": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "u2b_crop_resize_masks": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p,
                                       c_void_p, c_void_p]),
+    "u2b_upsample_ce_num_partials": (c_int64, [c_int64, c_int, c_int]),
+    "u2b_upsample_ce_supported": (c_int, [c_int, c_int]),
+    "u2b_upsample_ce": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int64, c_void_p,
+                                c_void_p, c_void_p]),
     "u2b_iou_match": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_void_p]),
     "u2b_conv2d_supported": (c_int, [c_int] * 6),

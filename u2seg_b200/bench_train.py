@@ -46,9 +46,7 @@ def run_train(args, ClockSampler, load_peaks, dist_info, run_kmeans=None):
     torch.manual_seed(0)
     static = os.environ.get("U2B_STATIC_GRAPH", "1") != "0"
     trainer = Trainer(cfg, amp_dtype=torch.bfloat16, device=dev, static_graph=static, g_max=20)
-    if world > 1:   # identical initial weights on every rank (DDP broadcasts rank 0's)
-        for t in list(trainer.model.parameters()) + list(trainer.model.buffers()):
-            dist.broadcast(t.data, 0)
+    trainer.broadcast_parameters(0)   # identical initial weights on every rank (DDP broadcasts rank 0's)
 
     pool_n = 4
     host_pool = [synthetic_batch(IMS_PER_GPU, H, W, NUM_CLASSES, SEM_CLASSES, seed=1234 + 97 * rank + i, pin=True)

@@ -225,13 +225,13 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int S, do
                                    const float* __restrict__ w, const float* __restrict__ b, float eps,
                                    float momentum, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float* __restrict__ stats, int C) {
-  // block = 32 channels x 8 strip lanes; lanes sum strided partial rows, then combine through shared memory
-  __shared__ double sh[2][8][32];
-  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+  // block = 8 channels x 32 strip lanes; lanes sum strided partial rows, then combine through shared memory
+  __shared__ double sh[2][32][8];
+  const int cl = threadIdx.x & 7, sl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cl;
   double s = 0.0, ss = 0.0;
   if (c < C)
-    for (int i = sl; i < S; i += 8) {
+    for (int i = sl; i < S; i += 32) {
       s += partials[static_cast<size_t>(i) * 2 * C + c];
       ss += partials[static_cast<size_t>(i) * 2 * C + C + c];
     }
@@ -239,7 +239,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int S, do
   sh[1][sl][cl] = ss;
   __syncthreads();
   if (sl != 0 || c >= C) return;
-  for (int q = 1; q < 8; ++q) {
+  for (int q = 1; q < 32; ++q) {
     s += sh[0][q][cl];
     ss += sh[1][q][cl];
   }
@@ -262,12 +262,12 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int S, do
 __global__ void bn_bwd_coeff_kernel(const float* __restrict__ partials, int S, double n_total,
                                     const float* __restrict__ stats, const float* __restrict__ w,
                                     float* __restrict__ coeff, float* __restrict__ gw_gb, int C) {
-  __shared__ float sh[2][8][32];
-  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+  __shared__ float sh[2][32][8];
+  const int cl = threadIdx.x & 7, sl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cl;
   float s1 = 0.f, s2 = 0.f;
   if (c < C)
-    for (int i = sl; i < S; i += 8) {
+    for (int i = sl; i < S; i += 32) {
       s1 += partials[static_cast<size_t>(i) * 2 * C + c];
       s2 += partials[static_cast<size_t>(i) * 2 * C + C + c];
     }
@@ -275,7 +275,7 @@ __global__ void bn_bwd_coeff_kernel(const float* __restrict__ partials, int S, d
   sh[1][sl][cl] = s2;
   __syncthreads();
   if (sl != 0 || c >= C) return;
-  for (int q = 1; q < 8; ++q) {
+  for (int q = 1; q < 32; ++q) {
     s1 += sh[0][q][cl];
     s2 += sh[1][q][cl];
   }
@@ -525,7 +525,7 @@ int u2b_bn_finalize(const float* partials, int S, double n_total, const float* w
                     float momentum, float* running_mean, float* running_var, float* stats, int C,
                     cudaStream_t stream) {
   U2B_CHECK_ARG(partials && stats && S > 0 && C > 0 && n_total > 0, "bn_finalize: bad arguments");
-  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, stream>>>(partials, S, n_total, w, b, eps, momentum, running_mean,
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, stream>>>(partials, S, n_total, w, b, eps, momentum, running_mean,
                                                           running_var, stats, C);
   U2B_LAUNCH_CHECK();
   return 0;
@@ -559,7 +559,7 @@ int u2b_bn_bwd_reduce(int dtype, const void* dy, const void* x, const void* y, c
 int u2b_bn_bwd_coeff(const float* partials, int S, double n_total, const float* stats, const float* w, float* coeff,
                      float* gw_gb, int C, cudaStream_t stream) {
   U2B_CHECK_ARG(partials && stats && coeff && S > 0 && C > 0 && n_total > 0, "bn_bwd_coeff: bad arguments");
-  bn_bwd_coeff_kernel<<<(C + 31) / 32, 256, 0, stream>>>(partials, S, n_total, stats, w, coeff, gw_gb, C);
+  bn_bwd_coeff_kernel<<<(C + 7) / 8, 256, 0, stream>>>(partials, S, n_total, stats, w, coeff, gw_gb, C);
   U2B_LAUNCH_CHECK();
   return 0;
 }

@@ -139,19 +139,37 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ ca
   }
 }
 
-// Sequential part of greedy NMS, on the device. One CTA walks the sorted boxes in blocks of 64: thread 0 resolves
-// the 64 intra-block decisions from the diagonal mask words (registers + shared memory only), then all threads OR
-// the kept rows into the `removed` bitmap of the later blocks (coalesced: thread j owns column word j).
-// Stops as soon as max_keep boxes are kept (proposal_utils.py:122 `keep[:post_nms_topk]`).
+// Sequential part of greedy NMS, on the device. One CTA walks the sorted boxes in blocks of 64. The 64 mask rows of
+// a block (64 x col_blocks words) are staged in shared memory with cp.async, double buffered, so that the global-load
+// latency of block b+1 hides behind the work on block b and nothing on the serial chain touches global memory:
+// thread 0 resolves the 64 intra-block decisions from the diagonal words (registers + shared memory), then thread j
+// ORs the kept rows' word j into `removed[j]` (one owner per word: no atomics). Stops as soon as max_keep boxes are
+// kept (proposal_utils.py:122 `keep[:post_nms_topk]`).
+__device__ __forceinline__ void nms_stage_tile(unsigned long long* __restrict__ dst,
+                                               const unsigned long long* __restrict__ mask, int b, int n,
+                                               int col_blocks) {
+  const int rows = min(64, n - b * 64);
+  const int words = rows * col_blocks;
+  const unsigned long long* src = mask + static_cast<size_t>(b) * 64 * col_blocks;
+  for (int i = threadIdx.x; i < words; i += blockDim.x) {
+    const unsigned int sa = static_cast<unsigned int>(__cvta_generic_to_shared(dst + i));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(src + i) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(256)
 nms_scan_kernel(const unsigned long long* __restrict__ mask, const int64_t* __restrict__ order,
                 const uint8_t* __restrict__ valid, int n, int col_blocks, int max_keep,
                 int64_t* __restrict__ keep, int* __restrict__ num_keep) {
-  extern __shared__ unsigned long long removed[];
-  __shared__ unsigned long long diag[64];
+  extern __shared__ unsigned long long nms_smem[];
+  unsigned long long* removed = nms_smem;                       // [col_blocks]
+  unsigned long long* tile0 = nms_smem + col_blocks;            // [2][64][col_blocks]
+  const size_t tile_words = static_cast<size_t>(64) * col_blocks;
   __shared__ unsigned long long s_kept;
   __shared__ int s_nk, s_stop;
   const int t = threadIdx.x;
+  nms_stage_tile(tile0, mask, 0, n, col_blocks);
   for (int i = t; i < col_blocks; i += blockDim.x) {
     unsigned long long r = 0ULL;
     if (valid)  // boxes flagged invalid (fixed-capacity buffers) start out removed
@@ -160,23 +178,33 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int64_t* __re
     removed[i] = r;
   }
   if (t == 0) { s_nk = 0; s_stop = 0; }
-  __syncthreads();
   for (int b = 0; b < col_blocks; ++b) {
     const int rows = min(64, n - b * 64);
-    if (t < rows) diag[t] = mask[static_cast<size_t>(b * 64 + t) * col_blocks + b];
-    __syncthreads();
+    unsigned long long* tile = tile0 + (b & 1) * tile_words;
+    if (b + 1 < col_blocks) {
+      nms_stage_tile(tile0 + ((b + 1) & 1) * tile_words, mask, b + 1, n, col_blocks);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();  // tile b visible to all; removed[] complete from block b-1
     const int base = s_nk;
-    if (t == 0) {  // registers + shared memory only: no global access on the serial chain
+    if (t == 0) {
+      // the 64 dependent decisions of this block: diagonal words in registers, fully unrolled, ALU only
+      unsigned long long d[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) d[i] = tile[static_cast<size_t>(i) * col_blocks + b];
       unsigned long long rem = removed[b], kw = 0ULL;
+      if (rows < 64) rem |= ~0ULL << rows;       // rows past n (stale shared memory) count as removed
       int cnt = base;
-      for (int i = 0; i < rows; ++i) {
-        if (!((rem >> i) & 1ULL)) {
-          ++cnt;
-          kw |= 1ULL << i;
-          rem |= diag[i];
-          if (cnt >= max_keep) { s_stop = 1; break; }
-        }
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const bool take = !((rem >> i) & 1ULL) && cnt < max_keep;
+        rem |= take ? d[i] : 0ULL;
+        kw |= take ? (1ULL << i) : 0ULL;
+        cnt += take ? 1 : 0;
       }
+      if (cnt >= max_keep) s_stop = 1;
       s_kept = kw;
     }
     __syncthreads();
@@ -185,28 +213,23 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int64_t* __re
       keep[base + __popcll(kw & ((1ULL << t) - 1ULL))] = order[b * 64 + t];
     if (t == 0) s_nk = base + __popcll(kw);
     if (s_stop) break;
-    // OR the kept rows into `removed` for the later blocks. Warp w owns rows w, w+8, ..; lanes own column words
-    // (coalesced 256 B row segments). The 8 loads of a warp are unconditional and independent (one L2 latency per
-    // column chunk instead of one per kept row), then folded into shared memory with 64-bit atomicOr.
     {
-      const int w = t >> 5, lane = t & 31;
-      for (int j0 = b + 1; j0 < col_blocks; j0 += 32) {
-        const int j = j0 + lane;
-        unsigned long long v[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int i = w + 8 * r;
-          const bool on = (j < col_blocks) && i < rows && ((kw >> i) & 1ULL);
-          v[r] = on ? mask[static_cast<size_t>(b * 64 + i) * col_blocks + j] : 0ULL;
-        }
+      // two threads per later column (kept rows 0..31 / 32..63), loads predicated and independent
+      const int half = t & 1;
+      const unsigned int bits = static_cast<unsigned int>(kw >> (32 * half));
+      const unsigned long long* trow = tile + static_cast<size_t>(32 * half) * col_blocks;
+      for (int j = b + 1 + (t >> 1); j < col_blocks; j += blockDim.x >> 1) {
         unsigned long long acc = 0ULL;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) acc |= v[r];
+        for (int i = 0; i < 32; ++i)
+          if ((bits >> i) & 1u) acc |= trow[static_cast<size_t>(i) * col_blocks + j];
         if (acc) atomicOr(&removed[j], acc);
       }
     }
-    __syncthreads();
+    __syncthreads();  // all reads of tile b done before it is re-staged two iterations later
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
   if (t == 0) *num_keep = s_nk;
 }
 
@@ -242,7 +265,8 @@ int u2b_batched_nms(const float* boxes, const int64_t* cats, const int64_t* orde
   U2B_CHECK_ARG(boxes && order && keep && workspace && n > 0, "batched_nms: bad arguments");
   U2B_CHECK_ARG(workspace_bytes >= u2b_nms_workspace_bytes(n), "batched_nms: workspace too small");
   const int cb = static_cast<int>((n + 63) / 64);
-  U2B_CHECK_ARG(static_cast<size_t>(cb) * 8 <= 200 * 1024, "batched_nms: n=%lld too large", (long long)n);
+  U2B_CHECK_ARG(static_cast<size_t>(cb) * 8 * 129 <= 220 * 1024, "batched_nms: n=%lld too large (<= %d boxes)",
+                (long long)n, 218 * 64);
   uint8_t* w = static_cast<uint8_t*>(workspace);
   float4* sboxes = reinterpret_cast<float4*>(w);
   int64_t* scats = reinterpret_cast<int64_t*>(w + static_cast<size_t>(n) * 16);
@@ -254,9 +278,11 @@ int u2b_batched_nms(const float* boxes, const int64_t* cats, const int64_t* orde
   dim3 grid(cb, cb);
   nms_mask_kernel<<<grid, 64, 0, stream>>>(sboxes, cats ? scats : nullptr, (int)n, iou_threshold, mask, cb);
   U2B_LAUNCH_CHECK();
-  const size_t smem = static_cast<size_t>(cb) * 8;
-  if (smem > 48 * 1024) {
-    U2B_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = static_cast<size_t>(cb) * 8 * 129;   // removed[cb] + 2 tiles of 64 x cb words
+  static bool scan_attr = false;
+  if (!scan_attr) {
+    U2B_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    scan_attr = true;
   }
   const int mk = (max_keep < 0 || max_keep > n) ? (int)n : (int)max_keep;
   if (mk == 0) {

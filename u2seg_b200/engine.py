@@ -9,6 +9,8 @@ backward; SyncBN statistics are exchanged inside the model. Loss scalars stay on
 """
 import math
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -35,17 +37,35 @@ class WarmupMultiStepLR:
         return self.base_lr * f
 
 
-class FlatGradients:
-    """All gradients as views into one flat fp32 buffer -> the DDP-equivalent is ONE all-reduce per step."""
+def _like_view(flat, off, p):
+    """A view of flat[off : off+p.numel()] with p's shape AND strides (p dense: contiguous or channels_last)."""
+    return torch.as_strided(flat, p.shape, p.stride(), off)
 
-    def __init__(self, params, device):
+
+def _aligned(n, a=64):
+    """Every tensor starts on a 64-element boundary of its flat buffer (>= 128 B: TMA descriptors of the tcgen05 conv
+    need 16-byte aligned bases, vectorised multi-tensor kernels 16 B too); the padding stays zero."""
+    return (n + a - 1) // a * a
+
+
+class FlatGradients:
+    """All gradients as views into one flat fp32 buffer -> the DDP-equivalent is ONE all-reduce per step.
+    `tail` lists tensors whose fp32 gradients live at the end of the buffer without being attached as `.grad`
+    (the bf16 compute weights of the static-graph trainer: their bf16 `.grad` is converted into that tail)."""
+
+    def __init__(self, params, device, tail=()):
         self.params = list(params)
-        total = sum(p.numel() for p in self.params)
+        self.n_head = sum(_aligned(p.numel()) for p in self.params)
+        total = self.n_head + sum(_aligned(p.numel()) for p in tail)
         self.flat = torch.zeros(total, dtype=torch.float32, device=device)
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            p.grad = _like_view(self.flat, off, p)
+            off += _aligned(p.numel())
+        self.tail_views = []
+        for p in tail:
+            self.tail_views.append(_like_view(self.flat, off, p))
+            off += _aligned(p.numel())
 
     def zero_(self):
         self.flat.zero_()
@@ -80,7 +100,13 @@ class Trainer:
         self.model.train()
         self.amp_dtype = amp_dtype if cfg.SOLVER.AMP.ENABLED else None
         self.params = [p for p in self.model.parameters() if p.requires_grad]
-        self.grads = FlatGradients(self.params, self.device)
+        self.lowp = static_graph and self.amp_dtype == torch.bfloat16 and os.environ.get("U2B_BF16_WEIGHTS", "1") != "0"
+        if self.lowp:
+            self._setup_lowp_weights()
+        else:
+            self.grads = FlatGradients(self.params, self.device)
+            self._upd_params, self._upd_grads = self.params, None
+            self._flat_views = [p.grad for p in self.params]
         # solver/build.py:119-139 get_default_optimizer_params: norm layers get WEIGHT_DECAY_NORM
         s = cfg.SOLVER
         norm_ids = set()
@@ -105,39 +131,109 @@ class Trainer:
 
     # ---------------- static-shape, whole-step CUDA graph ----------------
     @torch.no_grad()
+    def _setup_lowp_weights(self):
+        """Conv / linear parameters are consumed in bf16 under autocast (amp: train_loop.py:479-521). Instead of one
+        fp32->bf16 cast kernel per parameter per step (and one bf16->fp32 cast per weight gradient), the modules hold
+        bf16 COMPUTE copies (views of one flat bf16 buffer, refreshed by ONE kernel after the optimizer step) and the
+        fp32 MASTER weights live in a flat buffer owned by the trainer; the bf16 weight gradients are widened into the
+        tail of the flat fp32 gradient buffer by the same multi-tensor copy that gathers all gradients.
+        Numerically identical to autocast: same rounding of the same fp32 masters, same bf16 wgrad outputs."""
+        low_ids = set()
+        for m in self.model.modules():
+            if isinstance(m, (torch.nn.modules.conv._ConvNd, torch.nn.Linear)):
+                low_ids.update(id(p) for p in m.parameters(recurse=False) if p.requires_grad)
+        self._low_params = [p for p in self.params if id(p) in low_ids]
+        others = [p for p in self.params if id(p) not in low_ids]
+        n = sum(_aligned(p.numel()) for p in self._low_params)
+        self._master_flat = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self._w16_flat = torch.zeros(n, dtype=torch.bfloat16, device=self.device)
+        self.grads = FlatGradients(others, self.device, tail=self._low_params)
+        self._masters = {}
+        off = 0
+        for p in self._low_params:
+            master = _like_view(self._master_flat, off, p)
+            master.copy_(p.data)
+            w16 = _like_view(self._w16_flat, off, p)
+            w16.copy_(p.data)
+            p.data = w16
+            p.grad = None
+            self._masters[id(p)] = master
+            off += _aligned(p.numel())
+        tail = {id(p): v for p, v in zip(self._low_params, self.grads.tail_views)}
+        self._upd_params = [self._masters.get(id(p), p) for p in self.params]       # what SGD updates (fp32)
+        self._upd_grads = [tail.get(id(p), p.grad) for p in self.params]            # fp32 gradients, same order
+
+    def master_parameters(self):
+        """fp32 parameters by name (the bf16 compute copies are an implementation detail of the static step)."""
+        out = {}
+        for (name, p), m in zip(((n, q) for n, q in self.model.named_parameters() if q.requires_grad), self._upd_params):
+            out[name] = m
+        return out
+
+    @torch.no_grad()
+    def broadcast_parameters(self, src=0):
+        """DDP's initial broadcast: rank `src`'s parameters and buffers everywhere."""
+        if _world() == 1:
+            return
+        for t in list(self._upd_params) + list(self.model.buffers()):
+            dist.broadcast(t, src)
+        if self.lowp:
+            self._w16_flat.copy_(self._master_flat)
+
+    def _groups(self):
+        """(fp32 params, fp32 grads, weight decay) per optimizer group."""
+        idx = {id(p): i for i, p in enumerate(self.params)}
+        for g in self.optimizer.param_groups:
+            ii = [idx[id(p)] for p in g["params"]]
+            yield ([self._upd_params[i] for i in ii],
+                   [self._upd_grads[i] if self._upd_grads is not None else self._flat_views[i] for i in ii],
+                   g["weight_decay"])
+
+    @torch.no_grad()
     def _sgd_foreach(self):
         """solver/build.py:119-139 SGD(momentum, weight decay) with the learning rate read from a device scalar, so
         that the captured graph follows the LR schedule."""
         s = self.cfg.SOLVER
+        groups = list(self._groups())
         if self._mom_bufs is None:
-            self._mom_bufs = [[torch.zeros_like(p) for p in g["params"]] for g in self.optimizer.param_groups]
-        for g, bufs in zip(self.optimizer.param_groups, self._mom_bufs):
-            params = g["params"]
+            self._mom_bufs = [[torch.zeros_like(p) for p in params] for params, _, _ in groups]
+        for (params, grads, wd), bufs in zip(groups, self._mom_bufs):
             if not params:
                 continue
-            grads = [p.grad for p in params]
-            if g["weight_decay"] != 0:
-                torch._foreach_add_(grads, params, alpha=g["weight_decay"])
+            if wd != 0:
+                torch._foreach_add_(grads, params, alpha=wd)
             torch._foreach_mul_(bufs, s.MOMENTUM)
             torch._foreach_add_(bufs, grads)
             upd = torch._foreach_mul(bufs, self._lr_t)
             torch._foreach_sub_(params, upd)
+        if self.lowp:
+            self._w16_flat.copy_(self._master_flat)      # refresh the bf16 compute weights: one kernel
 
     @torch.no_grad()
     def _clip_foreach(self):
         if self.clip is None:
             return
-        grads = [p.grad for p in self.params]
+        grads = self._upd_grads if self._upd_grads is not None else self._flat_views
         norms = torch._foreach_norm(grads, self.clip.NORM_TYPE)
         coef = torch.clamp(self.clip.CLIP_VALUE / (torch.stack(norms) + 1e-6), max=1.0)
         torch._foreach_mul_(grads, list(coef.unbind(0)))
 
     def _static_step(self):
         from .modeling.static_train import forward_train_static
-        self.grads.zero_()
+        # .grad = None: autograd hands over each gradient tensor instead of launching one `grad += g` kernel per
+        # parameter; one multi-tensor copy then gathers (and, for bf16 weight gradients, widens) them into the flat
+        # fp32 buffer. Under graph capture the gradient tensors live in the graph's private pool.
+        for p in self.params:
+            p.grad = None
         with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
             loss_dict, flag = forward_train_static(self.model, *self._static_in)
         sum(loss_dict.values()).backward()
+        dst = self._upd_grads if self._upd_grads is not None else self._flat_views
+        have = [(d, p.grad) for d, p in zip(dst, self.params) if p.grad is not None]
+        if len(have) != len(self.params):
+            self.grads.zero_()                # parameters outside the graph of this step keep a zero gradient
+        with torch.no_grad():
+            torch._foreach_copy_([d for d, _ in have], [g for _, g in have])
         self.grads.all_reduce_mean()          # one NCCL all-reduce of the flat gradient buffer (captured with the graph)
         self._clip_foreach()
         self._sgd_foreach()

@@ -255,6 +255,52 @@ def crop_and_resize_masks(masks, boxes, mask_size, gt_index=None, return_values=
 
 
 # --------------------------------------------------------------------------------------
+# semantic-segmentation loss: bilinear upsampling + cross-entropy, fused (forward and backward in one kernel)
+# --------------------------------------------------------------------------------------
+class _UpsampleCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, targets, scale, ignore_index):
+        L = _lib.lib()
+        N, C, h, w = logits.shape
+        z = logits if (logits.is_contiguous(memory_format=torch.channels_last) and logits.stride(1) == 1) else \
+            logits.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        tg = targets.to(torch.int64).contiguous()
+        npart = L.u2b_upsample_ce_num_partials(N, h * scale, w * scale)
+        partials = torch.empty((npart, 2), dtype=torch.float32, device=logits.device)
+        need = ctx.needs_input_grad[0]
+        dz = torch.zeros((N, h, w, C), dtype=torch.float32, device=logits.device) if need else None
+        assert z.stride(1) == 1 and z.permute(0, 2, 3, 1).is_contiguous()
+        _lib.check(L.u2b_upsample_ce(_DTYPE_CODE[z.dtype], ctypes.c_void_p(z.data_ptr()), _lib.ptr(tg), N, h, w, C, scale, ignore_index,
+                                     _lib.ptr(dz), _lib.ptr(partials), _lib.stream_ptr()), "u2b_upsample_ce")
+        _lib.count_launches(1)
+        tot = partials.sum(0)
+        ctx.save_for_backward(dz, tot[1])
+        ctx.in_dtype = logits.dtype
+        return tot[0] / tot[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        dz, count = ctx.saved_tensors
+        gz = (dz * (g / count)).to(ctx.in_dtype).permute(0, 3, 1, 2)        # logical NCHW, NHWC storage
+        return gz, None, None, None
+
+
+def upsample_cross_entropy(logits, targets, scale, ignore_index):
+    """mean over non-ignored pixels of CE(bilinear_upsample(logits.float(), scale), targets)
+    (semantic_seg.py:255-267) without materialising anything of full resolution. logits (N,C,h,w); targets
+    (N, h*scale, w*scale) integer."""
+    _need_cuda(logits, "upsample_cross_entropy")
+    assert targets.shape == (logits.shape[0], logits.shape[2] * scale, logits.shape[3] * scale), \
+        "targets %s do not match logits %s x%d" % (tuple(targets.shape), tuple(logits.shape), scale)
+    return _UpsampleCE.apply(logits, targets, int(scale), int(ignore_index))
+
+
+def upsample_cross_entropy_supported(logits, scale):
+    return logits.is_cuda and logits.dtype in _DTYPE_CODE and float(scale) == int(scale) and \
+        bool(_lib.lib().u2b_upsample_ce_supported(logits.shape[1], int(scale)))
+
+
+# --------------------------------------------------------------------------------------
 # boxes: fused IoU + Matcher, NMS
 # --------------------------------------------------------------------------------------
 class Matcher:

@@ -197,6 +197,18 @@ def mask_rcnn_loss(pred_mask_logits, instances, gt_masks_per_image):
     return F.binary_cross_entropy_with_logits(pred.float(), gt_masks.to(torch.float32), reduction="mean")
 
 
+def mask_rcnn_loss_selected(mask_head, x, instances, gt_masks_per_image):
+    """mask_rcnn_loss(mask_head(x), ...) without materialising the logits of the classes the loss never reads."""
+    if x.shape[0] == 0:
+        return mask_head(x).sum() * 0
+    classes = torch.cat([i.gt_classes.to(torch.int64) for i in instances if len(i) > 0])
+    pred = mask_head.forward_selected(x, classes)
+    side = pred.shape[-1]
+    gt_masks = torch.cat([crop_and_resize_masks(m, i.proposal_boxes.tensor, side, gt_index=i.gt_mask_index)
+                          for i, m in zip(instances, gt_masks_per_image) if len(i) > 0])
+    return F.binary_cross_entropy_with_logits(pred.float(), gt_masks.to(torch.float32), reduction="mean")
+
+
 def mask_rcnn_inference(pred_mask_logits, pred_instances):
     """mask_head.py:115-158."""
     if pred_mask_logits.size(1) == 1:
@@ -234,6 +246,25 @@ class MaskRCNNConvUpsampleHead(nn.Sequential):
             c2_msra_fill(layer)
         nn.init.normal_(self.predictor.weight, std=0.001)
         nn.init.constant_(self.predictor.bias, 0)
+
+    def forward_selected(self, x, classes):
+        """Logits of ONE class per ROI, (R, S, S): exactly the entries that mask_head.py:95-97 (training, gt class)
+        and mask_head.py:141-143 (inference, predicted class) read from the (R, num_classes, S, S) predictor output.
+        With 800 pseudo-classes that output is 800x larger than what is used (321 MB per step at 256 ROIs), so the
+        1x1 predictor runs as a per-ROI dot product with the selected filter instead; unselected filters get a zero
+        gradient either way."""
+        for layer in self:
+            if layer is self.predictor:
+                break
+            x = layer(x)
+        R, C, S, _ = x.shape
+        w = self.predictor.weight.view(-1, C)
+        if w.shape[0] == 1:
+            classes = torch.zeros_like(classes)
+        rows = x.permute(0, 2, 3, 1).reshape(R, S * S, C)            # NHWC storage: a view
+        wsel = w[classes].to(rows.dtype)
+        out = torch.bmm(rows, wsel.unsqueeze(2)).squeeze(2) + self.predictor.bias[classes].to(rows.dtype)[:, None]
+        return out.view(R, S, S)
 
 
 @ROI_HEADS_REGISTRY.register()
@@ -380,7 +411,13 @@ class CascadeROIHeads(nn.Module):
         if self.mask_on:
             feats = [features[f] for f in self.mask_in_features]
             x = self.mask_pooler(feats, [i.pred_boxes for i in instances])
-            mask_rcnn_inference(self.mask_head(x), instances)
+            if x.shape[0] > 0:     # mask_head.py:141-143: only the predicted class's mask is read
+                cls = torch.cat([i.pred_classes for i in instances])
+                probs = self.mask_head.forward_selected(x, cls)[:, None].float().sigmoid()
+                for prob, inst in zip(probs.split([len(i) for i in instances], dim=0), instances):
+                    inst.pred_masks = prob
+            else:
+                mask_rcnn_inference(self.mask_head(x), instances)
         return instances
 
     def _forward_mask(self, features, instances, targets):
@@ -391,9 +428,8 @@ class CascadeROIHeads(nn.Module):
             fg.append(inst[sel.nonzero().squeeze(1)])
         feats = [features[f] for f in self.mask_in_features]
         x = self.mask_pooler(feats, [i.proposal_boxes for i in fg], tap=self._tap)
-        logits = self.mask_head(x)
         masks = [t.gt_masks.tensor if len(t) else None for t in targets]
-        return {"loss_mask": mask_rcnn_loss(logits, fg, masks)}
+        return {"loss_mask": mask_rcnn_loss_selected(self.mask_head, x, fg, masks)}
 
 
 def build_roi_heads(cfg, input_shape):

@@ -52,6 +52,10 @@ class SemSegFPNHead(nn.Module):
 
     def losses(self, predictions, targets):
         """semantic_seg.py:255-267: fp32 logits, bilinear x4, CE(mean, ignore) * weight."""
+        from ..layers import upsample_cross_entropy, upsample_cross_entropy_supported
+        if upsample_cross_entropy_supported(predictions, self.common_stride):
+            loss = upsample_cross_entropy(predictions, targets, self.common_stride, self.ignore_value)
+            return {"loss_sem_seg": loss * self.loss_weight}
         predictions = predictions.float()
         predictions = F.interpolate(predictions, scale_factor=self.common_stride, mode="bilinear", align_corners=False)
         loss = F.cross_entropy(predictions, targets, reduction="mean", ignore_index=self.ignore_value)

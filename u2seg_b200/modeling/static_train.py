@@ -183,11 +183,10 @@ def roi_heads_static(rh, images_size, features, proposals, prop_valid, gt_boxes,
     mok = torch.cat([f[:M] for f in fg0])
     mcls = torch.cat([c[:M] for c in cls0]).clamp(0, K - 1)
     xm = rh.mask_pooler(feats, mb, tap=tap)
-    logits = rh.mask_head(xm)
-    side = logits.shape[-1]
+    sel = rh.mask_head.forward_selected(xm, mcls).float()        # (N*M, S, S): the gt-class logits only
+    side = sel.shape[-1]
     with torch.no_grad():
         tgt = torch.cat([crop_and_resize_masks(gt_masks[n], mb[n], side, gt_index=gidx0[n][:M]) for n in range(N)])
-    sel = logits[torch.arange(logits.shape[0], device=dev), mcls].float()
     bce = F.binary_cross_entropy_with_logits(sel, tgt.to(torch.float32), reduction="none")
     denom = (mok.sum() * side * side).clamp(min=1).to(torch.float32)
     losses["loss_mask"] = (bce * mok[:, None, None].to(bce.dtype)).sum() / denom
