@@ -105,6 +105,17 @@ int u2b_crop_resize_masks(const uint8_t* masks, const int64_t* gt_index, const f
                           int64_t M, int H, int W, int P, uint8_t* out_bool, float* out_val,
                           u2b_stream_t stream);
 
+/* modeling/backbone/resnet.py:338-362 BasicStem.conv1: 7x7 stride-2 pad-3 convolution, 3 -> 64 channels, bf16 NHWC,
+ * no bias (a norm layer follows). x (N, H, W, 3); w (64, 7, 7, 3); y (N, OH, OW, 64), OH = (H - 1) / 2 + 1.
+ * Weight gradient (the image needs none): partials (u2b_stem_conv_wgrad_num_partials(N,H,W), 64, 160) fp32 receives
+ * one partial per persistent CTA; dW[co][r][s][ci] = sum over partials of [co][(r*7+s)*3+ci] (columns >= 147 are
+ * padding). */
+int u2b_stem_conv_supported(int Cin, int Cout, int R, int S, int stride, int pad);
+int u2b_stem_conv_fwd(const void* x, int64_t N, int H, int W, const void* w, void* y, u2b_stream_t stream);
+int u2b_stem_conv_wgrad_num_partials(int64_t N, int H, int W);
+int u2b_stem_conv_wgrad(const void* x, const void* dy, int64_t N, int H, int W, float* partials,
+                        u2b_stream_t stream);
+
 /* modeling/meta_arch/semantic_seg.py:255-267 SemSegFPNHead.losses: bilinear upsampling by `scale`
  * (F.interpolate, align_corners=False) of the stride-`scale` logits fused with F.cross_entropy(ignore_index) and
  * with the backward of both. logits (N, h, w, C) NHWC of dtype 0 = fp32 / 1 = fp16 / 2 = bf16; targets
@@ -181,6 +192,16 @@ int u2b_bn_bwd_reduce(int dtype, const void* dy, const void* x, const void* y, c
 /* coeff (3C): dx = A*dz + B*x + K; gw_gb (2C, nullable) = dgamma | dbeta (the local sums) */
 int u2b_bn_bwd_coeff(const float* partials, int S, double n_total, const float* stats, const float* w, float* coeff,
                      float* gw_gb, int C, u2b_stream_t stream);
+/* nn.GroupNorm(G, C) (layers/batch_norm.py get_norm "GN"; semantic_seg.py:180-200 head convs) on the same kernels:
+ * statistics are per image, so the caller runs u2b_bn_stats / u2b_bn_apply / u2b_bn_bwd_reduce / u2b_bn_bwd_apply on
+ * ONE image (P = H*W pixels) and these two fold the per-channel partial sums across each group of C/G channels.
+ * stats (4C) and coeff (3C) have the BN layout; gw_gb (2C) = dgamma | dbeta, summed over the batch when
+ * accumulate != 0. */
+int u2b_gn_supported(int C, int G);
+int u2b_gn_finalize(const float* partials, int S, int64_t HW, int G, const float* w, const float* b, float eps,
+                    float* stats, int C, u2b_stream_t stream);
+int u2b_gn_bwd_coeff(const float* partials, int S, int64_t HW, int G, const float* stats, const float* w,
+                     float* coeff, float* gw_gb, int accumulate, int C, u2b_stream_t stream);
 /* Data-parallel (SyncBN) variants with the cross-GPU reduction fused into the kernel: `sums` (2C, this rank's summed
  * partials) is stored into every peer's symmetric buffer over NVLink, published with release/acquire flags, and
  * reduced locally - no NCCL call. peers: device array of `world` device pointers (every rank's buffer of

@@ -77,3 +77,27 @@ def test_conv_autograd_and_linear():
     got = conv_tc.linear(a, lin.weight, lin.bias, relu=True)
     want = F.relu(F.linear(a.float(), lin.weight.bfloat16().float(), lin.bias))
     assert (got.float() - want).abs().max().item() <= 8e-3 * sc(want)
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 64, 96), (1, 37, 51), (2, 256, 320), (1, 8, 8)])
+def test_stem_conv_forward_and_weight_gradient(N, H, W):
+    """csrc/stem_conv.cu (resnet.py:338-362 BasicStem.conv1, 7x7/2 pad 3, 3->64) against F.conv2d in fp32 on the
+    same bf16-rounded operands. FLOAT tolerance: output is rounded to bf16 (2^-8 relative); the weight gradient is
+    accumulated in fp32 (1e-3 of its largest entry)."""
+    import torch.nn.functional as F
+    from u2seg_b200.modeling.conv_tc import _StemConv
+    g = torch.Generator().manual_seed(N * 1000 + H)
+    x = torch.randn(N, 3, H, W, generator=g).bfloat16().cuda().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(64, 3, 7, 7, generator=g) * 0.1).bfloat16().cuda().contiguous(memory_format=torch.channels_last)
+    w.requires_grad_(True)
+    y = _StemConv.apply(x, w)
+    wr = w.detach().float().requires_grad_(True)
+    yr = F.conv2d(x.float(), wr, None, 2, 3)
+    assert y.shape == yr.shape and y.dtype == torch.bfloat16
+    assert float((y.float() - yr).abs().max()) <= 2 ** -7 * float(yr.abs().max()) + 1e-6
+    gy = torch.randn(yr.shape, generator=g).bfloat16().cuda().contiguous(memory_format=torch.channels_last)
+    y.backward(gy)
+    yr.backward(gy.float())
+    assert w.grad.shape == w.shape
+    d = float((w.grad.float() - wr.grad).abs().max())
+    assert d <= 1e-2 * float(wr.grad.abs().max()), d      # w.grad itself is rounded to bf16 (2^-8)

@@ -281,3 +281,30 @@ def test_upsample_cross_entropy_all_ignored_is_nan_like_reference():
     got = upsample_cross_entropy(z, t, 4, 255)
     want = F.cross_entropy(F.interpolate(z, scale_factor=4, mode="bilinear", align_corners=False), t, ignore_index=255)
     assert torch.isnan(got) and torch.isnan(want)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("N,C,G,HW,relu", [(2, 128, 32, (33, 47), True), (3, 64, 32, (16, 16), False), (1, 256, 32, (8, 12), True)])
+def test_group_norm_relu_matches_torch(N, C, G, HW, relu, dtype, tol):
+    """fused NHWC GroupNorm(+ReLU) (csrc/batchnorm.cu gn_* + per-image BN kernels) against F.group_norm in fp32:
+    output, dx, dgamma, dbeta. FLOAT tolerance: 2e-4 fp32, 2e-2 bf16 (activation dtype rounding)."""
+    from u2seg_b200.modeling.fused_bn import gn_act, gn_supported
+    g = torch.Generator().manual_seed(C + N)
+    x = cl((torch.randn(N, C, *HW, generator=g) * 2 + 0.5).cuda().to(dtype))
+    gn = torch.nn.GroupNorm(G, C).cuda()
+    with torch.no_grad():
+        gn.weight.copy_(torch.rand(C, generator=g).cuda() + 0.5)
+        gn.bias.copy_(torch.randn(C, generator=g).cuda() * 0.2)
+    assert gn_supported(x, gn)
+    xa = x.clone().requires_grad_(True)
+    y = gn_act(xa, gn, relu)
+    xr = x.float().clone().requires_grad_(True)
+    w2, b2 = gn.weight.detach().clone().requires_grad_(True), gn.bias.detach().clone().requires_grad_(True)
+    yr = F.group_norm(xr, G, w2, b2, gn.eps)
+    yr = F.relu(yr) if relu else yr
+    assert y.dtype == dtype and float((y.float() - yr).abs().max()) <= tol * float(yr.abs().max())
+    gy = cl(torch.randn(yr.shape, generator=g).cuda().to(dtype))
+    y.backward(gy)
+    yr.backward(gy.float())
+    for got, want in ((xa.grad, xr.grad), (gn.weight.grad, w2.grad), (gn.bias.grad, b2.grad)):
+        assert float((got.float() - want).abs().max()) <= 2 * tol * float(want.abs().max()) + 1e-6

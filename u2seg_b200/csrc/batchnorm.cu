@@ -292,6 +292,94 @@ __global__ void bn_bwd_coeff_kernel(const float* __restrict__ partials, int S, d
   coeff[2 * C + c] = -A * s1 * inv_n - B * mu;
 }
 
+// ---- GroupNorm (layers/batch_norm.py get_norm "GN" -> nn.GroupNorm(32, C), sem-seg head) on the same per-channel
+// machinery: statistics are per IMAGE and per GROUP of C/G channels, so the strip partial sums of one image
+// (bn_reduce kernels with P = H*W) are folded across each group's channels here and written back as per-channel
+// mean | invstd | scale | shift (forward) or dx coefficients (backward); the apply kernels are the BN ones.
+// One CTA of 1024 threads: 1024/C strip lanes per channel. C a power of two <= 1024.
+template <typename Acc>
+__device__ __forceinline__ void gn_channel_sums(const float* __restrict__ partials, int S, int C, Acc* sh1, Acc* sh2) {
+  const int lanes = 1024 / C;
+  const int c = threadIdx.x % C, l = threadIdx.x / C;
+  Acc a = 0, b = 0;
+  for (int i = l; i < S; i += lanes) {
+    a += partials[static_cast<size_t>(i) * 2 * C + c];
+    b += partials[static_cast<size_t>(i) * 2 * C + C + c];
+  }
+  sh1[threadIdx.x] = a;
+  sh2[threadIdx.x] = b;
+  __syncthreads();
+  if (l == 0) {
+    for (int q = 1; q < lanes; ++q) {
+      a += sh1[q * C + c];
+      b += sh2[q * C + c];
+    }
+  }
+  __syncthreads();
+  if (l == 0) {
+    sh1[c] = a;
+    sh2[c] = b;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024)
+gn_finalize_kernel(const float* __restrict__ partials, int S, double m, int G, const float* __restrict__ w,
+                   const float* __restrict__ b, float eps, float* __restrict__ stats, int C) {
+  __shared__ double sh1[1024], sh2[1024];
+  gn_channel_sums<double>(partials, S, C, sh1, sh2);
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  const int cpg = C / G, g0 = (c / cpg) * cpg;
+  double s = 0.0, ss = 0.0;
+  for (int k = 0; k < cpg; ++k) {
+    s += sh1[g0 + k];
+    ss += sh2[g0 + k];
+  }
+  const double mu = s / m;
+  double var = ss / m - mu * mu;
+  if (var < 0.0) var = 0.0;
+  const float is = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float sc = (w ? w[c] : 1.f) * is;
+  stats[c] = static_cast<float>(mu);
+  stats[C + c] = is;
+  stats[2 * C + c] = sc;
+  stats[3 * C + c] = (b ? b[c] : 0.f) - static_cast<float>(mu) * sc;
+}
+
+// partials: (sum dz | sum dz*xhat) per channel of ONE image. coeff (3C): dx = A*dz + B*x + K.
+// gw_gb (2C): dgamma | dbeta, accumulated over the images of the batch when `accumulate`.
+__global__ void __launch_bounds__(1024)
+gn_bwd_coeff_kernel(const float* __restrict__ partials, int S, double m, int G, const float* __restrict__ stats,
+                    const float* __restrict__ w, float* __restrict__ coeff, float* __restrict__ gw_gb,
+                    int accumulate, int C) {
+  __shared__ float sh1[1024], sh2[1024];
+  __shared__ float gam[1024];
+  gn_channel_sums<float>(partials, S, C, sh1, sh2);
+  const int c = threadIdx.x;
+  if (c < C) gam[c] = w ? w[c] : 1.f;
+  __syncthreads();
+  if (c >= C) return;
+  const float s1 = sh1[c], s2 = sh2[c];
+  if (gw_gb) {
+    gw_gb[c] = (accumulate ? gw_gb[c] : 0.f) + s2;
+    gw_gb[C + c] = (accumulate ? gw_gb[C + c] : 0.f) + s1;
+  }
+  const int cpg = C / G, g0 = (c / cpg) * cpg;
+  float ds = 0.f, db = 0.f;
+  for (int k = 0; k < cpg; ++k) {
+    ds += gam[g0 + k] * sh1[g0 + k];
+    db += gam[g0 + k] * sh2[g0 + k];
+  }
+  const float mu = stats[c], is = stats[C + c];
+  const float inv_m = static_cast<float>(1.0 / m);
+  const float A = gam[c] * is;
+  const float B = -is * is * db * inv_m;
+  coeff[c] = A;
+  coeff[C + c] = B;
+  coeff[2 * C + c] = -is * ds * inv_m - B * mu;
+}
+
 // total_vec vectors of 8 channels; (blockDim*gridDim) % (C/8) == 0 so a thread's channels never change
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -560,6 +648,28 @@ int u2b_bn_bwd_coeff(const float* partials, int S, double n_total, const float* 
                      float* gw_gb, int C, cudaStream_t stream) {
   U2B_CHECK_ARG(partials && stats && coeff && S > 0 && C > 0 && n_total > 0, "bn_bwd_coeff: bad arguments");
   bn_bwd_coeff_kernel<<<(C + 7) / 8, 256, 0, stream>>>(partials, S, n_total, stats, w, coeff, gw_gb, C);
+  U2B_LAUNCH_CHECK();
+  return 0;
+}
+
+// GroupNorm glue for ONE image (see gn_finalize_kernel): partials from u2b_bn_stats / u2b_bn_bwd_reduce with P = H*W.
+int u2b_gn_supported(int C, int G) {
+  return u2b_bn_supported(C) && C <= 1024 && 1024 % C == 0 && G > 0 && C % G == 0;
+}
+
+int u2b_gn_finalize(const float* partials, int S, int64_t HW, int G, const float* w, const float* b, float eps,
+                    float* stats, int C, cudaStream_t stream) {
+  U2B_CHECK_ARG(partials && stats && S > 0 && HW > 0 && u2b_gn_supported(C, G), "gn_finalize: bad arguments");
+  gn_finalize_kernel<<<1, 1024, 0, stream>>>(partials, S, static_cast<double>(HW) * (C / G), G, w, b, eps, stats, C);
+  U2B_LAUNCH_CHECK();
+  return 0;
+}
+
+int u2b_gn_bwd_coeff(const float* partials, int S, int64_t HW, int G, const float* stats, const float* w,
+                     float* coeff, float* gw_gb, int accumulate, int C, cudaStream_t stream) {
+  U2B_CHECK_ARG(partials && stats && coeff && S > 0 && HW > 0 && u2b_gn_supported(C, G), "gn_bwd_coeff: bad arguments");
+  gn_bwd_coeff_kernel<<<1, 1024, 0, stream>>>(partials, S, static_cast<double>(HW) * (C / G), G, stats, w, coeff, gw_gb,
+                                              accumulate, C);
   U2B_LAUNCH_CHECK();
   return 0;
 }

@@ -233,7 +233,14 @@ class Trainer:
         if len(have) != len(self.params):
             self.grads.zero_()                # parameters outside the graph of this step keep a zero gradient
         with torch.no_grad():
-            torch._foreach_copy_([d for d, _ in have], [g for _, g in have])
+            # the multi-tensor fast path is all-or-nothing per call: keep same-dtype / same-layout pairs together
+            buckets = {}
+            for d, g in have:
+                buckets.setdefault((g.dtype, d.stride() == g.stride()), ([], []))
+                buckets[(g.dtype, d.stride() == g.stride())][0].append(d)
+                buckets[(g.dtype, d.stride() == g.stride())][1].append(g)
+            for dsts, srcs in buckets.values():
+                torch._foreach_copy_(dsts, srcs)
         self.grads.all_reduce_mean()          # one NCCL all-reduce of the flat gradient buffer (captured with the graph)
         self._clip_foreach()
         self._sgd_foreach()

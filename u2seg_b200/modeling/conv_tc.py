@@ -78,8 +78,52 @@ class _ConvTC(torch.autograd.Function):
             if mask[1]:
                 gw = g_w.to(weight.dtype)
         if has_bias and ctx.needs_input_grad[2]:
-            gb = gy.float().sum(dim=(0, 2, 3))
+            from .fused_bn import channel_sum
+            gb = channel_sum(gy)
         return gx, gw, gb, None, None, None
+
+
+class _StemConv(torch.autograd.Function):
+    """backbone/resnet.py:338-362 BasicStem.conv1 (7x7/2, 3 -> 64) on csrc/stem_conv.cu: forward and weight
+    gradient as mma.sync implicit GEMMs that stream the 64-channel side once."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        L = _lib.lib()
+        xc = _nhwc(x.to(torch.bfloat16))
+        N, _, H, W = xc.shape
+        w = weight.detach().to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()     # (64,7,7,3)
+        OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((N, OH, OW, 64), dtype=torch.bfloat16, device=x.device).permute(0, 3, 1, 2)
+        _lib.check(L.u2b_stem_conv_fwd(ctypes.c_void_p(xc.data_ptr()), N, H, W, ctypes.c_void_p(w.data_ptr()),
+                                       ctypes.c_void_p(y.data_ptr()), _lib.stream_ptr()), "u2b_stem_conv_fwd")
+        _lib.count_launches(1)
+        ctx.save_for_backward(xc)
+        ctx.wmeta = (weight.dtype,)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (xc,) = ctx.saved_tensors
+        if not ctx.needs_input_grad[1]:
+            return None, None
+        L = _lib.lib()
+        N, _, H, W = xc.shape
+        g = _nhwc(gy.to(torch.bfloat16))
+        nparts = int(L.u2b_stem_conv_wgrad_num_partials(N, H, W))
+        parts = torch.empty((nparts, 64, 160), dtype=torch.float32, device=xc.device)
+        _lib.check(L.u2b_stem_conv_wgrad(ctypes.c_void_p(xc.data_ptr()), ctypes.c_void_p(g.data_ptr()), N, H, W,
+                                         ctypes.c_void_p(parts.data_ptr()), _lib.stream_ptr()), "u2b_stem_conv_wgrad")
+        _lib.count_launches(1)
+        gw = parts.sum(0)[:, :147].reshape(64, 7, 7, 3).to(ctx.wmeta[0]).permute(0, 3, 1, 2)   # channels_last (64,3,7,7)
+        return None, gw
+
+
+def stem_eligible(x, m):
+    return (x.is_cuda and x.dim() == 4 and x.dtype == torch.bfloat16 and m.bias is None and m.groups == 1
+            and m.dilation == (1, 1) and not x.requires_grad
+            and bool(_lib.lib().u2b_stem_conv_supported(m.in_channels, m.out_channels, m.kernel_size[0], m.kernel_size[1],
+                                                        m.stride[0], m.padding[0])))
 
 
 def eligible(x, m):

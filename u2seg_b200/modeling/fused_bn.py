@@ -16,10 +16,11 @@ def _partials(S, C, device):
     """(S, 2C) fp32 workspace; one growing buffer per device (kernels are stream-ordered, each use is consumed by
     the finalize / coefficient kernel enqueued right after it)."""
     need = S * 2 * C
-    buf = _ws.get(device)
+    key = (device, torch.cuda.current_stream(device).cuda_stream)     # one workspace per stream: no cross-stream reuse
+    buf = _ws.get(key)
     if buf is None or buf.numel() < need:
         buf = torch.empty((max(need, 1 << 20),), dtype=torch.float32, device=device)
-        _ws[device] = buf
+        _ws[key] = buf
     return buf
 
 
@@ -74,6 +75,26 @@ def _nhwc(x):
 
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def channel_sum(x):
+    """sum over (N,H,W) of a logical (N,C,H,W) tensor -> (C,) fp32: the bias gradient of a convolution. Runs on the
+    BN statistics kernels (strip partial sums at HBM speed + one small column sum) instead of an fp32 copy of the
+    tensor followed by a generic reduction."""
+    L = _lib.lib()
+    C = x.shape[1]
+    if not (x.is_cuda and x.dtype in _CODE and x.dim() == 4 and x.numel() > 0 and L.u2b_bn_supported(C)):
+        return x.sum(dim=(0, 2, 3), dtype=torch.float32)
+    xc = _nhwc(x)
+    P = xc.numel() // C
+    s = _lib.stream_ptr()
+    S = int(L.u2b_bn_num_strips(P, C))
+    part = _partials(S, C, xc.device)
+    _lib.check(L.u2b_bn_stats(_CODE[xc.dtype], _p(xc), P, C, _p(part), s), "u2b_bn_stats")
+    sums = torch.empty((2 * C,), dtype=torch.float32, device=xc.device)
+    _lib.check(L.u2b_bn_sum_partials(_p(part), S, 2 * C, _p(sums), s), "u2b_bn_sum_partials")
+    _lib.count_launches(2)
+    return sums[:C]
 
 
 class _BNAct(torch.autograd.Function):
@@ -166,3 +187,77 @@ def bn_act(x, bn, residual=None, relu=False):
 def supported(x, bn):
     return (x.is_cuda and x.dtype in _CODE and x.dim() == 4 and bn.training and bn.affine
             and bool(_lib.lib().u2b_bn_supported(int(x.shape[1]))))
+
+
+class _GNAct(torch.autograd.Function):
+    """relu(GroupNorm(x)) on NHWC activations (layers/batch_norm.py get_norm("GN") = nn.GroupNorm(32, C), used by
+    the semantic head, semantic_seg.py:180-200). The reference's kernel needs NCHW-contiguous fp32: under channels_last
+    autocast that is a layout copy in, a layout copy out and the same again in backward. Here each image goes through
+    the strip-reduce / apply kernels of csrc/batchnorm.cu in place (NHWC, activation dtype) with the group statistics
+    folded by u2b_gn_finalize / u2b_gn_bwd_coeff; ReLU is fused in both directions."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, G, eps, relu):
+        L = _lib.lib()
+        s = _lib.stream_ptr()
+        xc = _nhwc(x)
+        N, C, H, W = xc.shape
+        HW = H * W
+        dt = _CODE[xc.dtype]
+        dev = xc.device
+        es = xc.element_size()
+        w32, b32 = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        S = int(L.u2b_bn_num_strips(HW, C))
+        part = _partials(S, C, dev)
+        stats = torch.empty((N, 4 * C), dtype=torch.float32, device=dev)
+        y = torch.empty((N, H, W, C), dtype=xc.dtype, device=dev).permute(0, 3, 1, 2)
+        for n in range(N):
+            xn = ctypes.c_void_p(xc.data_ptr() + n * HW * C * es)
+            yn = ctypes.c_void_p(y.data_ptr() + n * HW * C * es)
+            st = ctypes.c_void_p(stats.data_ptr() + n * 4 * C * 4)
+            _lib.check(L.u2b_bn_stats(dt, xn, HW, C, _p(part), s), "u2b_bn_stats")
+            _lib.check(L.u2b_gn_finalize(_p(part), S, HW, G, _p(w32), _p(b32), float(eps), st, C, s), "u2b_gn_finalize")
+            _lib.check(L.u2b_bn_apply(dt, xn, st, None, int(relu), yn, HW, C, s), "u2b_bn_apply")
+        _lib.count_launches(3 * N)
+        ctx.save_for_backward(xc, y if relu else torch.empty(0), w32, stats)
+        ctx.meta = (G, relu, weight.dtype, bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        L = _lib.lib()
+        s = _lib.stream_ptr()
+        xc, y, w32, stats = ctx.saved_tensors
+        G, relu, wdt, bdt = ctx.meta
+        N, C, H, W = xc.shape
+        HW = H * W
+        dt = _CODE[xc.dtype]
+        dev = xc.device
+        es = xc.element_size()
+        g = _nhwc(gy.to(xc.dtype))
+        S = int(L.u2b_bn_num_strips(HW, C))
+        part = _partials(S, C, dev)
+        coeff = torch.empty((3 * C,), dtype=torch.float32, device=dev)
+        gwb = torch.empty((2 * C,), dtype=torch.float32, device=dev)
+        dx = torch.empty((N, H, W, C), dtype=xc.dtype, device=dev).permute(0, 3, 1, 2)
+        for n in range(N):
+            off = n * HW * C * es
+            xn, gn, dn = (ctypes.c_void_p(t.data_ptr() + off) for t in (xc, g, dx))
+            yn = ctypes.c_void_p(y.data_ptr() + off) if relu else None
+            st = ctypes.c_void_p(stats.data_ptr() + n * 4 * C * 4)
+            _lib.check(L.u2b_bn_bwd_reduce(dt, gn, xn, yn, st, HW, C, _p(part), s), "u2b_bn_bwd_reduce")
+            _lib.check(L.u2b_gn_bwd_coeff(_p(part), S, HW, G, st, _p(w32), _p(coeff), _p(gwb), int(n > 0), C, s),
+                       "u2b_gn_bwd_coeff")
+            _lib.check(L.u2b_bn_bwd_apply(dt, gn, xn, yn, _p(coeff), dn, None, HW, C, s), "u2b_bn_bwd_apply")
+        _lib.count_launches(3 * N)
+        return dx, gwb[:C].to(wdt), gwb[C:].to(bdt), None, None, None
+
+
+def gn_supported(x, gn):
+    return (x.is_cuda and x.dtype in _CODE and x.dim() == 4 and gn.affine and x.numel() > 0
+            and bool(_lib.lib().u2b_gn_supported(int(x.shape[1]), int(gn.num_groups))))
+
+
+def gn_act(x, gn, relu=False):
+    """relu(GroupNorm(x)) for an nn.GroupNorm module; output keeps x's dtype and NHWC storage."""
+    return _GNAct.apply(x, gn.weight, gn.bias, int(gn.num_groups), float(gn.eps), bool(relu))

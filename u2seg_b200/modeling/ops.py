@@ -51,6 +51,8 @@ def batch_norm(x, bn, relu=False):
 
 
 FUSED_BN = True     # SyncBN + residual + ReLU through libu2b200 (csrc/batchnorm.cu) in training mode
+FUSED_GN = True     # GroupNorm + ReLU (semantic head) through the same NHWC kernels, per image
+STEM_KERNEL = True  # csrc/stem_conv.cu for the 7x7/2 3->64 stem (bf16 autocast only)
 
 
 def _norm_act(y, m, residual):
@@ -65,6 +67,12 @@ def _norm_act(y, m, residual):
                         m.norm.num_batches_tracked.add_(1)
                     return fused_bn.bn_act(y, m.norm, residual, is_relu)
             y = batch_norm(y, m.norm)
+        elif FUSED_GN and isinstance(m.norm, nn.GroupNorm) and residual is None and \
+                (m.activation is None or m.activation in (F.relu, F.relu_)):
+            from . import fused_bn
+            if fused_bn.gn_supported(y, m.norm):
+                return fused_bn.gn_act(y, m.norm, m.activation is not None)
+            y = m.norm(y)
         else:
             y = m.norm(y)
     if residual is not None:
@@ -81,6 +89,11 @@ def conv_norm_act(x, m, residual=None):
         y = conv_tc.try_conv(x, m, residual)
         if y is not None:
             return y
+    if STEM_KERNEL and m.in_channels == 3 and x.is_cuda:
+        from . import conv_tc
+        xa = x.to(torch.get_autocast_dtype("cuda")) if torch.is_autocast_enabled("cuda") else x
+        if conv_tc.stem_eligible(xa, m):
+            return _norm_act(conv_tc._StemConv.apply(xa, m.weight), m, residual)
     y = F.conv2d(x, m.weight, m.bias, m.stride, m.padding, m.dilation, m.groups)
     return _norm_act(y, m, residual)
 
