@@ -87,10 +87,11 @@ int u2b_roi_align_fwd(int dtype, int num_levels, const void* const* feats, const
                       const int32_t* ws, const float* scales, int64_t C, const float* rois5,
                       const int32_t* levels, int64_t K, int P, void* out, u2b_stream_t stream);
 
-/* backward of the above: accumulates into grad_feats[l] (N, H_l, W_l, C) fp32, zeroed by the caller. */
+/* backward of the above: accumulates grad_scale * d(out)/d(feats) into grad_feats[l] (N, H_l, W_l, C) fp32, zeroed
+ * by the caller. grad_scale folds cascade_rcnn.py:20-28 _ScaleGradient (1/num_stages) into the kernel; 1 otherwise. */
 int u2b_roi_align_bwd(int dtype, int num_levels, float* const* grad_feats, const int32_t* hs,
                       const int32_t* ws, const float* scales, int64_t C, const float* rois5,
-                      const int32_t* levels, int64_t K, int P, const void* grad_out,
+                      const int32_t* levels, int64_t K, int P, const void* grad_out, float grad_scale,
                       u2b_stream_t stream);
 
 /* layers/mask_ops.py:74-147 paste_masks_in_image: masks (N, M, M) fp32 probabilities, boxes (N, 4)
@@ -144,6 +145,8 @@ int u2b_iou_match(const float* gt, int64_t G, const uint8_t* gt_valid, const flo
  * (max_keep < 0: keep all). valid (n bytes in the ORIGINAL box order, nullable): boxes with valid[i] == 0 are
  * neither kept nor suppress anything (fixed-capacity buffers). No host synchronisation. */
 size_t u2b_nms_workspace_bytes(int64_t n);
+/* developer instrumentation of the scan kernel (tools/nms_profile.py); not part of the drop-in surface */
+int u2b_debug_nms_profile(int enable, uint64_t* out6);
 int u2b_batched_nms(const float* boxes, const int64_t* cats, const int64_t* order, const uint8_t* valid, int64_t n,
                     float iou_threshold, int64_t max_keep, int64_t* keep, int32_t* num_keep, void* workspace,
                     size_t workspace_bytes, u2b_stream_t stream);
@@ -217,6 +220,16 @@ int u2b_bn_xchg_bwd_coeff(const float* sums, const void* peers, int world, int r
 /* dx = A*dz + B*x + K; dres = dz when dres != NULL */
 int u2b_bn_bwd_apply(int dtype, const void* dy, const void* x, const void* y, const float* coeff, void* dx,
                      void* dres, int64_t P, int C, u2b_stream_t stream);
+
+/* solver/build.py:63-73 (per-parameter gradient-norm clipping) + solver/build.py:119-139 (torch.optim.SGD: weight
+ * decay, momentum, optional Nesterov) + the refresh of the bf16 compute weights, fused over flat buffers.
+ * grad / master / mom: n fp32 each, same offsets, every parameter starting on a 64-element boundary.
+ * seg_of_chunk (n/64 int32): parameter index owning each 64-element chunk, -1 for padding. seg_wd / seg_coef: per
+ * parameter weight decay and clip coefficient min(1, max_norm/(norm+1e-6)) (seg_coef nullable: no clipping).
+ * lr: device scalar. w16 (nullable): bf16 copy of master[w16_begin : n], refreshed in the same pass. */
+int u2b_sgd_step_segments(const float* grad, float* master, float* mom, void* w16, int64_t w16_begin,
+                          const int32_t* seg_of_chunk, const float* seg_wd, const float* seg_coef, const float* lr,
+                          float momentum, int nesterov, int64_t n, u2b_stream_t stream);
 
 #ifdef __cplusplus
 }

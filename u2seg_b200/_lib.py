@@ -34,7 +34,7 @@ SIGNATURES = {
     "u2b_roi_align_fwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                   c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "u2b_roi_align_bwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
-                                  c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+                                  c_void_p, c_int64, c_int, c_void_p, c_float, c_void_p]),
     "u2b_paste_masks": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "u2b_crop_resize_masks": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p,
                                       c_void_p, c_void_p]),
@@ -46,6 +46,9 @@ SIGNATURES = {
     "u2b_stem_conv_fwd": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "u2b_stem_conv_wgrad_num_partials": (c_int, [c_int64, c_int, c_int]),
     "u2b_stem_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "u2b_sgd_step_segments": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_float, c_int, c_int64, c_void_p]),
+    "u2b_debug_nms_profile": (c_int, [c_int, c_void_p]),
     "u2b_upsample_ce_num_partials": (c_int64, [c_int64, c_int, c_int]),
     "u2b_upsample_ce_supported": (c_int, [c_int, c_int]),
     "u2b_upsample_ce": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int64, c_void_p,

@@ -140,36 +140,52 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ ca
 }
 
 // Sequential part of greedy NMS, on the device. One CTA walks the sorted boxes in blocks of 64. The 64 mask rows of
-// a block (64 x col_blocks words) are staged in shared memory with cp.async, double buffered, so that the global-load
-// latency of block b+1 hides behind the work on block b and nothing on the serial chain touches global memory:
-// thread 0 resolves the 64 intra-block decisions from the diagonal words (registers + shared memory), then thread j
-// ORs the kept rows' word j into `removed[j]` (one owner per word: no atomics). Stops as soon as max_keep boxes are
-// kept (proposal_utils.py:122 `keep[:post_nms_topk]`).
-__device__ __forceinline__ void nms_stage_tile(unsigned long long* __restrict__ dst,
-                                               const unsigned long long* __restrict__ mask, int b, int n,
-                                               int col_blocks) {
-  const int rows = min(64, n - b * 64);
-  const int words = rows * col_blocks;
-  const unsigned long long* src = mask + static_cast<size_t>(b) * 64 * col_blocks;
-  for (int i = threadIdx.x; i < words; i += blockDim.x) {
-    const unsigned int sa = static_cast<unsigned int>(__cvta_generic_to_shared(dst + i));
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(src + i) : "memory");
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
+// a block (only the columns >= the block's own, rows padded to an even number of words) are staged in shared memory
+// by the TMA engine — one cp.async.bulk per row issued by a single thread, completion on an mbarrier, double
+// buffered — so the load of block b+1 hides behind the work on block b at a cost of 64 instructions per block, and
+// nothing on the serial chain touches global memory: thread 0 resolves the 64 intra-block decisions from the
+// diagonal words (registers), then two threads per later column OR the kept rows' words into `removed[]`.
+// Stops as soon as max_keep boxes are kept (proposal_utils.py:122 `keep[:post_nms_topk]`).
+// developer instrumentation: cycles thread 0 spends per phase of the scan (u2b_debug_nms_profile); off by default
+__device__ unsigned long long g_nms_prof[8];
+__device__ int g_nms_prof_on = 0;
 
 __global__ void __launch_bounds__(256)
 nms_scan_kernel(const unsigned long long* __restrict__ mask, const int64_t* __restrict__ order,
-                const uint8_t* __restrict__ valid, int n, int col_blocks, int max_keep,
+                const uint8_t* __restrict__ valid, int n, int col_blocks, int pitch, int max_keep,
                 int64_t* __restrict__ keep, int* __restrict__ num_keep) {
-  extern __shared__ unsigned long long nms_smem[];
-  unsigned long long* removed = nms_smem;                       // [col_blocks]
-  unsigned long long* tile0 = nms_smem + col_blocks;            // [2][64][col_blocks]
-  const size_t tile_words = static_cast<size_t>(64) * col_blocks;
+  extern __shared__ __align__(16) unsigned long long nms_smem[];
+  unsigned long long* tile0 = nms_smem;                                        // [2][64][pitch]
+  const size_t tile_words = static_cast<size_t>(64) * pitch;
+  unsigned long long* removed = nms_smem + 2 * tile_words;                     // [col_blocks]
+  __shared__ __align__(8) uint64_t full[2];
   __shared__ unsigned long long s_kept;
   __shared__ int s_nk, s_stop;
   const int t = threadIdx.x;
-  nms_stage_tile(tile0, mask, 0, n, col_blocks);
+  const int issuer = 32;            // warp 1 issues the copies; thread 0 (warp 0) runs the serial chain
+
+  auto stage = [&](int b) {         // called by the issuing thread only
+    const int rows = min(64, n - b * 64);
+    const int c0 = b & ~1;          // 16-byte aligned first column
+    const uint32_t row_bytes = static_cast<uint32_t>(pitch - c0) * 8u;
+    unsigned long long* dst = tile0 + (b & 1) * tile_words;
+    ptx::fence_proxy_async();
+    ptx::mbar_arrive_expect_tx(&full[b & 1], row_bytes * rows);
+    for (int i = 0; i < rows; ++i) {
+      const unsigned long long* src = mask + (static_cast<size_t>(b) * 64 + i) * pitch + c0;
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              ptx::smem_u32(dst + static_cast<size_t>(i) * pitch + c0)),
+          "l"(src), "r"(row_bytes), "r"(ptx::smem_u32(&full[b & 1]))
+          : "memory");
+    }
+  };
+
+  if (t == issuer) {
+    ptx::mbar_init(&full[0], 1);
+    ptx::mbar_init(&full[1], 1);
+    ptx::fence_barrier_init();
+  }
   for (int i = t; i < col_blocks; i += blockDim.x) {
     unsigned long long r = 0ULL;
     if (valid)  // boxes flagged invalid (fixed-capacity buffers) start out removed
@@ -178,59 +194,85 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int64_t* __re
     removed[i] = r;
   }
   if (t == 0) { s_nk = 0; s_stop = 0; }
+  __syncthreads();
+  if (t == issuer) stage(0);
+  const bool prof = g_nms_prof_on != 0 && t == 0;
+  long long pc[6] = {0, 0, 0, 0, 0, 0}, tp = prof ? clock64() : 0;
+#define U2B_NMS_TICK(k)              \
+  if (prof) {                        \
+    const long long now = clock64(); \
+    pc[k] += now - tp;               \
+    tp = now;                        \
+  }
   for (int b = 0; b < col_blocks; ++b) {
     const int rows = min(64, n - b * 64);
-    unsigned long long* tile = tile0 + (b & 1) * tile_words;
-    if (b + 1 < col_blocks) {
-      nms_stage_tile(tile0 + ((b + 1) & 1) * tile_words, mask, b + 1, n, col_blocks);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();  // tile b visible to all; removed[] complete from block b-1
+    const unsigned long long* tile = tile0 + (b & 1) * tile_words;
+    if (t == issuer && b + 1 < col_blocks) stage(b + 1);    // buffer (b+1)&1 was released by the sync ending block b-1
+    ptx::mbar_wait(&full[b & 1], (b >> 1) & 1);
+    U2B_NMS_TICK(0)
     const int base = s_nk;
     if (t == 0) {
-      // the 64 dependent decisions of this block: diagonal words in registers, fully unrolled, ALU only
-      unsigned long long d[64];
+      // the 64 dependent decisions of this block. Only 32-bit halves sit on the dependent chain (3 ALU ops per
+      // step: extract bit, make mask, OR-in the masked row): rows 0..31 are decided by the low half of `removed`,
+      // rows 32..63 by the high half (a row's word has no bits at or below its own index). The max_keep cut is taken
+      // afterwards: earlier decisions never depend on later ones.
+      const unsigned long long rem0 = removed[b] | (rows < 64 ? ~0ULL << rows : 0ULL);   // rows past n: removed
+      unsigned int rlo = static_cast<unsigned int>(rem0), rhi = static_cast<unsigned int>(rem0 >> 32);
+      unsigned int klo = 0u, khi = 0u;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) d[i] = tile[static_cast<size_t>(i) * col_blocks + b];
-      unsigned long long rem = removed[b], kw = 0ULL;
-      if (rows < 64) rem |= ~0ULL << rows;       // rows past n (stale shared memory) count as removed
-      int cnt = base;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        const bool take = !((rem >> i) & 1ULL) && cnt < max_keep;
-        rem |= take ? d[i] : 0ULL;
-        kw |= take ? (1ULL << i) : 0ULL;
-        cnt += take ? 1 : 0;
+      for (int i = 0; i < 32; ++i) {
+        const unsigned long long d = tile[static_cast<size_t>(i) * pitch + b];
+        const unsigned int m = ((rlo >> i) & 1u) - 1u;          // all ones when box i is still alive -> kept
+        rlo |= static_cast<unsigned int>(d) & m;
+        rhi |= static_cast<unsigned int>(d >> 32) & m;
+        klo |= m & (1u << i);
       }
-      if (cnt >= max_keep) s_stop = 1;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const unsigned int dh = static_cast<unsigned int>(tile[static_cast<size_t>(32 + i) * pitch + b] >> 32);
+        const unsigned int m = ((rhi >> i) & 1u) - 1u;
+        rhi |= dh & m;
+        khi |= m & (1u << i);
+      }
+      unsigned long long kw = (static_cast<unsigned long long>(khi) << 32) | klo;
+      const int room = max_keep - base;
+      if (__popcll(kw) >= room) {                // reached the cap inside this block: keep the first `room` only
+        while (__popcll(kw) > room) kw &= ~(1ULL << (63 - __clzll(static_cast<long long>(kw))));
+        s_stop = 1;
+      }
       s_kept = kw;
     }
+    U2B_NMS_TICK(1)
     __syncthreads();
+    U2B_NMS_TICK(2)
     const unsigned long long kw = s_kept;
     if (t < rows && ((kw >> t) & 1ULL))   // kept boxes of this block written in parallel, in order
       keep[base + __popcll(kw & ((1ULL << t) - 1ULL))] = order[b * 64 + t];
-    if (t == 0) s_nk = base + __popcll(kw);
     if (s_stop) break;
     {
-      // two threads per later column (kept rows 0..31 / 32..63), loads predicated and independent
-      const int half = t & 1;
+      // two threads per later column: warps 0-3 OR the kept rows 0..31, warps 4-7 rows 32..63 (the kept-bit pattern
+      // is uniform within a warp, so the row tests below are non-divergent and skipped rows cost nothing)
+      const int half = t >> 7;
       const unsigned int bits = static_cast<unsigned int>(kw >> (32 * half));
-      const unsigned long long* trow = tile + static_cast<size_t>(32 * half) * col_blocks;
-      for (int j = b + 1 + (t >> 1); j < col_blocks; j += blockDim.x >> 1) {
+      const unsigned long long* trow = tile + static_cast<size_t>(32 * half) * pitch;
+      for (int j = b + 1 + (t & 127); j < col_blocks; j += 128) {
         unsigned long long acc = 0ULL;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if ((bits >> i) & 1u) acc |= trow[static_cast<size_t>(i) * col_blocks + j];
+          if ((bits >> i) & 1u) acc |= trow[static_cast<size_t>(i) * pitch + j];
         if (acc) atomicOr(&removed[j], acc);
       }
     }
-    __syncthreads();  // all reads of tile b done before it is re-staged two iterations later
+    if (t == 0) s_nk = base + __popcll(kw);
+    U2B_NMS_TICK(3)
+    __syncthreads();  // removed[] complete, s_nk published, all reads of tile b done
+    U2B_NMS_TICK(4)
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#undef U2B_NMS_TICK
   __syncthreads();
-  if (t == 0) *num_keep = s_nk;
+  if (t == 0) *num_keep = s_stop ? s_nk + __popcll(s_kept) : s_nk;
+  if (prof)
+    for (int i = 0; i < 6; ++i) g_nms_prof[i] += static_cast<unsigned long long>(pc[i]);
 }
 
 __global__ void gather_sorted_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ cats,
@@ -247,9 +289,24 @@ __global__ void gather_sorted_kernel(const float4* __restrict__ boxes, const int
 
 extern "C" {
 
+// developer tool: enable != 0 switches the scan's phase counters on; out6 (host, nullable) receives and clears the
+// cycles accumulated so far: [wait tile, serial chain, barrier 1, keep + OR phase, barrier 2, unused]
+int u2b_debug_nms_profile(int enable, uint64_t* out6) {
+  unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  U2B_CUDA(cudaDeviceSynchronize());
+  if (out6) {
+    U2B_CUDA(cudaMemcpyFromSymbol(h, g_nms_prof, sizeof(h)));
+    for (int i = 0; i < 6; ++i) out6[i] = h[i];
+  }
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  U2B_CUDA(cudaMemcpyToSymbol(g_nms_prof, z, sizeof(z)));
+  U2B_CUDA(cudaMemcpyToSymbol(g_nms_prof_on, &enable, sizeof(int)));
+  return 0;
+}
+
 size_t u2b_nms_workspace_bytes(int64_t n) {
-  const size_t cb = static_cast<size_t>((n + 63) / 64);
-  return static_cast<size_t>(n) * 16 + static_cast<size_t>(n) * 8 + static_cast<size_t>(n) * cb * 8 + 256;
+  const size_t pitch = ((static_cast<size_t>((n + 63) / 64) + 1) / 2) * 2;      // mask row pitch: even number of words
+  return static_cast<size_t>(n) * 16 + static_cast<size_t>(n) * 8 + 16 + static_cast<size_t>(n) * pitch * 8 + 256;
 }
 
 // boxes (n,4) fp32 xyxy, cats (n) int64 or NULL, order (n) int64 = indices sorted by score descending
@@ -265,20 +322,22 @@ int u2b_batched_nms(const float* boxes, const int64_t* cats, const int64_t* orde
   U2B_CHECK_ARG(boxes && order && keep && workspace && n > 0, "batched_nms: bad arguments");
   U2B_CHECK_ARG(workspace_bytes >= u2b_nms_workspace_bytes(n), "batched_nms: workspace too small");
   const int cb = static_cast<int>((n + 63) / 64);
-  U2B_CHECK_ARG(static_cast<size_t>(cb) * 8 * 129 <= 220 * 1024, "batched_nms: n=%lld too large (<= %d boxes)",
-                (long long)n, 218 * 64);
+  const int pitch = (cb + 1) / 2 * 2;
+  const size_t smem = (static_cast<size_t>(pitch) * 128 + cb) * 8;   // 2 tiles of 64 x pitch words + removed[cb]
+  U2B_CHECK_ARG(smem <= 220 * 1024, "batched_nms: n=%lld too large (<= %d boxes)", (long long)n, 216 * 64);
+  U2B_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "batched_nms: workspace must be 16-byte aligned");
   uint8_t* w = static_cast<uint8_t*>(workspace);
   float4* sboxes = reinterpret_cast<float4*>(w);
   int64_t* scats = reinterpret_cast<int64_t*>(w + static_cast<size_t>(n) * 16);
-  unsigned long long* mask = reinterpret_cast<unsigned long long*>(w + static_cast<size_t>(n) * 24);
+  unsigned long long* mask =
+      reinterpret_cast<unsigned long long*>(w + (static_cast<size_t>(n) * 24 + 15) / 16 * 16);    // 16-byte aligned rows
   gather_sorted_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const float4*>(boxes), cats, order, (int)n, sboxes, scats);
   U2B_LAUNCH_CHECK();
   // lower-triangular blocks are never read by the scan (j starts at i>>6), no memset needed
   dim3 grid(cb, cb);
-  nms_mask_kernel<<<grid, 64, 0, stream>>>(sboxes, cats ? scats : nullptr, (int)n, iou_threshold, mask, cb);
+  nms_mask_kernel<<<grid, 64, 0, stream>>>(sboxes, cats ? scats : nullptr, (int)n, iou_threshold, mask, pitch);
   U2B_LAUNCH_CHECK();
-  const size_t smem = static_cast<size_t>(cb) * 8 * 129;   // removed[cb] + 2 tiles of 64 x cb words
   static bool scan_attr = false;
   if (!scan_attr) {
     U2B_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -289,7 +348,7 @@ int u2b_batched_nms(const float* boxes, const int64_t* cats, const int64_t* orde
     U2B_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int32_t), stream));
     return 0;
   }
-  nms_scan_kernel<<<1, 256, smem, stream>>>(mask, order, valid, (int)n, cb, mk, keep, num_keep);
+  nms_scan_kernel<<<1, 256, smem, stream>>>(mask, order, valid, (int)n, cb, pitch, mk, keep, num_keep);
   U2B_LAUNCH_CHECK();
   return 0;
 }

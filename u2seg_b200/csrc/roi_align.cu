@@ -183,11 +183,40 @@ roi_align_fwd_kernel(Pyramid pyr, int C, const float* __restrict__ rois,
   }
 }
 
+// One axis of torchvision's bilinear_interpolate: the two pixels a sample touches and their weights.
+struct AxisSample {
+  int lo, hi;
+  float wlo, whi;
+  bool valid;
+};
+__device__ __forceinline__ AxisSample axis_sample(float v, int size) {
+  AxisSample a;
+  a.valid = !(v < -1.0f || v > static_cast<float>(size));
+  if (v <= 0.f) v = 0.f;
+  a.lo = static_cast<int>(v);
+  if (a.lo >= size - 1) {
+    a.hi = a.lo = size - 1;
+    v = static_cast<float>(a.lo);
+  } else {
+    a.hi = a.lo + 1;
+  }
+  a.whi = v - a.lo;
+  a.wlo = 1.f - a.whi;
+  return a;
+}
+
 // grad_out: (K, P, P, C) of T; grad feature maps: fp32 NHWC per level (pre-zeroed by the caller).
+// One warp per output bin, lanes over channels. A bin's samples form a product grid and the bilinear weight of a
+// sample is wy * wx, so the total weight a feature pixel (py, px) receives from the bin factorises into
+// WY[py] * WX[px] (sums over the sample rows / columns that touch it). The kernel therefore issues ONE vector
+// atomic per touched pixel ((g+1)^2 of them for a g x g sample grid, samples being < 1 px apart) instead of four
+// per sample (4 g^2): 1.8x fewer for g = 2, 2.6x for g = 4. WX is computed once per bin, one pixel column per lane,
+// and broadcast with shuffles; bins wider than 32 columns (not produced by the level assignment) fall back to
+// the per-sample path.
 template <typename T>
 __global__ void __launch_bounds__(256)
 roi_align_bwd_kernel(Pyramid pyr, int C, const float* __restrict__ rois,
-                     const int32_t* __restrict__ levels, int K, int P, const T* __restrict__ gout) {
+                     const int32_t* __restrict__ levels, int K, int P, const T* __restrict__ gout, float grad_scale) {
   constexpr int VN = Vec<T>::N;
   const int lane = threadIdx.x & 31;
   const long long bin = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -201,15 +230,73 @@ roi_align_bwd_kernel(Pyramid pyr, int C, const float* __restrict__ rois,
   float* gfeat = pyr.grad[lvl] + static_cast<size_t>(b) * H * W * C;
   const BinGeom g = bin_geometry(r, pyr.scale[lvl], P);
   const T* go = gout + static_cast<size_t>(bin) * C;
+  const float y_base = g.start_h + ph * g.bin_h, x_base = g.start_w + pw * g.bin_w;
+
+  // pixel columns touched by the bin: [cx0, cx1]; lane j owns column cx0 + j
+  int cx0 = W, cx1 = -1;
+  for (int ix = 0; ix < g.grid_w; ++ix) {
+    const AxisSample a = axis_sample(x_base + (ix + 0.5f) * g.bin_w / static_cast<float>(g.grid_w), W);
+    if (a.valid) {
+      cx0 = min(cx0, a.lo);
+      cx1 = max(cx1, a.hi);
+    }
+  }
+  int cy0 = H, cy1 = -1;
+  for (int iy = 0; iy < g.grid_h; ++iy) {
+    const AxisSample a = axis_sample(y_base + (iy + 0.5f) * g.bin_h / static_cast<float>(g.grid_h), H);
+    if (a.valid) {
+      cy0 = min(cy0, a.lo);
+      cy1 = max(cy1, a.hi);
+    }
+  }
+  if (cx1 < cx0 || cy1 < cy0) return;             // every sample outside the map: no gradient
+  const int ncols = cx1 - cx0 + 1;
+  if (ncols <= 32) {
+    float wx_lane = 0.f;
+    {
+      const int cx = cx0 + lane;
+      for (int ix = 0; ix < g.grid_w; ++ix) {
+        const AxisSample a = axis_sample(x_base + (ix + 0.5f) * g.bin_w / static_cast<float>(g.grid_w), W);
+        if (a.valid) wx_lane += (a.lo == cx ? a.wlo : 0.f) + (a.hi == cx ? a.whi : 0.f);
+      }
+    }
+    const float inv_count = grad_scale / g.count;
+    for (int c0 = lane * VN; c0 < C || c0 - lane * VN < C; c0 += 32 * VN) {   // whole warp iterates together
+      const bool act = c0 < C;
+      float gv[VN];
+      if (act) {
+        Vec<T>::load(go + c0, gv);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) gv[i] *= inv_count;
+      }
+      for (int py = cy0; py <= cy1; ++py) {
+        float wy = 0.f;
+        for (int iy = 0; iy < g.grid_h; ++iy) {
+          const AxisSample a = axis_sample(y_base + (iy + 0.5f) * g.bin_h / static_cast<float>(g.grid_h), H);
+          if (a.valid) wy += (a.lo == py ? a.wlo : 0.f) + (a.hi == py ? a.whi : 0.f);
+        }
+        for (int j = 0; j < ncols; ++j) {
+          const float w = wy * __shfl_sync(0xffffffffu, wx_lane, j);
+          if (!act || w == 0.f) continue;
+          float* dst = gfeat + (static_cast<size_t>(py) * W + cx0 + j) * C + c0;
+#pragma unroll
+          for (int i = 0; i < VN; i += 4)
+            atomicAdd(reinterpret_cast<float4*>(dst + i),
+                      make_float4(w * gv[i], w * gv[i + 1], w * gv[i + 2], w * gv[i + 3]));
+        }
+      }
+    }
+    return;
+  }
   for (int c0 = lane * VN; c0 < C; c0 += 32 * VN) {
     float gv[VN];
     Vec<T>::load(go + c0, gv);
 #pragma unroll
-    for (int i = 0; i < VN; ++i) gv[i] /= g.count;
+    for (int i = 0; i < VN; ++i) gv[i] = gv[i] / g.count * grad_scale;
     for (int iy = 0; iy < g.grid_h; ++iy) {
-      const float y = g.start_h + ph * g.bin_h + (iy + 0.5f) * g.bin_h / static_cast<float>(g.grid_h);
+      const float y = y_base + (iy + 0.5f) * g.bin_h / static_cast<float>(g.grid_h);
       for (int ix = 0; ix < g.grid_w; ++ix) {
-        const float x = g.start_w + pw * g.bin_w + (ix + 0.5f) * g.bin_w / static_cast<float>(g.grid_w);
+        const float x = x_base + (ix + 0.5f) * g.bin_w / static_cast<float>(g.grid_w);
         const Sample s = make_sample(y, x, H, W);
         if (!s.valid) continue;
         const int offs[4] = {s.o1, s.o2, s.o3, s.o4};
@@ -288,7 +375,7 @@ int u2b_roi_align_fwd(int dtype, int num_levels, const void* const* feats, const
 // grad_feats[l]: (N, H_l, W_l, C) fp32, must be zero-initialised by the caller (accumulated into).
 int u2b_roi_align_bwd(int dtype, int num_levels, float* const* grad_feats, const int32_t* hs,
                       const int32_t* ws, const float* scales, int64_t C, const float* rois5,
-                      const int32_t* levels, int64_t K, int P, const void* grad_out,
+                      const int32_t* levels, int64_t K, int P, const void* grad_out, float grad_scale,
                       cudaStream_t stream) {
   if (K == 0) return 0;
   Pyramid p;
@@ -301,12 +388,12 @@ int u2b_roi_align_bwd(int dtype, int num_levels, float* const* grad_feats, const
   const long long bins = static_cast<long long>(K) * P * P;
   const unsigned grid = static_cast<unsigned>((bins + 7) / 8);
   if (dtype == 0)
-    roi_align_bwd_kernel<float><<<grid, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (const float*)grad_out);
+    roi_align_bwd_kernel<float><<<grid, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (const float*)grad_out, grad_scale);
   else if (dtype == 1)
-    roi_align_bwd_kernel<__half><<<grid, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (const __half*)grad_out);
+    roi_align_bwd_kernel<__half><<<grid, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (const __half*)grad_out, grad_scale);
   else if (dtype == 2)
     roi_align_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P,
-                                                                 (const __nv_bfloat16*)grad_out);
+                                                                 (const __nv_bfloat16*)grad_out, grad_scale);
   else {
     u2b_set_error("roi_align_bwd: unknown dtype %d", dtype);
     return U2B_ERR_BAD_ARG;

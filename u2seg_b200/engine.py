@@ -145,9 +145,22 @@ class Trainer:
         self._low_params = [p for p in self.params if id(p) in low_ids]
         others = [p for p in self.params if id(p) not in low_ids]
         n = sum(_aligned(p.numel()) for p in self._low_params)
-        self._master_flat = torch.zeros(n, dtype=torch.float32, device=self.device)
-        self._w16_flat = torch.zeros(n, dtype=torch.bfloat16, device=self.device)
         self.grads = FlatGradients(others, self.device, tail=self._low_params)
+        n_head = self.grads.n_head
+        # ONE fp32 master buffer for every parameter, laid out exactly like the flat gradient buffer: first the
+        # parameters that stay fp32 (norm layers; the modules' tensors become views of it), then the masters of the
+        # bf16 compute weights. Momentum uses the same offsets (csrc/optimizer.cu walks the three in lockstep).
+        self._master_all = torch.zeros(n_head + n, dtype=torch.float32, device=self.device)
+        self._mom_all = torch.zeros_like(self._master_all)
+        self._master_flat = self._master_all[n_head:]
+        self._w16_flat = torch.zeros(n, dtype=torch.bfloat16, device=self.device)
+        off = 0
+        for p in others:
+            v = _like_view(self._master_all, off, p)
+            v.copy_(p.data)
+            p.data = v
+            off += _aligned(p.numel())
+        assert off == n_head
         self._masters = {}
         off = 0
         for p in self._low_params:
@@ -162,6 +175,23 @@ class Trainer:
         tail = {id(p): v for p, v in zip(self._low_params, self.grads.tail_views)}
         self._upd_params = [self._masters.get(id(p), p) for p in self.params]       # what SGD updates (fp32)
         self._upd_grads = [tail.get(id(p), p.grad) for p in self.params]            # fp32 gradients, same order
+        # segment tables of the fused optimizer kernel: parameters in buffer order
+        seg_params = others + self._low_params
+        norm_ids = set()
+        for m in self.model.modules():
+            if isinstance(m, (torch.nn.modules.batchnorm._BatchNorm, torch.nn.GroupNorm)):
+                norm_ids.update(id(p) for p in m.parameters(recurse=False))
+        sv = self.cfg.SOLVER
+        chunk_seg = torch.full((self._master_all.numel() // 64,), -1, dtype=torch.int32)
+        off = 0
+        for i, p in enumerate(seg_params):
+            chunk_seg[off // 64:(off + _aligned(p.numel())) // 64] = i
+            off += _aligned(p.numel())
+        self._seg_chunk = chunk_seg.to(self.device)
+        self._seg_wd = torch.tensor([sv.WEIGHT_DECAY_NORM if id(p) in norm_ids else sv.WEIGHT_DECAY for p in seg_params],
+                                    dtype=torch.float32, device=self.device)
+        by_id = {id(p): g for p, g in zip(self.params, self._upd_grads)}
+        self._seg_grads = [by_id[id(p)] for p in seg_params]                         # fp32 gradient views, buffer order
 
     def master_parameters(self):
         """fp32 parameters by name (the bf16 compute copies are an implementation detail of the static step)."""
@@ -179,6 +209,26 @@ class Trainer:
             dist.broadcast(t, src)
         if self.lowp:
             self._w16_flat.copy_(self._master_flat)
+
+    @torch.no_grad()
+    def _fused_clip_sgd(self):
+        """Per-parameter gradient-norm clipping + SGD(momentum, weight decay) + refresh of the bf16 compute weights in
+        one pass over the flat buffers (csrc/optimizer.cu); the LR comes from a device scalar (graph-safe)."""
+        from . import _lib
+        import ctypes
+        sv = self.cfg.SOLVER
+        coef = None
+        if self.clip is not None:
+            assert self.clip.CLIP_TYPE == "norm"
+            norms = torch.stack(torch._foreach_norm(self._seg_grads, self.clip.NORM_TYPE))
+            coef = torch.clamp(self.clip.CLIP_VALUE / (norms + 1e-6), max=1.0).float().contiguous()
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None    # noqa: E731
+        _lib.check(_lib.lib().u2b_sgd_step_segments(p(self.grads.flat), p(self._master_all), p(self._mom_all),
+                                                    p(self._w16_flat), self.grads.n_head, p(self._seg_chunk),
+                                                    p(self._seg_wd), p(coef), p(self._lr_t), float(sv.MOMENTUM),
+                                                    int(bool(sv.NESTEROV)), self._master_all.numel(), _lib.stream_ptr()),
+                   "u2b_sgd_step_segments")
+        _lib.count_launches(1)
 
     def _groups(self):
         """(fp32 params, fp32 grads, weight decay) per optimizer group."""
@@ -242,25 +292,78 @@ class Trainer:
             for dsts, srcs in buckets.values():
                 torch._foreach_copy_(dsts, srcs)
         self.grads.all_reduce_mean()          # one NCCL all-reduce of the flat gradient buffer (captured with the graph)
-        self._clip_foreach()
-        self._sgd_foreach()
+        if self.lowp and os.environ.get("U2B_FUSED_OPT", "1") != "0":
+            self._fused_clip_sgd()
+        else:
+            self._clip_foreach()
+            self._sgd_foreach()
         return {k: v.detach() for k, v in loss_dict.items()}, flag
 
-    def _load_static_inputs(self, batched_inputs):
+    def _pack(self, batched_inputs):
+        """Reference-format batch (host or device tensors) -> padded device tensors. Host tensors are copied one by
+        one (pinned memory: asynchronous) before the device-side packing."""
         from .modeling.static_train import pack_batch
+        dev_batch = []
+        for d in batched_inputs:
+            dev_batch.append({"image": d["image"].to(self.device, non_blocking=True),
+                              "instances": d["instances"].to(self.device, non_blocking=True),
+                              "sem_seg": d["sem_seg"].to(self.device, non_blocking=True)})
         g_max = self.g_max or max(1, max(len(d["instances"]) for d in batched_inputs))
-        packed = pack_batch(batched_inputs, self.device, g_max)
-        if getattr(self, "_static_in", None) is None:
+        if self.g_max is None:
             self.g_max = g_max
+        return pack_batch(dev_batch, self.device, g_max)
+
+    def _load_static_inputs(self, batched_inputs):
+        packed = self._pack(batched_inputs)
+        if getattr(self, "_static_in", None) is None:
             self._static_in = [t.clone() for t in packed]
         else:
             for dst, src in zip(self._static_in, packed):
                 assert dst.shape == src.shape, "static_graph needs constant input shapes (%s vs %s)" % (dst.shape, src.shape)
                 dst.copy_(src, non_blocking=True)
 
+    def prefetch(self, batched_inputs):
+        """Stage the NEXT step's batch while the current step is still running on the GPU: host->device copies and
+        the packing run on a copy stream into staging buffers; the following run_step(None) only copies them
+        device-to-device into the graph's static inputs. (The reference overlaps data loading with compute through
+        DataLoader workers, data/build.py; H2D itself happens in rcnn.py:223-234 preprocess_image.)"""
+        assert self.static_graph, "prefetch() belongs to the static-graph step"
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._staged_evt, self._staging_free = torch.cuda.Event(), torch.cuda.Event()
+            self._staging, self._staged = None, False
+            self._staging_free.record(torch.cuda.current_stream(self.device))
+        cs = self._copy_stream
+        cs.wait_event(self._staging_free)          # the previous staged batch has been consumed
+        with torch.cuda.stream(cs):
+            packed = self._pack(batched_inputs)
+            if self._staging is None:
+                self._staging = [t.clone() for t in packed]
+            else:
+                for dst, src in zip(self._staging, packed):
+                    assert dst.shape == src.shape, "static_graph needs constant input shapes"
+                    dst.copy_(src, non_blocking=True)
+            self._staged_evt.record(cs)
+        self._staged = True
+
+    def _consume_staged(self):
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(self._staged_evt)
+        if getattr(self, "_static_in", None) is None:
+            self._static_in = [t.clone() for t in self._staging]
+        else:
+            for dst, src in zip(self._static_in, self._staging):
+                dst.copy_(src, non_blocking=True)
+        self._staging_free.record(main)
+        self._staged = False
+
     def _run_step_static(self, batched_inputs):
         self._lr_t.fill_(self.sched.lr(self.iter))
-        self._load_static_inputs(batched_inputs)
+        if batched_inputs is None:
+            assert getattr(self, "_staged", False), "run_step(None) needs a batch staged with prefetch()"
+            self._consume_staged()
+        else:
+            self._load_static_inputs(batched_inputs)
         if self._graph is None:
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()

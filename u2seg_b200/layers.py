@@ -99,8 +99,9 @@ class _MultiLevelROIAlign(torch.autograd.Function):
     """out[K, C, P, P] (channels_last) = ROIAlignV2 of rois on their assigned pyramid level."""
 
     @staticmethod
-    def forward(ctx, rois5, levels, P, scales, token, holder, *feats):
+    def forward(ctx, rois5, levels, P, scales, token, holder, grad_scale, *feats):
         ctx.holder = holder
+        ctx.grad_scale = float(grad_scale)
         L = _lib.lib()
         f0 = feats[0]
         _need_cuda(f0, "roi_align")
@@ -143,12 +144,13 @@ class _MultiLevelROIAlign(torch.autograd.Function):
             sc = _arr(ctypes.c_float, list(scales))
             _lib.check(L.u2b_roi_align_bwd(_DTYPE_CODE[dt], len(shapes), ptrs, hs, ws, sc, C, _lib.ptr(rois5),
                                            _lib.ptr(levels) if ctx.has_levels else None, K, P,
-                                           ctypes.c_void_p(g.data_ptr()), _lib.stream_ptr()), "u2b_roi_align_bwd")
+                                           ctypes.c_void_p(g.data_ptr()), ctx.grad_scale, _lib.stream_ptr()),
+                       "u2b_roi_align_bwd")
             _lib.count_launches(1)
         if shared:   # gradients reach the features through _PoolTap; the token only orders the backward passes
-            return (None, None, None, None, gout.new_zeros(()), None) + tuple(None for _ in shapes)
+            return (None, None, None, None, gout.new_zeros(()), None, None) + tuple(None for _ in shapes)
         outs = [t.permute(0, 3, 1, 2).to(dt) for t in grads]   # logical NCHW views of the NHWC grads
-        return (None, None, None, None, None, None) + tuple(outs)
+        return (None, None, None, None, None, None, None) + tuple(outs)
 
 
 class ROIAlign(nn.Module):
@@ -168,7 +170,7 @@ class ROIAlign(nn.Module):
     def forward(self, input, rois):
         assert rois.dim() == 2 and rois.size(1) == 5
         rois = _aligned(rois, torch.float32)
-        return _MultiLevelROIAlign.apply(rois, None, self.output_size, (self.spatial_scale,), None, None, input)
+        return _MultiLevelROIAlign.apply(rois, None, self.output_size, (self.spatial_scale,), None, None, 1.0, input)
 
 
 def convert_boxes_to_pooler_format(box_tensors):
@@ -196,9 +198,11 @@ class ROIPooler(nn.Module):
         assert len(scales) == self.max_level - self.min_level + 1
         self.canonical_level, self.canonical_box_size = canonical_level, canonical_box_size
 
-    def forward(self, x, box_lists, tap=None):
+    def forward(self, x, box_lists, tap=None, grad_scale=1.0):
         """x: list of (N,C,Hl,Wl); box_lists: list (per image) of (Ni,4) tensors (or objects with .tensor).
-        tap: optional FeatureTap over the same `x` shared by all pooling calls of the step."""
+        tap: optional FeatureTap over the same `x` shared by all pooling calls of the step.
+        grad_scale: factor applied to the gradient flowing back into the features (cascade_rcnn.py:20-28
+        _ScaleGradient fused into the backward kernel)."""
         boxes = [b.tensor if hasattr(b, "tensor") else b for b in box_lists]
         assert len(x) == len(self.scales) and len(boxes) == x[0].size(0)
         rois = _aligned(convert_boxes_to_pooler_format(boxes).float())
@@ -207,8 +211,9 @@ class ROIPooler(nn.Module):
             levels = assign_boxes_to_levels_rois(rois, self.min_level, self.max_level, self.canonical_box_size,
                                                  self.canonical_level)
         if tap is not None and tap.token is not None:
-            return _MultiLevelROIAlign.apply(rois, levels, self.output_size, self.scales, tap.token, tap.holder, *tap.feats)
-        return _MultiLevelROIAlign.apply(rois, levels, self.output_size, self.scales, None, None, *x)
+            return _MultiLevelROIAlign.apply(rois, levels, self.output_size, self.scales, tap.token, tap.holder,
+                                             grad_scale, *tap.feats)
+        return _MultiLevelROIAlign.apply(rois, levels, self.output_size, self.scales, None, None, grad_scale, *x)
 
 
 # --------------------------------------------------------------------------------------

@@ -59,7 +59,7 @@ class _ConvTC(torch.autograd.Function):
         stride, pad, relu, has_bias = ctx.meta
         dt = xc.dtype
         if relu:
-            gy = gy * (y > 0).to(gy.dtype)
+            gy = torch.ops.aten.threshold_backward(gy, y, 0)       # ReLU backward, one kernel
         gy = _nhwc(gy.to(dt))
         gx = gw = gb = None
         R = weight.shape[2]

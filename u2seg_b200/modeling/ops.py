@@ -98,7 +98,25 @@ def conv_norm_act(x, m, residual=None):
     return _norm_act(y, m, residual)
 
 
+def interpolate(x, **kw):
+    """F.interpolate in the activation dtype. Under CUDA autocast the upsampling ops are promoted to fp32, which
+    turns the FPN top-down path and the semantic head's level sum into fp32 tensors (2x the bytes of every later
+    add / cast); the kernels accumulate in fp32 internally either way, so only the stored result is bf16."""
+    if x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and torch.is_autocast_enabled("cuda"):
+        with torch.autocast("cuda", enabled=False):
+            return F.interpolate(x, **kw)
+    return F.interpolate(x, **kw)
+
+
+class Upsample(nn.Upsample):
+    """nn.Upsample through `interpolate` above (no parameters: state_dict unchanged)."""
+
+    def forward(self, x):
+        return interpolate(x, size=self.size, scale_factor=self.scale_factor, mode=self.mode,
+                           align_corners=self.align_corners)
+
+
 def lateral_add_upsample(lateral, feat, prev):
     """fpn.py:153-156: lateral(feat) + F.interpolate(prev, scale_factor=2, mode='nearest')."""
-    td = F.interpolate(prev, scale_factor=2.0, mode="nearest")
+    td = interpolate(prev, scale_factor=2.0, mode="nearest")
     return lateral(feat) + td

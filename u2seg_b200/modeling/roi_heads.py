@@ -388,9 +388,9 @@ class CascadeROIHeads(nn.Module):
         return proposals
 
     def _run_stage(self, feats, proposals, stage):
-        x = self.box_pooler(feats, [p.proposal_boxes for p in proposals], tap=self._tap)
-        if self.training:
-            x = _ScaleGradient.apply(x, 1.0 / self.num_cascade_stages)
+        # cascade_rcnn.py:283 _ScaleGradient(1/num_stages) on the pooled features: folded into the pooler's backward
+        x = self.box_pooler(feats, [p.proposal_boxes for p in proposals], tap=self._tap,
+                            grad_scale=1.0 / self.num_cascade_stages if self.training else 1.0)
         return self.box_predictor[stage](self.box_head[stage](x))
 
     def _create_proposals_from_boxes(self, boxes, image_sizes):

@@ -8,6 +8,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ..registry import SEM_SEG_HEADS_REGISTRY
+from . import ops
 from .backbone import Conv2d, ShapeSpec, c2_msra_fill, get_norm
 
 
@@ -30,7 +31,7 @@ class SemSegFPNHead(nn.Module):
                 c2_msra_fill(conv)
                 head_ops.append(conv)
                 if spec.stride != self.common_stride:
-                    head_ops.append(nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False))
+                    head_ops.append(ops.Upsample(scale_factor=2, mode="bilinear", align_corners=False))
             self.scale_heads.append(nn.Sequential(*head_ops))
             self.add_module(name, self.scale_heads[-1])
         self.predictor = Conv2d(c.CONVS_DIM, c.NUM_CLASSES, kernel_size=1, stride=1, padding=0)

@@ -164,8 +164,7 @@ def roi_heads_static(rh, images_size, features, proposals, prop_valid, gt_boxes,
                     nok.append(ok)
                     ngb.append(gt_boxes[n][midx])
                 cur_boxes, cur_cls, cur_ok, cur_gtb = nb, nc, nok, ngb
-        x = rh.box_pooler(feats, cur_boxes, tap=tap)
-        x = _ScaleGrad.apply(x, 1.0 / rh.num_cascade_stages)
+        x = rh.box_pooler(feats, cur_boxes, tap=tap, grad_scale=1.0 / rh.num_cascade_stages)   # cascade_rcnn.py:20-28,283
         scores, deltas = rh.box_predictor[k](rh.box_head[k](x))
         cls_all, ok_all = torch.cat(cur_cls), torch.cat(cur_ok)
         pb, gb = torch.cat(cur_boxes), torch.cat(cur_gtb)
@@ -240,6 +239,7 @@ def forward_train_static(model, images_u8, gt_boxes, gt_classes, gt_valid, gt_ma
 def pack_batch(batched_inputs, device, g_max=None):
     """list[dict] (reference input format, same-size images) -> the padded tensors forward_train_static takes."""
     imgs = torch.stack([d["image"] for d in batched_inputs]).to(device, non_blocking=True)
+    imgs = imgs.contiguous(memory_format=torch.channels_last)      # NHWC bytes: the normalisation below stays NHWC
     G = g_max or max(1, max(len(d["instances"]) for d in batched_inputs))
     N, H, W = len(batched_inputs), imgs.shape[-2], imgs.shape[-1]
     gb = torch.zeros((N, G, 4), dtype=torch.float32, device=device)
