@@ -207,3 +207,42 @@ def test_static_graph_trainer_runs_and_learns():
     assert all(h == h and h < 1e4 for h in hist)
     assert hist[-1] < hist[0]
     assert not torch.equal(tr.model.backbone.fpn_output3.weight.detach(), w0)
+
+
+def test_static_trainer_fused_optimizer_equals_foreach_optimizer():
+    """Trainer(static_graph=True) optimizer step in isolation: the fused clip+SGD+bf16-refresh kernel over the flat
+    master buffer (csrc/optimizer.cu) against the foreach path (torch multi-tensor ops on the per-parameter views,
+    solver/build.py:63-73,119-139) on the real parameter set, fed identical random gradients for 3 steps (the second
+    one large enough to clip). Also checks that the flat-buffer views do not alias."""
+    from u2seg_b200.config import get_u2seg_cfg
+    from u2seg_b200.engine import Trainer
+    cfg = get_u2seg_cfg(800)
+    trainers = []
+    for _ in range(2):
+        torch.manual_seed(0)
+        tr = Trainer(cfg, amp_dtype=torch.bfloat16, static_graph=True)
+        views = sorted((m.data_ptr(), m.data_ptr() + m.numel() * 4) for m in tr._upd_params)
+        assert all(a[1] <= b[0] for a, b in zip(views, views[1:])), "master views overlap"
+        lo, hi = tr._master_all.data_ptr(), tr._master_all.data_ptr() + tr._master_all.numel() * 4
+        assert all(lo <= a and b <= hi for a, b in views)
+        trainers.append(tr)
+    a, b = trainers
+    for x, y in zip(a._upd_params, b._upd_params):
+        assert torch.equal(x, y)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for step, scale in enumerate((1e-3, 3.0, 1e-2)):
+        for tr in (a, b):
+            tr._lr_t.fill_(0.01 * (step + 1))
+        for ga, gb in zip(a._upd_grads, b._upd_grads):        # identical gradients in both trainers' flat buffers
+            r = torch.randn(ga.shape, generator=g, device="cuda") * scale
+            ga.copy_(r)
+            gb.copy_(r)
+        a._fused_clip_sgd()
+        b._clip_foreach()
+        b._sgd_foreach()
+        torch.cuda.synchronize()
+        for (name, ma), mb in zip(a.master_parameters().items(), b.master_parameters().values()):
+            assert torch.allclose(ma, mb, rtol=1e-5, atol=1e-8), (step, name)                 # FLOAT: fma contraction only
+        assert torch.equal(a._w16_flat, a._master_flat.bfloat16())                            # bf16 refresh: exact rounding
+        for pa, pb in zip(a.params, b.params):                                                # what the modules see
+            assert torch.allclose(pa.detach().float(), pb.detach().float(), rtol=1e-2, atol=1e-8)   # bf16 copies: 1 ulp

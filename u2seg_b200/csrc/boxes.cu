@@ -246,23 +246,26 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int64_t* __re
     __syncthreads();
     U2B_NMS_TICK(2)
     const unsigned long long kw = s_kept;
-    if (t < rows && ((kw >> t) & 1ULL))   // kept boxes of this block written in parallel, in order
-      keep[base + __popcll(kw & ((1ULL << t) - 1ULL))] = order[b * 64 + t];
-    if (s_stop) break;
-    {
-      // two threads per later column: warps 0-3 OR the kept rows 0..31, warps 4-7 rows 32..63 (the kept-bit pattern
-      // is uniform within a warp, so the row tests below are non-divergent and skipped rows cost nothing)
+    if (!s_stop) {
+      // two threads per later column: warps 0-3 OR the kept rows 0..31, warps 4-7 rows 32..63. All 32 row words are
+      // loaded first (independent, back to back) and masked with the kept bits afterwards: no load latency is
+      // exposed per row and no divergence.
       const int half = t >> 7;
       const unsigned int bits = static_cast<unsigned int>(kw >> (32 * half));
       const unsigned long long* trow = tile + static_cast<size_t>(32 * half) * pitch;
       for (int j = b + 1 + (t & 127); j < col_blocks; j += 128) {
+        unsigned long long v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = trow[static_cast<size_t>(i) * pitch + j];
         unsigned long long acc = 0ULL;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if ((bits >> i) & 1u) acc |= trow[static_cast<size_t>(i) * pitch + j];
+        for (int i = 0; i < 32; ++i) acc |= ((bits >> i) & 1u) ? v[i] : 0ULL;
         if (acc) atomicOr(&removed[j], acc);
       }
     }
+    if (t < rows && ((kw >> t) & 1ULL))   // kept boxes of this block written in parallel, in order
+      keep[base + __popcll(kw & ((1ULL << t) - 1ULL))] = order[b * 64 + t];
+    if (s_stop) break;
     if (t == 0) s_nk = base + __popcll(kw);
     U2B_NMS_TICK(3)
     __syncthreads();  // removed[] complete, s_nk published, all reads of tile b done

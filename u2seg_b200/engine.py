@@ -39,7 +39,7 @@ class WarmupMultiStepLR:
 
 def _like_view(flat, off, p):
     """A view of flat[off : off+p.numel()] with p's shape AND strides (p dense: contiguous or channels_last)."""
-    return torch.as_strided(flat, p.shape, p.stride(), off)
+    return torch.as_strided(flat, p.shape, p.stride(), flat.storage_offset() + off)   # as_strided offsets are absolute
 
 
 def _aligned(n, a=64):
