@@ -218,7 +218,10 @@ def run_kmeans(args, emit=True):
     achieved = flops / (ms_assign * 1e-3) / 1e12
     roof = {"bound": "tensor", "kernel": "kmeans_assign_kernel (+prepare, refine)", "achieved": achieved,
             "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sus"],
-            "peak_source": peaks["src"] + " bf16 sustained", "traffic": None,
+            "peak_source": peaks["src"] + " bf16 sustained",
+            # dram__bytes_read.sum + dram__bytes_write.sum of kmeans_assign_kernel, one ncu --set full capture at the
+            # BASELINE size (profiles/r01_ncu_kmeans_assign_cl2.txt): 983.9 MB + 8.4 MB = the fp16 embeddings once
+            "traffic": (992.3e6 if (n_loc, KM_D, KM_K) == (1280000, 384, 800) else None), "traffic_unit": "bytes/launch",
             "algorithmic_flops_per_launch": flops, "ms_per_launch": ms_assign}
 
     line = {"metric": "kmeans_embeddings_per_sec", "value": value, "unit": "embeddings/s", "n_gpus": world,

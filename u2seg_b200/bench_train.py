@@ -179,7 +179,10 @@ def conv_tc_roofline(peaks):
     ach = flops / (ms * 1e-3) / 1e12
     return {"bound": "tensor", "kernel": "conv_tc_kernel<256,bf16> (tcgen05 implicit GEMM), FPN output2 / RPN p2 shape",
             "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": ach / peaks["tf_burst"],
-            "peak_source": peaks["src"] + " bf16 burst (kernel timed alone)", "traffic": None,
+            "peak_source": peaks["src"] + " bf16 burst (kernel timed alone)",
+            # dram read 68.3 MB + write 22.9 MB per launch, ncu --set full (profiles/r01_ncu_conv_tc_full_summary.txt);
+            # algorithmic bytes 135.4 MB (in + filter + out): the output is still L2-resident when the kernel ends
+            "traffic": 91.2e6, "traffic_unit": "bytes/launch",
             "algorithmic_flops_per_launch": flops, "ms_per_launch": ms}
 
 
