@@ -1,0 +1,98 @@
+"""Host logic of the static-graph trainer (u2seg_b200/engine.py) on CPU: flat master / gradient / momentum buffers,
+bf16 compute views, segment tables of the fused optimizer kernel, gradient gather, and the foreach optimizer path
+against torch.optim.SGD + per-parameter clip_grad_norm_ (detectron2/solver/build.py:63-73,119-139). No kernels run."""
+import pytest
+import torch
+
+
+@pytest.fixture(scope="module")
+def trainer():
+    from u2seg_b200.config import get_u2seg_cfg
+    from u2seg_b200.engine import Trainer
+    cfg = get_u2seg_cfg(800)
+    cfg.defrost()
+    cfg.MODEL.DEVICE = "cpu"
+    torch.manual_seed(0)
+    return Trainer(cfg, amp_dtype=torch.bfloat16, device=torch.device("cpu"), static_graph=True)
+
+
+def _span(t):
+    return t.data_ptr(), t.data_ptr() + t.numel() * t.element_size()
+
+
+def test_flat_buffers_layout(trainer):
+    tr = trainer
+    assert tr.lowp and len(tr.params) == 248
+    lo, hi = _span(tr._master_all)
+    spans = sorted(_span(m) for m in tr._upd_params)
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])), "master views overlap"
+    assert all(lo <= a and b <= hi for a, b in spans)
+    assert all((a - lo) % 256 == 0 for a, _ in spans)                       # 64-element (256-byte) boundaries
+    glo, ghi = _span(tr.grads.flat)
+    assert tr.grads.flat.numel() == tr._master_all.numel() == tr._mom_all.numel()
+    for m, g in zip(tr._upd_params, tr._upd_grads):                         # same offsets in master and gradient buffers
+        assert m.data_ptr() - lo == g.data_ptr() - glo and m.shape == g.shape and m.stride() == g.stride()
+        assert m.dtype == torch.float32 and g.dtype == torch.float32
+    wlo, whi = _span(tr._w16_flat)
+    n_head = tr.grads.n_head
+    for p in tr._low_params:                                                # bf16 compute copies mirror the master tail
+        m = tr._masters[id(p)]
+        assert p.dtype == torch.bfloat16 and wlo <= p.data_ptr() < whi
+        assert (p.data_ptr() - wlo) // 2 == (m.data_ptr() - lo) // 4 - n_head
+        assert torch.equal(p.detach(), m.bfloat16())
+    low = {id(p) for p in tr._low_params}
+    for p in tr.params:
+        if id(p) not in low:                                                # norm parameters ARE views of the master buffer
+            assert p.dtype == torch.float32 and lo <= p.data_ptr() < lo + n_head * 4
+
+
+def test_segment_tables_and_names(trainer):
+    tr = trainer
+    sv = tr.cfg.SOLVER
+    seg = tr._seg_chunk
+    assert seg.numel() * 64 == tr._master_all.numel() and int(seg.min()) == 0 and int(seg.max()) == 247
+    assert bool((seg[1:] >= seg[:-1]).all())                                # buffer order
+    counts = torch.bincount(seg.long(), minlength=248)
+    lo = tr._master_all.data_ptr()
+    seg_params = [p for p in tr.params if id(p) not in {id(q) for q in tr._low_params}] + tr._low_params
+    by_id = dict(zip((id(p) for p in tr.params), tr._upd_params))
+    names = dict((id(p), n) for n, p in tr.model.named_parameters())
+    for i, p in enumerate(seg_params):
+        m = by_id[id(p)]
+        first = (m.data_ptr() - lo) // 4 // 64
+        assert int(seg[first]) == i and int(counts[i]) == (p.numel() + 63) // 64
+        is_norm = ".norm." in names[id(p)]
+        assert float(tr._seg_wd[i]) == pytest.approx(sv.WEIGHT_DECAY_NORM if is_norm else sv.WEIGHT_DECAY)
+        assert tr._seg_grads[i].data_ptr() - tr.grads.flat.data_ptr() == m.data_ptr() - lo
+    mp = tr.master_parameters()
+    want = {n: p.shape for n, p in tr.model.named_parameters() if p.requires_grad}
+    assert list(mp) == list(want) and all(mp[n].shape == want[n] and mp[n].dtype == torch.float32 for n in want)
+
+
+def test_gather_then_foreach_optimizer_equals_torch_sgd(trainer):
+    tr = trainer
+    sv = tr.cfg.SOLVER
+    g = torch.Generator().manual_seed(7)
+    ref = [m.detach().clone().requires_grad_(True) for m in tr._upd_params]
+    norm = {id(p) for n, p in tr.model.named_parameters() if ".norm." in n}
+    opt = torch.optim.SGD([{"params": [r], "weight_decay": sv.WEIGHT_DECAY_NORM if id(p) in norm else sv.WEIGHT_DECAY}
+                           for r, p in zip(ref, tr.params)], lr=0.02, momentum=sv.MOMENTUM, nesterov=sv.NESTEROV)
+    tr._lr_t.fill_(0.02)
+    for step, scale in enumerate((1e-3, 5.0)):                              # the second step clips
+        for p, r in zip(tr.params, ref):
+            gr = torch.randn(p.shape, generator=g) * scale
+            p.grad = gr.to(p.dtype).contiguous(memory_format=torch.channels_last) if p.dim() == 4 else gr.to(p.dtype)
+            r.grad = p.grad.float().clone()                                 # what the fp32 buffer must receive
+        tr._gather_grads()
+        for dst, r in zip(tr._upd_grads, ref):
+            assert torch.equal(dst, r.grad)
+        for r in ref:
+            torch.nn.utils.clip_grad_norm_(r, tr.clip.CLIP_VALUE, tr.clip.NORM_TYPE)
+        opt.step()
+        tr._clip_foreach()
+        tr._sgd_foreach()
+        for m, r in zip(tr._upd_params, ref):
+            assert torch.allclose(m, r.detach(), rtol=1e-5, atol=1e-7), step
+        assert torch.equal(tr._w16_flat, tr._master_flat.bfloat16())
+    for p in tr.params:
+        p.grad = None

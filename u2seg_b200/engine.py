@@ -268,6 +268,24 @@ class Trainer:
         coef = torch.clamp(self.clip.CLIP_VALUE / (torch.stack(norms) + 1e-6), max=1.0)
         torch._foreach_mul_(grads, list(coef.unbind(0)))
 
+    @torch.no_grad()
+    def _gather_grads(self):
+        """Every parameter's `.grad` (handed over by autograd; bf16 for the bf16 compute weights) -> its fp32 view in
+        the flat gradient buffer, with as few multi-tensor copies as the layouts allow."""
+        dst = self._upd_grads if self._upd_grads is not None else self._flat_views
+        have = [(d, p.grad) for d, p in zip(dst, self.params) if p.grad is not None]
+        if len(have) != len(self.params):
+            self.grads.zero_()                # parameters outside the graph of this step keep a zero gradient
+        # the multi-tensor fast path is all-or-nothing per call: keep same-dtype / same-layout pairs together
+        buckets = {}
+        for d, g in have:
+            key = (g.dtype, d.stride() == g.stride())
+            buckets.setdefault(key, ([], []))
+            buckets[key][0].append(d)
+            buckets[key][1].append(g)
+        for dsts, srcs in buckets.values():
+            torch._foreach_copy_(dsts, srcs)
+
     def _static_step(self):
         from .modeling.static_train import forward_train_static
         # .grad = None: autograd hands over each gradient tensor instead of launching one `grad += g` kernel per
@@ -278,19 +296,7 @@ class Trainer:
         with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
             loss_dict, flag = forward_train_static(self.model, *self._static_in)
         sum(loss_dict.values()).backward()
-        dst = self._upd_grads if self._upd_grads is not None else self._flat_views
-        have = [(d, p.grad) for d, p in zip(dst, self.params) if p.grad is not None]
-        if len(have) != len(self.params):
-            self.grads.zero_()                # parameters outside the graph of this step keep a zero gradient
-        with torch.no_grad():
-            # the multi-tensor fast path is all-or-nothing per call: keep same-dtype / same-layout pairs together
-            buckets = {}
-            for d, g in have:
-                buckets.setdefault((g.dtype, d.stride() == g.stride()), ([], []))
-                buckets[(g.dtype, d.stride() == g.stride())][0].append(d)
-                buckets[(g.dtype, d.stride() == g.stride())][1].append(g)
-            for dsts, srcs in buckets.values():
-                torch._foreach_copy_(dsts, srcs)
+        self._gather_grads()
         self.grads.all_reduce_mean()          # one NCCL all-reduce of the flat gradient buffer (captured with the graph)
         if self.lowp and os.environ.get("U2B_FUSED_OPT", "1") != "0":
             self._fused_clip_sgd()
