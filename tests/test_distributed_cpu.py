@@ -113,3 +113,44 @@ def test_flat_gradient_allreduce_equals_mean_of_rank_gradients():
         gr = torch.cat([p.grad.flatten() for p in model.parameters()])
         tot = gr if tot is None else tot + gr
     assert torch.allclose(flat, tot / 2, rtol=1e-5, atol=1e-6)
+
+
+def _trainer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from u2seg_b200.config import get_u2seg_cfg
+    from u2seg_b200.engine import Trainer
+    cfg = get_u2seg_cfg(800)
+    cfg.defrost()
+    cfg.MODEL.DEVICE = "cpu"
+    torch.manual_seed(rank)                      # ranks start from DIFFERENT weights: the broadcast must fix that
+    tr = Trainer(cfg, amp_dtype=torch.bfloat16, device=torch.device("cpu"), static_graph=True)
+    before = tr._master_all.double().abs().sum()
+    tr.broadcast_parameters(0)
+    ok_w16 = torch.equal(tr._w16_flat, tr._master_flat.bfloat16())
+    views_ok = all(torch.equal(p.detach(), tr._masters[id(p)].bfloat16()) for p in tr._low_params)
+    # the step's gradient exchange: every rank fills its flat buffer, one all-reduce, mean
+    g = torch.Generator().manual_seed(100 + rank)
+    tr.grads.flat.copy_(torch.randn(tr.grads.flat.shape, generator=g))
+    mine = tr.grads.flat[:4096].clone()
+    tr.grads.all_reduce_mean()
+    q.put((rank, float(before), float(tr._master_all.double().abs().sum()), float(tr._master_all.double().sum()),
+           ok_w16, views_ok, mine, tr.grads.flat[:4096].clone()))
+    dist.destroy_process_group()
+
+
+def test_static_trainer_broadcast_and_flat_allreduce_two_ranks():
+    """engine.Trainer under a 2-rank job (gloo, CPU): DDP's initial broadcast (engine/defaults.py:60-79) leaves both ranks
+    with rank 0's fp32 masters and refreshed bf16 compute copies; the flat gradient buffer is averaged by ONE all-reduce."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_trainer_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    out = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    [p.join(60) for p in procs]
+    (_, b0, a0, s0, w0, v0, g0, m0), (_, b1, a1, s1, w1, v1, g1, m1) = out
+    assert b0 != b1                                   # different initial weights ...
+    assert a0 == a1 == b0 and s0 == s1                # ... identical (rank 0's) after the broadcast
+    assert w0 and w1 and v0 and v1
+    assert torch.allclose(m0, (g0 + g1) / 2, rtol=1e-6, atol=1e-7) and torch.equal(m0, m1)
