@@ -96,3 +96,24 @@ def test_gather_then_foreach_optimizer_equals_torch_sgd(trainer):
         assert torch.equal(tr._w16_flat, tr._master_flat.bfloat16())
     for p in tr.params:
         p.grad = None
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_decode_topk_level_equals_decode_all_then_gather(dtype):
+    """static_train.decode_topk_level (decode only the top-k anchors) is BIT-identical to the reference order
+    (rpn.py:497-533 decode every anchor, proposal_utils.py:67-84 top-k, gather)."""
+    from u2seg_b200.modeling.rpn import Box2BoxTransform
+    from u2seg_b200.modeling.static_train import decode_topk_level
+    g = torch.Generator().manual_seed(11)
+    N, A, k = 2, 5000, 300
+    b2b = Box2BoxTransform(weights=(1.0, 1.0, 1.0, 1.0))
+    c = torch.rand(A, 2, generator=g) * 512
+    wh = torch.rand(A, 2, generator=g) * 200 + 4
+    anchors = torch.cat([c - wh / 2, c + wh / 2], 1)
+    logits = torch.randn(N, A, generator=g).to(dtype)
+    deltas = (torch.randn(N, A, 4, generator=g) * 0.5).to(dtype)
+    sc, boxes = decode_topk_level(b2b, anchors, logits, deltas, k)
+    props = b2b.apply_deltas(deltas.reshape(-1, 4), anchors.unsqueeze(0).expand(N, -1, -1).reshape(-1, 4)).view(N, -1, 4)
+    sc_ref, idx = logits.float().topk(k, dim=1)
+    want = props[torch.arange(N)[:, None], idx]
+    assert torch.equal(sc, sc_ref) and torch.equal(boxes, want) and boxes.dtype == torch.float32

@@ -62,6 +62,19 @@ def _clip(b, size):
     return torch.stack((b[:, 0].clamp(0, w), b[:, 1].clamp(0, h), b[:, 2].clamp(0, w), b[:, 3].clamp(0, h)), dim=-1)
 
 
+def decode_topk_level(box2box, anchors_l, logits_l, deltas_l, k):
+    """Scores (N,k) and decoded boxes (N,k,4) of the k best-scoring anchors of one pyramid level
+    (rpn.py:497-533 _decode_proposals + proposal_utils.py:67-84 per-level top-k). Only the selected anchors are
+    decoded: apply_deltas is row-wise, so this is bit-identical to decoding all A*H*W anchors and gathering, at 1/30
+    to 1/100 of the elementwise work (the reference decodes 261,888 boxes per image to keep <= 9,000)."""
+    N = logits_l.shape[0]
+    sc, idx = logits_l.float().topk(k, dim=1)
+    dsel = torch.gather(deltas_l, 1, idx[:, :, None].expand(-1, -1, 4))
+    asel = anchors_l[idx]
+    boxes = box2box.apply_deltas(dsel.reshape(-1, 4), asel.reshape(-1, 4)).view(N, k, 4)
+    return sc, boxes
+
+
 def rpn_static(rpn, images_size, features, gt_boxes, gt_valid, flags):
     """proposal_generator/rpn.py:431-533 -> (proposals (N,P,4), prop_valid (N,P) bool, losses)."""
     feats = [features[f] for f in rpn.in_features]
@@ -97,13 +110,11 @@ def rpn_static(rpn, images_size, features, gt_boxes, gt_valid, flags):
     with torch.no_grad():
         pre, post = rpn.pre_nms_topk[True], rpn.post_nms_topk[True]
         tk_scores, tk_boxes, lvl_ids = [], [], []
-        bidx = torch.arange(N, device=anchors_t.device)
         for lid, (a, lg, dl) in enumerate(zip(anchors, logits, deltas)):
-            props = rpn.box2box_transform.apply_deltas(dl.reshape(-1, 4), a.tensor.unsqueeze(0).expand(N, -1, -1).reshape(-1, 4)).view(N, -1, 4)
             k = min(lg.shape[1], pre)
-            sc, idx = lg.float().topk(k, dim=1)
+            sc, boxes = decode_topk_level(rpn.box2box_transform, a.tensor, lg, dl, k)
             tk_scores.append(sc)
-            tk_boxes.append(props[bidx[:, None], idx])
+            tk_boxes.append(boxes)
             lvl_ids.append(torch.full((k,), lid, dtype=torch.int64, device=anchors_t.device))
         tk_scores, tk_boxes, lvl_ids = torch.cat(tk_scores, 1), torch.cat(tk_boxes, 1), torch.cat(lvl_ids)
         finite = torch.isfinite(tk_boxes).all(dim=2) & torch.isfinite(tk_scores)
