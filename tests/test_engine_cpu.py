@@ -117,3 +117,39 @@ def test_decode_topk_level_equals_decode_all_then_gather(dtype):
     sc_ref, idx = logits.float().topk(k, dim=1)
     want = props[torch.arange(N)[:, None], idx]
     assert torch.equal(sc, sc_ref) and torch.equal(boxes, want) and boxes.dtype == torch.float32
+
+
+def test_subsample_static_matches_reference_sampling_semantics(monkeypatch):
+    """static_train.subsample_static (random-key top-k over fixed shapes) against sampling.py:9-54 subsample_labels:
+    same counts (num_pos = min(#pos, int(n*frac)), num_neg = min(#neg, n - num_pos)), indices drawn from the right
+    candidate sets without repetition, positives first; and with the key generator replaced by the inverse of a fixed
+    permutation it selects EXACTLY `candidates[perm][:k]` (INT: bit exact)."""
+    from u2seg_b200.modeling import static_train
+    g = torch.Generator().manual_seed(3)
+    for n_pos, n_neg, n, frac in [(10, 5000, 256, 0.5), (300, 40, 256, 0.5), (0, 100, 64, 0.25), (700, 900, 512, 0.25)]:
+        total = n_pos + n_neg + 37
+        perm = torch.randperm(total, generator=g)
+        is_pos = torch.zeros(total, dtype=torch.bool)
+        is_neg = torch.zeros(total, dtype=torch.bool)
+        is_pos[perm[:n_pos]] = True
+        is_neg[perm[n_pos:n_pos + n_neg]] = True
+        idx, ok, fg = static_train.subsample_static(is_pos, is_neg, n, frac)
+        want_pos = min(n_pos, int(n * frac))
+        want_neg = min(n_neg, n - want_pos)
+        assert idx.shape == ok.shape == fg.shape == (n,)
+        assert int(fg.sum()) == want_pos and int(ok.sum()) == want_pos + want_neg
+        assert bool(ok[:want_pos + want_neg].all()) and not bool(ok[want_pos + want_neg:].any())     # real slots first
+        assert bool(fg[:want_pos].all())                                                             # positives first
+        sel = idx[ok]
+        assert sel.unique().numel() == sel.numel()                                                   # no repetition
+        assert bool(is_pos[idx[fg]].all()) and bool(is_neg[idx[ok & ~fg]].all())
+    # deterministic keys: rank of each element in a fixed permutation -> the reference's `candidates[randperm][:k]`
+    total, k = 1000, 64
+    mask = torch.rand(total, generator=g) < 0.3
+    order = torch.randperm(total, generator=g)
+    rank = torch.empty(total)
+    rank[order] = torch.arange(total, dtype=torch.float32) / total
+    monkeypatch.setattr(static_train, "_rand_keys", lambda m: rank.clone())
+    idx, ok = static_train._topk_select(mask, k)
+    want = order[mask[order]][:k]
+    assert torch.equal(idx[ok], want)
