@@ -153,3 +153,23 @@ def test_subsample_static_matches_reference_sampling_semantics(monkeypatch):
     idx, ok = static_train._topk_select(mask, k)
     want = order[mask[order]][:k]
     assert torch.equal(idx[ok], want)
+
+
+def test_pack_batch_pads_to_fixed_capacity():
+    """static_train.pack_batch: reference-format list[dict] -> fixed-capacity tensors (g_max GT slots with a validity
+    mask; images NHWC bytes). Padding slots must be inert: zero boxes, invalid, empty masks."""
+    from u2seg_b200.data_synth import synthetic_batch
+    from u2seg_b200.modeling.static_train import pack_batch
+    batch = synthetic_batch(2, 96, 128, 800, 28, seed=9, G=5, min_size=12, max_size=60, device="cpu")
+    imgs, gb, gc, gv, gm, sem = pack_batch(batch, torch.device("cpu"), g_max=8)
+    assert imgs.shape == (2, 3, 96, 128) and imgs.dtype == torch.uint8 and imgs.stride(1) == 1         # NHWC storage
+    assert gb.shape == (2, 8, 4) and gc.shape == (2, 8) and gv.shape == (2, 8) and gm.shape == (2, 8, 96, 128)
+    assert sem.shape == (2, 96, 128)
+    for n, d in enumerate(batch):
+        inst = d["instances"]
+        g = len(inst)
+        assert torch.equal(imgs[n], d["image"]) and torch.equal(sem[n], d["sem_seg"])
+        assert torch.equal(gb[n, :g], inst.gt_boxes.tensor) and torch.equal(gc[n, :g], inst.gt_classes)
+        assert torch.equal(gm[n, :g], inst.gt_masks.tensor)
+        assert bool(gv[n, :g].all()) and not bool(gv[n, g:].any())
+        assert float(gb[n, g:].abs().sum()) == 0 and not bool(gm[n, g:].any())
