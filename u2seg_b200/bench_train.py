@@ -55,6 +55,9 @@ def run_train(args, ClockSampler, load_peaks, dist_info, run_kmeans=None):
                  for i in range(pool_n)]
     dev_pool = [_to_device(b, dev) for b in host_pool]
     warm = max(3, args.warmup)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()        # ranks finish building their (CPU-generated) batch pools at different times
     for i in range(warm):
         trainer.run_step(dev_pool[i % pool_n])
     torch.cuda.synchronize()
