@@ -209,6 +209,28 @@ class Trainer:
             out[name] = m
         return out
 
+    def state_dict(self):
+        """model.state_dict() with the fp32 master values for the parameters the modules hold as bf16 compute copies:
+        what a checkpoint (DetectionCheckpointer, reference names and shapes) must contain."""
+        sd = self.model.state_dict()
+        for name, m in self.master_parameters().items():
+            sd[name] = m.detach().clone()
+        return sd
+
+    @torch.no_grad()
+    def load_state_dict(self, sd):
+        """inverse of state_dict(): loads parameters (into the fp32 masters when they exist) and buffers."""
+        masters = self.master_parameters()
+        own = self.model.state_dict()
+        missing = [k for k in own if k not in sd]
+        assert not missing, "missing keys: %s" % missing[:5]
+        for k, v in sd.items():
+            dst = masters.get(k, own.get(k))
+            assert dst is not None, "unexpected key %s" % k
+            dst.copy_(v.to(dst.device))
+        if self.lowp:
+            self._w16_flat.copy_(self._master_flat)
+
     @torch.no_grad()
     def broadcast_parameters(self, src=0):
         """DDP's initial broadcast: rank `src`'s parameters and buffers everywhere."""
