@@ -1,0 +1,93 @@
+"""GPU parity of the round-2 DRAFT fused detection losses (csrc/det_losses.cu) against their torch restatements
+(= the formulas of static_train.py, rpn.py:365-429 and fast_rcnn.py:307-352). Not validated on hardware yet: skipped
+unless U2B_RUN_DRAFT_TESTS=1."""
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("U2B_RUN_DRAFT_TESTS") != "1", reason="round-2 draft (set U2B_RUN_DRAFT_TESTS=1)")]
+
+
+def _boxes(n, g, lo=8.0, hi=200.0, size=640.0):
+    c = torch.rand(n, 2, generator=g) * size
+    wh = torch.rand(n, 2, generator=g) * (hi - lo) + lo
+    return torch.cat([c - wh / 2, c + wh / 2], 1)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+def test_rpn_losses_match_torch(dtype, tol):
+    from u2seg_b200.modeling.fused_losses import rpn_losses, rpn_losses_reference
+    from u2seg_b200.modeling.rpn import Box2BoxTransform
+    g = torch.Generator().manual_seed(1)
+    N, A, G = 2, 20000, 7
+    b2b = Box2BoxTransform(weights=(1.0, 1.0, 1.0, 1.0))
+    anchors, gt = _boxes(A, g).cuda(), torch.stack([_boxes(G, g), _boxes(G, g)]).cuda()
+    labels = torch.randint(-1, 2, (N, A), generator=g).to(torch.int8).cuda()
+    matched = torch.randint(0, G, (N, A), generator=g).cuda()
+    lg = (torch.randn(N, A, generator=g) * 3).to(dtype).cuda()
+    dl = (torch.randn(N, A, 4, generator=g) * 0.5).to(dtype).cuda()
+    la, da = lg.clone().requires_grad_(True), dl.clone().requires_grad_(True)
+    lb, db = lg.clone().requires_grad_(True), dl.clone().requires_grad_(True)
+    c1, l1 = rpn_losses(la, da, anchors, labels, matched, gt, b2b.weights)
+    c2, l2 = rpn_losses_reference(lb, db, anchors, labels, matched, gt, b2b)
+    assert abs(float(c1) - float(c2)) <= 1e-4 * abs(float(c2)) and abs(float(l1) - float(l2)) <= 1e-4 * abs(float(l2))
+    (c1 * 0.3 + l1 * 0.7).backward()
+    (c2 * 0.3 + l2 * 0.7).backward()
+    for got, want in ((la.grad, lb.grad), (da.grad, db.grad)):
+        assert float((got.float() - want.float()).abs().max()) <= tol * float(want.float().abs().max()) + 1e-7
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+def test_box_losses_match_torch(dtype, tol):
+    from u2seg_b200.modeling.fused_losses import box_losses, box_losses_reference
+    from u2seg_b200.modeling.rpn import Box2BoxTransform
+    g = torch.Generator().manual_seed(2)
+    R, K = 1024, 800
+    b2b = Box2BoxTransform(weights=(10.0, 10.0, 5.0, 5.0))
+    props, gtb = _boxes(R, g).cuda(), _boxes(R, g).cuda()
+    classes = torch.randint(0, K + 1, (R,), generator=g)
+    classes[torch.rand(R, generator=g) < 0.2] = -100
+    classes = classes.cuda()
+    sc = (torch.randn(R, K + 1, generator=g) * 2).to(dtype).cuda()
+    dl = (torch.randn(R, 4, generator=g) * 0.5).to(dtype).cuda()
+    sa, da = sc.clone().requires_grad_(True), dl.clone().requires_grad_(True)
+    sb, db = sc.clone().requires_grad_(True), dl.clone().requires_grad_(True)
+    ce1, l11, ref1 = box_losses(sa, da, classes, props, gtb, K, b2b)
+    ce2, l12, ref2 = box_losses_reference(sb, db, classes, props, gtb, K, b2b)
+    assert abs(float(ce1) - float(ce2)) <= 1e-4 * abs(float(ce2)) and abs(float(l11) - float(l12)) <= 1e-4 * abs(float(l12))
+    assert torch.allclose(ref1, ref2.float(), rtol=1e-5, atol=1e-3)
+    (ce1 * 0.5 + l11 * 2.0).backward()
+    (ce2 * 0.5 + l12 * 2.0).backward()
+    for got, want in ((sa.grad, sb.grad), (da.grad, db.grad)):
+        assert float((got.float() - want.float()).abs().max()) <= tol * float(want.float().abs().max()) + 1e-7
+
+
+def test_static_step_with_fused_losses_equals_torch_losses(monkeypatch):
+    """forward_train_static with the fused RPN / box-head loss kernels == the torch formulas: same 10 losses (1e-4) and
+    the same parameter gradients (1e-3 of each tensor's largest entry), fp32, deterministic samplers."""
+    from oracle import detector_oracle as do
+    from test_model_gpu import _build, _make_batch
+    from u2seg_b200.modeling import static_train
+    K, S = 800, 28
+    params = do.init_params(do.DetCfg(K, S), 0)
+    data = do.synthetic_batch(2, 192, 256, K, S, seed=13, G=5, min_size=20, max_size=120)
+    monkeypatch.setattr(static_train, "_rand_keys",
+                        lambda mask: torch.arange(mask.numel(), device=mask.device, dtype=torch.float32) / (mask.numel() + 1))
+    batch = _make_batch(data)
+    out = []
+    for fused in (False, True):
+        monkeypatch.setattr(static_train, "FUSED_DET_LOSSES", fused)
+        model = _build(K, params, True)
+        packed = static_train.pack_batch(batch, torch.device("cuda"), g_max=8)
+        losses, flag = static_train.forward_train_static(model, *packed)
+        assert not bool(flag)
+        sum(losses.values()).backward()
+        out.append(({k: float(v) for k, v in losses.items()}, {n: p.grad.clone() for n, p in model.named_parameters()}))
+    (la, ga), (lb, gb) = out
+    for k in la:
+        assert abs(la[k] - lb[k]) <= 1e-4 * abs(la[k]) + 1e-6, k
+    for n in ga:
+        d = float(ga[n].abs().max()) + 1e-12
+        assert float((ga[n] - gb[n]).abs().max()) <= 1e-3 * d + 1e-7, n

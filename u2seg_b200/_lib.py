@@ -46,6 +46,12 @@ SIGNATURES = {
     "u2b_stem_conv_fwd": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "u2b_stem_conv_wgrad_num_partials": (c_int, [c_int64, c_int, c_int]),
     "u2b_stem_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "u2b_rpn_losses_num_partials": (c_int64, [c_int64]),
+    "u2b_box_losses_num_partials": (c_int64, [c_int64]),
+    "u2b_rpn_losses": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "u2b_box_losses": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
+                               c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "u2b_sgd_step_segments": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_float, c_int, c_int64, c_void_p]),
     "u2b_debug_nms_profile": (c_int, [c_int, c_void_p]),
