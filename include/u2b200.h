@@ -94,6 +94,16 @@ int u2b_roi_align_bwd(int dtype, int num_levels, float* const* grad_feats, const
                       const int32_t* levels, int64_t K, int P, const void* grad_out, float grad_scale,
                       u2b_stream_t stream);
 
+/* Channel-major variants (round-2 draft): out / grad_out are (K, C, P, P) contiguous, the layout torch.flatten(x, 1)
+ * of the box head reads (box_head.py:99-106), so no transposing copy is needed on either side of the FC layers. */
+int u2b_roi_align_chw_supported(int64_t C, int P);
+int u2b_roi_align_fwd_chw(int dtype, int num_levels, const void* const* feats, const int32_t* hs, const int32_t* ws,
+                          const float* scales, int64_t C, const float* rois5, const int32_t* levels, int64_t K, int P,
+                          void* out, u2b_stream_t stream);
+int u2b_roi_align_bwd_chw(int dtype, int num_levels, float* const* grad_feats, const int32_t* hs, const int32_t* ws,
+                          const float* scales, int64_t C, const float* rois5, const int32_t* levels, int64_t K, int P,
+                          const void* grad_out, float grad_scale, u2b_stream_t stream);
+
 /* layers/mask_ops.py:74-147 paste_masks_in_image: masks (N, M, M) fp32 probabilities, boxes (N, 4)
  * fp32 -> out (N, H, W) bytes in {0,1} (= `img >= threshold`). */
 int u2b_paste_masks(const float* masks, const float* boxes, int64_t N, int M, int H, int W,

@@ -91,3 +91,28 @@ def test_static_step_with_fused_losses_equals_torch_losses(monkeypatch):
     for n in ga:
         d = float(ga[n].abs().max()) + 1e-12
         assert float((ga[n] - gb[n]).abs().max()) <= 1e-3 * d + 1e-7, n
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.bfloat16, 1e-2)])
+def test_roi_pooler_channel_major_layout_equals_nhwc_layout(dtype, tol):
+    """ROIPooler(chw_output=True) (csrc/roi_align.cu *_chw kernels) == the channels_last pooler: same values (identical
+    arithmetic per bin), same feature gradients up to the order of the fp32 atomics."""
+    from u2seg_b200.layers import ROIPooler
+    g = torch.Generator().manual_seed(4)
+    scales = (1 / 4, 1 / 8, 1 / 16, 1 / 32)
+    feats = [torch.randn(2, 256, 256 // 2 ** i, 320 // 2 ** i, generator=g).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+             for i in range(4)]
+    boxes = [_boxes(300, g, 8, 600, 1000).clamp(0, 1000).cuda() for _ in range(2)]
+    outs = []
+    for chw in (False, True):
+        fs = [f.clone().requires_grad_(True) for f in feats]
+        pooler = ROIPooler(7, scales, 0, "ROIAlignV2", chw_output=chw)
+        y = pooler(fs, boxes, grad_scale=1 / 3)
+        assert y.shape == (600, 256, 7, 7) and y.is_contiguous() == chw
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(5)).to(dtype).cuda()
+        y.backward(gy)
+        outs.append((y.detach().float(), [f.grad.float() for f in fs]))
+    (ya, ga), (yb, gb) = outs
+    assert torch.equal(ya, yb)
+    for a, b in zip(ga, gb):
+        assert float((a - b).abs().max()) <= max(tol, 1e-5) * float(a.abs().max()) + 1e-7

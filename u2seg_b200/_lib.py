@@ -35,6 +35,11 @@ SIGNATURES = {
                                   c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "u2b_roi_align_bwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                   c_void_p, c_int64, c_int, c_void_p, c_float, c_void_p]),
+    "u2b_roi_align_chw_supported": (c_int, [c_int64, c_int]),
+    "u2b_roi_align_fwd_chw": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                      c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "u2b_roi_align_bwd_chw": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                      c_void_p, c_int64, c_int, c_void_p, c_float, c_void_p]),
     "u2b_paste_masks": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "u2b_crop_resize_masks": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p,
                                       c_void_p, c_void_p]),
