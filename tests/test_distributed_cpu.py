@@ -19,6 +19,36 @@ def _free_port():
     return p
 
 
+def _run_ranks(target, nresults, timeout, world=2, attempts=3):
+    """spawn `world` workers (rank, world, port, queue) and collect `nresults` queue items; a rendezvous that fails
+    (the free port found above can be taken by another process before the workers bind it) is retried on a new port."""
+    import queue as _queue
+    last = None
+    for _ in range(attempts):
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=target, args=(r, world, port, q)) for r in range(world)]
+        [p.start() for p in procs]
+        import time
+        out, t0 = [], time.time()
+        while len(out) < nresults and time.time() - t0 < timeout:
+            try:
+                out.append(q.get(timeout=2))
+            except _queue.Empty:
+                if any(p.exitcode not in (None, 0) for p in procs):      # a worker died (e.g. rendezvous failed)
+                    break
+        if len(out) == nresults:
+            [p.join(60) for p in procs]
+            return out
+        last = [p.exitcode for p in procs]
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
+            p.join(10)
+    raise AssertionError("workers did not report after %d attempts (exit codes %r)" % (attempts, last))
+
+
 class _CpuState:
     """stand-in for clustering.KMeansState with the same assign/accumulate/finalize protocol"""
 
@@ -63,13 +93,7 @@ def _kmeans_worker(rank, world, port, q):
 
 
 def test_row_sharded_kmeans_equals_single_process_oracle():
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_kmeans_worker, args=(r, 2, port, q)) for r in range(2)]
-    [p.start() for p in procs]
-    labels, c = q.get(timeout=120)
-    [p.join(30) for p in procs]
+    (labels, c), = _run_ranks(_kmeans_worker, 1, 120)
     x = make_mixture(2000, 32, 20, seed=7, spread=1.0).float()
     want_l, want_c = kmeans_oracle(x, 3, K=12, Niter=4)
     assert torch.equal(labels, want_l)
@@ -96,13 +120,7 @@ def _grad_worker(rank, world, port, q):
 
 
 def test_flat_gradient_allreduce_equals_mean_of_rank_gradients():
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
-    [p.start() for p in procs]
-    flat = q.get(timeout=120)
-    [p.join(30) for p in procs]
+    flat, = _run_ranks(_grad_worker, 1, 120)
     torch.manual_seed(0)
     model = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.Flatten(), torch.nn.Linear(4 * 36, 5))
     tot = None
@@ -142,13 +160,7 @@ def _trainer_worker(rank, world, port, q):
 def test_static_trainer_broadcast_and_flat_allreduce_two_ranks():
     """engine.Trainer under a 2-rank job (gloo, CPU): DDP's initial broadcast (engine/defaults.py:60-79) leaves both ranks
     with rank 0's fp32 masters and refreshed bf16 compute copies; the flat gradient buffer is averaged by ONE all-reduce."""
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_trainer_worker, args=(r, 2, port, q)) for r in range(2)]
-    [p.start() for p in procs]
-    out = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
-    [p.join(60) for p in procs]
+    out = sorted(_run_ranks(_trainer_worker, 2, 300), key=lambda t: t[0])
     (_, b0, a0, s0, w0, v0, g0, m0), (_, b1, a1, s1, w1, v1, g1, m1) = out
     assert b0 != b1                                   # different initial weights ...
     assert a0 == a1 == b0 and s0 == s1                # ... identical (rank 0's) after the broadcast
