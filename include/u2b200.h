@@ -231,6 +231,13 @@ int u2b_bn_xchg_bwd_coeff(const float* sums, const void* peers, int world, int r
 int u2b_bn_bwd_apply(int dtype, const void* dy, const void* x, const void* y, const float* coeff, void* dx,
                      void* dres, int64_t P, int C, u2b_stream_t stream);
 
+/* nn.Upsample(scale_factor=s, mode="bilinear", align_corners=False) on NHWC activations (semantic_seg.py:195-199),
+ * round-2 draft. dir 0: out (N, h*s, w*s, C) = upsample(in (N, h, w, C)); dir 1: out (N, h, w, C) = gradient w.r.t. the
+ * input given in = gradient of the output (N, h*s, w*s, C) (gather form: deterministic). Even scales, C % 8 == 0. */
+int u2b_upsample_bilinear_supported(int C, int scale);
+int u2b_upsample_bilinear(int dtype, int dir, const void* in, void* out, int64_t N, int h, int w, int C, int scale,
+                          u2b_stream_t stream);
+
 /* Fused detection losses (value + closed-form gradient of the SUMMED loss in one pass; the caller applies the scalar
  * normaliser). dtype 0 = fp32 / 1 = fp16 / 2 = bf16 for the head outputs and their gradients.
  * u2b_rpn_losses - proposal_generator/rpn.py:365-429: logits (N, A), deltas (N, A, 4), anchors (A, 4) fp32, labels

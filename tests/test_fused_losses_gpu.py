@@ -116,3 +116,23 @@ def test_roi_pooler_channel_major_layout_equals_nhwc_layout(dtype, tol):
     assert torch.equal(ya, yb)
     for a, b in zip(ga, gb):
         assert float((a - b).abs().max()) <= max(tol, 1e-5) * float(a.abs().max()) + 1e-7
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("N,C,h,w,scale", [(2, 128, 33, 47, 2), (1, 64, 16, 16, 2), (1, 8, 5, 3, 4)])
+def test_upsample_bilinear_matches_interpolate(N, C, h, w, scale, dtype, tol):
+    """csrc/upsample.cu against F.interpolate(bilinear, align_corners=False) in fp32: values and input gradient."""
+    import torch.nn.functional as F
+    from u2seg_b200.layers import upsample_bilinear
+    g = torch.Generator().manual_seed(C + h)
+    x = torch.randn(N, C, h, w, generator=g).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    xa = x.clone().requires_grad_(True)
+    xb = x.float().clone().requires_grad_(True)
+    ya = upsample_bilinear(xa, scale)
+    yb = F.interpolate(xb, scale_factor=scale, mode="bilinear", align_corners=False)
+    assert ya.shape == yb.shape and ya.dtype == dtype
+    assert float((ya.float() - yb).abs().max()) <= tol * float(yb.abs().max()) + 1e-7
+    gy = torch.randn(yb.shape, generator=g).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    ya.backward(gy)
+    yb.backward(gy.float())
+    assert float((xa.grad.float() - xb.grad).abs().max()) <= tol * float(xb.grad.abs().max()) + 1e-6

@@ -314,6 +314,47 @@ def upsample_cross_entropy_supported(logits, scale):
 
 
 # --------------------------------------------------------------------------------------
+# bilinear upsampling on NHWC activations (round-2 draft, csrc/upsample.cu)
+# --------------------------------------------------------------------------------------
+class _UpsampleBilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        L = _lib.lib()
+        xc = to_nhwc(x)
+        N, C, h, w = xc.shape
+        y = torch.empty((N, h * scale, w * scale, C), dtype=xc.dtype, device=xc.device).permute(0, 3, 1, 2)
+        _lib.check(L.u2b_upsample_bilinear(_DTYPE_CODE[xc.dtype], 0, ctypes.c_void_p(xc.data_ptr()),
+                                           ctypes.c_void_p(y.data_ptr()), N, h, w, C, scale, _lib.stream_ptr()),
+                   "u2b_upsample_bilinear")
+        _lib.count_launches(1)
+        ctx.meta = (N, C, h, w, scale, xc.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        L = _lib.lib()
+        N, C, h, w, scale, dt = ctx.meta
+        g = to_nhwc(gy.to(dt))
+        dx = torch.empty((N, h, w, C), dtype=dt, device=g.device).permute(0, 3, 1, 2)
+        _lib.check(L.u2b_upsample_bilinear(_DTYPE_CODE[dt], 1, ctypes.c_void_p(g.data_ptr()),
+                                           ctypes.c_void_p(dx.data_ptr()), N, h, w, C, scale, _lib.stream_ptr()),
+                   "u2b_upsample_bilinear")
+        _lib.count_launches(1)
+        return dx, None
+
+
+def upsample_bilinear(x, scale):
+    """F.interpolate(x, scale_factor=scale, mode="bilinear", align_corners=False) for NHWC CUDA tensors."""
+    _need_cuda(x, "upsample_bilinear")
+    return _UpsampleBilinear.apply(x, int(scale))
+
+
+def upsample_bilinear_supported(x, scale):
+    return (x.is_cuda and x.dim() == 4 and x.dtype in _DTYPE_CODE and scale is not None and float(scale) == int(scale)
+            and bool(_lib.lib().u2b_upsample_bilinear_supported(x.shape[1], int(scale))))
+
+
+# --------------------------------------------------------------------------------------
 # boxes: fused IoU + Matcher, NMS
 # --------------------------------------------------------------------------------------
 class Matcher:
