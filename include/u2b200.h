@@ -239,7 +239,7 @@ int u2b_upsample_bilinear(int dtype, int dir, const void* in, void* out, int64_t
                           u2b_stream_t stream);
 
 /* Fused detection losses (value + closed-form gradient of the SUMMED loss in one pass; the caller applies the scalar
- * normaliser). dtype 0 = fp32 / 1 = fp16 / 2 = bf16 for the head outputs and their gradients.
+ * normaliser). dtype 0 = fp32 / 1 = fp16 / 2 = bf16 for the head outputs; gradients are always fp32.
  * u2b_rpn_losses - proposal_generator/rpn.py:365-429: logits (N, A), deltas (N, A, 4), anchors (A, 4) fp32, labels
  *   (N, A) int8 in {-1 ignore, 0, 1}, matched (N, A) int64 index into gt_boxes (N, G, 4) fp32, weights4 (host) =
  *   Box2BoxTransform weights. partials (u2b_rpn_losses_num_partials(N*A), 2) = [BCE sum, L1 sum] per CTA.
@@ -252,10 +252,10 @@ int64_t u2b_rpn_losses_num_partials(int64_t total);
 int64_t u2b_box_losses_num_partials(int64_t R);
 int u2b_rpn_losses(int dtype, const void* logits, const void* deltas, const float* anchors, const int8_t* labels,
                    const int64_t* matched, const float* gt_boxes, int64_t N, int64_t A, int G, const float* weights4,
-                   void* grad_logits, void* grad_deltas, float* partials, u2b_stream_t stream);
+                   float* grad_logits, float* grad_deltas, float* partials, u2b_stream_t stream);
 int u2b_box_losses(int dtype, const void* scores, const int64_t* classes, const void* deltas, const float* proposals,
                    const float* gt_boxes, int64_t R, int C, int K, const float* weights4, float scale_clamp,
-                   void* grad_scores, void* grad_deltas, float* refined, float* partials, u2b_stream_t stream);
+                   float* grad_scores, float* grad_deltas, float* refined, float* partials, u2b_stream_t stream);
 
 /* solver/build.py:63-73 (per-parameter gradient-norm clipping) + solver/build.py:119-139 (torch.optim.SGD: weight
  * decay, momentum, optional Nesterov) + the refresh of the bf16 compute weights, fused over flat buffers.

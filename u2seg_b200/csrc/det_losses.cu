@@ -1,7 +1,8 @@
 // Fused detection losses of the Panoptic-FPN step (forward value AND the closed-form gradient in one pass, like
 // semseg_loss.cu): each kernel reads the head outputs once, writes per-CTA partial sums of the loss and the gradient of
 // the SUMMED loss with respect to the head outputs; the caller applies the scalar normaliser (1/count, loss weight,
-// upstream gradient) with one tiny multiply. They replace ~80 (RPN) and ~60 per cascade stage (box head) library
+// upstream gradient) with one tiny multiply. Gradients are written in fp32 whatever the head dtype: the reference's
+// loss arithmetic is fp32 (autocast promotes the losses), the cast to bf16 happens after the scalar multiply. They replace ~80 (RPN) and ~60 per cascade stage (box head) library
 // launches of 2-4 us each in forward plus as many in backward.
 //
 //   u2b_rpn_losses: proposal_generator/rpn.py:365-429 RPN.losses
@@ -28,15 +29,6 @@ template <>
 __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 template <>
 __device__ __forceinline__ float ldf<__half>(const __half* p) { return __half2float(*p); }
-
-template <typename T>
-__device__ __forceinline__ void stf(T* p, float v);
-template <>
-__device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
-template <>
-__device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
-template <>
-__device__ __forceinline__ void stf<__half>(__half* p, float v) { *p = __float2half(v); }
 
 // box_regression.py:43-75 get_deltas(src, target) with weights w
 __device__ __forceinline__ void get_deltas(const float4 s, const float4 t, const float4 w, float (&d)[4]) {
@@ -82,7 +74,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 rpn_losses_kernel(const T* __restrict__ logits, const T* __restrict__ deltas, const float4* __restrict__ anchors,
                   const int8_t* __restrict__ labels, const int64_t* __restrict__ matched, const float4* __restrict__ gt,
-                  int G, long long A, long long total, float4 w, T* __restrict__ g_logits, T* __restrict__ g_deltas,
+                  int G, long long A, long long total, float4 w, float* __restrict__ g_logits, float* __restrict__ g_deltas,
                   float* __restrict__ partials) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   float l_cls = 0.f, l_loc = 0.f;
@@ -106,10 +98,10 @@ rpn_losses_kernel(const T* __restrict__ logits, const T* __restrict__ deltas, co
         gd[k] = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
       }
     }
-    if (g_logits) stf<T>(g_logits + i, gx);
+    if (g_logits) g_logits[i] = gx;
     if (g_deltas) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) stf<T>(g_deltas + i * 4 + k, gd[k]);
+      for (int k = 0; k < 4; ++k) g_deltas[i * 4 + k] = gd[k];
     }
   }
   block_sum2(l_cls, l_loc, partials);
@@ -121,7 +113,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 box_losses_kernel(const T* __restrict__ scores, const int64_t* __restrict__ classes, const T* __restrict__ deltas,
                   const float4* __restrict__ props, const float4* __restrict__ gtb, int R, int C, int K, float4 w,
-                  float scale_clamp, T* __restrict__ g_scores, T* __restrict__ g_deltas, float4* __restrict__ refined,
+                  float scale_clamp, float* __restrict__ g_scores, float* __restrict__ g_deltas, float4* __restrict__ refined,
                   float* __restrict__ partials) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -139,9 +131,9 @@ box_losses_kernel(const T* __restrict__ scores, const int64_t* __restrict__ clas
     const float lse = m + logf(sum);
     if (counted && lane == 0) l_ce = lse - ldf<T>(s + cls);
     if (g_scores) {
-      T* g = g_scores + static_cast<size_t>(row) * C;
+      float* g = g_scores + static_cast<size_t>(row) * C;
       for (int c = lane; c < C; c += 32)
-        stf<T>(g + c, counted ? expf(ldf<T>(s + c) - lse) - (c == cls ? 1.f : 0.f) : 0.f);
+        g[c] = counted ? expf(ldf<T>(s + c) - lse) - (c == cls ? 1.f : 0.f) : 0.f;
     }
     if (lane == 0) {
       const float4 p = props[row];
@@ -161,7 +153,7 @@ box_losses_kernel(const T* __restrict__ scores, const int64_t* __restrict__ clas
       }
       if (g_deltas) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) stf<T>(g_deltas + static_cast<size_t>(row) * 4 + k, gd[k]);
+        for (int k = 0; k < 4; ++k) g_deltas[static_cast<size_t>(row) * 4 + k] = gd[k];
       }
       if (refined) {                                     // box_regression.py:77-116 apply_deltas
         const float bw = p.z - p.x, bh = p.w - p.y;
@@ -186,7 +178,7 @@ int64_t u2b_box_losses_num_partials(int64_t R) { return (R + 7) / 8; }
 
 int u2b_rpn_losses(int dtype, const void* logits, const void* deltas, const float* anchors, const int8_t* labels,
                    const int64_t* matched, const float* gt_boxes, int64_t N, int64_t A, int G, const float* weights4,
-                   void* grad_logits, void* grad_deltas, float* partials, cudaStream_t stream) {
+                   float* grad_logits, float* grad_deltas, float* partials, cudaStream_t stream) {
   const long long total = N * A;
   if (total == 0) return 0;
   U2B_CHECK_ARG(logits && deltas && anchors && labels && matched && gt_boxes && weights4 && partials && G > 0,
@@ -197,7 +189,7 @@ int u2b_rpn_losses(int dtype, const void* logits, const void* deltas, const floa
   rpn_losses_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(logits), static_cast<const T*>(deltas),       \
                                                  reinterpret_cast<const float4*>(anchors), labels, matched,          \
                                                  reinterpret_cast<const float4*>(gt_boxes), G, A, total, w,          \
-                                                 static_cast<T*>(grad_logits), static_cast<T*>(grad_deltas), partials)
+                                                 grad_logits, grad_deltas, partials)
   if (dtype == 0) U2B_RPN(float);
   else if (dtype == 1) U2B_RPN(__half);
   else if (dtype == 2) U2B_RPN(__nv_bfloat16);
@@ -212,7 +204,7 @@ int u2b_rpn_losses(int dtype, const void* logits, const void* deltas, const floa
 
 int u2b_box_losses(int dtype, const void* scores, const int64_t* classes, const void* deltas, const float* proposals,
                    const float* gt_boxes, int64_t R, int C, int K, const float* weights4, float scale_clamp,
-                   void* grad_scores, void* grad_deltas, float* refined, float* partials, cudaStream_t stream) {
+                   float* grad_scores, float* grad_deltas, float* refined, float* partials, cudaStream_t stream) {
   if (R == 0) return 0;
   U2B_CHECK_ARG(scores && classes && deltas && proposals && gt_boxes && weights4 && partials && C > 0 && K >= 0 && K <= C,
                 "box_losses: bad arguments");
@@ -222,7 +214,7 @@ int u2b_box_losses(int dtype, const void* scores, const int64_t* classes, const 
   box_losses_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(scores), classes, static_cast<const T*>(deltas), \
                                                  reinterpret_cast<const float4*>(proposals),                          \
                                                  reinterpret_cast<const float4*>(gt_boxes), (int)R, C, K, w,          \
-                                                 scale_clamp, static_cast<T*>(grad_scores), static_cast<T*>(grad_deltas), \
+                                                 scale_clamp, grad_scores, grad_deltas,                                \
                                                  reinterpret_cast<float4*>(refined), partials)
   if (dtype == 0) U2B_BOX(float);
   else if (dtype == 1) U2B_BOX(__half);

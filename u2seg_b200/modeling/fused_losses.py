@@ -30,8 +30,8 @@ class _RPNLosses(torch.autograd.Function):
         lg, dl = logits.contiguous(), deltas.contiguous()
         assert dl.dtype == lg.dtype and dl.shape == (N, A, 4)
         need_l, need_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        g_l = torch.empty_like(lg) if need_l else None
-        g_d = torch.empty_like(dl) if need_d else None
+        g_l = torch.empty(lg.shape, dtype=torch.float32, device=lg.device) if need_l else None
+        g_d = torch.empty(dl.shape, dtype=torch.float32, device=lg.device) if need_d else None
         parts = torch.empty((int(L.u2b_rpn_losses_num_partials(N * A)), 2), dtype=torch.float32, device=lg.device)
         _lib.check(L.u2b_rpn_losses(_CODE[lg.dtype], _p(lg), _p(dl), _p(anchors.float().contiguous()),
                                     _p(labels.to(torch.int8).contiguous()), _p(matched.to(torch.int64).contiguous()),
@@ -40,14 +40,14 @@ class _RPNLosses(torch.autograd.Function):
         _lib.count_launches(1)
         tot = parts.sum(0)
         ctx.save_for_backward(g_l if need_l else torch.empty(0), g_d if need_d else torch.empty(0))
-        ctx.need = (need_l, need_d)
+        ctx.need = (need_l, need_d, lg.dtype)
         return tot[0], tot[1]
 
     @staticmethod
     def backward(ctx, g_cls, g_loc):
         g_l, g_d = ctx.saved_tensors
-        need_l, need_d = ctx.need
-        return (g_l * g_cls.to(g_l.dtype) if need_l else None, g_d * g_loc.to(g_d.dtype) if need_d else None,
+        need_l, need_d, dt = ctx.need
+        return ((g_l * g_cls).to(dt) if need_l else None, (g_d * g_loc).to(dt) if need_d else None,
                 None, None, None, None, None)
 
 
@@ -78,8 +78,8 @@ class _BoxLosses(torch.autograd.Function):
         sc, dl = scores.contiguous(), deltas.contiguous()
         assert dl.dtype == sc.dtype and dl.shape == (R, 4)
         need_s, need_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        g_s = torch.empty_like(sc) if need_s else None
-        g_d = torch.empty_like(dl) if need_d else None
+        g_s = torch.empty(sc.shape, dtype=torch.float32, device=sc.device) if need_s else None
+        g_d = torch.empty(dl.shape, dtype=torch.float32, device=sc.device) if need_d else None
         refined = torch.empty((R, 4), dtype=torch.float32, device=sc.device)
         parts = torch.empty((int(L.u2b_box_losses_num_partials(R)), 2), dtype=torch.float32, device=sc.device)
         _lib.check(L.u2b_box_losses(_CODE[sc.dtype], _p(sc), _p(classes.to(torch.int64).contiguous()), _p(dl),
@@ -89,15 +89,15 @@ class _BoxLosses(torch.autograd.Function):
         _lib.count_launches(1)
         tot = parts.sum(0)
         ctx.save_for_backward(g_s if need_s else torch.empty(0), g_d if need_d else torch.empty(0))
-        ctx.need = (need_s, need_d)
+        ctx.need = (need_s, need_d, sc.dtype)
         ctx.mark_non_differentiable(refined)
         return tot[0], tot[1], refined
 
     @staticmethod
     def backward(ctx, g_ce, g_l1, _g_refined):
         g_s, g_d = ctx.saved_tensors
-        need_s, need_d = ctx.need
-        return (g_s * g_ce.to(g_s.dtype) if need_s else None, g_d * g_l1.to(g_d.dtype) if need_d else None,
+        need_s, need_d, dt = ctx.need
+        return ((g_s * g_ce).to(dt) if need_s else None, (g_d * g_l1).to(dt) if need_d else None,
                 None, None, None, None, None, None)
 
 
