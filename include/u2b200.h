@@ -238,6 +238,14 @@ int u2b_upsample_bilinear_supported(int C, int scale);
 int u2b_upsample_bilinear(int dtype, int dir, const void* in, void* out, int64_t N, int h, int w, int C, int scale,
                           u2b_stream_t stream);
 
+/* Weight gradient of the NHWC convolutions on tcgen05 (round-2 draft, csrc/conv_wgrad_tc.cu): x (N,H,W,Cin),
+ * dy (N,OH,OW,Cout), fp16 (1) / bf16 (2). partials (u2b_conv2d_wgrad_ksplit(...), Cout, R, S, Cin) fp32 receives one
+ * partial per K split; dW (Cout,R,S,Cin) = their sum. Cin % 64 == 0, Cout % 128 == 0, 1x1 or 3x3 pad 1, stride 1|2. */
+int u2b_conv2d_wgrad_supported(int Cin, int Cout, int R, int S, int stride, int pad);
+int u2b_conv2d_wgrad_ksplit(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad);
+int u2b_conv2d_nhwc_wgrad(int dtype, const void* x, const void* dy, int N, int H, int W, int Cin, int Cout, int R, int S,
+                          int stride, int pad, float* partials, u2b_stream_t stream);
+
 /* Fused detection losses (value + closed-form gradient of the SUMMED loss in one pass; the caller applies the scalar
  * normaliser). dtype 0 = fp32 / 1 = fp16 / 2 = bf16 for the head outputs; gradients are always fp32.
  * u2b_rpn_losses - proposal_generator/rpn.py:365-429: logits (N, A), deltas (N, A, 4), anchors (A, 4) fp32, labels

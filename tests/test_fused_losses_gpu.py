@@ -136,3 +136,21 @@ def test_upsample_bilinear_matches_interpolate(N, C, h, w, scale, dtype, tol):
     ya.backward(gy)
     yb.backward(gy.float())
     assert float((xa.grad.float() - xb.grad).abs().max()) <= tol * float(xb.grad.abs().max()) + 1e-6
+
+
+@pytest.mark.parametrize("N,Cin,H,W,Cout,k,stride", [(2, 256, 64, 64, 256, 3, 1), (2, 128, 37, 51, 128, 3, 1), (1, 64, 32, 32, 128, 1, 1),
+                                                     (2, 128, 64, 64, 128, 3, 2), (256, 256, 14, 14, 256, 3, 1)])
+def test_tcgen05_wgrad_matches_library(N, Cin, H, W, Cout, k, stride):
+    """csrc/conv_wgrad_tc.cu against aten.convolution_backward (fp32 reference on the same bf16 operands)."""
+    from u2seg_b200.modeling.conv_tc import conv2d_nhwc_wgrad
+    g = torch.Generator().manual_seed(Cin + H)
+    pad = k // 2
+    x = torch.randn(N, Cin, H, W, generator=g).bfloat16().cuda().contiguous(memory_format=torch.channels_last)
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    gy = torch.randn(N, Cout, OH, OW, generator=g).bfloat16().cuda().contiguous(memory_format=torch.channels_last)
+    w = torch.zeros(Cout, Cin, k, k, device="cuda")
+    _, want, _ = torch.ops.aten.convolution_backward(gy.float(), x.float(), w, None, [stride, stride], [pad, pad], [1, 1],
+                                                     False, [0, 0], 1, [False, True, False])
+    got = conv2d_nhwc_wgrad(x, gy, k, k, stride, pad)
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 2e-3 * float(want.abs().max())       # fp32 accumulation, split-K order

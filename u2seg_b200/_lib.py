@@ -51,6 +51,10 @@ SIGNATURES = {
     "u2b_stem_conv_fwd": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "u2b_stem_conv_wgrad_num_partials": (c_int, [c_int64, c_int, c_int]),
     "u2b_stem_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "u2b_conv2d_wgrad_supported": (c_int, [c_int] * 6),
+    "u2b_conv2d_wgrad_ksplit": (c_int, [c_int] * 9),
+    "u2b_conv2d_nhwc_wgrad": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_int, c_void_p, c_void_p]),
     "u2b_upsample_bilinear_supported": (c_int, [c_int, c_int]),
     "u2b_upsample_bilinear": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     "u2b_rpn_losses_num_partials": (c_int64, [c_int64]),
