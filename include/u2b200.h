@@ -265,6 +265,15 @@ int u2b_box_losses(int dtype, const void* scores, const int64_t* classes, const 
                    const float* gt_boxes, int64_t R, int C, int K, const float* weights4, float scale_clamp,
                    float* grad_scores, float* grad_deltas, float* refined, float* partials, u2b_stream_t stream);
 
+/* rpn.py:497-533 + proposal_utils.py:85-121 for the anchors kept by the per-level top-k (round-2 draft): decode, clip to
+ * the image, validity (finite, both sides > min_size). sel (N, Ksel) int64 anchor indices into deltas (N, A, 4) /
+ * anchors (A, 4); scores (N, Ksel) fp32. boxes (N, Ksel, 4) fp32, valid (N, Ksel) bytes, *nonfinite (device int, caller
+ * zeroes it) set when a selected box / score is not finite. */
+int u2b_rpn_decode_selected(int dtype, const void* deltas, const float* anchors, const int64_t* sel, const float* scores,
+                            int64_t N, int64_t A, int Ksel, const float* weights4, float scale_clamp, float img_h,
+                            float img_w, float min_size, float* boxes, uint8_t* valid, int* nonfinite,
+                            u2b_stream_t stream);
+
 /* solver/build.py:63-73 (per-parameter gradient-norm clipping) + solver/build.py:119-139 (torch.optim.SGD: weight
  * decay, momentum, optional Nesterov) + the refresh of the bf16 compute weights, fused over flat buffers.
  * grad / master / mom: n fp32 each, same offsets, every parameter starting on a 64-element boundary.

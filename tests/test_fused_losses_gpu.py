@@ -154,3 +154,23 @@ def test_tcgen05_wgrad_matches_library(N, Cin, H, W, Cout, k, stride):
     got = conv2d_nhwc_wgrad(x, gy, k, k, stride, pad)
     assert got.shape == want.shape
     assert float((got - want).abs().max()) <= 2e-3 * float(want.abs().max())       # fp32 accumulation, split-K order
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_rpn_decode_selected_matches_torch(dtype):
+    from u2seg_b200.modeling.fused_losses import rpn_decode_selected, rpn_decode_selected_reference
+    from u2seg_b200.modeling.rpn import Box2BoxTransform
+    g = torch.Generator().manual_seed(6)
+    N, A, K = 2, 30000, 4000
+    b2b = Box2BoxTransform(weights=(1.0, 1.0, 1.0, 1.0))
+    anchors = _boxes(A, g, 4, 400, 1024).cuda()
+    deltas = (torch.randn(N, A, 4, generator=g) * 0.7).to(dtype).cuda()
+    deltas[0, 5] = float("inf")
+    sel = torch.stack([torch.randperm(A, generator=g)[:K] for _ in range(N)]).cuda()
+    sel[0, 0] = 5                                            # a non-finite box among the selected ones
+    scores = torch.randn(N, K, generator=g).cuda()
+    b1, v1, f1 = rpn_decode_selected(deltas, anchors, sel, scores, b2b, (800, 1024), 0.0)
+    b2, v2, f2 = rpn_decode_selected_reference(deltas, anchors, sel, scores, b2b, (800, 1024), 0.0)
+    assert bool(f1) and bool(f2) and torch.equal(v1, v2)
+    ok = v2
+    assert torch.allclose(b1[ok], b2[ok], rtol=1e-6, atol=1e-3)

@@ -169,6 +169,39 @@ box_losses_kernel(const T* __restrict__ scores, const int64_t* __restrict__ clas
   block_sum2(l_ce, l_l1, partials);
 }
 
+// proposal_generator/rpn.py:497-533 _decode_proposals + proposal_utils.py:85-121 (clip to the image, drop boxes
+// with a side <= min_size or non-finite coordinates) for the anchors selected by the per-level top-k only:
+// one thread per (image, selected anchor). boxes out (N, Ksel, 4) fp32 clipped, valid (N, Ksel) bytes; *nonfinite is
+// set to 1 if any selected box or score is not finite (the reference raises FloatingPointError there).
+template <typename T>
+__global__ void __launch_bounds__(256)
+rpn_decode_selected_kernel(const T* __restrict__ deltas, const float4* __restrict__ anchors,
+                           const int64_t* __restrict__ sel, const float* __restrict__ scores, long long A, int Ksel,
+                           long long total, float4 w, float scale_clamp, float img_h, float img_w, float min_size,
+                           float4* __restrict__ boxes, uint8_t* __restrict__ valid, int* __restrict__ nonfinite) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long n = i / Ksel, a = sel[i];
+  const float4 p = anchors[a];
+  const T* d = deltas + (n * A + a) * 4;
+  const float dv0 = ldf<T>(d), dv1 = ldf<T>(d + 1), dv2 = ldf<T>(d + 2), dv3 = ldf<T>(d + 3);
+  const float bw = p.z - p.x, bh = p.w - p.y;
+  const float cx = p.x + 0.5f * bw, cy = p.y + 0.5f * bh;
+  const float dx = dv0 / w.x, dy = dv1 / w.y;
+  const float dw = fminf(dv2 / w.z, scale_clamp), dh = fminf(dv3 / w.w, scale_clamp);
+  const float pcx = dx * bw + cx, pcy = dy * bh + cy;
+  const float pw = expf(dw) * bw, ph = expf(dh) * bh;
+  float x0 = pcx - 0.5f * pw, y0 = pcy - 0.5f * ph, x1 = pcx + 0.5f * pw, y1 = pcy + 0.5f * ph;
+  const bool fin = isfinite(x0) && isfinite(y0) && isfinite(x1) && isfinite(y1) && isfinite(scores[i]);
+  if (!fin) *nonfinite = 1;
+  x0 = fminf(fmaxf(x0, 0.f), img_w);      // Boxes.clip: x in [0, w], y in [0, h]
+  x1 = fminf(fmaxf(x1, 0.f), img_w);
+  y0 = fminf(fmaxf(y0, 0.f), img_h);
+  y1 = fminf(fmaxf(y1, 0.f), img_h);
+  boxes[i] = make_float4(x0, y0, x1, y1);
+  valid[i] = fin && (x1 - x0) > min_size && (y1 - y0) > min_size;
+}
+
 }  // namespace
 
 extern "C" {
@@ -224,6 +257,34 @@ int u2b_box_losses(int dtype, const void* scores, const int64_t* classes, const 
     return U2B_ERR_BAD_ARG;
   }
 #undef U2B_BOX
+  U2B_LAUNCH_CHECK();
+  return 0;
+}
+
+
+// sel (N, Ksel) int64: index of each selected anchor in [0, A); deltas (N, A, 4); anchors (A, 4); scores (N, Ksel) fp32.
+int u2b_rpn_decode_selected(int dtype, const void* deltas, const float* anchors, const int64_t* sel, const float* scores,
+                            int64_t N, int64_t A, int Ksel, const float* weights4, float scale_clamp, float img_h,
+                            float img_w, float min_size, float* boxes, uint8_t* valid, int* nonfinite,
+                            cudaStream_t stream) {
+  const long long total = N * Ksel;
+  if (total == 0) return 0;
+  U2B_CHECK_ARG(deltas && anchors && sel && scores && weights4 && boxes && valid && nonfinite, "rpn_decode_selected: null pointer");
+  const float4 w = make_float4(weights4[0], weights4[1], weights4[2], weights4[3]);
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+#define U2B_DEC(T)                                                                                                    \
+  rpn_decode_selected_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(deltas),                                \
+                                                          reinterpret_cast<const float4*>(anchors), sel, scores, A, Ksel, \
+                                                          total, w, scale_clamp, img_h, img_w, min_size,                 \
+                                                          reinterpret_cast<float4*>(boxes), valid, nonfinite)
+  if (dtype == 0) U2B_DEC(float);
+  else if (dtype == 1) U2B_DEC(__half);
+  else if (dtype == 2) U2B_DEC(__nv_bfloat16);
+  else {
+    u2b_set_error("rpn_decode_selected: unknown dtype %d", dtype);
+    return U2B_ERR_BAD_ARG;
+  }
+#undef U2B_DEC
   U2B_LAUNCH_CHECK();
   return 0;
 }

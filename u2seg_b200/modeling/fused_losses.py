@@ -115,3 +115,35 @@ def box_losses_reference(scores, deltas, classes, proposals, gt_boxes, num_fg_cl
     d = (deltas.float() - box2box.get_deltas(proposals, gt_boxes)).abs()
     l1 = torch.where(fg[:, None], d, torch.zeros((), dtype=d.dtype, device=d.device)).sum()
     return ce, l1, box2box.apply_deltas(deltas, proposals)
+
+
+def rpn_decode_selected(deltas, anchors, sel, scores, box2box, image_size, min_size):
+    """Decode + clip + validity of the anchors selected by the per-level top-k (rpn.py:497-533,
+    proposal_utils.py:85-121) in one kernel. deltas (N,A,4), anchors (A,4), sel (N,Ksel) int64, scores (N,Ksel).
+    Returns boxes (N,Ksel,4) fp32, valid (N,Ksel) bool, nonfinite (0-dim bool tensor)."""
+    L = _lib.lib()
+    N, A = deltas.shape[0], deltas.shape[1]
+    Ksel = sel.shape[1]
+    dl = deltas.contiguous()
+    boxes = torch.empty((N, Ksel, 4), dtype=torch.float32, device=dl.device)
+    valid = torch.empty((N, Ksel), dtype=torch.uint8, device=dl.device)
+    nonfinite = torch.zeros((), dtype=torch.int32, device=dl.device)
+    h, w = image_size
+    _lib.check(L.u2b_rpn_decode_selected(_CODE[dl.dtype], _p(dl), _p(anchors.float().contiguous()),
+                                         _p(sel.to(torch.int64).contiguous()), _p(scores.float().contiguous()), N, A, Ksel,
+                                         _w4(box2box.weights), float(box2box.scale_clamp), float(h), float(w),
+                                         float(min_size), _p(boxes), _p(valid), _p(nonfinite), _lib.stream_ptr()),
+               "u2b_rpn_decode_selected")
+    _lib.count_launches(1)
+    return boxes, valid.view(torch.bool), nonfinite != 0
+
+
+def rpn_decode_selected_reference(deltas, anchors, sel, scores, box2box, image_size, min_size):
+    N, Ksel = sel.shape
+    dsel = torch.gather(deltas, 1, sel[:, :, None].expand(-1, -1, 4))
+    b = box2box.apply_deltas(dsel.reshape(-1, 4), anchors[sel].reshape(-1, 4)).view(N, Ksel, 4)
+    finite = torch.isfinite(b).all(dim=2) & torch.isfinite(scores)
+    h, w = image_size
+    b = torch.stack((b[..., 0].clamp(0, w), b[..., 1].clamp(0, h), b[..., 2].clamp(0, w), b[..., 3].clamp(0, h)), dim=-1)
+    valid = finite & ((b[..., 2] - b[..., 0]) > min_size) & ((b[..., 3] - b[..., 1]) > min_size)
+    return b, valid, ~finite.all()

@@ -106,9 +106,11 @@ def rpn_static(rpn, images_size, features, gt_boxes, gt_valid, flags):
         gt_labels = torch.stack(labels_all)
         if not FUSED_DET_LOSSES:
             gt_anchor_deltas = torch.stack([rpn.box2box_transform.get_deltas(anchors_t, k) for k in matched_all])
+    deltas_cat = None
     if FUSED_DET_LOSSES:     # round-2 draft: one kernel for both RPN losses and their gradients (csrc/det_losses.cu)
         from .fused_losses import rpn_losses
-        obj, loc = rpn_losses(torch.cat(logits, dim=1), torch.cat(deltas, dim=1), anchors_t, gt_labels,
+        deltas_cat = torch.cat(deltas, dim=1)
+        obj, loc = rpn_losses(torch.cat(logits, dim=1), deltas_cat, anchors_t, gt_labels,
                               torch.stack(midx_all), gt_boxes, rpn.box2box_transform.weights)
     else:
         pos_mask = gt_labels == 1
@@ -122,6 +124,26 @@ def rpn_static(rpn, images_size, features, gt_boxes, gt_valid, flags):
     # ---- predict_proposals + find_top_rpn_proposals (rpn.py:482-533, proposal_utils.py:22-135) ----
     with torch.no_grad():
         pre, post = rpn.pre_nms_topk[True], rpn.post_nms_topk[True]
+        if FUSED_DET_LOSSES:   # round-2 draft: decode + clip + validity of the selected anchors in one kernel
+            from .fused_losses import rpn_decode_selected
+            sel, scs, lvl_ids, off = [], [], [], 0
+            for lid, lg in enumerate(logits):
+                k = min(lg.shape[1], pre)
+                sc, idx = lg.float().topk(k, dim=1)
+                sel.append(idx + off)
+                scs.append(sc)
+                lvl_ids.append(torch.full((k,), lid, dtype=torch.int64, device=anchors_t.device))
+                off += lg.shape[1]
+            tk_scores, lvl_ids = torch.cat(scs, 1), torch.cat(lvl_ids)
+            boxes_all, valid_all, nonfin = rpn_decode_selected(deltas_cat.detach(), anchors_t, torch.cat(sel, 1), tk_scores,
+                                                               rpn.box2box_transform, images_size, rpn.min_box_size)
+            flags.append(nonfin)
+            out_boxes, out_valid = [], []
+            for n in range(N):
+                keep, cnt = batched_nms_static(boxes_all[n], tk_scores[n], lvl_ids, rpn.nms_thresh, post, valid=valid_all[n])
+                out_boxes.append(boxes_all[n][keep])
+                out_valid.append(torch.arange(post, device=keep.device) < cnt)
+            return torch.stack(out_boxes), torch.stack(out_valid), losses
         tk_scores, tk_boxes, lvl_ids = [], [], []
         for lid, (a, lg, dl) in enumerate(zip(anchors, logits, deltas)):
             k = min(lg.shape[1], pre)
