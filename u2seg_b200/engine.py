@@ -3,12 +3,16 @@ detectron2/engine/{train_loop.py:479-521 AMPTrainer.run_step, defaults.py:60-79 
 defaults.py:253-321 DefaultPredictor} and detectron2/solver/build.py:63-139 (SGD momentum 0.9 +
 per-parameter gradient-norm clipping + WarmupMultiStepLR).
 
-Data parallelism (one process per GPU): every parameter's .grad is a view into ONE flat fp32 buffer, so
-the DDP-equivalent is a single NCCL all-reduce of that buffer per step (SUM / world), issued after
-backward; SyncBN statistics are exchanged inside the model. Loss scalars stay on the device.
+Data parallelism (one process per GPU): all gradients live in ONE flat fp32 buffer (dynamic step: every .grad is a
+view of it; static-graph step: autograd's gradients are gathered into it by a multi-tensor copy), so the
+DDP-equivalent is a single NCCL all-reduce of that buffer per step (SUM / world), issued after backward; SyncBN
+statistics are exchanged inside the model. Loss scalars stay on the device.
+
+Two step implementations share the kernels: the reference-shaped eager step (`static_graph=False`, any shapes) and the
+static-shape step replayed from one CUDA graph (`static_graph=True`: flat fp32 masters + bf16 compute weights, fused
+clip + SGD kernel, optional prefetch of the next batch on a copy stream).
 """
 import math
-
 import os
 
 import torch
@@ -87,9 +91,14 @@ class _BackboneTuple(torch.nn.Module):
 
 
 class Trainer:
-    """static_graph=True: the step runs through modeling/static_train.py (fixed-capacity device buffers, no host
-    synchronisation) and forward + backward + clip + SGD are captured in ONE CUDA graph that is replayed every step;
-    inputs are copied into static buffers. Requires same-size images and at most `g_max` instances per image."""
+    """train_loop.py:479-521 run_step + solver/build.py optimizer, on the B200 kernels.
+
+    static_graph=True: the step runs through modeling/static_train.py (fixed-capacity device buffers, no host
+    synchronisation) and forward + backward + all-reduce + clip + SGD are captured in ONE CUDA graph that is replayed
+    every step; inputs are copied into static buffers (`prefetch` stages the next batch meanwhile). Requires same-size
+    images and at most `g_max` instances per image. With bf16 autocast the conv / linear parameters become bf16
+    compute copies of fp32 masters held by the trainer (`master_parameters()` returns the fp32 values by name).
+    graph_backbone=True (eager step only): CUDA-graph just the static-shape backbone + FPN."""
 
     def __init__(self, cfg, model=None, amp_dtype=torch.bfloat16, device=None, graph_backbone=False,
                  static_graph=False, g_max=None):
@@ -199,6 +208,28 @@ class Trainer:
         for (name, p), m in zip(((n, q) for n, q in self.model.named_parameters() if q.requires_grad), self._upd_params):
             out[name] = m
         return out
+
+    def state_dict(self):
+        """model.state_dict() with the fp32 master values for the parameters the modules hold as bf16 compute copies:
+        what a checkpoint (DetectionCheckpointer, reference names and shapes) must contain."""
+        sd = self.model.state_dict()
+        for name, m in self.master_parameters().items():
+            sd[name] = m.detach().clone()
+        return sd
+
+    @torch.no_grad()
+    def load_state_dict(self, sd):
+        """inverse of state_dict(): loads parameters (into the fp32 masters when they exist) and buffers."""
+        masters = self.master_parameters()
+        own = self.model.state_dict()
+        missing = [k for k in own if k not in sd]
+        assert not missing, "missing keys: %s" % missing[:5]
+        for k, v in sd.items():
+            dst = masters.get(k, own.get(k))
+            assert dst is not None, "unexpected key %s" % k
+            dst.copy_(v.to(dst.device))
+        if self.lowp:
+            self._w16_flat.copy_(self._master_flat)
 
     @torch.no_grad()
     def broadcast_parameters(self, src=0):
