@@ -274,6 +274,13 @@ int u2b_rpn_decode_selected(int dtype, const void* deltas, const float* anchors,
                             float img_w, float min_size, float* boxes, uint8_t* valid, int* nonfinite,
                             u2b_stream_t stream);
 
+/* cascade_rcnn.py:193-236,271-299 relabelling of the refined boxes for cascade stage k > 0 on fixed-capacity slots
+ * (round-2 draft): clip, dead-slot handling, IoU matching against the image's valid GT boxes with threshold iou_thr
+ * (first maximum; foreground iff IoU >= thr), class K = background, -100 = dead slot, matched GT box. */
+int u2b_cascade_relabel(const float* refined, const uint8_t* ok_prev, const float* gt_boxes, const int64_t* gt_classes,
+                        const uint8_t* gt_valid, int64_t N, int R, int G, float img_h, float img_w, float iou_thr, int K,
+                        float* boxes, int64_t* classes, uint8_t* ok, float* gtb, u2b_stream_t stream);
+
 /* solver/build.py:63-73 (per-parameter gradient-norm clipping) + solver/build.py:119-139 (torch.optim.SGD: weight
  * decay, momentum, optional Nesterov) + the refresh of the bf16 compute weights, fused over flat buffers.
  * grad / master / mom: n fp32 each, same offsets, every parameter starting on a 64-element boundary.

@@ -174,3 +174,27 @@ def test_rpn_decode_selected_matches_torch(dtype):
     assert bool(f1) and bool(f2) and torch.equal(v1, v2)
     ok = v2
     assert torch.allclose(b1[ok], b2[ok], rtol=1e-6, atol=1e-3)
+
+
+def test_cascade_relabel_matches_torch_formulas():
+    """csrc/det_losses.cu cascade_relabel_kernel == the per-image clip / nonempty / Matcher / class-assignment ops of
+    static_train.roi_heads_static (INT outputs bit exact, boxes exact)."""
+    from u2seg_b200.layers import Matcher
+    from u2seg_b200.modeling.fused_losses import cascade_relabel, cascade_relabel_reference
+    g = torch.Generator().manual_seed(8)
+    N, R, G, K = 2, 512, 20, 800
+    gt = torch.stack([_boxes(G, g, 16, 300, 900).clamp(0, 1024) for _ in range(N)]).cuda()
+    gt_classes = torch.randint(0, K, (N, G), generator=g).cuda()
+    gt_valid = (torch.rand(N, G, generator=g) < 0.7).cuda()
+    gt_valid[1] = False                                        # an image without ground truth
+    src = gt[:, torch.randint(0, G, (R,), generator=g)]        # proposals near GT boxes -> a mix of fg / bg
+    refined = (src.cpu() + torch.randn(N, R, 4, generator=g) * 25).cuda()
+    refined[0, :7, 2] = refined[0, :7, 0] - 5                  # empty boxes
+    ok_prev = (torch.rand(N, R, generator=g) < 0.9).cuda()
+    for thr in (0.6, 0.7):
+        m = Matcher([thr], [0, 1], allow_low_quality_matches=False)
+        got = cascade_relabel(refined, ok_prev, gt, gt_classes, gt_valid, (1024, 1024), thr, K)
+        want = cascade_relabel_reference(refined, ok_prev, gt, gt_classes, gt_valid, (1024, 1024), m, K)
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]) and torch.equal(got[2], want[2])
+        live = want[2] & (want[1] != K)                        # the matched GT box only matters for foreground slots
+        assert torch.equal(got[3][live], want[3][live])

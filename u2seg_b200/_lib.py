@@ -65,6 +65,8 @@ SIGNATURES = {
                                c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "u2b_rpn_decode_selected": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p,
                                         c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "u2b_cascade_relabel": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_float,
+                                    c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "u2b_sgd_step_segments": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_float, c_int, c_int64, c_void_p]),
     "u2b_debug_nms_profile": (c_int, [c_int, c_void_p]),

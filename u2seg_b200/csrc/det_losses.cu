@@ -202,6 +202,52 @@ rpn_decode_selected_kernel(const T* __restrict__ deltas, const float4* __restric
   valid[i] = fin && (x1 - x0) > min_size && (y1 - y0) > min_size;
 }
 
+// Cascade stage k > 0 relabelling (cascade_rcnn.py:271-299 _create_proposals_from_boxes + :193-236
+// _match_and_label_boxes) on fixed-capacity slots, one thread per (image, slot): clip the refined box to the image,
+// drop empty boxes (keep the slot, mark it dead), match against the image's <= G ground-truth boxes with the stage's IoU
+// threshold (Matcher([thr], [0, 1], allow_low_quality_matches=False): first maximum, foreground iff IoU >= thr) and
+// emit class (K = background, -100 = dead slot) and the matched GT box. structures/boxes.py:336-358 pairwise_iou.
+__global__ void __launch_bounds__(256)
+cascade_relabel_kernel(const float4* __restrict__ refined, const uint8_t* __restrict__ ok_prev,
+                       const float4* __restrict__ gt_boxes, const int64_t* __restrict__ gt_classes,
+                       const uint8_t* __restrict__ gt_valid, int R, int G, long long total, float img_h, float img_w,
+                       float iou_thr, int K, float4* __restrict__ boxes, int64_t* __restrict__ classes,
+                       uint8_t* __restrict__ ok_out, float4* __restrict__ gtb) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long n = i / R;
+  float4 b = refined[i];
+  b.x = fminf(fmaxf(b.x, 0.f), img_w);
+  b.z = fminf(fmaxf(b.z, 0.f), img_w);
+  b.y = fminf(fmaxf(b.y, 0.f), img_h);
+  b.w = fminf(fmaxf(b.w, 0.f), img_h);
+  const bool ok = ok_prev[i] != 0 && (b.z - b.x) > 0.f && (b.w - b.y) > 0.f;
+  if (!ok) b = make_float4(0.f, 0.f, 1.f, 1.f);            // placeholder box of dead slots
+  const float area_b = (b.z - b.x) * (b.w - b.y);
+  float best = -1.f;
+  int best_j = 0;
+  bool any_gt = false;
+  const float4* g = gt_boxes + n * G;
+  for (int j = 0; j < G; ++j) {
+    if (!gt_valid[n * G + j]) continue;
+    any_gt = true;
+    const float4 t = g[j];
+    const float iw = fminf(b.z, t.z) - fmaxf(b.x, t.x), ih = fminf(b.w, t.w) - fmaxf(b.y, t.y);
+    const float inter = (iw > 0.f && ih > 0.f) ? iw * ih : 0.f;
+    const float iou = inter > 0.f ? inter / (area_b + (t.z - t.x) * (t.w - t.y) - inter) : 0.f;
+    if (iou > best) {          // first maximum
+      best = iou;
+      best_j = j;
+    }
+  }
+  long long cls = K;
+  if (any_gt && best >= iou_thr) cls = gt_classes[n * G + best_j];
+  boxes[i] = b;
+  classes[i] = ok ? cls : -100;
+  ok_out[i] = ok;
+  gtb[i] = g[best_j];
+}
+
 }  // namespace
 
 extern "C" {
@@ -285,6 +331,23 @@ int u2b_rpn_decode_selected(int dtype, const void* deltas, const float* anchors,
     return U2B_ERR_BAD_ARG;
   }
 #undef U2B_DEC
+  U2B_LAUNCH_CHECK();
+  return 0;
+}
+
+
+// refined (N, R, 4) fp32, ok_prev (N, R) bytes, gt_boxes (N, G, 4), gt_classes (N, G) int64, gt_valid (N, G) bytes.
+// Outputs: boxes (N, R, 4), classes (N, R) int64, ok (N, R) bytes, gtb (N, R, 4).
+int u2b_cascade_relabel(const float* refined, const uint8_t* ok_prev, const float* gt_boxes, const int64_t* gt_classes,
+                        const uint8_t* gt_valid, int64_t N, int R, int G, float img_h, float img_w, float iou_thr, int K,
+                        float* boxes, int64_t* classes, uint8_t* ok, float* gtb, cudaStream_t stream) {
+  const long long total = N * R;
+  if (total == 0) return 0;
+  U2B_CHECK_ARG(refined && ok_prev && gt_boxes && gt_classes && gt_valid && boxes && classes && ok && gtb && G > 0,
+                "cascade_relabel: bad arguments");
+  cascade_relabel_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(refined), ok_prev, reinterpret_cast<const float4*>(gt_boxes), gt_classes, gt_valid, R, G,
+      total, img_h, img_w, iou_thr, K, reinterpret_cast<float4*>(boxes), classes, ok, reinterpret_cast<float4*>(gtb));
   U2B_LAUNCH_CHECK();
   return 0;
 }

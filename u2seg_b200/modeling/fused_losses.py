@@ -147,3 +147,47 @@ def rpn_decode_selected_reference(deltas, anchors, sel, scores, box2box, image_s
     b = torch.stack((b[..., 0].clamp(0, w), b[..., 1].clamp(0, h), b[..., 2].clamp(0, w), b[..., 3].clamp(0, h)), dim=-1)
     valid = finite & ((b[..., 2] - b[..., 0]) > min_size) & ((b[..., 3] - b[..., 1]) > min_size)
     return b, valid, ~finite.all()
+
+
+def cascade_relabel(refined, ok_prev, gt_boxes, gt_classes, gt_valid, image_size, iou_thr, num_classes):
+    """cascade_rcnn.py:193-236,271-299 for stage k > 0 on fixed-capacity slots, all images in one launch.
+    refined (N,R,4), ok_prev (N,R) bool, gt_boxes (N,G,4), gt_classes (N,G), gt_valid (N,G) bool ->
+    boxes (N,R,4), classes (N,R) int64 (K background, -100 dead), ok (N,R) bool, matched GT boxes (N,R,4)."""
+    L = _lib.lib()
+    N, R = refined.shape[0], refined.shape[1]
+    G = gt_boxes.shape[1]
+    dev = refined.device
+    boxes = torch.empty((N, R, 4), dtype=torch.float32, device=dev)
+    classes = torch.empty((N, R), dtype=torch.int64, device=dev)
+    ok = torch.empty((N, R), dtype=torch.uint8, device=dev)
+    gtb = torch.empty((N, R, 4), dtype=torch.float32, device=dev)
+    h, w = image_size
+    _lib.check(L.u2b_cascade_relabel(_p(refined.float().contiguous()), _p(ok_prev.to(torch.uint8).contiguous()),
+                                     _p(gt_boxes.float().contiguous()), _p(gt_classes.to(torch.int64).contiguous()),
+                                     _p(gt_valid.to(torch.uint8).contiguous()), N, R, G, float(h), float(w), float(iou_thr),
+                                     int(num_classes), _p(boxes), _p(classes), _p(ok), _p(gtb), _lib.stream_ptr()),
+               "u2b_cascade_relabel")
+    _lib.count_launches(1)
+    return boxes, classes, ok.view(torch.bool), gtb
+
+
+def cascade_relabel_reference(refined, ok_prev, gt_boxes, gt_classes, gt_valid, image_size, matcher, num_classes):
+    """the per-image torch formulas of static_train.roi_heads_static (stage k > 0)."""
+    from .static_train import _clip, _nonempty
+    K = num_classes
+    dev = refined.device
+    dummy = torch.cat([torch.zeros(2, device=dev), torch.ones(2, device=dev)])
+    nb, nc, nok, ngb = [], [], [], []
+    for n in range(refined.shape[0]):
+        b = _clip(refined[n], image_size)
+        ok = ok_prev[n] & _nonempty(b)
+        b = torch.where(ok[:, None], b, dummy)
+        midx, lab = matcher.match_boxes(gt_boxes[n], b, gt_valid=gt_valid[n])
+        cls = gt_classes[n][midx]
+        cls = torch.where(lab == 0, torch.full_like(cls, K), cls)
+        cls = torch.where(gt_valid[n].any(), cls, torch.full_like(cls, K))
+        nb.append(b)
+        nc.append(torch.where(ok, cls, torch.full_like(cls, -100)))
+        nok.append(ok)
+        ngb.append(gt_boxes[n][midx])
+    return torch.stack(nb), torch.stack(nc), torch.stack(nok), torch.stack(ngb)

@@ -194,7 +194,14 @@ def roi_heads_static(rh, images_size, features, proposals, prop_valid, gt_boxes,
     losses = {}
     cur_boxes, cur_cls, cur_ok, cur_gtb = boxes0, cls0, ok0, gtb0
     for k in range(rh.num_cascade_stages):
-        if k > 0:
+        if k > 0 and FUSED_DET_LOSSES:     # round-2 draft: one kernel relabels every slot of every image
+            from .fused_losses import cascade_relabel
+            with torch.no_grad():
+                rb, rc, rok, rgb = cascade_relabel(torch.stack([b.detach() for b in prev_boxes]), torch.stack(cur_ok),
+                                                   gt_boxes, gt_classes, gt_valid, images_size,
+                                                   rh.proposal_matchers[k].thresholds[1], K)
+                cur_boxes, cur_cls, cur_ok, cur_gtb = list(rb), list(rc), list(rok), list(rgb)
+        elif k > 0:
             with torch.no_grad():
                 nb, nc, nok, ngb = [], [], [], []
                 for n in range(N):
