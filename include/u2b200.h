@@ -94,6 +94,16 @@ int u2b_roi_align_bwd(int dtype, int num_levels, float* const* grad_feats, const
                       const int32_t* levels, int64_t K, int P, const void* grad_out, float grad_scale,
                       u2b_stream_t stream);
 
+/* Channel-major variants (round-2 draft): out / grad_out are (K, C, P, P) contiguous, the layout torch.flatten(x, 1)
+ * of the box head reads (box_head.py:99-106), so no transposing copy is needed on either side of the FC layers. */
+int u2b_roi_align_chw_supported(int64_t C, int P);
+int u2b_roi_align_fwd_chw(int dtype, int num_levels, const void* const* feats, const int32_t* hs, const int32_t* ws,
+                          const float* scales, int64_t C, const float* rois5, const int32_t* levels, int64_t K, int P,
+                          void* out, u2b_stream_t stream);
+int u2b_roi_align_bwd_chw(int dtype, int num_levels, float* const* grad_feats, const int32_t* hs, const int32_t* ws,
+                          const float* scales, int64_t C, const float* rois5, const int32_t* levels, int64_t K, int P,
+                          const void* grad_out, float grad_scale, u2b_stream_t stream);
+
 /* layers/mask_ops.py:74-147 paste_masks_in_image: masks (N, M, M) fp32 probabilities, boxes (N, 4)
  * fp32 -> out (N, H, W) bytes in {0,1} (= `img >= threshold`). */
 int u2b_paste_masks(const float* masks, const float* boxes, int64_t N, int M, int H, int W,
@@ -220,6 +230,56 @@ int u2b_bn_xchg_bwd_coeff(const float* sums, const void* peers, int world, int r
 /* dx = A*dz + B*x + K; dres = dz when dres != NULL */
 int u2b_bn_bwd_apply(int dtype, const void* dy, const void* x, const void* y, const float* coeff, void* dx,
                      void* dres, int64_t P, int C, u2b_stream_t stream);
+
+/* nn.Upsample(scale_factor=s, mode="bilinear", align_corners=False) on NHWC activations (semantic_seg.py:195-199),
+ * round-2 draft. dir 0: out (N, h*s, w*s, C) = upsample(in (N, h, w, C)); dir 1: out (N, h, w, C) = gradient w.r.t. the
+ * input given in = gradient of the output (N, h*s, w*s, C) (gather form: deterministic). Even scales, C % 8 == 0. */
+int u2b_upsample_bilinear_supported(int C, int scale);
+int u2b_upsample_bilinear(int dtype, int dir, const void* in, void* out, int64_t N, int h, int w, int C, int scale,
+                          u2b_stream_t stream);
+
+/* Weight gradient of the NHWC convolutions on tcgen05 (round-2 draft, csrc/conv_wgrad_tc.cu): x (N,H,W,Cin),
+ * dy (N,OH,OW,Cout), fp16 (1) / bf16 (2). partials (u2b_conv2d_wgrad_ksplit(...), Cout, R, S, Cin) fp32 receives one
+ * partial per K split; dW (Cout,R,S,Cin) = their sum. Cin % 64 == 0, Cout % 128 == 0, 1x1 or 3x3 pad 1, stride 1|2. */
+int u2b_conv2d_wgrad_supported(int Cin, int Cout, int R, int S, int stride, int pad);
+int u2b_conv2d_wgrad_ksplit(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad);
+int u2b_conv2d_nhwc_wgrad(int dtype, const void* x, const void* dy, int N, int H, int W, int Cin, int Cout, int R, int S,
+                          int stride, int pad, float* partials, u2b_stream_t stream);
+
+/* Fused detection losses (value + closed-form gradient of the SUMMED loss in one pass; the caller applies the scalar
+ * normaliser). dtype 0 = fp32 / 1 = fp16 / 2 = bf16 for the head outputs; gradients are always fp32.
+ * u2b_rpn_losses - proposal_generator/rpn.py:365-429: logits (N, A), deltas (N, A, 4), anchors (A, 4) fp32, labels
+ *   (N, A) int8 in {-1 ignore, 0, 1}, matched (N, A) int64 index into gt_boxes (N, G, 4) fp32, weights4 (host) =
+ *   Box2BoxTransform weights. partials (u2b_rpn_losses_num_partials(N*A), 2) = [BCE sum, L1 sum] per CTA.
+ *   grad_logits / grad_deltas nullable.
+ * u2b_box_losses - roi_heads/fast_rcnn.py:307-352 (class-agnostic regression): scores (R, C), classes (R) int64
+ *   (-100 = ignored slot, K = background), deltas (R, 4), proposals / gt_boxes (R, 4) fp32. partials
+ *   (u2b_box_losses_num_partials(R), 2) = [CE sum, L1 sum over foreground rows]. refined (R, 4) fp32 (nullable) =
+ *   apply_deltas(deltas, proposals), the next cascade stage's boxes (cascade_rcnn.py:271-299). */
+int64_t u2b_rpn_losses_num_partials(int64_t total);
+int64_t u2b_box_losses_num_partials(int64_t R);
+int u2b_rpn_losses(int dtype, const void* logits, const void* deltas, const float* anchors, const int8_t* labels,
+                   const int64_t* matched, const float* gt_boxes, int64_t N, int64_t A, int G, const float* weights4,
+                   float* grad_logits, float* grad_deltas, float* partials, u2b_stream_t stream);
+int u2b_box_losses(int dtype, const void* scores, const int64_t* classes, const void* deltas, const float* proposals,
+                   const float* gt_boxes, int64_t R, int C, int K, const float* weights4, float scale_clamp,
+                   float* grad_scores, float* grad_deltas, float* refined, float* partials, u2b_stream_t stream);
+
+/* rpn.py:497-533 + proposal_utils.py:85-121 for the anchors kept by the per-level top-k (round-2 draft): decode, clip to
+ * the image, validity (finite, both sides > min_size). sel (N, Ksel) int64 anchor indices into deltas (N, A, 4) /
+ * anchors (A, 4); scores (N, Ksel) fp32. boxes (N, Ksel, 4) fp32, valid (N, Ksel) bytes, *nonfinite (device int, caller
+ * zeroes it) set when a selected box / score is not finite. */
+int u2b_rpn_decode_selected(int dtype, const void* deltas, const float* anchors, const int64_t* sel, const float* scores,
+                            int64_t N, int64_t A, int Ksel, const float* weights4, float scale_clamp, float img_h,
+                            float img_w, float min_size, float* boxes, uint8_t* valid, int* nonfinite,
+                            u2b_stream_t stream);
+
+/* cascade_rcnn.py:193-236,271-299 relabelling of the refined boxes for cascade stage k > 0 on fixed-capacity slots
+ * (round-2 draft): clip, dead-slot handling, IoU matching against the image's valid GT boxes with threshold iou_thr
+ * (first maximum; foreground iff IoU >= thr), class K = background, -100 = dead slot, matched GT box. */
+int u2b_cascade_relabel(const float* refined, const uint8_t* ok_prev, const float* gt_boxes, const int64_t* gt_classes,
+                        const uint8_t* gt_valid, int64_t N, int R, int G, float img_h, float img_w, float iou_thr, int K,
+                        float* boxes, int64_t* classes, uint8_t* ok, float* gtb, u2b_stream_t stream);
 
 /* solver/build.py:63-73 (per-parameter gradient-norm clipping) + solver/build.py:119-139 (torch.optim.SGD: weight
  * decay, momentum, optional Nesterov) + the refresh of the bf16 compute weights, fused over flat buffers.

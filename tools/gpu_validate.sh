@@ -4,6 +4,7 @@
 #   gpurun --timeout 1500 -- 'bash tools/gpu_validate.sh full'      whole -m gpu suite + full bench line + reference arm
 #   gpurun --timeout 900 -- 'bash tools/gpu_validate.sh profile'    ncu launch list of one graph replay + phase summary
 #   gpurun --gpus 2 --timeout 900 -- 'bash tools/gpu_validate.sh multi 2'   torchrun tests + N-GPU bench
+#   gpurun --timeout 1500 -- 'bash tools/gpu_validate.sh drafts'    round-2 draft kernels: parity tests, then the bench per flag
 # Results land in gpurun_out/ (merged back by gpurun); every step is under its own `timeout`.
 set -u
 mode=${1:-quick}
@@ -40,5 +41,15 @@ case "$mode" in
     U2B_BENCH_SKIP_CPU=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 \
         --master-port 29511 bench.py --gpus "$n" --steps 20 --warmup 3 > "gpurun_out/bench_n$n.json" 2> "gpurun_out/bench_n$n.err"
     echo "bench rc=$?"; tail -c 300 "gpurun_out/bench_n$n.err"; line "gpurun_out/bench_n$n.json" ;;
-  *) echo "usage: $0 quick|full|profile|multi [N]"; exit 2 ;;
+  drafts)
+    # round-2 drafts (never run on hardware in round 1): their parity tests first, then the step with everything on
+    U2B_RUN_DRAFT_TESTS=1 timeout 600 python -m pytest tests/test_fused_losses_gpu.py -m gpu -q 2>&1 | tail -15
+    for flags in "U2B_UPSAMPLE_KERNEL=1" "U2B_ROI_CHW=1" "U2B_FUSED_DET_LOSSES=1" "U2B_TC_WGRAD=1" \
+                 "U2B_UPSAMPLE_KERNEL=1 U2B_ROI_CHW=1 U2B_FUSED_DET_LOSSES=1 U2B_TC_WGRAD=1"; do
+      echo "== $flags"
+      env $flags U2B_BENCH_SKIP_CPU=1 U2B_BENCH_SKIP_KMEANS=1 timeout 200 python bench.py --steps 20 --warmup 3 \
+          > gpurun_out/bench_drafts.json 2> gpurun_out/bench_drafts.err || tail -c 600 gpurun_out/bench_drafts.err
+      line gpurun_out/bench_drafts.json
+    done ;;
+  *) echo "usage: $0 quick|full|profile|multi [N]|drafts"; exit 2 ;;
 esac

@@ -35,6 +35,11 @@ SIGNATURES = {
                                   c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "u2b_roi_align_bwd": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                   c_void_p, c_int64, c_int, c_void_p, c_float, c_void_p]),
+    "u2b_roi_align_chw_supported": (c_int, [c_int64, c_int]),
+    "u2b_roi_align_fwd_chw": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                      c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "u2b_roi_align_bwd_chw": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                      c_void_p, c_int64, c_int, c_void_p, c_float, c_void_p]),
     "u2b_paste_masks": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "u2b_crop_resize_masks": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p,
                                       c_void_p, c_void_p]),
@@ -46,6 +51,22 @@ SIGNATURES = {
     "u2b_stem_conv_fwd": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "u2b_stem_conv_wgrad_num_partials": (c_int, [c_int64, c_int, c_int]),
     "u2b_stem_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "u2b_conv2d_wgrad_supported": (c_int, [c_int] * 6),
+    "u2b_conv2d_wgrad_ksplit": (c_int, [c_int] * 9),
+    "u2b_conv2d_nhwc_wgrad": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_int, c_void_p, c_void_p]),
+    "u2b_upsample_bilinear_supported": (c_int, [c_int, c_int]),
+    "u2b_upsample_bilinear": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
+    "u2b_rpn_losses_num_partials": (c_int64, [c_int64]),
+    "u2b_box_losses_num_partials": (c_int64, [c_int64]),
+    "u2b_rpn_losses": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "u2b_box_losses": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
+                               c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "u2b_rpn_decode_selected": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p,
+                                        c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "u2b_cascade_relabel": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_float,
+                                    c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "u2b_sgd_step_segments": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_float, c_int, c_int64, c_void_p]),
     "u2b_debug_nms_profile": (c_int, [c_int, c_void_p]),

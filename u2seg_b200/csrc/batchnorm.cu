@@ -105,6 +105,9 @@ struct V8<__nv_bfloat16> {
 };
 
 constexpr int BN_THREADS = 256;
+#ifndef BN_STRIPS_PER_SM
+#define BN_STRIPS_PER_SM 4
+#endif
 constexpr int BN_VPB = 32;  // channel vectors (of 8) per block -> 256 channels per channel group
 
 inline int vecs_per_block(int C) { return (C / 8 < BN_VPB) ? C / 8 : BN_VPB; }
@@ -112,14 +115,16 @@ inline int channel_groups(int C) { return (C / 8 + BN_VPB - 1) / BN_VPB; }
 inline int num_strips(long long P, int C) {
   const int lanes = BN_THREADS / vecs_per_block(C);
   long long s = P / (static_cast<long long>(lanes) * 8);
-  const long long cap = static_cast<long long>(u2b_num_sms()) * 2 / channel_groups(C);
+  // r2 draft: 4 strips per SM (was 2). ncu (profiles/r01_ncu_full_stem_fwd_bn_reduce.txt): 23 % occupancy and 2.1 TB/s
+  // on 67 MB tensors with 2 CTAs/SM; more CTAs in flight hide the DRAM latency of the short strips of small layers.
+  const long long cap = static_cast<long long>(u2b_num_sms()) * BN_STRIPS_PER_SM / channel_groups(C);
   if (s > cap) s = cap;
   if (s < 1) s = 1;
   return static_cast<int>(s);
 }
 
 template <typename T, int MODE>
-__global__ void __launch_bounds__(BN_THREADS)
+__global__ void __launch_bounds__(BN_THREADS, (MODE == 0 ? 4 : 2))
 bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ x, const T* __restrict__ y,
                  const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int C,
                  int vpb, float* __restrict__ partials) {
@@ -213,11 +218,20 @@ bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ x, const T* __re
   }
 }
 
-__global__ void bn_sum_partials_kernel(const float* __restrict__ partials, int S, int C2, float* __restrict__ sums) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C2) return;
+// block = 8 columns x 32 strip lanes (like bn_finalize_kernel): the S rows are summed by 32 lanes in parallel and
+// combined in a fixed order, instead of one thread walking all S rows serially.
+__global__ void __launch_bounds__(256)
+bn_sum_partials_kernel(const float* __restrict__ partials, int S, int C2, float* __restrict__ sums) {
+  __shared__ float sh[32][8];
+  const int cl = threadIdx.x & 7, sl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cl;
   float s = 0.f;
-  for (int i = 0; i < S; ++i) s += partials[static_cast<size_t>(i) * C2 + c];
+  if (c < C2)
+    for (int i = sl; i < S; i += 32) s += partials[static_cast<size_t>(i) * C2 + c];
+  sh[sl][cl] = s;
+  __syncthreads();
+  if (sl != 0 || c >= C2) return;
+  for (int q = 1; q < 32; ++q) s += sh[q][cl];
   sums[c] = s;
 }
 
@@ -602,7 +616,7 @@ int u2b_bn_stats(int dtype, const void* x, int64_t P, int C, float* partials, cu
 // sums[0:C2] = sum over the S partial rows (used when the sums are all-reduced across ranks before finalize/coeff)
 int u2b_bn_sum_partials(const float* partials, int S, int C2, float* sums, cudaStream_t stream) {
   U2B_CHECK_ARG(partials && sums && S > 0 && C2 > 0, "bn_sum_partials: bad arguments");
-  bn_sum_partials_kernel<<<(C2 + 127) / 128, 128, 0, stream>>>(partials, S, C2, sums);
+  bn_sum_partials_kernel<<<(C2 + 7) / 8, 256, 0, stream>>>(partials, S, C2, sums);
   U2B_LAUNCH_CHECK();
   return 0;
 }

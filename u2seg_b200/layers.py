@@ -99,9 +99,10 @@ class _MultiLevelROIAlign(torch.autograd.Function):
     """out[K, C, P, P] (channels_last) = ROIAlignV2 of rois on their assigned pyramid level."""
 
     @staticmethod
-    def forward(ctx, rois5, levels, P, scales, token, holder, grad_scale, *feats):
+    def forward(ctx, rois5, levels, P, scales, token, holder, grad_scale, chw, *feats):
         ctx.holder = holder
         ctx.grad_scale = float(grad_scale)
+        ctx.chw = bool(chw)
         L = _lib.lib()
         f0 = feats[0]
         _need_cuda(f0, "roi_align")
@@ -109,15 +110,20 @@ class _MultiLevelROIAlign(torch.autograd.Function):
         feats_cl = [to_nhwc(f) for f in feats]
         C = f0.shape[1]
         K = rois5.shape[0]
-        out = torch.empty((K, P, P, C), dtype=dt, device=f0.device).permute(0, 3, 1, 2)   # (K,C,P,P), NHWC storage
+        if ctx.chw:    # round-2 draft: (K,C,P,P) contiguous, what the box head's flatten reads
+            assert L.u2b_roi_align_chw_supported(C, P), "channel-major ROIAlign: C=%d P=%d not supported" % (C, P)
+            out = torch.empty((K, C, P, P), dtype=dt, device=f0.device)
+        else:
+            out = torch.empty((K, P, P, C), dtype=dt, device=f0.device).permute(0, 3, 1, 2)   # (K,C,P,P), NHWC storage
         if K > 0:
             ptrs = _arr(ctypes.c_void_p, [f.data_ptr() for f in feats_cl])
             hs = _arr(ctypes.c_int32, [f.shape[2] for f in feats_cl])
             ws = _arr(ctypes.c_int32, [f.shape[3] for f in feats_cl])
             sc = _arr(ctypes.c_float, list(scales))
-            _lib.check(L.u2b_roi_align_fwd(_DTYPE_CODE[dt], len(feats_cl), ptrs, hs, ws, sc, C, _lib.ptr(rois5),
-                                           _lib.ptr(levels) if levels is not None else None, K, P,
-                                           ctypes.c_void_p(out.data_ptr()), _lib.stream_ptr()), "u2b_roi_align_fwd")
+            fwd = L.u2b_roi_align_fwd_chw if ctx.chw else L.u2b_roi_align_fwd
+            _lib.check(fwd(_DTYPE_CODE[dt], len(feats_cl), ptrs, hs, ws, sc, C, _lib.ptr(rois5),
+                           _lib.ptr(levels) if levels is not None else None, K, P,
+                           ctypes.c_void_p(out.data_ptr()), _lib.stream_ptr()), "u2b_roi_align_fwd")
             _lib.count_launches(1)
         ctx.save_for_backward(rois5, levels if levels is not None else torch.empty(0))
         ctx.has_levels = levels is not None
@@ -137,20 +143,20 @@ class _MultiLevelROIAlign(torch.autograd.Function):
         else:
             grads = [torch.zeros((s[0], s[2], s[3], s[1]), dtype=torch.float32, device=gout.device) for s in shapes]
         if K > 0:
-            g = to_nhwc(gout.to(dt))
+            g = gout.to(dt).contiguous() if ctx.chw else to_nhwc(gout.to(dt))
             ptrs = _arr(ctypes.c_void_p, [t.data_ptr() for t in grads])
             hs = _arr(ctypes.c_int32, [s[2] for s in shapes])
             ws = _arr(ctypes.c_int32, [s[3] for s in shapes])
             sc = _arr(ctypes.c_float, list(scales))
-            _lib.check(L.u2b_roi_align_bwd(_DTYPE_CODE[dt], len(shapes), ptrs, hs, ws, sc, C, _lib.ptr(rois5),
-                                           _lib.ptr(levels) if ctx.has_levels else None, K, P,
-                                           ctypes.c_void_p(g.data_ptr()), ctx.grad_scale, _lib.stream_ptr()),
-                       "u2b_roi_align_bwd")
+            bwd = L.u2b_roi_align_bwd_chw if ctx.chw else L.u2b_roi_align_bwd
+            _lib.check(bwd(_DTYPE_CODE[dt], len(shapes), ptrs, hs, ws, sc, C, _lib.ptr(rois5),
+                           _lib.ptr(levels) if ctx.has_levels else None, K, P,
+                           ctypes.c_void_p(g.data_ptr()), ctx.grad_scale, _lib.stream_ptr()), "u2b_roi_align_bwd")
             _lib.count_launches(1)
         if shared:   # gradients reach the features through _PoolTap; the token only orders the backward passes
-            return (None, None, None, None, gout.new_zeros(()), None, None) + tuple(None for _ in shapes)
+            return (None, None, None, None, gout.new_zeros(()), None, None, None) + tuple(None for _ in shapes)
         outs = [t.permute(0, 3, 1, 2).to(dt) for t in grads]   # logical NCHW views of the NHWC grads
-        return (None, None, None, None, None, None, None) + tuple(outs)
+        return (None, None, None, None, None, None, None, None) + tuple(outs)
 
 
 class ROIAlign(nn.Module):
@@ -170,7 +176,7 @@ class ROIAlign(nn.Module):
     def forward(self, input, rois):
         assert rois.dim() == 2 and rois.size(1) == 5
         rois = _aligned(rois, torch.float32)
-        return _MultiLevelROIAlign.apply(rois, None, self.output_size, (self.spatial_scale,), None, None, 1.0, input)
+        return _MultiLevelROIAlign.apply(rois, None, self.output_size, (self.spatial_scale,), None, None, 1.0, False, input)
 
 
 def convert_boxes_to_pooler_format(box_tensors):
@@ -186,8 +192,9 @@ class ROIPooler(nn.Module):
     levels instead of per-level nonzero + roi_align + index_put_."""
 
     def __init__(self, output_size, scales, sampling_ratio=0, pooler_type="ROIAlignV2", canonical_box_size=224,
-                 canonical_level=4):
+                 canonical_level=4, chw_output=False):
         super().__init__()
+        self.chw_output = bool(chw_output)     # round-2 draft: (M,C,P,P) contiguous instead of channels_last
         import math
         assert pooler_type == "ROIAlignV2" and sampling_ratio == 0
         self.output_size = output_size if isinstance(output_size, int) else output_size[0]
@@ -212,8 +219,9 @@ class ROIPooler(nn.Module):
                                                  self.canonical_level)
         if tap is not None and tap.token is not None:
             return _MultiLevelROIAlign.apply(rois, levels, self.output_size, self.scales, tap.token, tap.holder,
-                                             grad_scale, *tap.feats)
-        return _MultiLevelROIAlign.apply(rois, levels, self.output_size, self.scales, None, None, grad_scale, *x)
+                                             grad_scale, self.chw_output, *tap.feats)
+        return _MultiLevelROIAlign.apply(rois, levels, self.output_size, self.scales, None, None, grad_scale,
+                                         self.chw_output, *x)
 
 
 # --------------------------------------------------------------------------------------
@@ -303,6 +311,47 @@ def upsample_cross_entropy(logits, targets, scale, ignore_index):
 def upsample_cross_entropy_supported(logits, scale):
     return logits.is_cuda and logits.dtype in _DTYPE_CODE and float(scale) == int(scale) and \
         bool(_lib.lib().u2b_upsample_ce_supported(logits.shape[1], int(scale)))
+
+
+# --------------------------------------------------------------------------------------
+# bilinear upsampling on NHWC activations (round-2 draft, csrc/upsample.cu)
+# --------------------------------------------------------------------------------------
+class _UpsampleBilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        L = _lib.lib()
+        xc = to_nhwc(x)
+        N, C, h, w = xc.shape
+        y = torch.empty((N, h * scale, w * scale, C), dtype=xc.dtype, device=xc.device).permute(0, 3, 1, 2)
+        _lib.check(L.u2b_upsample_bilinear(_DTYPE_CODE[xc.dtype], 0, ctypes.c_void_p(xc.data_ptr()),
+                                           ctypes.c_void_p(y.data_ptr()), N, h, w, C, scale, _lib.stream_ptr()),
+                   "u2b_upsample_bilinear")
+        _lib.count_launches(1)
+        ctx.meta = (N, C, h, w, scale, xc.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        L = _lib.lib()
+        N, C, h, w, scale, dt = ctx.meta
+        g = to_nhwc(gy.to(dt))
+        dx = torch.empty((N, h, w, C), dtype=dt, device=g.device).permute(0, 3, 1, 2)
+        _lib.check(L.u2b_upsample_bilinear(_DTYPE_CODE[dt], 1, ctypes.c_void_p(g.data_ptr()),
+                                           ctypes.c_void_p(dx.data_ptr()), N, h, w, C, scale, _lib.stream_ptr()),
+                   "u2b_upsample_bilinear")
+        _lib.count_launches(1)
+        return dx, None
+
+
+def upsample_bilinear(x, scale):
+    """F.interpolate(x, scale_factor=scale, mode="bilinear", align_corners=False) for NHWC CUDA tensors."""
+    _need_cuda(x, "upsample_bilinear")
+    return _UpsampleBilinear.apply(x, int(scale))
+
+
+def upsample_bilinear_supported(x, scale):
+    return (x.is_cuda and x.dim() == 4 and x.dtype in _DTYPE_CODE and scale is not None and float(scale) == int(scale)
+            and bool(_lib.lib().u2b_upsample_bilinear_supported(x.shape[1], int(scale))))
 
 
 # --------------------------------------------------------------------------------------

@@ -28,6 +28,30 @@ def conv2d_nhwc(x, w_ohwi, stride, pad, bias=None, residual=None, relu=False):
     return out
 
 
+TC_WGRAD = __import__("os").environ.get("U2B_TC_WGRAD", "0") == "1"     # round-2 draft (csrc/conv_wgrad_tc.cu)
+
+
+def wgrad_supported(x, weight, stride, pad):
+    Cout, Cin, R, S = weight.shape
+    return (x.is_cuda and x.dtype in _CODE and
+            bool(_lib.lib().u2b_conv2d_wgrad_supported(Cin, Cout, R, S, stride, pad)))
+
+
+def conv2d_nhwc_wgrad(x, gy, R, S, stride, pad):
+    """dW of conv(x, W) given dY, on tcgen05 (round-2 draft). x (N,Cin,H,W), gy (N,Cout,OH,OW), both channels_last
+    half tensors. Returns fp32 logical (Cout,Cin,R,S) with OHWI (channels_last) storage."""
+    L = _lib.lib()
+    N, Cin, H, W = x.shape
+    Cout = gy.shape[1]
+    ks = int(L.u2b_conv2d_wgrad_ksplit(N, H, W, Cin, Cout, R, S, stride, pad))
+    parts = torch.empty((ks, Cout, R, S, Cin), dtype=torch.float32, device=x.device)
+    _lib.check(L.u2b_conv2d_nhwc_wgrad(_CODE[x.dtype], ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(gy.data_ptr()), N, H, W,
+                                       Cin, Cout, R, S, stride, pad, ctypes.c_void_p(parts.data_ptr()), _lib.stream_ptr()),
+               "u2b_conv2d_nhwc_wgrad")
+    _lib.count_launches(1)
+    return parts.sum(0).permute(0, 3, 1, 2)
+
+
 def set_cluster(cl):
     """thread-block cluster size of the conv kernel (1 = no multicast, 2, 4)."""
     _lib.check(_lib.lib().u2b_conv2d_set_cluster(int(cl)), "u2b_conv2d_set_cluster")
@@ -68,7 +92,9 @@ class _ConvTC(torch.autograd.Function):
             wt = weight.detach().to(dt).flip(2, 3).permute(1, 2, 3, 0).contiguous()  # (Cin,R,S,Cout)
             gx = conv2d_nhwc(gy, wt, 1, R - 1 - pad, None, None, False)
         need_gx_lib = ctx.needs_input_grad[0] and gx is None
-        mask = [need_gx_lib, ctx.needs_input_grad[1], False]
+        if TC_WGRAD and ctx.needs_input_grad[1] and wgrad_supported(xc, weight, stride, pad):
+            gw = conv2d_nhwc_wgrad(xc, gy, weight.shape[2], weight.shape[3], stride, pad).to(weight.dtype)   # r2 draft
+        mask = [need_gx_lib, ctx.needs_input_grad[1] and gw is None, False]
         if mask[0] or mask[1]:
             w_dt = weight.detach().to(dt)
             g_in, g_w, _ = torch.ops.aten.convolution_backward(gy, xc, w_dt, None, [stride, stride], [pad, pad], [1, 1],

@@ -6,6 +6,8 @@ convolutions, all weight gradients and the batch-norm statistics go through the 
 (cuDNN via F.conv2d, ATen batch_norm; counted as library calls, like cuBLAS), in channels_last. ROI pooling,
 NMS, matching, mask ops and k-means always run in libu2b200.
 """
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn.functional as F
@@ -52,6 +54,7 @@ def batch_norm(x, bn, relu=False):
 
 FUSED_BN = True     # SyncBN + residual + ReLU through libu2b200 (csrc/batchnorm.cu) in training mode
 FUSED_GN = True     # GroupNorm + ReLU (semantic head) through the same NHWC kernels, per image
+UPSAMPLE_KERNEL = os.environ.get("U2B_UPSAMPLE_KERNEL", "0") == "1"   # round-2 draft, not validated on hardware
 STEM_KERNEL = True  # csrc/stem_conv.cu for the 7x7/2 3->64 stem (bf16 autocast only)
 
 
@@ -112,6 +115,10 @@ class Upsample(nn.Upsample):
     """nn.Upsample through `interpolate` above (no parameters: state_dict unchanged)."""
 
     def forward(self, x):
+        if UPSAMPLE_KERNEL and self.mode == "bilinear" and self.align_corners is False and self.size is None:
+            from ..layers import upsample_bilinear, upsample_bilinear_supported    # round-2 draft (csrc/upsample.cu)
+            if upsample_bilinear_supported(x, self.scale_factor):
+                return upsample_bilinear(x, self.scale_factor)
         return interpolate(x, size=self.size, scale_factor=self.scale_factor, mode=self.mode,
                            align_corners=self.align_corners)
 

@@ -285,7 +285,10 @@ class CascadeROIHeads(nn.Module):
         cascade_w, cascade_ious = cfg.MODEL.ROI_BOX_CASCADE_HEAD.BBOX_REG_WEIGHTS, cfg.MODEL.ROI_BOX_CASCADE_HEAD.IOUS
         assert len(cascade_w) == len(cascade_ious) and cascade_ious[0] == rh.IOU_THRESHOLDS[0]
         self.num_cascade_stages = len(cascade_ious)
-        self.box_pooler = ROIPooler(bh.POOLER_RESOLUTION, scales, 0, "ROIAlignV2")
+        import os
+        # round-2 draft (off by default): pool straight into the (K, C*P*P) layout the FC layers flatten to
+        self.box_pooler = ROIPooler(bh.POOLER_RESOLUTION, scales, 0, "ROIAlignV2",
+                                    chw_output=os.environ.get("U2B_ROI_CHW", "0") == "1")
         pooled = ShapeSpec(channels=in_channels, width=bh.POOLER_RESOLUTION, height=bh.POOLER_RESOLUTION)
         heads, predictors, matchers = [], [], []
         for iou, w in zip(cascade_ious, cascade_w):

@@ -15,6 +15,8 @@ gt_valid (N,G) bool, gt_masks (N,G,H,W) bool, sem_seg (N,H,W); all images of a b
 """
 import math
 
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -22,6 +24,9 @@ from ..layers import FeatureTap, batched_nms_static, crop_and_resize_masks
 from ..structures import Boxes
 
 # sampling keys: uniform random numbers by default; tests swap in a deterministic key function
+# round-2 draft (csrc/det_losses.cu), not validated on hardware at the end of round 1: off unless explicitly enabled
+FUSED_DET_LOSSES = os.environ.get("U2B_FUSED_DET_LOSSES", "0") == "1"
+
 _rand_keys = lambda mask: torch.rand(mask.shape, dtype=torch.float32, device=mask.device)  # noqa: E731
 
 
@@ -87,7 +92,7 @@ def rpn_static(rpn, images_size, features, gt_boxes, gt_valid, flags):
     A = anchors_t.shape[0]
     # ---- label_and_sample_anchors (rpn.py:307-363) ----
     with torch.no_grad():
-        labels_all, matched_all = [], []
+        labels_all, matched_all, midx_all = [], [], []
         for n in range(N):
             midx, lab = rpn.anchor_matcher.match_boxes(gt_boxes[n], anchors_t, gt_valid=gt_valid[n])
             idx, ok, fg = subsample_static(lab == 1, lab == 0, rpn.batch_size_per_image, rpn.positive_fraction)
@@ -95,20 +100,50 @@ def rpn_static(rpn, images_size, features, gt_boxes, gt_valid, flags):
             # unselected slots are redirected to a scratch element (index A) so they can never collide with a selected anchor
             out.scatter_(0, torch.where(ok, idx, torch.full_like(idx, A)), fg.to(torch.int8))
             labels_all.append(out[:A])
-            matched_all.append(gt_boxes[n][midx])
+            midx_all.append(midx)
+            if not FUSED_DET_LOSSES:
+                matched_all.append(gt_boxes[n][midx])
         gt_labels = torch.stack(labels_all)
-        gt_anchor_deltas = torch.stack([rpn.box2box_transform.get_deltas(anchors_t, k) for k in matched_all])
-    pos_mask = gt_labels == 1
-    loc = _masked_l1(torch.cat(deltas, dim=1), gt_anchor_deltas, pos_mask)
-    valid = gt_labels >= 0
-    obj = F.binary_cross_entropy_with_logits(torch.cat(logits, dim=1).float(), gt_labels.to(torch.float32),
-                                             weight=valid.to(torch.float32), reduction="sum")
+        if not FUSED_DET_LOSSES:
+            gt_anchor_deltas = torch.stack([rpn.box2box_transform.get_deltas(anchors_t, k) for k in matched_all])
+    deltas_cat = None
+    if FUSED_DET_LOSSES:     # round-2 draft: one kernel for both RPN losses and their gradients (csrc/det_losses.cu)
+        from .fused_losses import rpn_losses
+        deltas_cat = torch.cat(deltas, dim=1)
+        obj, loc = rpn_losses(torch.cat(logits, dim=1), deltas_cat, anchors_t, gt_labels,
+                              torch.stack(midx_all), gt_boxes, rpn.box2box_transform.weights)
+    else:
+        pos_mask = gt_labels == 1
+        loc = _masked_l1(torch.cat(deltas, dim=1), gt_anchor_deltas, pos_mask)
+        valid = gt_labels >= 0
+        obj = F.binary_cross_entropy_with_logits(torch.cat(logits, dim=1).float(), gt_labels.to(torch.float32),
+                                                 weight=valid.to(torch.float32), reduction="sum")
     normalizer = rpn.batch_size_per_image * N
     losses = {"loss_rpn_cls": obj / normalizer * rpn.loss_weight["loss_rpn_cls"],
               "loss_rpn_loc": loc / normalizer * rpn.loss_weight["loss_rpn_loc"]}
     # ---- predict_proposals + find_top_rpn_proposals (rpn.py:482-533, proposal_utils.py:22-135) ----
     with torch.no_grad():
         pre, post = rpn.pre_nms_topk[True], rpn.post_nms_topk[True]
+        if FUSED_DET_LOSSES:   # round-2 draft: decode + clip + validity of the selected anchors in one kernel
+            from .fused_losses import rpn_decode_selected
+            sel, scs, lvl_ids, off = [], [], [], 0
+            for lid, lg in enumerate(logits):
+                k = min(lg.shape[1], pre)
+                sc, idx = lg.float().topk(k, dim=1)
+                sel.append(idx + off)
+                scs.append(sc)
+                lvl_ids.append(torch.full((k,), lid, dtype=torch.int64, device=anchors_t.device))
+                off += lg.shape[1]
+            tk_scores, lvl_ids = torch.cat(scs, 1), torch.cat(lvl_ids)
+            boxes_all, valid_all, nonfin = rpn_decode_selected(deltas_cat.detach(), anchors_t, torch.cat(sel, 1), tk_scores,
+                                                               rpn.box2box_transform, images_size, rpn.min_box_size)
+            flags.append(nonfin)
+            out_boxes, out_valid = [], []
+            for n in range(N):
+                keep, cnt = batched_nms_static(boxes_all[n], tk_scores[n], lvl_ids, rpn.nms_thresh, post, valid=valid_all[n])
+                out_boxes.append(boxes_all[n][keep])
+                out_valid.append(torch.arange(post, device=keep.device) < cnt)
+            return torch.stack(out_boxes), torch.stack(out_valid), losses
         tk_scores, tk_boxes, lvl_ids = [], [], []
         for lid, (a, lg, dl) in enumerate(zip(anchors, logits, deltas)):
             k = min(lg.shape[1], pre)
@@ -159,7 +194,14 @@ def roi_heads_static(rh, images_size, features, proposals, prop_valid, gt_boxes,
     losses = {}
     cur_boxes, cur_cls, cur_ok, cur_gtb = boxes0, cls0, ok0, gtb0
     for k in range(rh.num_cascade_stages):
-        if k > 0:
+        if k > 0 and FUSED_DET_LOSSES:     # round-2 draft: one kernel relabels every slot of every image
+            from .fused_losses import cascade_relabel
+            with torch.no_grad():
+                rb, rc, rok, rgb = cascade_relabel(torch.stack([b.detach() for b in prev_boxes]), torch.stack(cur_ok),
+                                                   gt_boxes, gt_classes, gt_valid, images_size,
+                                                   rh.proposal_matchers[k].thresholds[1], K)
+                cur_boxes, cur_cls, cur_ok, cur_gtb = list(rb), list(rc), list(rok), list(rgb)
+        elif k > 0:
             with torch.no_grad():
                 nb, nc, nok, ngb = [], [], [], []
                 for n in range(N):
@@ -181,6 +223,13 @@ def roi_heads_static(rh, images_size, features, proposals, prop_valid, gt_boxes,
         pb, gb = torch.cat(cur_boxes), torch.cat(cur_gtb)
         count = ok_all.sum().clamp(min=1).to(torch.float32)
         # fast_rcnn.py:307-352: mean CE over the sampled rows; L1 over the foreground rows / #rows
+        if FUSED_DET_LOSSES:   # round-2 draft: CE + L1 + refined boxes in one kernel (dead slots carry class -100)
+            from .fused_losses import box_losses
+            ce, l1, refined = box_losses(scores, deltas, cls_all, pb, gb, K, rh.box_predictor[k].box2box_transform)
+            losses["loss_cls_stage%d" % k] = ce / count
+            losses["loss_box_reg_stage%d" % k] = l1 / count * rh.box_predictor[k].loss_weight["loss_box_reg"]
+            prev_boxes = refined.split(R)
+            continue
         ce = F.cross_entropy(scores.float(), cls_all, reduction="sum", ignore_index=-100)
         losses["loss_cls_stage%d" % k] = ce / count
         fg = ok_all & (cls_all >= 0) & (cls_all < K)
