@@ -1,7 +1,7 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) in this
 container through the dependency stubs in oracle/ref_stubs (test infrastructure only).
 
-    python oracle/make_golden.py [kmeans] [ops] [model] ...
+    python oracle/make_golden.py [kmeans] [ops] [model] [baseline] ...
 
 The fixtures travel to the GPU box; /root/reference does not. Each fixture stores the inputs
 (or the seed that regenerates them) and the reference's outputs.
@@ -62,7 +62,7 @@ if __name__ == "__main__":
         sys.exit(0)
     if "kmeans" in what:
         gen_kmeans()
-    if "ops" in what or "model" in what:
+    if "ops" in what or "model" in what or "baseline" in what:
         sys.path.insert(0, STUBS)
         sys.path.insert(0, REF)
         from oracle import make_golden_detector as mgd
@@ -70,3 +70,5 @@ if __name__ == "__main__":
             mgd.gen_ops(GOLD)
         if "model" in what:
             mgd.gen_model(GOLD)
+        if "baseline" in what:      # BASELINE config 2 (2 x 1024x1024, G=20): ~1 min per fixture on 8 vCPU
+            mgd.gen_model_baseline(GOLD)

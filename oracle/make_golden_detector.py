@@ -182,3 +182,50 @@ def gen_ops(gold_dir):
     out["crop_out"] = np.packbits(BitMasks(gm).crop_and_resize(cb, 28).numpy(), axis=None)
     np.savez_compressed(os.path.join(gold_dir, "detector_ops.npz"), **out)
     print("wrote detector_ops.npz with", len(out), "arrays")
+
+
+def gen_model_baseline(gold_dir):
+    """BASELINE.json config 2: u2seg_R50_800 training step on 2 x 1024x1024 synthetic images with G=20 instances
+    (SURVEY 8(d) recipe), run through the UNMODIFIED reference on CPU (fp32). Two fixtures:
+      * sampler "randperm": the reference's own torch.randperm draws after torch.manual_seed(seed) (sampling.py:44-47);
+        the product's dynamic path consumes the same CPU permutations (tests inject rpn._randperm);
+      * sampler "first": torch.randperm replaced by arange for the duration of the forward, i.e. "first k candidates
+        in index order" - the only deterministic rule the fixed-capacity static path can reproduce exactly.
+    Stored: the 10 losses, per-parameter gradient L2 norms of all 248 parameters, and two small gradient slices.
+    """
+    import time
+    from detectron2.utils.events import EventStorage
+    cfgo = do.DetCfg(num_classes=800)
+    params = do.init_params(cfgo, seed=0)
+    cfg, model = build_reference_model(800, True)
+    H, W, seed, G, lo, hi = 1024, 1024, 1234, 20, 32, 512
+    data = do.synthetic_batch(2, H, W, 800, 28, seed=seed, G=G, min_size=lo, max_size=hi)
+    batch = reference_inputs(*data, train=True)
+    real_randperm = torch.randperm
+    for sampler in ("randperm", "first"):
+        model.load_state_dict(params)       # also resets the BN running statistics
+        model.zero_grad(set_to_none=True)
+        if sampler == "first":
+            torch.randperm = lambda n, *a, device=None, **k: torch.arange(n, device=device)
+        try:
+            torch.manual_seed(seed)
+            t0 = time.time()
+            with EventStorage():
+                losses = model(batch)
+            sum(losses.values()).backward()
+        finally:
+            torch.randperm = real_randperm
+        ref_losses = {k: float(v) for k, v in losses.items()}
+        print("reference [%s] %.1f s" % (sampler, time.time() - t0), ref_losses)
+        named = dict(model.named_parameters())
+        gnames = sorted(n for n, p in named.items() if p.grad is not None)
+        gnorms = np.array([float(named[n].grad.double().norm()) for n in gnames], dtype=np.float64)
+        np.savez_compressed(
+            os.path.join(gold_dir, "detector_train_1024_%s.npz" % sampler),
+            keys=np.array(list(ref_losses.keys())), values=np.array(list(ref_losses.values()), dtype=np.float64),
+            grad_names=np.array(gnames), grad_norms=gnorms,
+            grad_fpn_output3_first8=named["backbone.fpn_output3.weight"].grad[:8].numpy().copy(),
+            grad_res4_0_conv1_first8=named["backbone.bottom_up.res4.0.conv1.weight"].grad[:8].numpy().copy(),
+            grad_cls_score2_first4=named["roi_heads.box_predictor.2.cls_score.weight"].grad[:4].numpy().copy(),
+            running_mean_stem=model.state_dict()["backbone.bottom_up.stem.conv1.norm.running_mean"].numpy().copy(),
+            meta=np.array([2, H, W, 800, 28, seed, G, lo, hi], dtype=np.int64))

@@ -186,7 +186,7 @@ def test_trainer_state_dict_round_trip(trainer):
     assert all(sd[k].shape == ref[k].shape for k in sd)
     assert all(sd[k].dtype == torch.float32 for k in pnames)
     low = next(n for n, p in tr.model.named_parameters() if p.dtype == torch.bfloat16)
-    assert not torch.equal(sd[low], ref[low].float()) or True          # masters carry more bits than the bf16 copies
+    assert not torch.equal(sd[low], ref[low].float())                  # masters carry more bits than the bf16 copies
     assert torch.equal(sd[low].bfloat16(), ref[low])
     sd2 = {k: (v * 0.5 if v.is_floating_point() else v) for k, v in sd.items()}
     tr.load_state_dict(sd2)
@@ -194,3 +194,36 @@ def test_trainer_state_dict_round_trip(trainer):
         assert torch.equal(v, sd2[k]), k
     assert torch.equal(tr._w16_flat, tr._master_flat.bfloat16())
     tr.load_state_dict(sd)
+
+
+def test_trainer_checkpoint_round_trip_and_non_strict_load(trainer):
+    """Trainer.checkpoint(): model + momentum + iteration (what the reference checkpointer saves); load_state_dict
+    strict=False returns (missing, unexpected) like DetectionCheckpointer's backbone-only pretrain load; shape
+    mismatches raise instead of broadcasting."""
+    tr = trainer
+    ck = tr.checkpoint()
+    assert set(ck) == {"model", "optimizer", "iteration", "scaler"} and len(ck["optimizer"]["momentum"]) == 248
+    mom = tr._momentum_by_name()
+    name = "backbone.fpn_output3.weight"
+    assert mom[name].shape == tr.master_parameters()[name].shape
+    mom[name].fill_(0.25)
+    assert float(tr._mom_all.sum()) == pytest.approx(0.25 * mom[name].numel())   # a view of the flat momentum buffer
+    ck2 = tr.checkpoint()
+    mom[name].zero_()
+    it = tr.iter
+    tr.iter = 123
+    tr.load_checkpoint(ck2)
+    assert float(tr._momentum_by_name()[name].mean()) == 0.25 and tr.iter == it
+    tr._mom_all.zero_()
+    # backbone-only pretrain: every other key is reported missing, nothing raises
+    backbone_only = {k: v for k, v in ck["model"].items() if k.startswith("backbone.bottom_up.")}
+    backbone_only["fc1000.weight"] = torch.zeros(3)
+    missing, unexpected = tr.load_state_dict(backbone_only, strict=False)
+    assert unexpected == ["fc1000.weight"] and all(not k.startswith("backbone.bottom_up.") for k in missing) and missing
+    with pytest.raises(AssertionError):
+        tr.load_state_dict(backbone_only)
+    bad = dict(ck["model"])
+    bad[name] = bad[name][:1]
+    with pytest.raises(ValueError):
+        tr.load_state_dict(bad)
+    tr.load_state_dict(ck["model"])

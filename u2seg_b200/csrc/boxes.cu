@@ -14,13 +14,7 @@ namespace {
 
 constexpr int MAX_GT = 1024;
 
-// boxes.py:310-358, same op order: inter>0 ? inter/(area1+area2-inter) : 0
-__device__ __forceinline__ float iou_ref(const float4 g, float garea, const float4 a, float aarea) {
-  const float w = fmaxf(fminf(g.z, a.z) - fmaxf(g.x, a.x), 0.f);
-  const float h = fmaxf(fminf(g.w, a.w) - fmaxf(g.y, a.y), 0.f);
-  const float inter = w * h;
-  return inter > 0.f ? inter / (garea + aarea - inter) : 0.f;
-}
+using ptx_free::iou_ref;
 
 __global__ void __launch_bounds__(256)
 iou_match_kernel(const float4* __restrict__ gt, int G, const uint8_t* __restrict__ gt_valid,
@@ -41,7 +35,7 @@ iou_match_kernel(const float4* __restrict__ gt, int G, const uint8_t* __restrict
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a < A) {
     const float4 p = pred[a];
-    const float parea = (p.z - p.x) * (p.w - p.y);
+    const float parea = __fmul_rn(p.z - p.x, p.w - p.y);   // rounded on its own, as boxes.py:area()
     float best = -1.f;
     int bi = 0;
     for (int g = 0; g < G; ++g) {
@@ -91,7 +85,7 @@ match_label_kernel(const float4* __restrict__ gt, int G, const uint8_t* __restri
     if (v >= thresholds[i] && v < thresholds[i + 1]) lab = labels[i];
   if (gt_max_bits) {
     const float4 p = pred[a];
-    const float parea = (p.z - p.x) * (p.w - p.y);
+    const float parea = __fmul_rn(p.z - p.x, p.w - p.y);   // rounded on its own, as boxes.py:area()
     for (int g = 0; g < G; ++g)
       if (iou_ref(sgt[g], sarea[g], p, parea) == smax[g]) {
         lab = 1;

@@ -45,6 +45,19 @@ int u2b_encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const
                     CUtensorMapFloatOOBfill oob);
 
 #ifdef __CUDACC__
+namespace ptx_free {
+// structures/boxes.py:310-358 pairwise_iou, same op order: inter>0 ? inter/(area1+area2-inter) : 0.
+// One definition for every kernel that must agree bit for bit on IoU (matcher, cascade relabelling).
+__device__ __forceinline__ float iou_ref(const float4 g, float garea, const float4 a, float aarea) {
+  const float w = fmaxf(fminf(g.z, a.z) - fmaxf(g.x, a.x), 0.f);
+  const float h = fmaxf(fminf(g.w, a.w) - fmaxf(g.y, a.y), 0.f);
+  const float inter = w * h;
+  return inter > 0.f ? inter / (garea + aarea - inter) : 0.f;
+}
+}  // namespace ptx_free
+#endif
+
+#ifdef __CUDACC__
 // =====================================================================================
 // PTX wrappers: mbarrier, TMA, tcgen05 (Blackwell 5th-gen tensor cores + TMEM)
 // =====================================================================================

@@ -223,7 +223,8 @@ cascade_relabel_kernel(const float4* __restrict__ refined, const uint8_t* __rest
   b.w = fminf(fmaxf(b.w, 0.f), img_h);
   const bool ok = ok_prev[i] != 0 && (b.z - b.x) > 0.f && (b.w - b.y) > 0.f;
   if (!ok) b = make_float4(0.f, 0.f, 1.f, 1.f);            // placeholder box of dead slots
-  const float area_b = (b.z - b.x) * (b.w - b.y);
+  // same arithmetic as boxes.cu iou_match_kernel (areas rounded on their own: no fma contraction with the sum)
+  const float area_b = __fmul_rn(b.z - b.x, b.w - b.y);
   float best = -1.f;
   int best_j = 0;
   bool any_gt = false;
@@ -232,9 +233,7 @@ cascade_relabel_kernel(const float4* __restrict__ refined, const uint8_t* __rest
     if (!gt_valid[n * G + j]) continue;
     any_gt = true;
     const float4 t = g[j];
-    const float iw = fminf(b.z, t.z) - fmaxf(b.x, t.x), ih = fminf(b.w, t.w) - fmaxf(b.y, t.y);
-    const float inter = (iw > 0.f && ih > 0.f) ? iw * ih : 0.f;
-    const float iou = inter > 0.f ? inter / (area_b + (t.z - t.x) * (t.w - t.y) - inter) : 0.f;
+    const float iou = ptx_free::iou_ref(t, __fmul_rn(t.z - t.x, t.w - t.y), b, area_b);
     if (iou > best) {          // first maximum
       best = iou;
       best_j = j;

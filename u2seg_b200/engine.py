@@ -132,6 +132,9 @@ class Trainer:
         self.graph_backbone = graph_backbone and _world() == 1
         self._graph_tried = False
         self.static_graph = static_graph
+        if static_graph:      # fixed input shapes on every rank: the in-kernel SyncBN exchange may assume equal counts
+            from .modeling import fused_bn
+            fused_bn.EQUAL_SHAPES_ACROSS_RANKS = True
         self.g_max = g_max
         self._graph = None
         self._lr_t = torch.zeros((), dtype=torch.float32, device=self.device)
@@ -217,19 +220,83 @@ class Trainer:
             sd[name] = m.detach().clone()
         return sd
 
+    def _momentum_by_name(self):
+        """name -> momentum buffer (fp32) for every trainable parameter, whichever step implementation owns it."""
+        names = [n for n, q in self.model.named_parameters() if q.requires_grad]
+        if self.lowp:                                     # flat buffer with the masters' offsets
+            out, base = {}, self._master_all.data_ptr()
+            for n, m in zip(names, self._upd_params):
+                off = (m.data_ptr() - base) // 4
+                out[n] = _like_view(self._mom_all, off, m)
+            return out
+        if self.static_graph:                             # foreach step: per-group lists, created lazily
+            if self._mom_bufs is None:
+                self._mom_bufs = [[torch.zeros_like(p) for p in params] for params, _, _ in self._groups()]
+            idx = {id(p): n for n, p in zip(names, self._upd_params)}
+            out = {}
+            for (params, _, _), bufs in zip(self._groups(), self._mom_bufs):
+                for p, b in zip(params, bufs):
+                    out[idx[id(p)]] = b
+            return out
+        out = {}
+        for n, p in zip(names, self.params):              # eager step: torch.optim.SGD state
+            st = self.optimizer.state.get(p, {})
+            if st.get("momentum_buffer") is not None:
+                out[n] = st["momentum_buffer"]
+        return out
+
+    def checkpoint(self):
+        """What the reference's checkpointer saves (engine/train_loop.py + fvcore Checkpointer: model, optimizer,
+        scheduler position, iteration): {"model": state_dict(), "optimizer": {"momentum": {name: buf}}, "iteration": it,
+        "scaler": GradScaler state or None}. A resume from it is equivalent to never having stopped."""
+        return {"model": self.state_dict(),
+                "optimizer": {"momentum": {k: v.detach().clone() for k, v in self._momentum_by_name().items()}},
+                "iteration": self.iter,
+                "scaler": self.scaler.state_dict() if self.scaler is not None else None}
+
     @torch.no_grad()
-    def load_state_dict(self, sd):
-        """inverse of state_dict(): loads parameters (into the fp32 masters when they exist) and buffers."""
+    def load_checkpoint(self, ckpt, strict=True):
+        res = self.load_state_dict(ckpt["model"], strict=strict)
+        mom = ckpt.get("optimizer", {}).get("momentum", {})
+        if mom:
+            if not self.lowp and not self.static_graph:   # eager step: seed torch.optim.SGD's state
+                names = [n for n, q in self.model.named_parameters() if q.requires_grad]
+                for n, p in zip(names, self.params):
+                    if n in mom:
+                        self.optimizer.state[p]["momentum_buffer"] = mom[n].to(p.device, torch.float32).clone()
+            else:
+                own = self._momentum_by_name()
+                for k, v in mom.items():
+                    if k in own:
+                        assert own[k].shape == v.shape, "momentum shape mismatch for %s" % k
+                        own[k].copy_(v.to(own[k].device))
+        self.iter = int(ckpt.get("iteration", self.iter))
+        if self.scaler is not None and ckpt.get("scaler") is not None:
+            self.scaler.load_state_dict(ckpt["scaler"])
+        return res
+
+    @torch.no_grad()
+    def load_state_dict(self, sd, strict=True):
+        """inverse of state_dict(): loads parameters (into the fp32 masters when they exist) and buffers. strict=False
+        (what DetectionCheckpointer does for a backbone-only MODEL.WEIGHTS pretrain) skips absent / unknown keys and
+        returns them: (missing_keys, unexpected_keys). Shapes must match exactly - no silent broadcasting."""
         masters = self.master_parameters()
         own = self.model.state_dict()
         missing = [k for k in own if k not in sd]
-        assert not missing, "missing keys: %s" % missing[:5]
+        unexpected = [k for k in sd if k not in own]
+        if strict:
+            assert not missing, "missing keys: %s" % missing[:5]
+            assert not unexpected, "unexpected keys: %s" % unexpected[:5]
         for k, v in sd.items():
             dst = masters.get(k, own.get(k))
-            assert dst is not None, "unexpected key %s" % k
+            if dst is None:
+                continue
+            if tuple(dst.shape) != tuple(v.shape):
+                raise ValueError("shape mismatch for %s: checkpoint %s vs model %s" % (k, tuple(v.shape), tuple(dst.shape)))
             dst.copy_(v.to(dst.device))
         if self.lowp:
             self._w16_flat.copy_(self._master_flat)
+        return missing, unexpected
 
     @torch.no_grad()
     def broadcast_parameters(self, src=0):
@@ -285,7 +352,11 @@ class Trainer:
                 torch._foreach_add_(grads, params, alpha=wd)
             torch._foreach_mul_(bufs, s.MOMENTUM)
             torch._foreach_add_(bufs, grads)
-            upd = torch._foreach_mul(bufs, self._lr_t)
+            if s.NESTEROV:                                 # torch.optim.SGD: d_p = grad + momentum * buf
+                step = torch._foreach_add(grads, bufs, alpha=s.MOMENTUM)
+                upd = torch._foreach_mul(step, self._lr_t)
+            else:
+                upd = torch._foreach_mul(bufs, self._lr_t)
             torch._foreach_sub_(params, upd)
         if self.lowp:
             self._w16_flat.copy_(self._master_flat)      # refresh the bf16 compute weights: one kernel
@@ -405,11 +476,16 @@ class Trainer:
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()
             side.wait_stream(cur)
-            with torch.cuda.stream(side):     # warm-up outside capture: lazy initialisations, autotuning, workspaces
+            # warm-up outside capture (lazy initialisations, autotuning, workspaces) must leave NO trace in the training
+            # state: the reference applies one update per batch (train_loop.py:479-521). Parameters, momentum, BN
+            # running statistics / counters and the device RNG are snapshotted and restored around it.
+            snap = self._snapshot_training_state()
+            with torch.cuda.stream(side):
                 for _ in range(3):
                     self._static_step()
             cur.wait_stream(side)
             torch.cuda.synchronize()
+            self._restore_training_state(snap)
             from . import _lib
             self._graph = torch.cuda.CUDAGraph()
             l0 = _lib.launch_count
@@ -422,6 +498,32 @@ class Trainer:
         self.iter += 1
         losses, self.nonfinite_flag = self._static_out
         return losses
+
+    @torch.no_grad()
+    def _snapshot_training_state(self):
+        snap = {"buffers": [b.detach().clone() for b in self.model.buffers()],
+                "rng": torch.cuda.get_rng_state(self.device), "cpu_rng": torch.get_rng_state()}
+        if self.lowp:
+            snap["flat"] = [t.clone() for t in (self._master_all, self._mom_all, self._w16_flat)]
+        else:
+            snap["params"] = [p.detach().clone() for p in self._upd_params]
+        return snap
+
+    @torch.no_grad()
+    def _restore_training_state(self, snap):
+        for b, v in zip(self.model.buffers(), snap["buffers"]):
+            b.copy_(v)
+        if self.lowp:
+            for t, v in zip((self._master_all, self._mom_all, self._w16_flat), snap["flat"]):
+                t.copy_(v)
+        else:
+            for p, v in zip(self._upd_params, snap["params"]):
+                p.copy_(v)
+            if self._mom_bufs is not None:          # created (zero) by the first foreach step
+                for bufs in self._mom_bufs:
+                    torch._foreach_zero_(bufs)
+        torch.cuda.set_rng_state(snap["rng"], self.device)
+        torch.set_rng_state(snap["cpu_rng"])
 
     def check_finite(self):
         """proposal_utils.py:105-110 divergence guard, read off the critical path (costs one host sync)."""

@@ -184,7 +184,16 @@ def bn_act(x, bn, residual=None, relu=False):
                         0.1 if bn.momentum is None else bn.momentum, relu)
 
 
+# The fused multi-GPU path takes the group's element count as P * world, i.e. it assumes every rank holds the same
+# N*H*W. That is guaranteed only by the static-graph trainer (fixed input shapes; engine.Trainer sets this flag). The
+# reference-shaped eager step pads each rank's multi-scale batch on its own (MIN_SIZE_TRAIN 240..1024), so there the
+# model falls back to nn.SyncBatchNorm's own function, which all-gathers the per-rank counts (ops.batch_norm).
+EQUAL_SHAPES_ACROSS_RANKS = False
+
+
 def supported(x, bn):
+    if _world() > 1 and not EQUAL_SHAPES_ACROSS_RANKS:
+        return False
     return (x.is_cuda and x.dtype in _CODE and x.dim() == 4 and bn.training and bn.affine
             and bool(_lib.lib().u2b_bn_supported(int(x.shape[1]))))
 
