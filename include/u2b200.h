@@ -177,6 +177,20 @@ int u2b_conv2d_nhwc_fwd(int dtype, const void* x, int N, int H, int W, int Cin, 
                         int R, int S, int stride, int pad, const float* bias, const void* residual, int relu,
                         void* out, u2b_stream_t stream);
 
+/* Second-generation kernel (csrc/conv2.cu): a cluster of TWO CTAs (one SM pair) computes a 256 x {64,128,256} tile with
+ * tcgen05.mma.cta_group::2 (each SM stages half of the filter tile), batched TMEM reads, TMA-store epilogue. Same
+ * shapes and layouts as u2b_conv2d_nhwc_fwd; no residual operand. `stats` (optional) receives, per 128-pixel output
+ * tile, the per-channel sum and sum of squares of the ROUNDED outputs: (u2b_conv2_stats_rows(...), 2*Cout) fp32, the
+ * partial-row layout u2b_bn_finalize consumes (S = rows) - the statistics pass of the SyncBN that follows the conv
+ * (layers/batch_norm.py:187 via layers/wrappers.py:127-134) without re-reading the activation. */
+int u2b_conv2_supported(int Cin, int Cout, int R, int S, int stride, int pad);
+int64_t u2b_conv2_stats_rows(int N, int H, int W, int R, int S, int stride, int pad);
+/* 0 = choose the tile width per problem (default); 64 / 128 / 256 force it (benchmarking) */
+int u2b_conv2_set_tile_n(int bn);
+int u2b_conv2_nhwc_fwd(int dtype, const void* x, int N, int H, int W, int Cin, const void* w, int Cout, int R, int S,
+                       int stride, int pad, const float* bias, int relu, void* out, float* stats,
+                       u2b_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Training-mode (Sync)BatchNorm on NHWC activations (P = N*H*W pixels, C % 8 == 0 channels), fused with the
  * residual add and ReLU that follow it. Replaces nn.SyncBatchNorm (detectron2/layers/batch_norm.py:187) inside

@@ -62,7 +62,7 @@ if __name__ == "__main__":
         sys.exit(0)
     if "kmeans" in what:
         gen_kmeans()
-    if "ops" in what or "model" in what or "baseline" in what:
+    if {"ops", "model", "baseline", "baseline64"} & set(what):
         sys.path.insert(0, STUBS)
         sys.path.insert(0, REF)
         from oracle import make_golden_detector as mgd
@@ -72,3 +72,5 @@ if __name__ == "__main__":
             mgd.gen_model(GOLD)
         if "baseline" in what:      # BASELINE config 2 (2 x 1024x1024, G=20): ~1 min per fixture on 8 vCPU
             mgd.gen_model_baseline(GOLD)
+        if "baseline64" in what:    # float64 run of the same step: the rounding-noise yardstick (several minutes)
+            mgd.gen_model_baseline_fp64(GOLD)

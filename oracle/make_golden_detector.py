@@ -229,3 +229,44 @@ def gen_model_baseline(gold_dir):
             grad_cls_score2_first4=named["roi_heads.box_predictor.2.cls_score.weight"].grad[:4].numpy().copy(),
             running_mean_stem=model.state_dict()["backbone.bottom_up.stem.conv1.norm.running_mean"].numpy().copy(),
             meta=np.array([2, H, W, 800, 28, seed, G, lo, hi], dtype=np.int64))
+
+
+def gen_model_baseline_fp64(gold_dir):
+    """Rounding-noise yardstick for the BASELINE-config fixture: the same unmodified reference step ('first' sampler) run
+    in float64 on CPU. Stored next to the fp32 values: losses and per-parameter gradient norms in fp64, and the reference's
+    OWN fp32-vs-fp64 deviation per parameter - the precision any fp32 implementation of this step can be held to (the
+    backward pass goes through 61 batch-norm layers; some gradient norms are reproducible only to a few 1e-3 in fp32)."""
+    import time
+    from detectron2.utils.events import EventStorage
+    cfgo = do.DetCfg(num_classes=800)
+    params = do.init_params(cfgo, seed=0)
+    cfg, model = build_reference_model(800, True)
+    H, W, seed, G, lo, hi = 1024, 1024, 1234, 20, 32, 512
+    data = do.synthetic_batch(2, H, W, 800, 28, seed=seed, G=G, min_size=lo, max_size=hi)
+    batch = reference_inputs(*data, train=True)
+    for d in batch:
+        d["instances"].gt_boxes.tensor = d["instances"].gt_boxes.tensor.double()
+    model.load_state_dict(params)
+    model = model.double()
+    real_randperm = torch.randperm
+    torch.randperm = lambda n, *a, device=None, **k: torch.arange(n, device=device)
+    try:
+        torch.manual_seed(seed)
+        t0 = time.time()
+        with EventStorage():
+            losses = model(batch)
+        sum(losses.values()).backward()
+    finally:
+        torch.randperm = real_randperm
+    print("reference fp64 [first] %.1f s" % (time.time() - t0), {k: float(v) for k, v in losses.items()})
+    g32 = np.load(os.path.join(gold_dir, "detector_train_1024_first.npz"))
+    named = dict(model.named_parameters())
+    gnames = [str(n) for n in g32["grad_names"]]
+    gn64 = np.array([float(named[n].grad.norm()) for n in gnames], dtype=np.float64)
+    dev = np.abs(g32["grad_norms"] - gn64) / np.maximum(gn64, 1e-300)
+    l64 = np.array([float(losses[str(k)]) for k in g32["keys"]], dtype=np.float64)
+    print("reference fp32 vs fp64: losses max rel %.2e; gradient norms median %.2e p95 %.2e max %.2e (%s)"
+          % (np.max(np.abs(g32["values"] - l64) / np.maximum(1, np.abs(l64))), np.median(dev), np.sort(dev)[int(0.95 * (len(dev) - 1))],
+             dev.max(), gnames[int(dev.argmax())]))
+    np.savez_compressed(os.path.join(gold_dir, "detector_train_1024_first_fp64.npz"), keys=g32["keys"], values=l64,
+                        grad_names=g32["grad_names"], grad_norms=gn64, ref_fp32_rel_dev=dev, meta=g32["meta"])

@@ -101,3 +101,45 @@ def test_stem_conv_forward_and_weight_gradient(N, H, W):
     assert w.grad.shape == w.shape
     d = float((w.grad.float() - wr.grad).abs().max())
     assert d <= 1e-2 * float(wr.grad.abs().max()), d      # w.grad itself is rounded to bf16 (2^-8)
+
+
+# ---- second-generation kernel: cta_group::2 pair tiles, TMA-store epilogue, fused BN statistics (csrc/conv2.cu) ----
+SHAPES2 = SHAPES + [
+    (2, 256, 24, 8, 256, 3, 1),      # 3 m-tiles: odd tile count -> padding CTA in the last pair
+    (1, 64, 8, 16, 64, 1, 1),        # a single 128-pixel tile: one pair, the peer only pads
+    (1, 1024, 1, 300, 1024, 1, 1),   # Linear as a (1,1,M,K) image, ragged M
+    (2, 2048, 10, 12, 512, 1, 1),    # res5 conv1: K = 2048, small M -> narrow tiles
+]
+
+
+@pytest.mark.parametrize("tile_n", [0, 64])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", SHAPES2)
+def test_conv2_forward_and_bn_statistics(shape, dtype, tile_n):
+    from u2seg_b200.modeling.conv_tc import conv2_nhwc, set_tile_n
+    N, Cin, H, W, Cout, k, stride = shape
+    set_tile_n(tile_n)
+    try:
+        g = torch.Generator(device="cuda").manual_seed(hash(shape) % 1000)
+        x = torch.randn(N, Cin, H, W, device="cuda", generator=g).to(dtype)
+        x = x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)                 # real NHWC strides (also for H == 1)
+        w = (torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5).to(dtype)
+        b = torch.randn(Cout, device="cuda", generator=g)
+        pad = k // 2
+        for bias, relu in ((None, False), (b, True)):
+            y, st = conv2_nhwc(x, w.permute(0, 2, 3, 1).contiguous(), stride, pad, bias, relu, want_stats=True)
+            want = _ref(x, w, bias, stride, pad, None, relu)
+            assert y.shape == want.shape and y.dtype == dtype
+            err = (y.float() - want).abs().max().item()
+            scale = want.abs().max().item()
+            tol = (1e-3 if dtype == torch.float16 else 8e-3) * scale
+            assert err <= tol, (shape, dtype, bias is not None, relu, err, scale)
+            # statistics are those of the tensor as stored (rounded), summed in fp32: compare with a double sum
+            yd = y.double()
+            s1, s2 = yd.sum(dim=(0, 2, 3)), (yd * yd).sum(dim=(0, 2, 3))
+            got1, got2 = st[:, :Cout].double().sum(0), st[:, Cout:].double().sum(0)
+            n = y.numel() / Cout
+            assert (got1 - s1).abs().max().item() <= 1e-4 * n ** 0.5 * max(1.0, yd.abs().max().item())
+            assert ((got2 - s2).abs() / (s2.abs() + 1e-6)).max().item() <= 1e-4
+    finally:
+        set_tile_n(0)

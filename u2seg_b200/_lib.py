@@ -80,6 +80,11 @@ SIGNATURES = {
     "u2b_conv2d_set_cluster": (c_int, [c_int]),
     "u2b_conv2d_nhwc_fwd": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                     c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "u2b_conv2_supported": (c_int, [c_int] * 6),
+    "u2b_conv2_stats_rows": (c_int64, [c_int] * 7),
+    "u2b_conv2_set_tile_n": (c_int, [c_int]),
+    "u2b_conv2_nhwc_fwd": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                   c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "u2b_bn_supported": (c_int, [c_int]),
     "u2b_bn_num_strips": (c_int, [c_int64, c_int]),
     "u2b_bn_stats": (c_int, [c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p]),

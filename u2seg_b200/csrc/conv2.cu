@@ -1,0 +1,537 @@
+// 2-CTA (tcgen05.mma.cta_group::2) implicit-GEMM convolution / GEMM on sm_100a: NHWC fp16/bf16 operands, fp32
+// accumulation in TMEM, bf16/fp16 NHWC output. Second generation of csrc/conv_tc.cu (which stays as the cta_group::1
+// variant); call sites on the u2seg hot path: detectron2/layers/wrappers.py:127 (every F.conv2d of
+// backbone/resnet.py:149-176, backbone/fpn.py:77-88, proposal_generator/rpn.py:116-134, roi_heads/mask_head.py:242-262,
+// meta_arch/semantic_seg.py:196-214) and, viewed as a 1x1 convolution over a (1,1,M,K) image, the nn.Linear layers
+// (roi_heads/box_head.py:70,94-97, roi_heads/fast_rcnn.py:236-239).
+//
+// GEMM view: M = N*OH*OW output pixels, N = Cout, K = R*S*Cin. A thread-block CLUSTER OF TWO CTAs (one SM pair)
+// computes a 256 x BN output tile:
+//   A: each CTA TMA-loads its own 128-pixel box {64 ch, BW*stride, BH*stride, 1} of the NHWC input at the filter tap's
+//      shifted origin (zero padding / ragged edges = TMA out-of-bounds fill; im2col is never materialised);
+//   B: each CTA loads HALF of the (BN x 64) filter tile (BN/2 rows); the pair's UMMA reads both halves, so every SM
+//      stages and reads half the B bytes of the 1-CTA kernel (the shared-memory port is what capped conv_tc);
+//   D: 256 x BN fp32 accumulator, rows 0-127 in the leader's TMEM, rows 128-255 in the peer's, double buffered;
+//      ONE thread of the leader CTA issues tcgen05.mma.cta_group::2 (M=256, N=BN, K=16) for the pair.
+// Pipelines: smem ring full/empty (TMA of both CTAs -> leader's `full`; tcgen05.commit multicast -> both `empty`),
+// TMEM full/empty (commit multicast -> both epilogues; both epilogues -> leader's `T_empty`).
+// Epilogue (4 warps per CTA): batched tcgen05.ld (64 columns per wait), + bias, ReLU, round to bf16, stage 128 x 64
+// chunks in swizzled shared memory and write them with TMA stores (coalesced 128-byte rows, ragged tiles clipped by
+// the TMA unit). Optionally emits per-channel sum / sum-of-squares of the ROUNDED output tile (one partial row per
+// 128-pixel tile, deterministic): the statistics pass of the SyncBN that follows almost every conv of the backbone
+// (layers/batch_norm.py:187) costs no extra read of the activation.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA only), 2 = TMEM allocator, 4-7 = epilogue.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "../../include/u2b200.h"
+
+namespace {
+
+constexpr int BM = 128;  // rows per CTA; the pair computes 256
+constexpr int BK = 64;
+constexpr int A_BYTES = BM * BK * 2;    // 16 KB
+constexpr int STG_BYTES = BM * 64 * 2;  // epilogue staging chunk: 128 rows x 64 channels
+constexpr int C2_THREADS = 256;
+
+struct Conv2Params {
+  int N, H, W, Cin, Cout, R, S, stride, pad, OH, OW;
+  int BW, BH, tiles_w, tiles_h, tiles_m, tiles_n, kblocks_c;
+  int num_work;  // (m pair, n tile)
+  int relu;
+  const float* bias;
+  float* stats;  // (tiles_m, 2*Cout) fp32 partial sums [sum | sum of squares] or NULL
+};
+
+template <int BN>
+struct Cfg2 {
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the filter tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 5 : (BN == 128 ? 7 : 8);
+  static constexpr int STG_OFF = STAGES * STAGE_BYTES;
+  static constexpr int STAT_OFF = STG_OFF + 2 * STG_BYTES;
+  static constexpr int BAR_OFF = STAT_OFF + 4 * 2 * BN * 4;
+  static constexpr int SMEM_BYTES = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
+// ---- PTX used only by the 2-CTA kernel ----
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t cta_addr, uint32_t rank) {
+  uint32_t out;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(cta_addr), "r"(rank));
+  return out;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(ptx::smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0x3ff) == 0 && clock64() - t0 > U2B_MBAR_TIMEOUT_CYCLES) {
+      printf("u2b conv2: mbarrier timeout block %d thread %d bar@%u parity %u\n", blockIdx.x, threadIdx.x,
+             ptx::smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+// TMA loads whose completion bytes land on the LEADER CTA's mbarrier (cluster address), executed by both CTAs
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(ptx::smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(ptx::smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(ptx::smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {  // whole warp, both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (count 1) on the mbarrier at this CTA-relative offset in both CTAs of the pair once all prior MMAs retire
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          ptx::smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2r(float& a, float& b) {  // rounds a, b in place (what the tensor stores)
+  if (BF16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    const float2 f = __bfloat1622float2(v);
+    a = f.x;
+    b = f.y;
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __half2 v = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(v);
+    a = f.x;
+    b = f.y;
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+}
+
+// sum over the 32 lanes of v[j], left in lane j's v[0] (31 shuffles instead of 32 x 5)
+template <int OFF>
+__device__ __forceinline__ void transpose_reduce_step(float* v, int lane) {
+  const bool up = (lane & OFF) != 0;
+#pragma unroll
+  for (int i = 0; i < OFF; ++i) {
+    const float send = up ? v[i] : v[i + OFF];
+    const float keep = up ? v[i + OFF] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+  }
+}
+__device__ __forceinline__ float transpose_reduce32(float* v, int lane) {
+  transpose_reduce_step<16>(v, lane);
+  transpose_reduce_step<8>(v, lane);
+  transpose_reduce_step<4>(v, lane);
+  transpose_reduce_step<2>(v, lane);
+  transpose_reduce_step<1>(v, lane);
+  return v[0];
+}
+
+template <int BN, bool BF16>
+__global__ void __launch_bounds__(C2_THREADS, 1)
+conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+             const __grid_constant__ CUtensorMap tmap_y, const Conv2Params p) {
+  using Cfg = Cfg2<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* stg = smem + Cfg::STG_OFF;
+  float* sstat = reinterpret_cast<float*>(smem + Cfg::STAT_OFF);  // [4 quadrants][2*BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* T_full = empty + Cfg::STAGES;
+  uint64_t* T_empty = T_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(T_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_x);
+    ptx::prefetch_tmap(&tmap_w);
+    ptx::prefetch_tmap(&tmap_y);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      ptx::mbar_init(&full[i], 1);   // leader's producer (expect_tx covers both CTAs' bytes)
+      ptx::mbar_init(&empty[i], 1);  // one multicast commit per use
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&T_full[i], 1);
+      ptx::mbar_init(&T_empty[i], 8);  // 4 epilogue warps x 2 CTAs (only the leader's copy is used)
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc2(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish2();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();  // the peer's barriers exist before any remote arrive / complete_tx
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int kblocks = p.R * p.S * p.kblocks_c;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      for (int work = cluster_id; work < p.num_work; work += num_clusters) {
+        const int tn = work % p.tiles_n;
+        int tm = (work / p.tiles_n) * 2 + static_cast<int>(rank);
+        if (tm >= p.tiles_m) tm = p.tiles_m - 1;  // padding CTA of an odd tile count: valid loads, no stores
+        const int owb = tm % p.tiles_w, ohb = (tm / p.tiles_w) % p.tiles_h, n = tm / (p.tiles_w * p.tiles_h);
+        const int x_base = owb * p.BW * p.stride - p.pad, y_base = ohb * p.BH * p.stride - p.pad;
+        for (int r = 0; r < p.R; ++r)
+          for (int s = 0; s < p.S; ++s)
+            for (int cb = 0; cb < p.kblocks_c; ++cb) {
+              ptx::mbar_wait(&empty[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              const uint32_t full_leader = mapa_rank(ptx::smem_u32(&full[stage]), 0);
+              if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+              tma_load_4d_2sm(sa, &tmap_x, full_leader, cb * BK, x_base + s, y_base + r, n);
+              const int kcol = ((r * p.S + s) * p.kblocks_c + cb) * BK;
+              tma_load_2d_2sm(sa + A_BYTES, &tmap_w, full_leader, kcol, tn * BN + static_cast<int>(rank) * (BN / 2));
+              if (++stage == Cfg::STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && ptx::elect_one()) {
+      const uint32_t idesc = ptx::umma_idesc_f16(2 * BM, BN, BF16 ? 1u : 0u);
+      const uint32_t sbase = ptx::smem_u32(smem);
+      uint32_t stage = 0, phase = 0, acc_it = 0;
+      for (int work = cluster_id; work < p.num_work; work += num_clusters, ++acc_it) {
+        const uint32_t buf = acc_it & 1, tphase = (acc_it >> 1) & 1;
+        mbar_wait_cluster(&T_empty[buf], tphase ^ 1);  // both CTAs' epilogues have drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait_cluster(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t a_desc = ptx::umma_desc_sw128(sbase + stage * Cfg::STAGE_BYTES);
+          const uint64_t b_desc = ptx::umma_desc_sw128(sbase + stage * Cfg::STAGE_BYTES + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16_2sm(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_2sm(&empty[stage]);
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&T_full[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int epi_tid = threadIdx.x - 128;
+    const int bh = row / p.BW, bw = row % p.BW;
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+    uint32_t acc_it = 0, chunk_it = 0;
+    for (int work = cluster_id; work < p.num_work; work += num_clusters, ++acc_it) {
+      const int tn = work % p.tiles_n, tm_raw = (work / p.tiles_n) * 2 + static_cast<int>(rank);
+      const bool store_tile = tm_raw < p.tiles_m;
+      const int tm = store_tile ? tm_raw : p.tiles_m - 1;
+      const int owb = tm % p.tiles_w, ohb = (tm / p.tiles_w) % p.tiles_h, n = tm / (p.tiles_w * p.tiles_h);
+      const bool valid = (ohb * p.BH + bh) < p.OH && (owb * p.BW + bw) < p.OW && store_tile;
+      const uint32_t buf = acc_it & 1, tphase = (acc_it >> 1) & 1;
+      ptx::mbar_wait(&T_full[buf], tphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c, ++chunk_it) {
+        uint8_t* sbuf = stg + (chunk_it & 1) * STG_BYTES;
+        uint32_t v[64];
+        tmem_ld32(taddr + c * 64, v);
+        tmem_ld32(taddr + c * 64 + 32, v + 32);
+        ptx::tmem_ld_wait();
+        float f[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + tn * BN + c * 64);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 b = __ldg(b4 + j);
+            f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        uint32_t pk[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pk[j] = pack2r<BF16>(f[2 * j], f[2 * j + 1]);
+        // the TMA store issued two chunks ago (same staging buffer) must have finished reading shared memory
+        if (epi_tid == 0) bulk_wait_group_read<1>();
+        ptx::named_bar_sync(1, 128);
+        const uint32_t srow = ptx::smem_u32(sbuf) + static_cast<uint32_t>(row) * 128u;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ sw) << 4)), "r"(pk[4 * j]),
+                       "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                       : "memory");
+        ptx::fence_proxy_async();
+        ptx::named_bar_sync(1, 128);
+        if (epi_tid == 0 && store_tile) {
+          tma_store_4d(&tmap_y, sbuf, tn * BN + c * 64, owb * p.BW, ohb * p.BH, n);
+          bulk_commit_group();
+        }
+        if (p.stats) {  // per-channel sum / sum of squares of this warp's 32 rows (rounded values; dead rows masked)
+          const float m = valid ? 1.f : 0.f;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float a[32], b[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              a[j] = f[h * 32 + j] * m;
+              b[j] = a[j] * a[j];
+            }
+            const float s1 = transpose_reduce32(a, lane);
+            const float s2 = transpose_reduce32(b, lane);
+            sstat[q * 2 * BN + c * 64 + h * 32 + lane] = s1;
+            sstat[q * 2 * BN + BN + c * 64 + h * 32 + lane] = s2;
+          }
+        }
+      }
+      // this CTA's half of the accumulator is in registers / stored: hand the TMEM buffer back to the MMA issuer
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(mapa_rank(ptx::smem_u32(&T_empty[buf]), 0));
+      if (p.stats) {
+        ptx::named_bar_sync(1, 128);
+        if (store_tile) {
+          float* dst = p.stats + static_cast<size_t>(tm) * 2 * p.Cout;
+          for (int i = epi_tid; i < 2 * BN; i += 128) {
+            const float s = (sstat[i] + sstat[2 * BN + i]) + (sstat[4 * BN + i] + sstat[6 * BN + i]);
+            dst[(i < BN ? 0 : p.Cout - BN) + tn * BN + i] = s;
+          }
+        }
+        ptx::named_bar_sync(1, 128);
+      }
+    }
+    if (epi_tid == 0) bulk_wait_group_all();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();  // no CTA may exit while its peer can still read its smem / arrive on its barriers
+  if (warp == 2) tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN, bool BF16>
+int launch_conv2(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const Conv2Params& p,
+                 cudaStream_t stream) {
+  using Cfg = Cfg2<BN>;
+  static bool attr = false;
+  if (!attr) {
+    U2B_CUDA(cudaFuncSetAttribute(conv2_kernel<BN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::SMEM_BYTES));
+    attr = true;
+  }
+  int clusters = u2b_num_sms() / 2;
+  if (clusters > p.num_work) clusters = p.num_work;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * 2);
+  cfg.blockDim = dim3(C2_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  U2B_CUDA(cudaLaunchKernelEx(&cfg, conv2_kernel<BN, BF16>, tx, tw, ty, p));
+  return 0;
+}
+
+int g_conv2_bn = 0;  // 0 = automatic tile width; 64 / 128 / 256 force it (u2b_conv2_set_tile_n, benchmarking)
+
+void conv2_geometry(Conv2Params& p, int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad) {
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.stride = stride; p.pad = pad;
+  p.OH = (H + 2 * pad - R) / stride + 1;
+  p.OW = (W + 2 * pad - S) / stride + 1;
+  long long best = -1;  // the 128-pixel tile shape with the least padding
+  for (int bw = 128; bw >= 8; bw >>= 1) {
+    const int bh = 128 / bw;
+    const long long cost = static_cast<long long>((p.OW + bw - 1) / bw) * bw * ((p.OH + bh - 1) / bh) * bh;
+    if (best < 0 || cost < best) {
+      best = cost;
+      p.BW = bw;
+      p.BH = bh;
+    }
+  }
+  p.tiles_w = (p.OW + p.BW - 1) / p.BW;
+  p.tiles_h = (p.OH + p.BH - 1) / p.BH;
+  p.tiles_m = p.tiles_w * p.tiles_h * N;
+  p.kblocks_c = Cin / BK;
+}
+
+int conv2_pick_bn(const Conv2Params& p) {
+  if (g_conv2_bn && p.Cout % g_conv2_bn == 0) return g_conv2_bn;
+  const int pairs = (p.tiles_m + 1) / 2, want = u2b_num_sms() / 2;
+  // widest tile that still gives every SM pair a work item; otherwise the narrowest (most parallelism)
+  for (int bn = 256; bn >= 64; bn >>= 1)
+    if (p.Cout % bn == 0 && pairs * (p.Cout / bn) >= want) return bn;
+  for (int bn = 64; bn <= 256; bn <<= 1)
+    if (p.Cout % bn == 0) return bn;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// 1 if (shape) is handled by the 2-CTA tcgen05 kernel
+int u2b_conv2_supported(int Cin, int Cout, int R, int S, int stride, int pad) {
+  if (Cin <= 0 || Cin % 64 != 0 || Cout <= 0 || Cout % 64 != 0) return 0;
+  if (!((R == 1 && S == 1 && pad == 0) || (R == 3 && S == 3 && pad == 1))) return 0;
+  if (stride != 1 && stride != 2) return 0;
+  return 1;
+}
+
+// rows of the BN-statistics partial buffer (one per 128-pixel output tile) for this problem
+int64_t u2b_conv2_stats_rows(int N, int H, int W, int R, int S, int stride, int pad) {
+  Conv2Params p;
+  conv2_geometry(p, N, H, W, 64, 64, R, S, stride, pad);
+  return p.tiles_m;
+}
+
+int u2b_conv2_set_tile_n(int bn) {
+  U2B_CHECK_ARG(bn == 0 || bn == 64 || bn == 128 || bn == 256, "conv2_set_tile_n: 0 (auto), 64, 128 or 256");
+  g_conv2_bn = bn;
+  return 0;
+}
+
+// dtype: 1 = fp16, 2 = bf16. x: (N,H,W,Cin) NHWC. w: (Cout,R,S,Cin). out: (N,OH,OW,Cout) NHWC. bias: Cout fp32 or NULL.
+// stats: NULL, or (u2b_conv2_stats_rows, 2*Cout) fp32: row t = [sum_c | sumsq_c] of the rounded outputs of tile t
+// (every row and column is written; feed it to u2b_bn_finalize with S = rows).
+int u2b_conv2_nhwc_fwd(int dtype, const void* x, int N, int H, int W, int Cin, const void* w, int Cout, int R, int S,
+                       int stride, int pad, const float* bias, int relu, void* out, float* stats,
+                       cudaStream_t stream) {
+  U2B_CHECK_ARG(x && w && out && N > 0 && H > 0 && W > 0, "conv2_nhwc_fwd: bad arguments");
+  U2B_CHECK_ARG(dtype == 1 || dtype == 2, "conv2_nhwc_fwd: dtype must be fp16(1) or bf16(2)");
+  if (!u2b_conv2_supported(Cin, Cout, R, S, stride, pad)) {
+    u2b_set_error("conv2_nhwc_fwd: unsupported shape Cin=%d Cout=%d k=%dx%d stride=%d pad=%d", Cin, Cout, R, S, stride,
+                  pad);
+    return U2B_ERR_UNSUPPORTED;
+  }
+  Conv2Params p;
+  conv2_geometry(p, N, H, W, Cin, Cout, R, S, stride, pad);
+  const int BN = conv2_pick_bn(p);
+  p.tiles_n = Cout / BN;
+  p.num_work = ((p.tiles_m + 1) / 2) * p.tiles_n;
+  p.relu = relu;
+  p.bias = bias;
+  p.stats = stats;
+  const CUtensorMapDataType tdt = dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap tx, tw, ty;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t box[4] = {BK, (uint32_t)(p.BW * stride), (uint32_t)(p.BH * stride), 1};
+    uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    int rc = u2b_encode_tmap(&tx, tdt, 4, x, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)R * S * Cin, (uint64_t)Cout};
+    uint64_t strides[1] = {(uint64_t)R * S * Cin * 2};
+    uint32_t box[2] = {BK, (uint32_t)(BN / 2)};
+    int rc = u2b_encode_tmap(&tw, tdt, 2, w, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)p.OW, (uint64_t)p.OH, (uint64_t)N};
+    uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)p.OW * Cout * 2, (uint64_t)p.OH * p.OW * Cout * 2};
+    uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+    int rc = u2b_encode_tmap(&ty, tdt, 4, out, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc) return rc;
+  }
+  const bool bf = dtype == 2;
+  if (BN == 256) return bf ? launch_conv2<256, true>(tx, tw, ty, p, stream) : launch_conv2<256, false>(tx, tw, ty, p, stream);
+  if (BN == 128) return bf ? launch_conv2<128, true>(tx, tw, ty, p, stream) : launch_conv2<128, false>(tx, tw, ty, p, stream);
+  if (BN == 64) return bf ? launch_conv2<64, true>(tx, tw, ty, p, stream) : launch_conv2<64, false>(tx, tw, ty, p, stream);
+  return U2B_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

@@ -89,10 +89,14 @@ class _PoolTap(torch.autograd.Function):
 class FeatureTap:
     """Create once per forward pass over the list of pyramid levels, pass as `tap=` to every ROIPooler call."""
 
-    def __init__(self, feats):
+    def __init__(self, feats, prealloc=False):
         self.holder = _GradHolder()
         self.feats = [f.detach() for f in feats]
         self.token = _PoolTap.apply(self.holder, *feats) if any(f.requires_grad for f in feats) else None
+        if prealloc and self.token is not None:
+            # pooling calls issued from several CUDA streams (box cascade on one, mask branch on another) scatter into the
+            # same maps in backward: the zero-fill must be ordered before ALL of them, i.e. happen here, before the fork
+            self.holder.get([tuple(f.shape) for f in feats], feats[0].device)
 
 
 class _MultiLevelROIAlign(torch.autograd.Function):

@@ -28,6 +28,35 @@ def conv2d_nhwc(x, w_ohwi, stride, pad, bias=None, residual=None, relu=False):
     return out
 
 
+def conv2_stats_rows(x_shape, R, S, stride, pad):
+    N, _, H, W = x_shape
+    return int(_lib.lib().u2b_conv2_stats_rows(N, H, W, R, S, stride, pad))
+
+
+def conv2_nhwc(x, w_ohwi, stride, pad, bias=None, relu=False, want_stats=False):
+    """2-CTA tcgen05 kernel (csrc/conv2.cu). x: logical (N,Cin,H,W) channels_last half tensor; w_ohwi: (Cout,R,S,Cin).
+    Returns y, or (y, stats) with stats (tiles, 2*Cout) fp32 partial [sum | sumsq] rows of the rounded outputs."""
+    L = _lib.lib()
+    N, Cin, H, W = x.shape
+    Cout, R, S, _ = w_ohwi.shape
+    OH, OW = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+    out = torch.empty((N, OH, OW, Cout), dtype=x.dtype, device=x.device).permute(0, 3, 1, 2)   # NHWC storage
+    stats = None
+    if want_stats:
+        stats = torch.empty((conv2_stats_rows(x.shape, R, S, stride, pad), 2 * Cout), dtype=torch.float32, device=x.device)
+    if out.numel():
+        _lib.check(L.u2b_conv2_nhwc_fwd(_CODE[x.dtype], ctypes.c_void_p(x.data_ptr()), N, H, W, Cin,
+                                        ctypes.c_void_p(w_ohwi.data_ptr()), Cout, R, S, stride, pad, _lib.ptr(bias), int(relu),
+                                        ctypes.c_void_p(out.data_ptr()), _lib.ptr(stats), _lib.stream_ptr()),
+                   "u2b_conv2_nhwc_fwd")
+        _lib.count_launches(1)
+    return (out, stats) if want_stats else out
+
+
+def set_tile_n(bn):
+    _lib.check(_lib.lib().u2b_conv2_set_tile_n(int(bn)), "u2b_conv2_set_tile_n")
+
+
 TC_WGRAD = __import__("os").environ.get("U2B_TC_WGRAD", "0") == "1"     # round-2 draft (csrc/conv_wgrad_tc.cu)
 
 

@@ -29,6 +29,48 @@ FUSED_DET_LOSSES = os.environ.get("U2B_FUSED_DET_LOSSES", "0") == "1"
 
 _rand_keys = lambda mask: torch.rand(mask.shape, dtype=torch.float32, device=mask.device)  # noqa: E731
 
+# Independent branches of the forward pass are issued on side streams (captured as parallel branches of the step's CUDA
+# graph; autograd replays each branch's backward on the stream of its forward): the proposal path (top-k, decode,
+# per-image NMS with its single-CTA scan) next to the RPN losses, the mask branch next to cascade stages 0-2, the
+# semantic head next to everything. Most of these kernels fill a few SMs only.
+MULTI_STREAM = os.environ.get("U2B_MULTI_STREAM", "1") == "1"
+_streams = {}
+
+
+def _side(name):
+    dev = torch.cuda.current_device()
+    st = _streams.get((dev, name))
+    if st is None:
+        st = _streams[(dev, name)] = torch.cuda.Stream()
+    return st
+
+
+class _Fork:
+    """with _Fork(name): ... runs the body on a side stream ordered after the current stream's work so far;
+    .join() makes the current stream wait for it. Tensors that cross are kept alive by the caller until the join."""
+
+    def __init__(self, name, enabled=True):
+        self.enabled = enabled and MULTI_STREAM and torch.cuda.is_available()
+        self.name = name
+
+    def __enter__(self):
+        if self.enabled:
+            self.main = torch.cuda.current_stream()
+            self.side = _side(self.name)
+            self.side.wait_stream(self.main)
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.enabled:
+            torch.cuda.current_stream().wait_stream(self.side)
+
 
 def _topk_select(mask, k):
     """indices (k,) of up to k True entries of `mask` chosen uniformly at random, and a bool (k,) telling which of the
@@ -90,6 +132,10 @@ def rpn_static(rpn, images_size, features, gt_boxes, gt_valid, flags):
     deltas = [x.view(N, -1, 4, x.shape[-2], x.shape[-1]).permute(0, 3, 4, 1, 2).flatten(1, -2) for x in deltas]
     anchors_t = Boxes.cat(anchors).tensor
     A = anchors_t.shape[0]
+    fork = _Fork("rpn_proposals")
+    with fork:
+        proposals, prop_valid = _rpn_proposals_static(rpn, images_size, anchors, anchors_t, [lg.detach() for lg in logits],
+                                                      [d.detach() for d in deltas], flags)
     # ---- label_and_sample_anchors (rpn.py:307-363) ----
     with torch.no_grad():
         labels_all, matched_all, midx_all = [], [], []
@@ -106,8 +152,7 @@ def rpn_static(rpn, images_size, features, gt_boxes, gt_valid, flags):
         gt_labels = torch.stack(labels_all)
         if not FUSED_DET_LOSSES:
             gt_anchor_deltas = torch.stack([rpn.box2box_transform.get_deltas(anchors_t, k) for k in matched_all])
-    deltas_cat = None
-    if FUSED_DET_LOSSES:     # round-2 draft: one kernel for both RPN losses and their gradients (csrc/det_losses.cu)
+    if FUSED_DET_LOSSES:     # one kernel for both RPN losses and their gradients (csrc/det_losses.cu)
         from .fused_losses import rpn_losses
         deltas_cat = torch.cat(deltas, dim=1)
         obj, loc = rpn_losses(torch.cat(logits, dim=1), deltas_cat, anchors_t, gt_labels,
@@ -121,47 +166,61 @@ def rpn_static(rpn, images_size, features, gt_boxes, gt_valid, flags):
     normalizer = rpn.batch_size_per_image * N
     losses = {"loss_rpn_cls": obj / normalizer * rpn.loss_weight["loss_rpn_cls"],
               "loss_rpn_loc": loc / normalizer * rpn.loss_weight["loss_rpn_loc"]}
-    # ---- predict_proposals + find_top_rpn_proposals (rpn.py:482-533, proposal_utils.py:22-135) ----
-    with torch.no_grad():
-        pre, post = rpn.pre_nms_topk[True], rpn.post_nms_topk[True]
-        if FUSED_DET_LOSSES:   # round-2 draft: decode + clip + validity of the selected anchors in one kernel
-            from .fused_losses import rpn_decode_selected
-            sel, scs, lvl_ids, off = [], [], [], 0
-            for lid, lg in enumerate(logits):
-                k = min(lg.shape[1], pre)
-                sc, idx = lg.float().topk(k, dim=1)
-                sel.append(idx + off)
-                scs.append(sc)
-                lvl_ids.append(torch.full((k,), lid, dtype=torch.int64, device=anchors_t.device))
-                off += lg.shape[1]
-            tk_scores, lvl_ids = torch.cat(scs, 1), torch.cat(lvl_ids)
-            boxes_all, valid_all, nonfin = rpn_decode_selected(deltas_cat.detach(), anchors_t, torch.cat(sel, 1), tk_scores,
-                                                               rpn.box2box_transform, images_size, rpn.min_box_size)
-            flags.append(nonfin)
-            out_boxes, out_valid = [], []
-            for n in range(N):
-                keep, cnt = batched_nms_static(boxes_all[n], tk_scores[n], lvl_ids, rpn.nms_thresh, post, valid=valid_all[n])
-                out_boxes.append(boxes_all[n][keep])
-                out_valid.append(torch.arange(post, device=keep.device) < cnt)
-            return torch.stack(out_boxes), torch.stack(out_valid), losses
-        tk_scores, tk_boxes, lvl_ids = [], [], []
-        for lid, (a, lg, dl) in enumerate(zip(anchors, logits, deltas)):
+    fork.join()
+    return proposals, prop_valid, losses
+
+
+def _nms_per_image(boxes, scores, lvl_ids, valid, thresh, post):
+    """batched NMS of every image (proposal_utils.py:112-122), images on separate streams: the scan is one CTA each."""
+    N = boxes.shape[0]
+    out_boxes, out_valid, forks = [None] * N, [None] * N, []
+    for n in range(N):
+        f = _Fork("rpn_nms%d" % n, enabled=n > 0)
+        with f:
+            keep, cnt = batched_nms_static(boxes[n], scores[n], lvl_ids, thresh, post, valid=valid[n])
+            out_boxes[n] = boxes[n][keep]
+            out_valid[n] = torch.arange(post, device=keep.device) < cnt
+        forks.append(f)
+    for f in forks:
+        f.join()
+    return torch.stack(out_boxes), torch.stack(out_valid)
+
+
+@torch.no_grad()
+def _rpn_proposals_static(rpn, images_size, anchors, anchors_t, logits, deltas, flags):
+    """predict_proposals + find_top_rpn_proposals (rpn.py:482-533, proposal_utils.py:22-135) on fixed-capacity
+    buffers -> proposals (N,post,4), valid (N,post)."""
+    pre, post = rpn.pre_nms_topk[True], rpn.post_nms_topk[True]
+    if FUSED_DET_LOSSES:   # decode + clip + validity of the selected anchors in one kernel
+        from .fused_losses import rpn_decode_selected
+        deltas_cat = torch.cat(deltas, dim=1)
+        sel, scs, lvl_ids, off = [], [], [], 0
+        for lid, lg in enumerate(logits):
             k = min(lg.shape[1], pre)
-            sc, boxes = decode_topk_level(rpn.box2box_transform, a.tensor, lg, dl, k)
-            tk_scores.append(sc)
-            tk_boxes.append(boxes)
+            sc, idx = lg.float().topk(k, dim=1)
+            sel.append(idx + off)
+            scs.append(sc)
             lvl_ids.append(torch.full((k,), lid, dtype=torch.int64, device=anchors_t.device))
-        tk_scores, tk_boxes, lvl_ids = torch.cat(tk_scores, 1), torch.cat(tk_boxes, 1), torch.cat(lvl_ids)
-        finite = torch.isfinite(tk_boxes).all(dim=2) & torch.isfinite(tk_scores)
-        flags.append(~finite.all())      # proposal_utils.py:105-110 FloatingPointError, checked off the critical path
-        out_boxes, out_valid = [], []
-        for n in range(N):
-            b = _clip(tk_boxes[n], images_size)
-            v = finite[n] & ((b[:, 2] - b[:, 0]) > rpn.min_box_size) & ((b[:, 3] - b[:, 1]) > rpn.min_box_size)
-            keep, cnt = batched_nms_static(b, tk_scores[n], lvl_ids, rpn.nms_thresh, post, valid=v)
-            out_boxes.append(b[keep])
-            out_valid.append(torch.arange(post, device=b.device) < cnt)
-    return torch.stack(out_boxes), torch.stack(out_valid), losses
+            off += lg.shape[1]
+        tk_scores, lvl_ids = torch.cat(scs, 1), torch.cat(lvl_ids)
+        boxes_all, valid_all, nonfin = rpn_decode_selected(deltas_cat, anchors_t, torch.cat(sel, 1), tk_scores,
+                                                           rpn.box2box_transform, images_size, rpn.min_box_size)
+        flags.append(nonfin)
+        return _nms_per_image(boxes_all, tk_scores, lvl_ids, valid_all, rpn.nms_thresh, post)
+    tk_scores, tk_boxes, lvl_ids = [], [], []
+    for lid, (a, lg, dl) in enumerate(zip(anchors, logits, deltas)):
+        k = min(lg.shape[1], pre)
+        sc, boxes = decode_topk_level(rpn.box2box_transform, a.tensor, lg, dl, k)
+        tk_scores.append(sc)
+        tk_boxes.append(boxes)
+        lvl_ids.append(torch.full((k,), lid, dtype=torch.int64, device=anchors_t.device))
+    tk_scores, tk_boxes, lvl_ids = torch.cat(tk_scores, 1), torch.cat(tk_boxes, 1), torch.cat(lvl_ids)
+    finite = torch.isfinite(tk_boxes).all(dim=2) & torch.isfinite(tk_scores)
+    flags.append(~finite.all())      # proposal_utils.py:105-110 FloatingPointError, checked off the critical path
+    N = tk_boxes.shape[0]
+    b = torch.stack([_clip(tk_boxes[n], images_size) for n in range(N)])
+    v = finite & ((b[..., 2] - b[..., 0]) > rpn.min_box_size) & ((b[..., 3] - b[..., 1]) > rpn.min_box_size)
+    return _nms_per_image(b, tk_scores, lvl_ids, v, rpn.nms_thresh, post)
 
 
 def roi_heads_static(rh, images_size, features, proposals, prop_valid, gt_boxes, gt_classes, gt_valid, gt_masks):
@@ -170,7 +229,7 @@ def roi_heads_static(rh, images_size, features, proposals, prop_valid, gt_boxes,
     dev = proposals.device
     R = rh.batch_size_per_image
     feats = [features[f] for f in rh.box_in_features]
-    tap = FeatureTap(feats)
+    tap = FeatureTap(feats, prealloc=MULTI_STREAM)
     dummy = torch.cat([torch.zeros(2, device=dev), torch.ones(2, device=dev)])     # placeholder box of dead slots
     # ---- label_and_sample_proposals ----
     with torch.no_grad():
@@ -192,6 +251,9 @@ def roi_heads_static(rh, images_size, features, proposals, prop_valid, gt_boxes,
             gidx0.append(midx[idx])
             gtb0.append(gt_boxes[n][midx[idx]])
     losses = {}
+    mask_fork = _Fork("mask_branch")
+    with mask_fork:
+        loss_mask = _mask_branch_static(rh, feats, tap, boxes0, cls0, fg0, gidx0, gt_masks, K, R)
     cur_boxes, cur_cls, cur_ok, cur_gtb = boxes0, cls0, ok0, gtb0
     for k in range(rh.num_cascade_stages):
         if k > 0 and FUSED_DET_LOSSES:     # round-2 draft: one kernel relabels every slot of every image
@@ -236,7 +298,15 @@ def roi_heads_static(rh, images_size, features, proposals, prop_valid, gt_boxes,
         tgt = rh.box_predictor[k].box2box_transform.get_deltas(pb, gb)
         losses["loss_box_reg_stage%d" % k] = _masked_l1(deltas, tgt, fg) / count * rh.box_predictor[k].loss_weight["loss_box_reg"]
         prev_boxes = rh.box_predictor[k].box2box_transform.apply_deltas(deltas, pb).split(R)
-    # ---- mask branch on the stage-0 foreground slots (first quarter of every image's slots) ----
+    mask_fork.join()
+    losses["loss_mask"] = loss_mask
+    return losses
+
+
+def _mask_branch_static(rh, feats, tap, boxes0, cls0, fg0, gidx0, gt_masks, K, R):
+    """mask branch on the stage-0 foreground slots (first quarter of every image's slots): roi_heads.py:818-846 +
+    mask_head.py:33-112."""
+    N = len(boxes0)
     M = int(R * rh.positive_fraction)
     mb = [b[:M] for b in boxes0]
     mok = torch.cat([f[:M] for f in fg0])
@@ -248,8 +318,7 @@ def roi_heads_static(rh, images_size, features, proposals, prop_valid, gt_boxes,
         tgt = torch.cat([crop_and_resize_masks(gt_masks[n], mb[n], side, gt_index=gidx0[n][:M]) for n in range(N)])
     bce = F.binary_cross_entropy_with_logits(sel, tgt.to(torch.float32), reduction="none")
     denom = (mok.sum() * side * side).clamp(min=1).to(torch.float32)
-    losses["loss_mask"] = (bce * mok[:, None, None].to(bce.dtype)).sum() / denom
-    return losses
+    return (bce * mok[:, None, None].to(bce.dtype)).sum() / denom
 
 
 class _ScaleGrad(torch.autograd.Function):
@@ -279,17 +348,15 @@ def forward_train_static(model, images_u8, gt_boxes, gt_classes, gt_valid, gt_ma
     if model._bn_counters:
         torch._foreach_add_(model._bn_counters, 1)
     features = model.backbone(x)
-    main = torch.cuda.current_stream()
-    if model._side_stream is None:
-        model._side_stream = torch.cuda.Stream()
-    model._side_stream.wait_stream(main)
-    with torch.cuda.stream(model._side_stream):
+    sem_fork = _Fork("sem_seg_head", enabled=True)
+    sem_fork.enabled = torch.cuda.is_available()      # always forked (round-1 behaviour), also with U2B_MULTI_STREAM=0
+    with sem_fork:
         _, sem_losses = model.sem_seg_head(features, sem_seg)
     flags = []
     proposals, prop_valid, rpn_losses = rpn_static(model.proposal_generator, (H, W), features, gt_boxes, gt_valid, flags)
     det_losses = roi_heads_static(model.roi_heads, (H, W), features, proposals, prop_valid, gt_boxes, gt_classes,
                                   gt_valid, gt_masks)
-    main.wait_stream(model._side_stream)
+    sem_fork.join()
     losses = dict(sem_losses)
     losses.update(rpn_losses)
     losses.update(det_losses)
