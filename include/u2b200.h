@@ -190,6 +190,38 @@ int u2b_conv2_set_tile_n(int bn);
 int u2b_conv2_nhwc_fwd(int dtype, const void* x, int N, int H, int W, int Cin, const void* w, int Cout, int R, int S,
                        int stride, int pad, const float* bias, int relu, void* out, float* stats,
                        u2b_stream_t stream);
+/* Input gradient of a stride-1 'same' convolution, dX = conv(dY, rot180(W)^T), on the same kernel: the FORWARD filter
+ * (Cout,R,S,Cin) is read in place as an MN-major UMMA operand (no transposed copy), taps flipped by index arithmetic.
+ * dy (N,H,W,Cout) -> dx (N,H,W,Cin), NHWC; Cin % 128 == 0, Cout % 64 == 0. */
+int u2b_conv2_dgrad_supported(int Cin, int Cout, int R, int S, int stride, int pad);
+int u2b_conv2_nhwc_dgrad(int dtype, const void* dy, int N, int H, int W, int Cout, const void* w, int Cin, int R, int S,
+                         int pad, void* dx, u2b_stream_t stream);
+
+/* Weight gradient on the 2-CTA tcgen05 kernel (csrc/conv_wgrad2.cu): dW[co,r,s,ci] = sum over output pixels of
+ * dY[n,oh,ow,co] * X[n,oh*stride+r-pad,ow*stride+s-pad,ci] - the backward of the F.conv2d at layers/wrappers.py:127 and
+ * (1x1 over a (1,1,M,K) image) of nn.Linear at roi_heads/box_head.py:70. Shapes: (Cout % 256 == 0 and Cin % 128 == 0)
+ * or (Cin % 256 == 0 and Cout % 128 == 0); kernel 1x1 (pad 0) or 3x3 (pad 1); stride 1 or 2. x, dy fp16 (1) / bf16 (2)
+ * NHWC; dw (Cout,R,S,Cin) in out_dtype (0 fp32, 1 fp16, 2 bf16); workspace holds the split-K partials, summed in a fixed
+ * order (deterministic). */
+int u2b_conv_wgrad2_supported(int Cin, int Cout, int R, int S, int stride, int pad);
+int64_t u2b_conv_wgrad2_workspace_floats(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad);
+int u2b_conv_wgrad2(int dtype, const void* x, const void* dy, int N, int H, int W, int Cin, int Cout, int R, int S,
+                    int stride, int pad, float* workspace, int out_dtype, void* dw, u2b_stream_t stream);
+
+/* Mask-head predictor + loss restricted to the class the loss reads (csrc/mask_loss.cu): replaces the 1x1 predictor conv,
+ * the class gather and binary_cross_entropy_with_logits of detectron2/modeling/roi_heads/mask_head.py:33-112 (and their
+ * backward) for fixed-capacity ROI slots. x (R, P, C): ROI features after the deconv+ReLU, NHWC rows, fp16 (1) / bf16 (2);
+ * w (K, C) in x's dtype, bias (K) fp32; classes (R) int64; target (R, P) bool; ok (R) bool (dead slots contribute 0).
+ * fwd: loss_per_roi[r] = sum_p bce(z[r,p], t[r,p]) * ok[r], g[r,p] = (sigmoid(z) - t) * ok[r].
+ * bwd: upstream = device scalar d/d(loss sum); dx (R, P, C); dw (K, C), db (K) fp32 zero-filled by the caller;
+ *      workspace R * (C + 1) floats. Deterministic (no atomics). C % 256 == 0, C <= 1024. */
+int u2b_mask_loss_supported(int C);
+int u2b_mask_loss_fwd(int dtype, const void* x, const void* w, const float* bias, const int64_t* classes,
+                      const uint8_t* target, const uint8_t* ok, int64_t R, int P, int C, float* g, float* loss_per_roi,
+                      u2b_stream_t stream);
+int u2b_mask_loss_bwd(int dtype, const void* x, const void* w, const int64_t* classes, const float* g,
+                      const float* upstream, int64_t R, int P, int C, void* dx, float* dw, float* db, float* workspace,
+                      u2b_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Training-mode (Sync)BatchNorm on NHWC activations (P = N*H*W pixels, C % 8 == 0 channels), fused with the

@@ -202,6 +202,8 @@ def gen_model_baseline(gold_dir):
     data = do.synthetic_batch(2, H, W, 800, 28, seed=seed, G=G, min_size=lo, max_size=hi)
     batch = reference_inputs(*data, train=True)
     real_randperm = torch.randperm
+    captured = {}
+    model.proposal_generator.register_forward_hook(lambda mod, inp, out: captured.__setitem__("proposals", out[0]))
     for sampler in ("randperm", "first"):
         model.load_state_dict(params)       # also resets the BN running statistics
         model.zero_grad(set_to_none=True)
@@ -228,6 +230,9 @@ def gen_model_baseline(gold_dir):
             grad_res4_0_conv1_first8=named["backbone.bottom_up.res4.0.conv1.weight"].grad[:8].numpy().copy(),
             grad_cls_score2_first4=named["roi_heads.box_predictor.2.cls_score.weight"].grad[:4].numpy().copy(),
             running_mean_stem=model.state_dict()["backbone.bottom_up.stem.conv1.norm.running_mean"].numpy().copy(),
+            # the RPN's output (rpn.py:431-480): post-NMS proposals per image in score order, before GT boxes are appended.
+            # Lets a reduced-precision run be compared downstream of the (discontinuous) top-k / NMS selection.
+            proposal_boxes=np.stack([pr.proposal_boxes.tensor.numpy() for pr in captured["proposals"]]),
             meta=np.array([2, H, W, 800, 28, seed, G, lo, hi], dtype=np.int64))
 
 
@@ -250,6 +255,12 @@ def gen_model_baseline_fp64(gold_dir):
     model = model.double()
     real_randperm = torch.randperm
     torch.randperm = lambda n, *a, device=None, **k: torch.arange(n, device=device)
+    # layers/nms.py:20 calls torchvision with boxes.float() and the scores as they are: torchvision wants equal dtypes,
+    # so the float64 run hands it float32 scores too (selection only; nothing differentiable passes through NMS)
+    import importlib
+    d2nms = importlib.import_module("detectron2.layers.nms")
+    real_bnms = d2nms.box_ops.batched_nms
+    d2nms.box_ops.batched_nms = lambda b, sc, i, t: real_bnms(b.float(), sc.float(), i, t)
     try:
         torch.manual_seed(seed)
         t0 = time.time()
@@ -258,6 +269,7 @@ def gen_model_baseline_fp64(gold_dir):
         sum(losses.values()).backward()
     finally:
         torch.randperm = real_randperm
+        d2nms.box_ops.batched_nms = real_bnms
     print("reference fp64 [first] %.1f s" % (time.time() - t0), {k: float(v) for k, v in losses.items()})
     g32 = np.load(os.path.join(gold_dir, "detector_train_1024_first.npz"))
     named = dict(model.named_parameters())
@@ -268,5 +280,12 @@ def gen_model_baseline_fp64(gold_dir):
     print("reference fp32 vs fp64: losses max rel %.2e; gradient norms median %.2e p95 %.2e max %.2e (%s)"
           % (np.max(np.abs(g32["values"] - l64) / np.maximum(1, np.abs(l64))), np.median(dev), np.sort(dev)[int(0.95 * (len(dev) - 1))],
              dev.max(), gnames[int(dev.argmax())]))
+    slices = {"grad_fpn_output3_first8": named["backbone.fpn_output3.weight"].grad[:8].numpy().copy(),
+              "grad_res4_0_conv1_first8": named["backbone.bottom_up.res4.0.conv1.weight"].grad[:8].numpy().copy(),
+              "grad_cls_score2_first4": named["roi_heads.box_predictor.2.cls_score.weight"].grad[:4].numpy().copy()}
+    # element-wise deviation of the reference's own fp32 gradients from the fp64 ones, relative to the slice's max |g|
+    slice_dev = {k + "_ref_fp32_dev": float(np.abs(g32[k].astype(np.float64) - v).max() / np.abs(v).max()) for k, v in slices.items()}
+    print("reference fp32 vs fp64, element-wise on the stored slices:", slice_dev)
     np.savez_compressed(os.path.join(gold_dir, "detector_train_1024_first_fp64.npz"), keys=g32["keys"], values=l64,
-                        grad_names=g32["grad_names"], grad_norms=gn64, ref_fp32_rel_dev=dev, meta=g32["meta"])
+                        grad_names=g32["grad_names"], grad_norms=gn64, ref_fp32_rel_dev=dev, meta=g32["meta"],
+                        **slices, **{k: np.array(v) for k, v in slice_dev.items()})

@@ -143,3 +143,58 @@ def test_conv2_forward_and_bn_statistics(shape, dtype, tile_n):
             assert ((got2 - s2).abs() / (s2.abs() + 1e-6)).max().item() <= 1e-4
     finally:
         set_tile_n(0)
+
+
+# ---- 2-CTA tcgen05 weight gradient (csrc/conv_wgrad2.cu) ----
+WGRAD2_SHAPES = [
+    # N, Cin, H, W, Cout, k, stride
+    (2, 256, 64, 64, 256, 3, 1),      # FPN output / RPN / mask_fcn / res4 conv2 class: 9 taps x split-K
+    (2, 256, 40, 24, 128, 3, 1),      # sem-seg head: only Cin is a multiple of 256 -> swapped operands (D = dW^T)
+    (2, 512, 16, 16, 512, 3, 1),      # res5 conv2
+    (2, 256, 33, 47, 256, 3, 2),      # stride 2 on odd sizes (res4.0 conv2)
+    (2, 256, 32, 32, 1024, 1, 1),     # res4 conv3 1x1
+    (2, 1024, 20, 28, 256, 1, 1),     # fpn lateral4 / res4 conv1, ragged
+    (2, 512, 32, 32, 1024, 1, 2),     # stride-2 shortcut
+    (2, 128, 40, 40, 512, 1, 1),      # res3 conv3: Cb = 128 -> BN 128
+    (3, 256, 14, 14, 256, 3, 1),      # 14x14 ROI maps
+    (1, 1024, 1, 300, 1024, 1, 1),    # Linear fc2 as a (1,1,M,K) image, ragged M
+    (1, 12544, 1, 512, 1024, 1, 1),   # Linear fc1
+]
+
+
+@pytest.mark.parametrize("shape", WGRAD2_SHAPES)
+def test_conv_wgrad2_matches_fp32_reference(shape):
+    from u2seg_b200.modeling.conv_tc import conv_wgrad2, wgrad2_supported
+    N, Cin, H, W, Cout, k, stride = shape
+    pad = k // 2
+    g = torch.Generator(device="cuda").manual_seed(hash(shape) % 1000)
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g).bfloat16().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    gy = torch.randn(N, Cout, OH, OW, device="cuda", generator=g).bfloat16().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    assert wgrad2_supported(x, Cout, k, k, stride, pad)
+    w = torch.zeros(Cout, Cin, k, k, device="cuda")
+    torch.backends.cudnn.allow_tf32 = False
+    _, want, _ = torch.ops.aten.convolution_backward(gy.float(), x.float(), w, None, [stride, stride], [pad, pad], [1, 1],
+                                                     False, [0, 0], 1, [False, True, False])
+    got = conv_wgrad2(x, gy, k, k, stride, pad, torch.float32)
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 2e-3 * float(want.abs().max())       # fp32 accumulation, split-K order
+    got16 = conv_wgrad2(x, gy, k, k, stride, pad, torch.bfloat16)
+    assert float((got16.float() - want).abs().max()) <= 8e-3 * float(want.abs().max())
+
+
+@pytest.mark.parametrize("shape", [s for s in SHAPES2 if s[6] == 1 and s[1] % 128 == 0])
+def test_conv2_dgrad_reads_the_forward_filter_in_place(shape):
+    """dX = conv(dY, rot180(W)^T) on the 2-CTA kernel with the forward (Cout,R,S,Cin) filter as an MN-major operand."""
+    from u2seg_b200.modeling.conv_tc import conv2_nhwc_dgrad
+    N, Cin, H, W, Cout, k, stride = shape
+    pad = k // 2
+    g = torch.Generator(device="cuda").manual_seed(hash(shape) % 1000 + 1)
+    gy = torch.randn(N, Cout, H, W, device="cuda", generator=g).bfloat16().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    w = (torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cout * k * k) ** 0.5).bfloat16()
+    torch.backends.cudnn.allow_tf32 = False
+    want = torch.ops.aten.convolution_backward(gy.float(), torch.zeros(N, Cin, H, W, device="cuda"), w.float(), None, [1, 1],
+                                               [pad, pad], [1, 1], False, [0, 0], 1, [True, False, False])[0]
+    got = conv2_nhwc_dgrad(gy, w.permute(0, 2, 3, 1).contiguous(), pad)
+    assert got.shape == want.shape
+    assert float((got.float() - want).abs().max()) <= 8e-3 * float(want.abs().max())

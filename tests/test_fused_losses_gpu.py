@@ -1,13 +1,10 @@
-"""GPU parity of the round-2 DRAFT fused detection losses (csrc/det_losses.cu) against their torch restatements
-(= the formulas of static_train.py, rpn.py:365-429 and fast_rcnn.py:307-352). Not validated on hardware yet: skipped
-unless U2B_RUN_DRAFT_TESTS=1."""
-import os
-
+"""GPU parity of the fused detection-loss kernels (csrc/det_losses.cu, csrc/mask_loss.cu, csrc/upsample.cu, the 1-CTA
+weight-gradient kernel csrc/conv_wgrad_tc.cu) against their torch restatements (= the formulas of static_train.py,
+rpn.py:365-429, fast_rcnn.py:307-352, mask_head.py:33-112)."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("U2B_RUN_DRAFT_TESTS") != "1", reason="round-2 draft (set U2B_RUN_DRAFT_TESTS=1)")]
+pytestmark = pytest.mark.gpu
 
 
 def _boxes(n, g, lo=8.0, hi=200.0, size=640.0):
@@ -195,6 +192,41 @@ def test_cascade_relabel_matches_torch_formulas():
         m = Matcher([thr], [0, 1], allow_low_quality_matches=False)
         got = cascade_relabel(refined, ok_prev, gt, gt_classes, gt_valid, (1024, 1024), thr, K)
         want = cascade_relabel_reference(refined, ok_prev, gt, gt_classes, gt_valid, (1024, 1024), m, K)
-        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]) and torch.equal(got[2], want[2])
+        for j, what in enumerate(("boxes", "classes", "ok")):
+            if not torch.equal(got[j], want[j]):
+                a, b = got[j].reshape(got[j].shape[0] * got[j].shape[1], -1), want[j].reshape(want[j].shape[0] * want[j].shape[1], -1)
+                bad = (a != b).any(dim=1).nonzero().flatten()
+                raise AssertionError("%s differ in %d slots, e.g. slot %d: kernel %s vs torch %s (refined %s, ok_prev %s)"
+                                     % (what, bad.numel(), int(bad[0]), a[bad[0]].tolist(), b[bad[0]].tolist(),
+                                        refined.reshape(-1, 4)[bad[0]].tolist(), bool(ok_prev.reshape(-1)[bad[0]])))
         live = want[2] & (want[1] != K)                        # the matched GT box only matters for foreground slots
         assert torch.equal(got[3][live], want[3][live])
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_mask_loss_selected_matches_torch(dtype):
+    """csrc/mask_loss.cu (predictor of the GT class + BCE-with-logits + closed-form backward) vs the torch formulas
+    (bmm with the gathered filter rows, F.binary_cross_entropy_with_logits, autograd)."""
+    from u2seg_b200.modeling.fused_losses import mask_loss_selected, mask_loss_selected_reference
+    g = torch.Generator().manual_seed(11)
+    R, C, S, K = 37, 256, 28, 800
+    x = (torch.randn(R, C, S, S, generator=g) * 0.5).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(K, C, 1, 1, generator=g) * 0.05).cuda()
+    b = (torch.randn(K, generator=g) * 0.1).cuda()
+    cls = torch.randint(0, K, (R,), generator=g).cuda()
+    cls[5] = cls[2]
+    cls[9] = cls[2]                                            # several ROIs of one class: their filter gradients add up
+    tgt = (torch.rand(R, S, S, generator=g) < 0.4).cuda()
+    ok = (torch.rand(R, generator=g) < 0.8).cuda()
+    outs = []
+    for fn in (mask_loss_selected, mask_loss_selected_reference):
+        xx, ww, bb = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        loss = fn(xx, ww, bb, cls, tgt, ok)
+        (loss / 1000.0).backward()
+        outs.append((loss.detach().float(), xx.grad.float(), ww.grad.float(), bb.grad.float()))
+    (l1, gx1, gw1, gb1), (l2, gx2, gw2, gb2) = outs
+    assert abs(float(l1) - float(l2)) <= 2e-4 * abs(float(l2))
+    assert float((gx1 - gx2).abs().max()) <= 1e-2 * float(gx2.abs().max())            # dX is stored in bf16 / fp16
+    assert float((gw1 - gw2).abs().max()) <= 2e-3 * float(gw2.abs().max())
+    assert float((gb1 - gb2).abs().max()) <= 2e-3 * float(gb2.abs().max()) + 1e-7
+    assert float(gx1[~ok].abs().max()) == 0.0                                          # dead slots: exactly zero

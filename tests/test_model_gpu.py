@@ -141,7 +141,7 @@ def test_bf16_step_with_tcgen05_convs_close_to_library_convs(monkeypatch):
     data = do.synthetic_batch(2, 256, 320, K, S, seed=seed, G=6, min_size=24, max_size=160)
     monkeypatch.setattr(rpn, "_randperm", _cpu_randperm)
     out = {}
-    for policy in ("none", "large3x3"):
+    for policy in ("none", "all"):
         monkeypatch.setattr(ops, "TCGEN05_CONV_POLICY", policy)
         model = _build(K, params, True)
         torch.manual_seed(seed)
@@ -150,9 +150,12 @@ def test_bf16_step_with_tcgen05_convs_close_to_library_convs(monkeypatch):
         sum(losses.values()).backward()
         gn = {n: float(p.grad.float().norm()) for n, p in model.named_parameters()}
         out[policy] = ({k: float(v) for k, v in losses.items()}, gn)
-    (la, ga), (lb, gb) = out["none"], out["large3x3"]
+    (la, ga), (lb, gb) = out["none"], out["all"]
     for k in la:
-        assert abs(la[k] - lb[k]) <= 2e-2 * max(1.0, abs(la[k])), (k, la[k], lb[k])
+        # the box-regression losses average over the few foreground ROIs that survive the (discontinuous) top-k + NMS
+        # proposal selection, which two bf16 implementations resolve differently: looser bound there
+        tol = 5e-2 if "box_reg" in k else 2e-2
+        assert abs(la[k] - lb[k]) <= tol * max(1.0, abs(la[k])), (k, la[k], lb[k])
     for n in ("backbone.fpn_output2.weight", "proposal_generator.rpn_head.conv.weight", "roi_heads.mask_head.mask_fcn1.weight",
               "sem_seg_head.p2.0.weight", "backbone.bottom_up.res2.0.conv1.weight"):
         assert all(map(lambda v: v == v and v < float("inf"), (ga[n], gb[n])))

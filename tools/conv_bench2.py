@@ -17,37 +17,38 @@ SHAPES = [  # name, N, Cin, H, W, Cout, k, stride
     ("fc1_as_conv", 1, 12544, 1, 1024, 1024, 1, 1), ("fc2_as_conv", 1, 1024, 1, 1024, 1024, 1, 1),
     ("mask_deconv_as_1x1", 256, 256, 14, 14, 1024, 1, 1),
 ]
-flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-def timeit(fn, n=10):
-    for _ in range(3): fn()
-    torch.cuda.synchronize()
-    tot = 0.0
-    for _ in range(n):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-        tot += e0.elapsed_time(e1)
-    return tot / n
-torch.backends.cudnn.benchmark = True
-only = sys.argv[1:] 
-for name, N, Cin, H, W, Cout, k, s in SHAPES:
-    if only and not any(o in name for o in only): continue
-    x = torch.randn(N, Cin, H, W, device="cuda").bfloat16().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
-    w = torch.randn(Cout, Cin, k, k, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
-    wo = w.permute(0, 2, 3, 1).contiguous()
-    pad = k // 2
-    OH, OW = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
-    fl = 2.0 * N * OH * OW * Cout * Cin * k * k
-    set_cluster(2)
-    t1 = timeit(lambda: conv2d_nhwc(x, wo, s, pad))
-    res = []
-    for bn in (0, 256, 128, 64):
-        if bn and Cout % bn: res.append(float("nan")); continue
-        set_tile_n(bn)
-        res.append(timeit(lambda: conv2_nhwc(x, wo, s, pad)))
-    set_tile_n(0)
-    ts = timeit(lambda: conv2_nhwc(x, wo, s, pad, want_stats=True))
-    t2 = timeit(lambda: F.conv2d(x, w, None, s, pad))
-    tf = lambda t: fl / t / 1e9
-    print("%-20s %7.1f GF | tc1 %.3f ms %6.0f | conv2 auto %.3f ms %6.0f TF/s (bn256 %.3f bn128 %.3f bn64 %.3f) +stats %.3f | cudnn %.3f ms %6.0f TF/s | conv2/cudnn %.2fx"
-          % (name, fl / 1e9, t1, tf(t1), res[0], tf(res[0]), res[1], res[2], res[3], ts, t2, tf(t2), t2 / res[0]), flush=True)
+if __name__ == "__main__":
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    def timeit(fn, n=10):
+        for _ in range(3): fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(n):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / n
+    torch.backends.cudnn.benchmark = True
+    only = sys.argv[1:] 
+    for name, N, Cin, H, W, Cout, k, s in SHAPES:
+        if only and not any(o in name for o in only): continue
+        x = torch.randn(N, Cin, H, W, device="cuda").bfloat16().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        w = torch.randn(Cout, Cin, k, k, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+        wo = w.permute(0, 2, 3, 1).contiguous()
+        pad = k // 2
+        OH, OW = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
+        fl = 2.0 * N * OH * OW * Cout * Cin * k * k
+        set_cluster(2)
+        t1 = timeit(lambda: conv2d_nhwc(x, wo, s, pad))
+        res = []
+        for bn in (0, 256, 128, 64):
+            if bn and Cout % bn: res.append(float("nan")); continue
+            set_tile_n(bn)
+            res.append(timeit(lambda: conv2_nhwc(x, wo, s, pad)))
+        set_tile_n(0)
+        ts = timeit(lambda: conv2_nhwc(x, wo, s, pad, want_stats=True))
+        t2 = timeit(lambda: F.conv2d(x, w, None, s, pad))
+        tf = lambda t: fl / t / 1e9
+        print("%-20s %7.1f GF | tc1 %.3f ms %6.0f | conv2 auto %.3f ms %6.0f TF/s (bn256 %.3f bn128 %.3f bn64 %.3f) +stats %.3f | cudnn %.3f ms %6.0f TF/s | conv2/cudnn %.2fx"
+              % (name, fl / 1e9, t1, tf(t1), res[0], tf(res[0]), res[1], res[2], res[3], ts, t2, tf(t2), t2 / res[0]), flush=True)

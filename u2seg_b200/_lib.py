@@ -85,6 +85,18 @@ SIGNATURES = {
     "u2b_conv2_set_tile_n": (c_int, [c_int]),
     "u2b_conv2_nhwc_fwd": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                    c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "u2b_conv2_dgrad_supported": (c_int, [c_int] * 6),
+    "u2b_conv2_nhwc_dgrad": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p]),
+    "u2b_conv_wgrad2_supported": (c_int, [c_int] * 6),
+    "u2b_conv_wgrad2_workspace_floats": (c_int64, [c_int] * 9),
+    "u2b_conv_wgrad2": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_void_p, c_int, c_void_p, c_void_p]),
+    "u2b_mask_loss_supported": (c_int, [c_int]),
+    "u2b_mask_loss_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                  c_void_p, c_void_p, c_void_p]),
+    "u2b_mask_loss_bwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "u2b_bn_supported": (c_int, [c_int]),
     "u2b_bn_num_strips": (c_int, [c_int64, c_int]),
     "u2b_bn_stats": (c_int, [c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p]),

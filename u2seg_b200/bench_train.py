@@ -116,7 +116,8 @@ def run_train(args, ClockSampler, load_peaks, dist_info, run_kmeans=None):
     e2e_value = IMS_PER_GPU * world / float(tt)
 
     achieved = FLOP_PER_IMAGE * (value / world) / 1e12
-    conv_roof = conv_tc_roofline(peaks)
+    conv_roof = in_step_conv_roofline(trainer, dev_pool[0], peaks, ms_step)
+    iso_roof = conv_tc_roofline(peaks)
     line = {
         "metric": "u2seg_R50_800_train_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -133,19 +134,28 @@ def run_train(args, ClockSampler, load_peaks, dist_info, run_kmeans=None):
                         "sem_seg) copied H2D on a copy stream while the previous step computes; the 10 losses read "
                         "back every step"},
         "roofline": conv_roof,
+        "roofline_isolated": iso_roof,
         "step_roofline": {"bound": "tensor", "what": "whole training step: conv/GEMM flop of SURVEY 8(d) "
                                                      "minus the unused mask-predictor channels (1.8985 TFLOP/image fwd+bwd) / step time",
                           "achieved": achieved, "peak": peaks["tf_sus"], "unit": "TFLOP/s",
                           "frac": achieved / peaks["tf_sus"], "peak_source": peaks["src"] + " bf16 sustained"},
-        "conv_policy": "tcgen05 conv_tc for 3x3 stride-1 convs with Cin,Cout>=128 (fwd+dgrad); cuDNN elsewhere and for wgrad",
+        "conv_policy": _conv_policy_text(),
         "step_mode": ("static shapes (fixed-capacity device buffers, no host sync), forward+backward+all-reduce+clip+SGD "
                       "replayed from one CUDA graph") if static else "dynamic shapes (reference-shaped), eager",
         "final_loss": loss_total,
     }
     if run_kmeans is not None and not os.environ.get("U2B_BENCH_SKIP_KMEANS"):
         km = run_kmeans(args, emit=False)     # (the trainer and its graph stay alive: 180 GB of HBM is ample)     # second half of BASELINE.json's metric: k-means embeddings/s
-        line["kmeans"] = {k: km[k] for k in ("metric", "value", "unit", "ms_per_step", "roofline", "e2e", "gpu_launches",
-                                             "config", "scaling") if k in km}
+        line["kmeans"] = {k: km[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "roofline", "e2e",
+                                             "gpu_launches", "clocks", "config", "scaling", "cpu_baseline") if k in km}
+    if rank == 0 and world == 1 and not os.environ.get("U2B_BENCH_SKIP_INFER"):
+        # BASELINE.json configs[4]: u2seg_R50_300 panoptic inference + the ROIAlign / paste_masks HBM rooflines
+        from .bench_infer import run_infer
+        del trainer
+        torch.cuda.empty_cache()
+        inf = run_infer(args, ClockSampler, load_peaks, dist_info, emit=False)
+        line["infer"] = {k: inf[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "e2e", "gpu_launches", "clocks",
+                                            "config", "roofline", "rooflines") if k in inf}
     if rank == 0 and world == 1 and not os.environ.get("U2B_BENCH_SKIP_CPU"):
         line["cpu_baseline"] = cpu_train_sample(1)
     if rank == 0:
@@ -161,11 +171,73 @@ def run_train(args, ClockSampler, load_peaks, dist_info, run_kmeans=None):
         os._exit(0)
 
 
+def _conv_policy_text():
+    from .modeling import conv_tc, ops
+    if ops.TCGEN05_CONV_POLICY == "all":
+        return ("tcgen05 2-CTA kernels (csrc/conv2.cu, conv_wgrad2.cu) for every conv with Cin,Cout %% 64 == 0 (1x1 and 3x3, "
+                "stride 1 and 2: forward; stride-1 input gradient; weight gradient when Cout or Cin %% 256 == 0) and the box-head "
+                "Linear layers; library (cuDNN/cuBLAS) for the rest (Cout 3/4/12/28/801 heads, 64-channel wgrads, stride-2 dgrads); "
+                "conv2=%s wgrad2=%s" % (conv_tc.USE_CONV2, conv_tc.USE_WGRAD2))
+    return "policy %s (conv2=%s wgrad2=%s)" % (ops.TCGEN05_CONV_POLICY, conv_tc.USE_CONV2, conv_tc.USE_WGRAD2)
+
+
+def in_step_conv_roofline(trainer, batch, peaks, ms_step):
+    """The dominant hand-written kernel AS IT RUNS INSIDE THE STEP: one extra, eager execution of the static step (the
+    same kernel sequence the CUDA graph replays: same shapes, same tensors, cache state of a real step) with every
+    tcgen05 launch bracketed by CUDA events on its launching stream. Launches are grouped by (direction, shape); the
+    group with the most time is reported against the SUSTAINED bf16 peak (a kernel timed inside a long step), next to
+    the aggregate over all tcgen05 launches of the step. Training state is restored afterwards."""
+    from .modeling import conv_tc
+    if not trainer.static_graph:
+        return conv_tc_roofline(peaks)
+    snap = trainer._snapshot_training_state()
+    trainer._load_static_inputs(batch)
+    torch.cuda.synchronize()
+    conv_tc.TIMING = []
+    try:
+        trainer._static_step()
+        torch.cuda.synchronize()
+        recs = conv_tc.TIMING
+    finally:
+        conv_tc.TIMING = None
+    trainer._restore_training_state(snap)
+    groups = {}
+    for kind, key, flop, e0, e1 in recs:
+        gkey = (kind, key)
+        d = groups.setdefault(gkey, [0, 0.0, 0.0])
+        d[0] += 1
+        d[1] += e0.elapsed_time(e1)
+        d[2] += flop
+    if not groups:
+        return conv_tc_roofline(peaks)
+    tot_ms = sum(v[1] for v in groups.values())
+    tot_flop = sum(v[2] for v in groups.values())
+    (kind, key), (cnt, ms, flop) = max(groups.items(), key=lambda kv: kv[1][1])
+    N, Hh, Ww, Cin, Cout, R, stride = key
+    ach = flop / (ms * 1e-3) / 1e12
+    name = {"fwd": "conv2_kernel (tcgen05 cta_group::2 implicit GEMM, forward)",
+            "dgrad": "conv2_kernel (tcgen05 cta_group::2, input gradient, filter read MN-major)",
+            "wgrad": "conv_wgrad2_kernel (tcgen05 cta_group::2, weight gradient)"}[kind]
+    return {"bound": "tensor", "kernel": "%s, %dx%d conv %d->%d stride %d on %dx%dx%d px, %d launches per step"
+                                         % (name, R, R, Cin, Cout, stride, N, Hh, Ww, cnt),
+            "in_step": True, "achieved": ach, "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sus"],
+            "peak_source": peaks["src"] + " bf16 sustained (kernel timed inside the step)",
+            "traffic": None, "algorithmic_flops_per_launch": flop / cnt, "ms_per_launch": ms / cnt,
+            "share_of_step_time": ms / ms_step,
+            "all_tcgen05_launches": {"launches_per_step": len(recs), "flop_per_step": tot_flop, "ms_per_step": tot_ms,
+                                     "achieved": tot_flop / (tot_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                     "frac": tot_flop / (tot_ms * 1e-3) / 1e12 / peaks["tf_sus"],
+                                     "share_of_step_time": tot_ms / ms_step,
+                                     "share_of_step_flop": tot_flop / (FLOP_PER_IMAGE * IMS_PER_GPU)},
+            "method": "CUDA events on the launching stream around each launch of one eager execution of the static step"}
+
+
 def conv_tc_roofline(peaks):
-    """Dominant hand-written kernel of the step: conv_tc_kernel on the FPN-output / RPN-head 3x3 (256->256 on
-    2x256x256 px, 154.6 GFLOP per launch = 2*M*Cout*9*Cin). Timed live with CUDA events on the launch stream,
-    back-to-back launches on distinct buffers larger than L2 in aggregate."""
-    from .modeling.conv_tc import conv2d_nhwc
+    """The same kernel in isolation (micro-benchmark): FPN-output / RPN-head 3x3 (256->256 on 2x256x256 px, 154.6 GFLOP per
+    launch = 2*M*Cout*9*Cin), back-to-back launches on distinct buffers larger than L2 in aggregate, CUDA events on the
+    launch stream."""
+    from .modeling import conv_tc as _ct
+    conv2d_nhwc = (lambda x, w, s, p: _ct.conv2_nhwc(x, w, s, p)) if _ct.USE_CONV2 else _ct.conv2d_nhwc
     N, C, Hh, Ww = 2, 256, 256, 256
     xs = [torch.randn(N, C, Hh, Ww, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last) for _ in range(4)]
     w = (torch.randn(C, 3, 3, C, device="cuda") * 0.02).bfloat16()
@@ -182,12 +254,11 @@ def conv_tc_roofline(peaks):
     ms = e0.elapsed_time(e1) / reps
     flops = 2.0 * N * Hh * Ww * C * C * 9
     ach = flops / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "conv_tc_kernel<256,bf16> (tcgen05 implicit GEMM), FPN output2 / RPN p2 shape",
-            "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": ach / peaks["tf_burst"],
+    return {"bound": "tensor", "kernel": "%s<256,bf16> (tcgen05 implicit GEMM), FPN output2 / RPN p2 shape, isolated"
+                                         % ("conv2_kernel" if _ct.USE_CONV2 else "conv_tc_kernel"),
+            "in_step": False, "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": ach / peaks["tf_burst"],
             "peak_source": peaks["src"] + " bf16 burst (kernel timed alone)",
-            # dram read 68.3 MB + write 22.9 MB per launch, ncu --set full (profiles/r01_ncu_conv_tc_full_summary.txt);
-            # algorithmic bytes 135.4 MB (in + filter + out): the output is still L2-resident when the kernel ends
-            "traffic": 91.2e6, "traffic_unit": "bytes/launch",
+            "traffic": None, "traffic_unit": "bytes/launch",
             "algorithmic_flops_per_launch": flops, "ms_per_launch": ms}
 
 
@@ -224,11 +295,17 @@ def cpu_train_sample(steps, n_images=1):
 
 
 def reference_line(args):
-    r = cpu_train_sample(max(1, min(args.steps, 3)), n_images=1)
+    """bench.py --impl reference: the reference's CPU path (oracle port: torch CPU ops = the library calls the reference
+    itself makes; /root/reference does not exist on the GPU box) on the arm's own config: 2 images of 1024x1024 per step,
+    forward + backward. Bounded: 1 untimed + at most 3 timed steps (~10 s each on 32 threads); `steps` is what was timed."""
+    timed = max(1, min(args.steps, 3))
+    r = cpu_train_sample(timed, n_images=IMS_PER_GPU)
     return {"impl": "reference", "metric": "u2seg_R50_800_train_images_per_sec", "value": r["value"], "unit": "images/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["s_per_step"] * 1e3,
+            "n_gpus": args.gpus, "steps": timed, "warmup": 1, "ms_per_step": r["s_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "u2seg_R50_800.yaml training step, synthetic 1024x1024 (oracle port of the reference "
-                                   "CPU path; 1 image per step sample)"},
+            "config": {"workload": "u2seg_R50_800.yaml training step (PanopticFPN R50-FPN, SyncBN, CascadeROIHeads, "
+                                   "800 classes), batch 2/GPU, synthetic 1024x1024 COCO-panoptic-shaped inputs, fwd+bwd "
+                                   "(oracle port of the reference's CPU path, fp32)", "global_batch": IMS_PER_GPU,
+                       "image_size": [H, W], "requested_steps": args.steps, "requested_warmup": args.warmup},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

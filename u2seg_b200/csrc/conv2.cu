@@ -15,12 +15,15 @@
 //      ONE thread of the leader CTA issues tcgen05.mma.cta_group::2 (M=256, N=BN, K=16) for the pair.
 // Pipelines: smem ring full/empty (TMA of both CTAs -> leader's `full`; tcgen05.commit multicast -> both `empty`),
 // TMEM full/empty (commit multicast -> both epilogues; both epilogues -> leader's `T_empty`).
-// Epilogue (4 warps per CTA): batched tcgen05.ld (64 columns per wait), + bias, ReLU, round to bf16, stage 128 x 64
-// chunks in swizzled shared memory and write them with TMA stores (coalesced 128-byte rows, ragged tiles clipped by
-// the TMA unit). Optionally emits per-channel sum / sum-of-squares of the ROUNDED output tile (one partial row per
-// 128-pixel tile, deterministic): the statistics pass of the SyncBN that follows almost every conv of the backbone
-// (layers/batch_norm.py:187) costs no extra read of the activation.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA only), 2 = TMEM allocator, 4-7 = epilogue.
+// Epilogue (8 warps per CTA: two per TMEM lane quadrant, each pair of quadrant-mates alternates over the 64-column
+// chunks): tcgen05.ld of 32 columns per wait, + bias, ReLU, round to bf16, stage 128 x 64 chunks in swizzled shared
+// memory and write them with TMA stores (coalesced 128-byte rows, ragged tiles clipped by the TMA unit). Optionally emits
+// per-channel sum / sum-of-squares of the ROUNDED output tile (read back from the staged chunk, conflict-free; one partial
+// row per 128-pixel tile, deterministic): the statistics pass of the SyncBN that follows almost every conv of the
+// backbone (layers/batch_norm.py:187) costs no extra read of the activation.
+// Input gradient: dX = conv(dY, rot180(W)^T) is the same kernel reading the UNTRANSPOSED (Cout,R,S,Cin) filter as an
+// MN-major B operand (GEMM-K = Cout is the slow axis of the filter rows), taps flipped by index arithmetic.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA only), 2 = TMEM allocator, 4-11 = epilogue.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -32,12 +35,15 @@ constexpr int BM = 128;  // rows per CTA; the pair computes 256
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;    // 16 KB
 constexpr int STG_BYTES = BM * 64 * 2;  // epilogue staging chunk: 128 rows x 64 channels
-constexpr int C2_THREADS = 256;
+constexpr int C2_THREADS = 384;
+constexpr int EPI_THREADS = 256;  // warps 4..11
 
 struct Conv2Params {
   int N, H, W, Cin, Cout, R, S, stride, pad, OH, OW;
   int BW, BH, tiles_w, tiles_h, tiles_m, tiles_n, kblocks_c;
+  int lbw;       // log2(BW): tile rows -> (bh, bw) by shift / mask
   int num_work;  // (m pair, n tile)
+  int b_mn;      // 0: filter (Cout_gemm, R*S*K) K-major rows (forward); 1: dgrad, filter (K, R, S, Cout_gemm) read MN-major, taps flipped
   int relu;
   const float* bias;
   float* stats;  // (tiles_m, 2*Cout) fp32 partial sums [sum | sum of squares] or NULL
@@ -49,7 +55,7 @@ struct Cfg2 {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 5 : (BN == 128 ? 7 : 8);
   static constexpr int STG_OFF = STAGES * STAGE_BYTES;
-  static constexpr int STAT_OFF = STG_OFF + 2 * STG_BYTES;
+  static constexpr int STAT_OFF = STG_OFF + 2 * STG_BYTES;  // one staging chunk per epilogue half
   static constexpr int BAR_OFF = STAT_OFF + 4 * 2 * BN * 4;
   static constexpr int SMEM_BYTES = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
@@ -158,40 +164,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 }
 
 template <bool BF16>
-__device__ __forceinline__ uint32_t pack2r(float& a, float& b) {  // rounds a, b in place (what the tensor stores)
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
   if (BF16) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    const float2 f = __bfloat1622float2(v);
-    a = f.x;
-    b = f.y;
     return *reinterpret_cast<uint32_t*>(&v);
   } else {
     __half2 v = __floats2half2_rn(a, b);
-    const float2 f = __half22float2(v);
-    a = f.x;
-    b = f.y;
     return *reinterpret_cast<uint32_t*>(&v);
   }
 }
-
-// sum over the 32 lanes of v[j], left in lane j's v[0] (31 shuffles instead of 32 x 5)
-template <int OFF>
-__device__ __forceinline__ void transpose_reduce_step(float* v, int lane) {
-  const bool up = (lane & OFF) != 0;
-#pragma unroll
-  for (int i = 0; i < OFF; ++i) {
-    const float send = up ? v[i] : v[i + OFF];
-    const float keep = up ? v[i + OFF] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+template <bool BF16>
+__device__ __forceinline__ float2 unpack2(uint32_t u) {
+  if (BF16) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  } else {
+    return __half22float2(*reinterpret_cast<__half2*>(&u));
   }
-}
-__device__ __forceinline__ float transpose_reduce32(float* v, int lane) {
-  transpose_reduce_step<16>(v, lane);
-  transpose_reduce_step<8>(v, lane);
-  transpose_reduce_step<4>(v, lane);
-  transpose_reduce_step<2>(v, lane);
-  transpose_reduce_step<1>(v, lane);
-  return v[0];
 }
 
 template <int BN, bool BF16>
@@ -226,7 +214,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&T_full[i], 1);
-      ptx::mbar_init(&T_empty[i], 8);  // 4 epilogue warps x 2 CTAs (only the leader's copy is used)
+      ptx::mbar_init(&T_empty[i], 16);  // 8 epilogue warps x 2 CTAs (only the leader's copy is used)
     }
     ptx::fence_barrier_init();
   }
@@ -259,8 +247,18 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
               const uint32_t full_leader = mapa_rank(ptx::smem_u32(&full[stage]), 0);
               if (leader) ptx::mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
               tma_load_4d_2sm(sa, &tmap_x, full_leader, cb * BK, x_base + s, y_base + r, n);
-              const int kcol = ((r * p.S + s) * p.kblocks_c + cb) * BK;
-              tma_load_2d_2sm(sa + A_BYTES, &tmap_w, full_leader, kcol, tn * BN + static_cast<int>(rank) * (BN / 2));
+              if (!p.b_mn) {
+                const int kcol = ((r * p.S + s) * p.kblocks_c + cb) * BK;
+                tma_load_2d_2sm(sa + A_BYTES, &tmap_w, full_leader, kcol, tn * BN + static_cast<int>(rank) * (BN / 2));
+              } else {
+                // filter rows = GEMM-K channels (cb*64 .. +63), columns = flipped tap x this CTA's BN/2 output channels:
+                // boxes of [64 K rows][64 N columns] = the MN-major SW128 operand layout (next 64-column block 8 KB on)
+                const int tap = (p.R - 1 - r) * p.S + (p.S - 1 - s);
+                const int col0 = tap * p.Cout + tn * BN + static_cast<int>(rank) * (BN / 2);
+#pragma unroll
+                for (int j = 0; j < BN / 128; ++j)
+                  tma_load_2d_2sm(sa + A_BYTES + j * (64 * 128), &tmap_w, full_leader, col0 + j * 64, cb * BK);
+              }
               if (++stage == Cfg::STAGES) {
                 stage = 0;
                 phase ^= 1;
@@ -270,7 +268,8 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     }
   } else if (warp == 1) {
     if (leader && ptx::elect_one()) {
-      const uint32_t idesc = ptx::umma_idesc_f16(2 * BM, BN, BF16 ? 1u : 0u);
+      const uint32_t idesc = ptx::umma_idesc_f16(2 * BM, BN, BF16 ? 1u : 0u) | (p.b_mn ? (1u << 16) : 0u);  // bit 16: B MN-major
+      const uint32_t b_step = p.b_mn ? 128u : 2u;   // K = 16: 16 rows of 128 B (MN-major) or 32 B along the row (K-major)
       const uint32_t sbase = ptx::smem_u32(smem);
       uint32_t stage = 0, phase = 0, acc_it = 0;
       for (int work = cluster_id; work < p.num_work; work += num_clusters, ++acc_it) {
@@ -282,10 +281,11 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
           mbar_wait_cluster(&full[stage], phase);
           ptx::tc_fence_after();
           const uint64_t a_desc = ptx::umma_desc_sw128(sbase + stage * Cfg::STAGE_BYTES);
-          const uint64_t b_desc = ptx::umma_desc_sw128(sbase + stage * Cfg::STAGE_BYTES + A_BYTES);
+          uint64_t b_desc = ptx::umma_desc_sw128(sbase + stage * Cfg::STAGE_BYTES + A_BYTES);
+          if (p.b_mn) b_desc |= static_cast<uint64_t>((64 * 128) >> 4) << 16;   // LBO: next 64-column block
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_f16_2sm(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            umma_f16_2sm(tmem_d, a_desc + 2 * k, b_desc + b_step * k, idesc, (kb | k) != 0);
           umma_commit_2sm(&empty[stage]);
           if (++stage == Cfg::STAGES) {
             stage = 0;
@@ -296,96 +296,108 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
       }
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;
+    const int q = warp & 3;                    // TMEM lane quadrant this warp may read
+    const int half = (warp - 4) >> 2;          // the two warps of a quadrant alternate over the 64-column chunks
     const int row = q * 32 + lane;
-    const int epi_tid = threadIdx.x - 128;
-    const int bh = row / p.BW, bw = row % p.BW;
+    const int epi_tid = threadIdx.x - 128;     // 0..255
+    const int half_tid = epi_tid & 127;
     const uint32_t sw = static_cast<uint32_t>(row & 7);
-    uint32_t acc_it = 0, chunk_it = 0;
+    uint8_t* sbuf = stg + half * STG_BYTES;
+    const uint32_t srow = ptx::smem_u32(sbuf) + static_cast<uint32_t>(row) * 128u;
+    const uint32_t t_empty_leader = mapa_rank(ptx::smem_u32(&T_empty[0]), 0);
+    uint32_t acc_it = 0;
     for (int work = cluster_id; work < p.num_work; work += num_clusters, ++acc_it) {
       const int tn = work % p.tiles_n, tm_raw = (work / p.tiles_n) * 2 + static_cast<int>(rank);
       const bool store_tile = tm_raw < p.tiles_m;
       const int tm = store_tile ? tm_raw : p.tiles_m - 1;
       const int owb = tm % p.tiles_w, ohb = (tm / p.tiles_w) % p.tiles_h, n = tm / (p.tiles_w * p.tiles_h);
-      const bool valid = (ohb * p.BH + bh) < p.OH && (owb * p.BW + bw) < p.OW && store_tile;
+      const bool tile_full = (ohb + 1) * p.BH <= p.OH && (owb + 1) * p.BW <= p.OW;
       const uint32_t buf = acc_it & 1, tphase = (acc_it >> 1) & 1;
       ptx::mbar_wait(&T_full[buf], tphase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c, ++chunk_it) {
-        uint8_t* sbuf = stg + (chunk_it & 1) * STG_BYTES;
-        uint32_t v[64];
-        tmem_ld32(taddr + c * 64, v);
-        tmem_ld32(taddr + c * 64 + 32, v + 32);
-        ptx::tmem_ld_wait();
-        float f[64];
-#pragma unroll
-        for (int j = 0; j < 64; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + tn * BN + c * 64);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float4 b = __ldg(b4 + j);
-            f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
-          }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
+      for (int c = half; c < BN / 64; c += 2) {
         uint32_t pk[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) pk[j] = pack2r<BF16>(f[2 * j], f[2 * j + 1]);
-        // the TMA store issued two chunks ago (same staging buffer) must have finished reading shared memory
-        if (epi_tid == 0) bulk_wait_group_read<1>();
-        ptx::named_bar_sync(1, 128);
-        const uint32_t srow = ptx::smem_u32(sbuf) + static_cast<uint32_t>(row) * 128u;
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 64 + h * 32, v);
+          ptx::tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + tn * BN + c * 64 + h * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[h * 16 + j] = pack2<BF16>(f[2 * j], f[2 * j + 1]);
+        }
+        // this half's previous TMA store must have finished reading the staging chunk before it is overwritten
+        if (half_tid == 0) bulk_wait_group_read<0>();
+        ptx::named_bar_sync(1 + half, 128);
 #pragma unroll
         for (uint32_t j = 0; j < 8; ++j)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ sw) << 4)), "r"(pk[4 * j]),
                        "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
                        : "memory");
         ptx::fence_proxy_async();
-        ptx::named_bar_sync(1, 128);
-        if (epi_tid == 0 && store_tile) {
+        ptx::named_bar_sync(1 + half, 128);
+        if (half_tid == 0 && store_tile) {
           tma_store_4d(&tmap_y, sbuf, tn * BN + c * 64, owb * p.BW, ohb * p.BH, n);
           bulk_commit_group();
         }
-        if (p.stats) {  // per-channel sum / sum of squares of this warp's 32 rows (rounded values; dead rows masked)
-          const float m = valid ? 1.f : 0.f;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float a[32], b[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              a[j] = f[h * 32 + j] * m;
-              b[j] = a[j] * a[j];
+        if (p.stats) {
+          // per-channel sum / sum of squares of the staged (rounded) chunk: this warp takes rows q*32..q*32+31, lane l
+          // the channel pair (2l, 2l+1); for a fixed row the 32 lanes touch 32 distinct banks (16-byte slot
+          // (l>>2)^(row&7), word l&3). Rows outside the image (ragged / padding tiles) are skipped.
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          const uint32_t base = ptx::smem_u32(sbuf) + static_cast<uint32_t>(lane & 3) * 4u;
+          const uint32_t slot = static_cast<uint32_t>(lane >> 2);
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            const int r2 = q * 32 + rr;
+            bool ok = store_tile;
+            if (!tile_full) ok = ok && (ohb * p.BH + (r2 >> p.lbw)) < p.OH && (owb * p.BW + (r2 & (p.BW - 1))) < p.OW;
+            uint32_t u;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(base + static_cast<uint32_t>(r2) * 128u + ((slot ^ (r2 & 7)) << 4)));
+            const float2 x = unpack2<BF16>(u);
+            if (ok) {
+              s0 += x.x; s1 += x.y;
+              q0 = fmaf(x.x, x.x, q0); q1 = fmaf(x.y, x.y, q1);
             }
-            const float s1 = transpose_reduce32(a, lane);
-            const float s2 = transpose_reduce32(b, lane);
-            sstat[q * 2 * BN + c * 64 + h * 32 + lane] = s1;
-            sstat[q * 2 * BN + BN + c * 64 + h * 32 + lane] = s2;
           }
+          float* st = sstat + q * 2 * BN + c * 64 + 2 * lane;
+          *reinterpret_cast<float2*>(st) = make_float2(s0, s1);
+          *reinterpret_cast<float2*>(st + BN) = make_float2(q0, q1);
         }
       }
-      // this CTA's half of the accumulator is in registers / stored: hand the TMEM buffer back to the MMA issuer
+      // this warp's share of the accumulator has been read: hand the TMEM buffer back to the MMA issuer
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(mapa_rank(ptx::smem_u32(&T_empty[buf]), 0));
+      if (lane == 0) mbar_arrive_remote(t_empty_leader + buf * 8);
       if (p.stats) {
-        ptx::named_bar_sync(1, 128);
+        ptx::named_bar_sync(3, EPI_THREADS);
         if (store_tile) {
           float* dst = p.stats + static_cast<size_t>(tm) * 2 * p.Cout;
-          for (int i = epi_tid; i < 2 * BN; i += 128) {
-            const float s = (sstat[i] + sstat[2 * BN + i]) + (sstat[4 * BN + i] + sstat[6 * BN + i]);
-            dst[(i < BN ? 0 : p.Cout - BN) + tn * BN + i] = s;
+          for (int i = epi_tid; i < 2 * BN; i += EPI_THREADS) {
+            const float sum = (sstat[i] + sstat[2 * BN + i]) + (sstat[4 * BN + i] + sstat[6 * BN + i]);
+            dst[(i < BN ? 0 : p.Cout - BN) + tn * BN + i] = sum;
           }
         }
-        ptx::named_bar_sync(1, 128);
+        ptx::named_bar_sync(3, EPI_THREADS);
       }
     }
-    if (epi_tid == 0) bulk_wait_group_all();
+    if (half_tid == 0) bulk_wait_group_all();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -437,21 +449,81 @@ void conv2_geometry(Conv2Params& p, int N, int H, int W, int Cin, int Cout, int 
       p.BH = bh;
     }
   }
+  p.lbw = 0;
+  while ((1 << p.lbw) < p.BW) ++p.lbw;
   p.tiles_w = (p.OW + p.BW - 1) / p.BW;
   p.tiles_h = (p.OH + p.BH - 1) / p.BH;
   p.tiles_m = p.tiles_w * p.tiles_h * N;
   p.kblocks_c = Cin / BK;
 }
 
-int conv2_pick_bn(const Conv2Params& p) {
-  if (g_conv2_bn && p.Cout % g_conv2_bn == 0) return g_conv2_bn;
+int conv2_pick_bn(const Conv2Params& p, int min_bn) {
+  if (g_conv2_bn >= min_bn && p.Cout % g_conv2_bn == 0) return g_conv2_bn;
   const int pairs = (p.tiles_m + 1) / 2, want = u2b_num_sms() / 2;
   // widest tile that still gives every SM pair a work item; otherwise the narrowest (most parallelism)
-  for (int bn = 256; bn >= 64; bn >>= 1)
+  for (int bn = 256; bn >= min_bn; bn >>= 1)
     if (p.Cout % bn == 0 && pairs * (p.Cout / bn) >= want) return bn;
-  for (int bn = 64; bn <= 256; bn <<= 1)
+  for (int bn = min_bn; bn <= 256; bn <<= 1)
     if (p.Cout % bn == 0) return bn;
   return 0;
+}
+
+// x: (N,H,W,Kc) NHWC activations whose Kc channels are the GEMM-K axis; out: (N,OH,OW,Nc). b_mn = 0: w is (Nc, R*S*Kc)
+// K-major rows (forward). b_mn = 1: w is the forward filter (Kc, R*S*Nc) read MN-major with flipped taps (dgrad).
+int conv2_run(int dtype, const void* x, int N, int H, int W, int Kc, const void* w, int Nc, int R, int S, int stride,
+              int pad, int b_mn, const float* bias, int relu, void* out, float* stats, cudaStream_t stream) {
+  Conv2Params p;
+  conv2_geometry(p, N, H, W, Kc, Nc, R, S, stride, pad);
+  const int BN = conv2_pick_bn(p, b_mn ? 128 : 64);
+  if (BN == 0) {
+    u2b_set_error("conv2: no tile width for %d output channels (mode %d)", Nc, b_mn);
+    return U2B_ERR_UNSUPPORTED;
+  }
+  p.tiles_n = Nc / BN;
+  p.num_work = ((p.tiles_m + 1) / 2) * p.tiles_n;
+  p.b_mn = b_mn;
+  p.relu = relu;
+  p.bias = bias;
+  p.stats = stats;
+  const CUtensorMapDataType tdt = dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap tx, tw, ty;
+  {
+    uint64_t dims[4] = {(uint64_t)Kc, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t strides[3] = {(uint64_t)Kc * 2, (uint64_t)W * Kc * 2, (uint64_t)H * W * Kc * 2};
+    uint32_t box[4] = {BK, (uint32_t)(p.BW * stride), (uint32_t)(p.BH * stride), 1};
+    uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    int rc = u2b_encode_tmap(&tx, tdt, 4, x, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc) return rc;
+  }
+  if (!b_mn) {
+    uint64_t dims[2] = {(uint64_t)R * S * Kc, (uint64_t)Nc};
+    uint64_t strides[1] = {(uint64_t)R * S * Kc * 2};
+    uint32_t box[2] = {BK, (uint32_t)(BN / 2)};
+    int rc = u2b_encode_tmap(&tw, tdt, 2, w, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc) return rc;
+  } else {
+    uint64_t dims[2] = {(uint64_t)R * S * Nc, (uint64_t)Kc};
+    uint64_t strides[1] = {(uint64_t)R * S * Nc * 2};
+    uint32_t box[2] = {64, 64};
+    int rc = u2b_encode_tmap(&tw, tdt, 2, w, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)Nc, (uint64_t)p.OW, (uint64_t)p.OH, (uint64_t)N};
+    uint64_t strides[3] = {(uint64_t)Nc * 2, (uint64_t)p.OW * Nc * 2, (uint64_t)p.OH * p.OW * Nc * 2};
+    uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+    int rc = u2b_encode_tmap(&ty, tdt, 4, out, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc) return rc;
+  }
+  const bool bf = dtype == 2;
+  if (BN == 256) return bf ? launch_conv2<256, true>(tx, tw, ty, p, stream) : launch_conv2<256, false>(tx, tw, ty, p, stream);
+  if (BN == 128) return bf ? launch_conv2<128, true>(tx, tw, ty, p, stream) : launch_conv2<128, false>(tx, tw, ty, p, stream);
+  if (BN == 64) return bf ? launch_conv2<64, true>(tx, tw, ty, p, stream) : launch_conv2<64, false>(tx, tw, ty, p, stream);
+  return U2B_ERR_UNSUPPORTED;
 }
 
 }  // namespace
@@ -492,46 +564,26 @@ int u2b_conv2_nhwc_fwd(int dtype, const void* x, int N, int H, int W, int Cin, c
                   pad);
     return U2B_ERR_UNSUPPORTED;
   }
-  Conv2Params p;
-  conv2_geometry(p, N, H, W, Cin, Cout, R, S, stride, pad);
-  const int BN = conv2_pick_bn(p);
-  p.tiles_n = Cout / BN;
-  p.num_work = ((p.tiles_m + 1) / 2) * p.tiles_n;
-  p.relu = relu;
-  p.bias = bias;
-  p.stats = stats;
-  const CUtensorMapDataType tdt = dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  CUtensorMap tx, tw, ty;
-  {
-    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
-    uint32_t box[4] = {BK, (uint32_t)(p.BW * stride), (uint32_t)(p.BH * stride), 1};
-    uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
-    int rc = u2b_encode_tmap(&tx, tdt, 4, x, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc) return rc;
+  return conv2_run(dtype, x, N, H, W, Cin, w, Cout, R, S, stride, pad, 0, bias, relu, out, stats, stream);
+}
+
+// 1 if the input gradient of this (stride-1) convolution runs on the kernel with the untransposed filter
+int u2b_conv2_dgrad_supported(int Cin, int Cout, int R, int S, int stride, int pad) {
+  if (stride != 1 || Cin <= 0 || Cin % 128 != 0 || Cout <= 0 || Cout % 64 != 0) return 0;
+  return (R == 1 && S == 1 && pad == 0) || (R == 3 && S == 3 && pad == 1);
+}
+
+// dX = conv(dY, rot180(W)^T) for a stride-1 'same' convolution. dy: (N,H,W,Cout) NHWC; w: the FORWARD filter
+// (Cout,R,S,Cin), read in place as an MN-major operand; dx: (N,H,W,Cin) NHWC.
+int u2b_conv2_nhwc_dgrad(int dtype, const void* dy, int N, int H, int W, int Cout, const void* w, int Cin, int R, int S,
+                         int pad, void* dx, cudaStream_t stream) {
+  U2B_CHECK_ARG(dy && w && dx && N > 0 && H > 0 && W > 0, "conv2_nhwc_dgrad: bad arguments");
+  U2B_CHECK_ARG(dtype == 1 || dtype == 2, "conv2_nhwc_dgrad: dtype must be fp16(1) or bf16(2)");
+  if (!u2b_conv2_dgrad_supported(Cin, Cout, R, S, 1, pad)) {
+    u2b_set_error("conv2_nhwc_dgrad: unsupported shape Cin=%d Cout=%d k=%dx%d pad=%d", Cin, Cout, R, S, pad);
+    return U2B_ERR_UNSUPPORTED;
   }
-  {
-    uint64_t dims[2] = {(uint64_t)R * S * Cin, (uint64_t)Cout};
-    uint64_t strides[1] = {(uint64_t)R * S * Cin * 2};
-    uint32_t box[2] = {BK, (uint32_t)(BN / 2)};
-    int rc = u2b_encode_tmap(&tw, tdt, 2, w, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc) return rc;
-  }
-  {
-    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)p.OW, (uint64_t)p.OH, (uint64_t)N};
-    uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)p.OW * Cout * 2, (uint64_t)p.OH * p.OW * Cout * 2};
-    uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
-    int rc = u2b_encode_tmap(&ty, tdt, 4, out, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc) return rc;
-  }
-  const bool bf = dtype == 2;
-  if (BN == 256) return bf ? launch_conv2<256, true>(tx, tw, ty, p, stream) : launch_conv2<256, false>(tx, tw, ty, p, stream);
-  if (BN == 128) return bf ? launch_conv2<128, true>(tx, tw, ty, p, stream) : launch_conv2<128, false>(tx, tw, ty, p, stream);
-  if (BN == 64) return bf ? launch_conv2<64, true>(tx, tw, ty, p, stream) : launch_conv2<64, false>(tx, tw, ty, p, stream);
-  return U2B_ERR_UNSUPPORTED;
+  return conv2_run(dtype, dy, N, H, W, Cout, w, Cin, R, S, 1, R - 1 - pad, 1, nullptr, 0, dx, nullptr, stream);
 }
 
 }  // extern "C"

@@ -28,6 +28,29 @@ def conv2d_nhwc(x, w_ohwi, stride, pad, bias=None, residual=None, relu=False):
     return out
 
 
+# bench.py's in-step roofline: when TIMING is a list, every tcgen05 launch below is bracketed by CUDA events on the
+# launching stream and recorded as (kind, shape key, flop, start event, end event)
+TIMING = None
+
+
+class _Timed:
+    def __init__(self, kind, key, flop):
+        self.on = TIMING is not None
+        if self.on:
+            self.rec = (kind, key, float(flop), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+
+    def __enter__(self):
+        if self.on:
+            self.rec[3].record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.rec[4].record()
+            TIMING.append(self.rec)
+        return False
+
+
 def conv2_stats_rows(x_shape, R, S, stride, pad):
     N, _, H, W = x_shape
     return int(_lib.lib().u2b_conv2_stats_rows(N, H, W, R, S, stride, pad))
@@ -45,12 +68,35 @@ def conv2_nhwc(x, w_ohwi, stride, pad, bias=None, relu=False, want_stats=False):
     if want_stats:
         stats = torch.empty((conv2_stats_rows(x.shape, R, S, stride, pad), 2 * Cout), dtype=torch.float32, device=x.device)
     if out.numel():
-        _lib.check(L.u2b_conv2_nhwc_fwd(_CODE[x.dtype], ctypes.c_void_p(x.data_ptr()), N, H, W, Cin,
-                                        ctypes.c_void_p(w_ohwi.data_ptr()), Cout, R, S, stride, pad, _lib.ptr(bias), int(relu),
-                                        ctypes.c_void_p(out.data_ptr()), _lib.ptr(stats), _lib.stream_ptr()),
-                   "u2b_conv2_nhwc_fwd")
+        with _Timed("fwd", (N, H, W, Cin, Cout, R, stride), 2.0 * N * OH * OW * Cout * Cin * R * S):
+            _lib.check(L.u2b_conv2_nhwc_fwd(_CODE[x.dtype], ctypes.c_void_p(x.data_ptr()), N, H, W, Cin,
+                                            ctypes.c_void_p(w_ohwi.data_ptr()), Cout, R, S, stride, pad, _lib.ptr(bias),
+                                            int(relu), ctypes.c_void_p(out.data_ptr()), _lib.ptr(stats), _lib.stream_ptr()),
+                       "u2b_conv2_nhwc_fwd")
         _lib.count_launches(1)
     return (out, stats) if want_stats else out
+
+
+def conv2_dgrad_supported(gy, weight, stride, pad):
+    Cout, Cin, R, S = weight.shape
+    return (USE_CONV2 and gy.is_cuda and gy.dtype in _CODE
+            and bool(_lib.lib().u2b_conv2_dgrad_supported(Cin, Cout, R, S, stride, pad)))
+
+
+def conv2_nhwc_dgrad(gy, w_ohwi, pad):
+    """dX of a stride-1 'same' conv on the 2-CTA kernel, reading the FORWARD filter (Cout,R,S,Cin) in place.
+    gy: logical (N,Cout,H,W) channels_last half tensor. Returns logical (N,Cin,H,W), NHWC storage."""
+    L = _lib.lib()
+    N, Cout, H, W = gy.shape
+    _, R, S, Cin = w_ohwi.shape
+    dx = torch.empty((N, H, W, Cin), dtype=gy.dtype, device=gy.device).permute(0, 3, 1, 2)
+    if dx.numel():
+        with _Timed("dgrad", (N, H, W, Cin, Cout, R, 1), 2.0 * N * H * W * Cout * Cin * R * S):
+            _lib.check(L.u2b_conv2_nhwc_dgrad(_CODE[gy.dtype], ctypes.c_void_p(gy.data_ptr()), N, H, W, Cout,
+                                              ctypes.c_void_p(w_ohwi.data_ptr()), Cin, R, S, pad,
+                                              ctypes.c_void_p(dx.data_ptr()), _lib.stream_ptr()), "u2b_conv2_nhwc_dgrad")
+        _lib.count_launches(1)
+    return dx
 
 
 def set_tile_n(bn):
@@ -81,6 +127,32 @@ def conv2d_nhwc_wgrad(x, gy, R, S, stride, pad):
     return parts.sum(0).permute(0, 3, 1, 2)
 
 
+USE_WGRAD2 = __import__("os").environ.get("U2B_WGRAD2", "1") == "1"   # 2-CTA tcgen05 weight gradient (csrc/conv_wgrad2.cu)
+_OUT_CODE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def wgrad2_supported(x, Cout, R, S, stride, pad):
+    return (USE_WGRAD2 and x.is_cuda and x.dtype in _CODE
+            and bool(_lib.lib().u2b_conv_wgrad2_supported(int(x.shape[1]), int(Cout), R, S, stride, pad)))
+
+
+def conv_wgrad2(x, gy, R, S, stride, pad, out_dtype=torch.float32):
+    """dW of conv(x, W) given dY on the 2-CTA tcgen05 kernel. x (N,Cin,H,W), gy (N,Cout,OH,OW): channels_last half
+    tensors. Returns logical (Cout,Cin,R,S) in out_dtype with OHWI (channels_last) storage."""
+    L = _lib.lib()
+    N, Cin, H, W = x.shape
+    Cout = gy.shape[1]
+    nws = int(L.u2b_conv_wgrad2_workspace_floats(N, H, W, Cin, Cout, R, S, stride, pad))
+    ws = torch.empty((nws,), dtype=torch.float32, device=x.device)
+    dw = torch.empty((Cout, R, S, Cin), dtype=out_dtype, device=x.device)
+    with _Timed("wgrad", (N, H, W, Cin, Cout, R, stride), 2.0 * N * gy.shape[2] * gy.shape[3] * Cout * Cin * R * S):
+        _lib.check(L.u2b_conv_wgrad2(_CODE[x.dtype], ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(gy.data_ptr()), N, H, W,
+                                     Cin, Cout, R, S, stride, pad, ctypes.c_void_p(ws.data_ptr()), _OUT_CODE[out_dtype],
+                                     ctypes.c_void_p(dw.data_ptr()), _lib.stream_ptr()), "u2b_conv_wgrad2")
+    _lib.count_launches(2)
+    return dw.permute(0, 3, 1, 2)
+
+
 def set_cluster(cl):
     """thread-block cluster size of the conv kernel (1 = no multicast, 2, 4)."""
     _lib.check(_lib.lib().u2b_conv2d_set_cluster(int(cl)), "u2b_conv2d_set_cluster")
@@ -94,20 +166,40 @@ def _nhwc(x):
     return x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
 
 
+USE_CONV2 = __import__("os").environ.get("U2B_CONV2", "1") == "1"    # 2-CTA kernel (csrc/conv2.cu) for forward and dgrad
+
+
+def _conv_fwd(xc, w_ohwi, stride, pad, bias, relu, want_stats=False):
+    if USE_CONV2:
+        return conv2_nhwc(xc, w_ohwi, stride, pad, bias, relu, want_stats)
+    y = conv2d_nhwc(xc, w_ohwi, stride, pad, bias, None, relu)
+    return (y, None) if want_stats else y
+
+
 class _ConvTC(torch.autograd.Function):
+    """y = [relu](conv(x, W) + b) on the tcgen05 kernels; with want_stats also the per-tile BN statistics partials of y
+    (non-differentiable; consumed by fused_bn.bn_act so that the SyncBN after the conv needs no reduction pass)."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad, relu):
+    def forward(ctx, x, weight, bias, stride, pad, relu, want_stats=False):
         dt = x.dtype
         xc = _nhwc(x)
         w = weight.detach().to(dt).permute(0, 2, 3, 1).contiguous()              # (Cout,R,S,Cin)
         b = bias.detach().float().contiguous() if bias is not None else None
-        y = conv2d_nhwc(xc, w, stride, pad, b, None, relu)
+        stats = None
+        if want_stats:
+            y, stats = _conv_fwd(xc, w, stride, pad, b, relu, True)
+        else:
+            y = _conv_fwd(xc, w, stride, pad, b, relu)
         ctx.save_for_backward(xc, weight, y if relu else torch.empty(0))
         ctx.meta = (stride, pad, relu, bias is not None)
-        return y
+        if want_stats and stats is not None:
+            ctx.mark_non_differentiable(stats)
+            return y, stats
+        return (y, None) if want_stats else y
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, _gstats=None):
         xc, weight, y = ctx.saved_tensors
         stride, pad, relu, has_bias = ctx.meta
         dt = xc.dtype
@@ -118,11 +210,18 @@ class _ConvTC(torch.autograd.Function):
         R = weight.shape[2]
         if ctx.needs_input_grad[0] and stride == 1:
             # dX = conv(dY, rot180(W)^T), same padding for 1x1/3x3 'same' convs: the forward kernel again
-            wt = weight.detach().to(dt).flip(2, 3).permute(1, 2, 3, 0).contiguous()  # (Cin,R,S,Cout)
-            gx = conv2d_nhwc(gy, wt, 1, R - 1 - pad, None, None, False)
+            if conv2_dgrad_supported(gy, weight, stride, pad):
+                # the forward filter (Cout,R,S,Cin) as it is: read MN-major, taps flipped inside the kernel
+                gx = conv2_nhwc_dgrad(gy, weight.detach().to(dt).permute(0, 2, 3, 1).contiguous(), pad)
+            else:
+                wt = weight.detach().to(dt).flip(2, 3).permute(1, 2, 3, 0).contiguous() if R > 1 else \
+                    weight.detach().to(dt).permute(1, 2, 3, 0).contiguous()           # (Cin,R,S,Cout)
+                gx = _conv_fwd(gy, wt, 1, R - 1 - pad, None, False)
         need_gx_lib = ctx.needs_input_grad[0] and gx is None
-        if TC_WGRAD and ctx.needs_input_grad[1] and wgrad_supported(xc, weight, stride, pad):
-            gw = conv2d_nhwc_wgrad(xc, gy, weight.shape[2], weight.shape[3], stride, pad).to(weight.dtype)   # r2 draft
+        if ctx.needs_input_grad[1] and wgrad2_supported(xc, weight.shape[0], R, weight.shape[3], stride, pad):
+            gw = conv_wgrad2(xc, gy, R, weight.shape[3], stride, pad, weight.dtype)
+        elif TC_WGRAD and ctx.needs_input_grad[1] and wgrad_supported(xc, weight, stride, pad):
+            gw = conv2d_nhwc_wgrad(xc, gy, weight.shape[2], weight.shape[3], stride, pad).to(weight.dtype)   # 1-CTA draft
         mask = [need_gx_lib, ctx.needs_input_grad[1] and gw is None, False]
         if mask[0] or mask[1]:
             w_dt = weight.detach().to(dt)
@@ -135,7 +234,7 @@ class _ConvTC(torch.autograd.Function):
         if has_bias and ctx.needs_input_grad[2]:
             from .fused_bn import channel_sum
             gb = channel_sum(gy)
-        return gx, gw, gb, None, None, None
+        return gx, gw, gb, None, None, None, None
 
 
 class _StemConv(torch.autograd.Function):
@@ -197,18 +296,77 @@ def try_conv(x, m, residual=None):
         return None
     is_relu = m.activation in (F.relu, F.relu_)
     fuse_relu = m.norm is None and residual is None and is_relu
+    if (USE_CONV2 and ops.FUSED_BN and isinstance(m.norm, torch.nn.BatchNorm2d) and (m.activation is None or is_relu)):
+        from . import fused_bn
+        if fused_bn.supported(x, m.norm):
+            # SyncBN statistics come out of the conv epilogue (csrc/conv2.cu): no reduction pass over the activation
+            y, stats = _ConvTC.apply(x, m.weight, m.bias, m.stride[0], m.padding[0], False, True)
+            if m.norm.num_batches_tracked is not None and not getattr(m.norm, "_counter_batched", False):
+                m.norm.num_batches_tracked.add_(1)
+            return fused_bn.bn_act(y, m.norm, residual, is_relu, partials=stats)
     y = _ConvTC.apply(x, m.weight, m.bias, m.stride[0], m.padding[0], fuse_relu)
     if fuse_relu:
         return y
     return ops._norm_act(y, m, residual)
 
 
+class _LinearTC(torch.autograd.Function):
+    """y = [relu](x W^T + b) for nn.Linear (roi_heads/box_head.py:70,94-97): forward and input gradient on the 2-CTA
+    tcgen05 kernel, the (M, K) rows viewed as a (1,1,M,K) NHWC image under a 1x1 convolution; the weight gradient
+    dY^T X is a plain GEMM (library call until the tcgen05 wgrad kernel covers it)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        M, K = x.shape
+        Nout = weight.shape[0]
+        dt = x.dtype
+        x2 = x.contiguous()
+        w = weight.detach().to(dt).contiguous()
+        b = bias.detach().float().contiguous() if bias is not None else None
+        y = conv2_nhwc(x2.view(1, 1, M, K).permute(0, 3, 1, 2), w.view(Nout, 1, 1, K), 1, 0, b, relu)
+        y2 = y.permute(0, 2, 3, 1).reshape(M, Nout)                     # NHWC storage: a view
+        ctx.save_for_backward(x2, weight, y2 if relu else torch.empty(0))
+        ctx.meta = (relu, bias is not None)
+        return y2
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, weight, y2 = ctx.saved_tensors
+        relu, has_bias = ctx.meta
+        dt = x2.dtype
+        M, K = x2.shape
+        Nout = weight.shape[0]
+        if relu:
+            gy = torch.ops.aten.threshold_backward(gy, y2, 0)
+        gy = gy.to(dt).contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            w4 = weight.detach().to(dt).contiguous().view(Nout, 1, 1, K)
+            g4 = gy.view(1, 1, M, Nout).permute(0, 3, 1, 2)
+            if K % 128 == 0:      # dX = dY W: the weight as it is, read MN-major by the kernel (no transposed copy)
+                g = conv2_nhwc_dgrad(g4, w4, 0)
+            else:
+                g = conv2_nhwc(g4, weight.detach().to(dt).t().contiguous().view(K, 1, 1, Nout), 1, 0, None, False)
+            gx = g.permute(0, 2, 3, 1).reshape(M, K)
+        if ctx.needs_input_grad[1]:
+            x4 = x2.view(1, 1, M, K).permute(0, 3, 1, 2)
+            if wgrad2_supported(x4, Nout, 1, 1, 1, 0):       # dW = dY^T X with the rows as the GEMM-K (pixel) axis
+                gw = conv_wgrad2(x4, gy.view(1, 1, M, Nout).permute(0, 3, 1, 2), 1, 1, 1, 0, weight.dtype).reshape(Nout, K)
+            else:
+                gw = torch.mm(gy.t(), x2).to(weight.dtype)
+        if has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum(0, dtype=torch.float32)
+        return gx, gw, gb, None
+
+
+def linear_eligible(x, weight):
+    return (USE_CONV2 and x.is_cuda and x.dim() == 2 and x.dtype in _CODE and x.shape[1] % 64 == 0
+            and weight.shape[0] % 64 == 0 and x.shape[0] > 0)
+
+
 def linear(x, weight, bias, relu=False):
-    """nn.Linear through the same kernel: (M,K) rows as a (1,1,M,K) NHWC image, 1x1 conv."""
-    M, K = x.shape
-    if not (x.is_cuda and x.dtype in _CODE and K % 64 == 0 and weight.shape[0] % 64 == 0):
+    """nn.Linear on the tcgen05 kernel when the shape allows (K, Nout multiples of 64), else the library."""
+    if not linear_eligible(x, weight):
         y = F.linear(x, weight.to(x.dtype), bias.to(x.dtype) if bias is not None else None)
         return F.relu(y) if relu else y
-    x4 = x.contiguous().view(1, 1, M, K).permute(0, 3, 1, 2)         # logical (1,K,1,M), NHWC storage
-    y = _ConvTC.apply(x4, weight.view(weight.shape[0], K, 1, 1), bias, 1, 0, relu)
-    return y.permute(0, 2, 3, 1).reshape(M, weight.shape[0])
+    return _LinearTC.apply(x, weight, bias, relu)

@@ -99,7 +99,7 @@ def channel_sum(x):
 
 class _BNAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, running_mean, running_var, eps, momentum, relu):
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, eps, momentum, relu, partials=None):
         L = _lib.lib()
         s = _lib.stream_ptr()
         xc = _nhwc(x)
@@ -108,9 +108,13 @@ class _BNAct(torch.autograd.Function):
         dt = _CODE[xc.dtype]
         dev = xc.device
         world = _world()
-        S = int(L.u2b_bn_num_strips(P, C))
-        part = _partials(S, C, dev)
-        _lib.check(L.u2b_bn_stats(dt, _p(xc), P, C, _p(part), s), "u2b_bn_stats")
+        if partials is not None:      # (S, 2C) [sum | sumsq] rows from the producing conv's epilogue (csrc/conv2.cu)
+            assert partials.shape[1] == 2 * C and partials.dtype == torch.float32 and partials.is_contiguous()
+            part, S = partials, int(partials.shape[0])
+        else:
+            S = int(L.u2b_bn_num_strips(P, C))
+            part = _partials(S, C, dev)
+            _lib.check(L.u2b_bn_stats(dt, _p(xc), P, C, _p(part), s), "u2b_bn_stats")
         stats = torch.empty((4 * C,), dtype=torch.float32, device=dev)   # mean | invstd | scale | shift
         n_total = float(P) * world
         done = False
@@ -175,13 +179,14 @@ class _BNAct(torch.autograd.Function):
         dres = torch.empty((N, H, W, C), dtype=xc.dtype, device=dev).permute(0, 3, 1, 2) if has_res else None
         _lib.check(L.u2b_bn_bwd_apply(dt, _p(g), _p(xc), _p(yy), _p(coeff), _p(dx), _p(dres), P, C, s), "u2b_bn_bwd_apply")
         _lib.count_launches(3)
-        return dx, gwb[:C].to(weight.dtype), gwb[C:].to(weight.dtype), dres, None, None, None, None, None
+        return dx, gwb[:C].to(weight.dtype), gwb[C:].to(weight.dtype), dres, None, None, None, None, None, None
 
 
-def bn_act(x, bn, residual=None, relu=False):
-    """relu(SyncBN_train(x) + residual) for a BatchNorm2d-like module `bn` in training mode."""
+def bn_act(x, bn, residual=None, relu=False, partials=None):
+    """relu(SyncBN_train(x) + residual) for a BatchNorm2d-like module `bn` in training mode. `partials`: optional
+    per-tile statistics of x computed by the kernel that produced it (skips the reduction pass)."""
     return _BNAct.apply(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, bn.eps,
-                        0.1 if bn.momentum is None else bn.momentum, relu)
+                        0.1 if bn.momentum is None else bn.momentum, relu, partials)
 
 
 # The fused multi-GPU path takes the group's element count as P * world, i.e. it assumes every rank holds the same

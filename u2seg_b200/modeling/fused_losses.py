@@ -1,9 +1,8 @@
 """Fused detection losses over libu2b200 (csrc/det_losses.cu): one kernel computes the summed loss and its closed-form
 gradient with respect to the head outputs; autograd only multiplies by the upstream scalar.
 
-STATUS: round-2 draft. Written at the end of round 1 without GPU time left to validate it; OFF by default
-(`U2B_FUSED_DET_LOSSES=1` switches the static step over), covered by tests/test_fused_losses_gpu.py which compares with
-the torch restatements below (the formulas static_train.py uses today)."""
+Used by the static-shape training step (modeling/static_train.py, `U2B_FUSED_DET_LOSSES=0` falls back to the torch
+formulas); tests/test_fused_losses_gpu.py compares every kernel with the torch restatements below."""
 import ctypes
 
 import torch
@@ -33,9 +32,13 @@ class _RPNLosses(torch.autograd.Function):
         g_l = torch.empty(lg.shape, dtype=torch.float32, device=lg.device) if need_l else None
         g_d = torch.empty(dl.shape, dtype=torch.float32, device=lg.device) if need_d else None
         parts = torch.empty((int(L.u2b_rpn_losses_num_partials(N * A)), 2), dtype=torch.float32, device=lg.device)
-        _lib.check(L.u2b_rpn_losses(_CODE[lg.dtype], _p(lg), _p(dl), _p(anchors.float().contiguous()),
-                                    _p(labels.to(torch.int8).contiguous()), _p(matched.to(torch.int64).contiguous()),
-                                    _p(gt_boxes.float().contiguous()), N, A, gt_boxes.shape[1], _w4(weights),
+        # converted operands are bound to names for the duration of the call: a temporary handed to _p() inline is freed
+        # before the launch and its block may be recycled by the NEXT inline conversion (stream-ordered, so its kernel
+        # would overwrite this operand before ours reads it)
+        an, lb, mt, gb = (anchors.float().contiguous(), labels.to(torch.int8).contiguous(),
+                          matched.to(torch.int64).contiguous(), gt_boxes.float().contiguous())
+        _lib.check(L.u2b_rpn_losses(_CODE[lg.dtype], _p(lg), _p(dl), _p(an), _p(lb), _p(mt), _p(gb), N, A, gt_boxes.shape[1],
+                                    _w4(weights),
                                     _p(g_l), _p(g_d), _p(parts), _lib.stream_ptr()), "u2b_rpn_losses")
         _lib.count_launches(1)
         tot = parts.sum(0)
@@ -82,8 +85,8 @@ class _BoxLosses(torch.autograd.Function):
         g_d = torch.empty(dl.shape, dtype=torch.float32, device=sc.device) if need_d else None
         refined = torch.empty((R, 4), dtype=torch.float32, device=sc.device)
         parts = torch.empty((int(L.u2b_box_losses_num_partials(R)), 2), dtype=torch.float32, device=sc.device)
-        _lib.check(L.u2b_box_losses(_CODE[sc.dtype], _p(sc), _p(classes.to(torch.int64).contiguous()), _p(dl),
-                                    _p(proposals.float().contiguous()), _p(gt_boxes.float().contiguous()), R, C,
+        cl, pr, gb = classes.to(torch.int64).contiguous(), proposals.float().contiguous(), gt_boxes.float().contiguous()
+        _lib.check(L.u2b_box_losses(_CODE[sc.dtype], _p(sc), _p(cl), _p(dl), _p(pr), _p(gb), R, C,
                                     int(num_fg_classes), _w4(weights), float(scale_clamp), _p(g_s), _p(g_d), _p(refined),
                                     _p(parts), _lib.stream_ptr()), "u2b_box_losses")
         _lib.count_launches(1)
@@ -129,8 +132,8 @@ def rpn_decode_selected(deltas, anchors, sel, scores, box2box, image_size, min_s
     valid = torch.empty((N, Ksel), dtype=torch.uint8, device=dl.device)
     nonfinite = torch.zeros((), dtype=torch.int32, device=dl.device)
     h, w = image_size
-    _lib.check(L.u2b_rpn_decode_selected(_CODE[dl.dtype], _p(dl), _p(anchors.float().contiguous()),
-                                         _p(sel.to(torch.int64).contiguous()), _p(scores.float().contiguous()), N, A, Ksel,
+    an, se, sc = anchors.float().contiguous(), sel.to(torch.int64).contiguous(), scores.float().contiguous()
+    _lib.check(L.u2b_rpn_decode_selected(_CODE[dl.dtype], _p(dl), _p(an), _p(se), _p(sc), N, A, Ksel,
                                          _w4(box2box.weights), float(box2box.scale_clamp), float(h), float(w),
                                          float(min_size), _p(boxes), _p(valid), _p(nonfinite), _lib.stream_ptr()),
                "u2b_rpn_decode_selected")
@@ -162,9 +165,9 @@ def cascade_relabel(refined, ok_prev, gt_boxes, gt_classes, gt_valid, image_size
     ok = torch.empty((N, R), dtype=torch.uint8, device=dev)
     gtb = torch.empty((N, R, 4), dtype=torch.float32, device=dev)
     h, w = image_size
-    _lib.check(L.u2b_cascade_relabel(_p(refined.float().contiguous()), _p(ok_prev.to(torch.uint8).contiguous()),
-                                     _p(gt_boxes.float().contiguous()), _p(gt_classes.to(torch.int64).contiguous()),
-                                     _p(gt_valid.to(torch.uint8).contiguous()), N, R, G, float(h), float(w), float(iou_thr),
+    rf, okp, gb, gc, gv = (refined.float().contiguous(), ok_prev.to(torch.uint8).contiguous(), gt_boxes.float().contiguous(),
+                           gt_classes.to(torch.int64).contiguous(), gt_valid.to(torch.uint8).contiguous())
+    _lib.check(L.u2b_cascade_relabel(_p(rf), _p(okp), _p(gb), _p(gc), _p(gv), N, R, G, float(h), float(w), float(iou_thr),
                                      int(num_classes), _p(boxes), _p(classes), _p(ok), _p(gtb), _lib.stream_ptr()),
                "u2b_cascade_relabel")
     _lib.count_launches(1)
@@ -191,3 +194,69 @@ def cascade_relabel_reference(refined, ok_prev, gt_boxes, gt_classes, gt_valid, 
         nok.append(ok)
         ngb.append(gt_boxes[n][midx])
     return torch.stack(nb), torch.stack(nc), torch.stack(nok), torch.stack(ngb)
+
+
+class _MaskLossSelected(torch.autograd.Function):
+    """sum over live ROIs and pixels of BCE-with-logits of the GT-class mask logits (mask_head.py:33-112), predictor
+    included: csrc/mask_loss.cu. Returns the loss SUM (the caller divides by the live pixel count)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, classes, target, ok):
+        L = _lib.lib()
+        R, C, S, _ = x.shape
+        P = S * S
+        xr = x.permute(0, 2, 3, 1)                                   # NHWC storage -> (R, S, S, C) rows
+        if not xr.is_contiguous():
+            xr = xr.contiguous()
+        K = weight.shape[0]
+        w = weight.detach().reshape(K, C).to(x.dtype).contiguous()
+        b = bias.detach().float().contiguous() if bias is not None else None
+        cls = classes.to(torch.int64).contiguous()
+        tg = target.reshape(R, P).to(torch.uint8).contiguous()
+        okb = ok.to(torch.uint8).contiguous()
+        g = torch.empty((R, P), dtype=torch.float32, device=x.device)
+        per = torch.empty((R,), dtype=torch.float32, device=x.device)
+        _lib.check(L.u2b_mask_loss_fwd(_CODE[x.dtype], _p(xr), _p(w), _p(b), _p(cls), _p(tg), _p(okb), R, P, C, _p(g), _p(per),
+                                       _lib.stream_ptr()), "u2b_mask_loss_fwd")
+        _lib.count_launches(1)
+        ctx.save_for_backward(xr, w, cls, g)
+        ctx.meta = (weight.shape, weight.dtype, bias is not None, bias.dtype if bias is not None else None, K)
+        return per.sum()
+
+    @staticmethod
+    def backward(ctx, gout):
+        L = _lib.lib()
+        xr, w, cls, g = ctx.saved_tensors
+        wshape, wdt, has_bias, bdt, K = ctx.meta
+        R, S, _, C = xr.shape
+        P = S * S
+        dx = torch.empty_like(xr)
+        dw = torch.zeros((K, C), dtype=torch.float32, device=xr.device)
+        db = torch.zeros((K,), dtype=torch.float32, device=xr.device)
+        ws = torch.empty((R * (C + 1),), dtype=torch.float32, device=xr.device)
+        up = gout.detach().float().reshape(1).contiguous()
+        _lib.check(L.u2b_mask_loss_bwd(_CODE[xr.dtype], _p(xr), _p(w), _p(cls), _p(g), _p(up), R, P, C, _p(dx), _p(dw), _p(db),
+                                       _p(ws), _lib.stream_ptr()), "u2b_mask_loss_bwd")
+        _lib.count_launches(2)
+        return (dx.permute(0, 3, 1, 2), dw.to(wdt).reshape(wshape), db.to(bdt) if has_bias else None, None, None, None)
+
+
+def mask_loss_supported(x):
+    return (x.is_cuda and x.dim() == 4 and x.dtype in (torch.float16, torch.bfloat16) and x.shape[0] > 0
+            and bool(_lib.lib().u2b_mask_loss_supported(int(x.shape[1]))))
+
+
+def mask_loss_selected(x, weight, bias, classes, target, ok):
+    """x (R,C,S,S) features entering the mask predictor (channels_last), weight (K,C,1,1), bias (K), classes (R),
+    target (R,S,S) bool, ok (R) bool -> sum over live ROIs / pixels of BCE(logit of the ROI's class, target)."""
+    return _MaskLossSelected.apply(x, weight, bias, classes, target, ok)
+
+
+def mask_loss_selected_reference(x, weight, bias, classes, target, ok):
+    """the torch formulas of static_train._mask_branch_static (forward_selected + BCE + masking)."""
+    R, C, S, _ = x.shape
+    rows = x.permute(0, 2, 3, 1).reshape(R, S * S, C).float()
+    w = weight.reshape(-1, C).to(x.dtype).float()[classes]
+    z = torch.bmm(rows, w.unsqueeze(2)).squeeze(2) + bias.float()[classes][:, None]
+    bce = F.binary_cross_entropy_with_logits(z.view(R, S, S), target.to(torch.float32), reduction="none")
+    return (bce * ok[:, None, None].to(bce.dtype)).sum()

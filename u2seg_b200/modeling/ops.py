@@ -14,12 +14,14 @@ import torch.nn.functional as F
 from torch import nn
 
 # Which convolutions run on the hand-written tcgen05 kernel (csrc/conv_tc.cu) instead of the library (cuDNN):
-#   "large3x3" (default): 3x3 stride-1 convs with Cin >= 128 — FPN outputs, RPN head conv, mask head, sem-seg head:
+#   "large3x3" (round-1 default): 3x3 stride-1 convs with Cin >= 128 — FPN outputs, RPN head conv, mask head, sem-seg head:
 #                         57% of the step's forward MACs; forward and input-gradient (dgrad) both use conv_tc
 #                         (measured 1.35 PFLOP/s on the 256->256 3x3 at 2x256x256, 0.89x cuDNN); weight gradients
 #                         stay in the library this round;
-#   "all": every shape conv_tc supports;  "none": library only.
-TCGEN05_CONV_POLICY = "large3x3"
+#   "all" (default since round 2, 2-CTA kernel csrc/conv2.cu): every shape the kernels support - 1x1 and 3x3, stride 1
+#          and 2, Cin and Cout multiples of 64 - forward and stride-1 input gradient, plus the box-head Linear layers;
+#   "none": library only.
+TCGEN05_CONV_POLICY = os.environ.get("U2B_CONV_POLICY", "all")
 USE_TCGEN05_CONV = True
 
 
@@ -54,7 +56,7 @@ def batch_norm(x, bn, relu=False):
 
 FUSED_BN = True     # SyncBN + residual + ReLU through libu2b200 (csrc/batchnorm.cu) in training mode
 FUSED_GN = True     # GroupNorm + ReLU (semantic head) through the same NHWC kernels, per image
-UPSAMPLE_KERNEL = os.environ.get("U2B_UPSAMPLE_KERNEL", "0") == "1"   # round-2 draft, not validated on hardware
+UPSAMPLE_KERNEL = os.environ.get("U2B_UPSAMPLE_KERNEL", "1") == "1"   # NHWC bilinear x2 forward / backward (csrc/upsample.cu)
 STEM_KERNEL = True  # csrc/stem_conv.cu for the 7x7/2 3->64 stem (bf16 autocast only)
 
 

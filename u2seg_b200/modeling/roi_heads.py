@@ -71,6 +71,14 @@ class FastRCNNConvFCHead(nn.Sequential):
 
     def forward(self, x):
         x = torch.flatten(x, start_dim=1)
+        if x.is_cuda and torch.is_autocast_enabled("cuda"):
+            from . import conv_tc, ops
+            dt = torch.get_autocast_dtype("cuda")
+            if ops.TCGEN05_CONV_POLICY == "all" and ops.USE_TCGEN05_CONV and conv_tc.linear_eligible(x.to(dt), self.fcs[0].weight):
+                x = x.to(dt)
+                for fc in self.fcs:      # fc + ReLU in one tcgen05 launch (box_head.py:94-97)
+                    x = conv_tc.linear(x, fc.weight, fc.bias, relu=True)
+                return x
         for fc in self.fcs:
             x = F.relu(fc(x))
         return x

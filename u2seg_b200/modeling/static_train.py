@@ -24,8 +24,11 @@ from ..layers import FeatureTap, batched_nms_static, crop_and_resize_masks
 from ..structures import Boxes
 
 # sampling keys: uniform random numbers by default; tests swap in a deterministic key function
-# round-2 draft (csrc/det_losses.cu), not validated on hardware at the end of round 1: off unless explicitly enabled
-FUSED_DET_LOSSES = os.environ.get("U2B_FUSED_DET_LOSSES", "0") == "1"
+# RPN / box-head losses with closed-form gradients, decode + clip of the selected anchors, cascade relabelling as one
+# kernel each (csrc/det_losses.cu); U2B_FUSED_DET_LOSSES=0 falls back to the torch formulas
+FUSED_DET_LOSSES = os.environ.get("U2B_FUSED_DET_LOSSES", "1") == "1"
+# mask predictor + BCE + their backward as two kernels (csrc/mask_loss.cu); half-precision activations only
+FUSED_MASK_LOSS = os.environ.get("U2B_FUSED_MASK_LOSS", "1") == "1"
 
 _rand_keys = lambda mask: torch.rand(mask.shape, dtype=torch.float32, device=mask.device)  # noqa: E731
 
@@ -312,6 +315,21 @@ def _mask_branch_static(rh, feats, tap, boxes0, cls0, fg0, gidx0, gt_masks, K, R
     mok = torch.cat([f[:M] for f in fg0])
     mcls = torch.cat([c[:M] for c in cls0]).clamp(0, K - 1)
     xm = rh.mask_pooler(feats, mb, tap=tap)
+    if FUSED_MASK_LOSS:
+        from .fused_losses import mask_loss_selected, mask_loss_supported
+        head = rh.mask_head
+        xf = xm
+        for layer in head:                                       # mask_fcn1..4, deconv, ReLU; the predictor is fused below
+            if layer is head.predictor:
+                break
+            xf = layer(xf)
+        if mask_loss_supported(xf) and head.predictor.weight.shape[0] > 1:
+            side = xf.shape[-1]
+            with torch.no_grad():
+                tgt = torch.cat([crop_and_resize_masks(gt_masks[n], mb[n], side, gt_index=gidx0[n][:M]) for n in range(N)])
+            total = mask_loss_selected(xf, head.predictor.weight, head.predictor.bias, mcls, tgt, mok)
+            denom = (mok.sum() * side * side).clamp(min=1).to(torch.float32)
+            return total / denom
     sel = rh.mask_head.forward_selected(xm, mcls).float()        # (N*M, S, S): the gt-class logits only
     side = sel.shape[-1]
     with torch.no_grad():
