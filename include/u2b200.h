@@ -197,6 +197,14 @@ int u2b_conv2_dgrad_supported(int Cin, int Cout, int R, int S, int stride, int p
 int u2b_conv2_nhwc_dgrad(int dtype, const void* dy, int N, int H, int W, int Cout, const void* w, int Cin, int R, int S,
                          int pad, void* dx, u2b_stream_t stream);
 
+/* ConvTranspose2d(kernel 2, stride 2) forward, NHWC, on the 2-CTA kernel (roi_heads/mask_head.py:256 `deconv` + ReLU):
+ * y[n,2h+i,2w+j,co] = [relu](bias[co] + sum_ci x[n,h,w,ci] * w[ci,co,i,j]); w is the channels_last weight, physical
+ * (Cin,2,2,Cout), read in place. Its input gradient is u2b_conv2_nhwc_fwd(dy, w as a (Cin,2,2,Cout) OHWI filter, 2x2,
+ * stride 2, pad 0); its weight gradient u2b_conv_wgrad2 of that convolution. Cin % 64 == 0, Cout % 128 == 0. */
+int u2b_deconv2x2_supported(int Cin, int Cout);
+int u2b_deconv2x2_nhwc_fwd(int dtype, const void* x, int N, int H, int W, int Cin, const void* w, int Cout,
+                           const float* bias, int relu, void* y, u2b_stream_t stream);
+
 /* Weight gradient on the 2-CTA tcgen05 kernel (csrc/conv_wgrad2.cu): dW[co,r,s,ci] = sum over output pixels of
  * dY[n,oh,ow,co] * X[n,oh*stride+r-pad,ow*stride+s-pad,ci] - the backward of the F.conv2d at layers/wrappers.py:127 and
  * (1x1 over a (1,1,M,K) image) of nn.Linear at roi_heads/box_head.py:70. Shapes: (Cout % 256 == 0 and Cin % 128 == 0)
@@ -223,6 +231,21 @@ int u2b_mask_loss_bwd(int dtype, const void* x, const void* w, const int64_t* cl
                       const float* upstream, int64_t R, int P, int C, void* dx, float* dw, float* db, float* workspace,
                       u2b_stream_t stream);
 
+/* GeneralizedRCNN.preprocess_image + ImageList.from_tensors (meta_arch/rcnn.py:223-234, structures/image_list.py:59-129)
+ * for a batch of same-size uint8 NHWC images: (x - mean[c]) / std[c] in fp32 (subtract, IEEE divide), zero padding up to
+ * (Hp, Wp), one rounding to out_dtype (0 fp32, 1 fp16, 2 bf16). mean3 / std3: host arrays of 3 floats. */
+int u2b_preprocess_u8_nhwc(const uint8_t* img, int N, int H, int W, int Hp, int Wp, const float* mean3, const float* std3,
+                           int out_dtype, void* out, u2b_stream_t stream);
+
+/* NHWC pooling (csrc/pool.cu), fp16 (1) / bf16 (2), C % 8 == 0.
+ * max pool 3x3 / stride 2 / pad 1 of the ResNet stem (backbone/resnet.py:358): forward also records, per pooled element,
+ * the window position (kh*3+kw, 1 byte) of the first maximum in scan order (ATen's tie rule); backward gathers with it.
+ * sum2x2: gradient of a nearest x2 upsampling (backbone/fpn.py:153): y[n,h,w] = sum of x over the 2x2 block. */
+int u2b_maxpool3x3s2_fwd(int dtype, const void* x, int N, int H, int W, int C, void* y, uint8_t* idx, u2b_stream_t stream);
+int u2b_maxpool3x3s2_bwd(int dtype, const void* dy, const uint8_t* idx, int N, int H, int W, int C, void* dx,
+                         u2b_stream_t stream);
+int u2b_sum2x2_nhwc(int dtype, const void* x, int N, int H, int W, int C, void* y, u2b_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Training-mode (Sync)BatchNorm on NHWC activations (P = N*H*W pixels, C % 8 == 0 channels), fused with the
  * residual add and ReLU that follow it. Replaces nn.SyncBatchNorm (detectron2/layers/batch_norm.py:187) inside
@@ -245,6 +268,11 @@ int u2b_bn_finalize(const float* partials, int S, double n_total, const float* w
 /* y = [relu](x * scale[c] + shift[c] [+ residual]) */
 int u2b_bn_apply(int dtype, const void* x, const float* stats, const void* residual, int relu, void* y, int64_t P,
                  int C, u2b_stream_t stream);
+/* y = [relu](x * scale[c] + shift[c] + nearest_upsample_x2(residual)): the FPN top-down sum (backbone/fpn.py:153-156)
+ * folded into the lateral conv's SyncBN pass. x, y (N,H,W,C); residual (N,H/2,W/2,C); H, W even. */
+int u2b_bn_apply_resup(int dtype, const void* x, const float* stats, const void* residual, int relu, void* y, int N, int H,
+                       int W, int C, u2b_stream_t stream);
+
 /* partials[s] = (sum dz | sum dz*xhat), dz = dy * (y > 0) when y != NULL (fused ReLU backward) */
 int u2b_bn_bwd_reduce(int dtype, const void* dy, const void* x, const void* y, const float* stats, int64_t P, int C,
                       float* partials, u2b_stream_t stream);

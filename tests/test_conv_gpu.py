@@ -198,3 +198,26 @@ def test_conv2_dgrad_reads_the_forward_filter_in_place(shape):
     got = conv2_nhwc_dgrad(gy, w.permute(0, 2, 3, 1).contiguous(), pad)
     assert got.shape == want.shape
     assert float((got.float() - want).abs().max()) <= 8e-3 * float(want.abs().max())
+
+
+def test_deconv2x2_forward_and_backward_match_torch():
+    """ConvTranspose2d(256, 256, 2, stride 2) + ReLU of the mask head (mask_head.py:256-262) on the tcgen05 kernels:
+    forward (four interleaved GEMMs), input gradient (2x2 / stride-2 conv), weight gradient (wgrad2), bias gradient."""
+    from u2seg_b200.modeling import conv_tc
+    torch.manual_seed(0)
+    m = torch.nn.ConvTranspose2d(256, 256, 2, stride=2).cuda().to(memory_format=torch.channels_last)
+    x = torch.randn(5, 256, 14, 14, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = conv_tc.deconv2x2(x, m, relu=True)
+    assert y is not None and y.shape == (5, 256, 28, 28)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    wr = m.weight.detach().bfloat16().float().requires_grad_(True)
+    br = m.bias.detach().clone().requires_grad_(True)
+    yr = F.relu(F.conv_transpose2d(xr, wr, br, stride=2))
+    yr.backward(gy.float())
+    sc = lambda t: t.abs().max().item()      # noqa: E731
+    assert (y.float() - yr).abs().max().item() <= 8e-3 * sc(yr)
+    assert (x.grad.float() - xr.grad).abs().max().item() <= 2e-2 * sc(xr.grad)
+    assert (m.weight.grad.float() - wr.grad).abs().max().item() <= 2e-2 * sc(wr.grad)
+    assert (m.bias.grad.float() - br.grad).abs().max().item() <= 2e-2 * sc(br.grad)

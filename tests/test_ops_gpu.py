@@ -308,3 +308,67 @@ def test_group_norm_relu_matches_torch(N, C, G, HW, relu, dtype, tol):
     yr.backward(gy.float())
     for got, want in ((xa.grad, xr.grad), (gn.weight.grad, w2.grad), (gn.bias.grad, b2.grad)):
         assert float((got.float() - want).abs().max()) <= 2 * tol * float(want.abs().max()) + 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(2, 64, 64, 96), (1, 64, 33, 47), (2, 16, 8, 8)])
+def test_maxpool3x3s2_matches_torch_including_ties(shape, dtype):
+    """csrc/pool.cu vs F.max_pool2d (resnet.py:358) on post-ReLU-like data with many exact ties (zeros and repeated
+    bf16 values): pooled values bit-exact, gradients bit-exact (first maximum in scan order receives the gradient)."""
+    import torch.nn.functional as F
+    from u2seg_b200.modeling.ops import max_pool_3x3_s2
+    g = torch.Generator().manual_seed(5)
+    N, C, H, W = shape
+    x = (torch.randn(N, C, H, W, generator=g).clamp(min=0) * 4).round() / 4        # coarse grid: plenty of equal neighbours
+    x = x.to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya = max_pool_3x3_s2(xa)
+    yb = F.max_pool2d(xb, kernel_size=3, stride=2, padding=1)
+    assert torch.equal(ya, yb)
+    gy = torch.randn(yb.shape, generator=g).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    ya.backward(gy)
+    yb.backward(gy)
+    assert torch.allclose(xa.grad.float(), xb.grad.float(), rtol=1e-2, atol=1e-3)      # <= 4 bf16 terms summed in fp32 vs ATen
+    assert torch.equal(xa.grad != 0, xb.grad != 0)                                     # same routing, also on ties
+
+
+def test_fpn_lateral_sum_folded_into_bn_matches_unfused():
+    """ops.lateral_add_upsample: lateral 1x1 conv + SyncBN + nearest-x2(prev) in the BN apply pass (csrc/batchnorm.cu
+    bn_apply_resup, csrc/pool.cu sum2x2) vs the unfused torch composition, forward and backward."""
+    import torch.nn.functional as F
+    from u2seg_b200.modeling import ops
+    from u2seg_b200.modeling.backbone import Conv2d
+    torch.manual_seed(0)
+    lat = Conv2d(512, 256, kernel_size=1, bias=False, norm=torch.nn.BatchNorm2d(256)).cuda().train()
+    feat = torch.randn(2, 512, 32, 48, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    prev = torch.randn(2, 256, 16, 24, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    outs = []
+    for fused in (True, False):
+        ops.FUSED_FPN_SUM = fused
+        try:
+            f, p = feat.clone().requires_grad_(True), prev.clone().requires_grad_(True)
+            lat.zero_grad()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = ops.lateral_add_upsample(lat, f, p)
+            gy = torch.randn(y.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)).to(y.dtype)
+            y.backward(gy)
+            outs.append((y.float(), f.grad.float(), p.grad.float(), lat.weight.grad.float().clone()))
+        finally:
+            ops.FUSED_FPN_SUM = True
+    for a, b in zip(*outs):
+        assert float((a - b).abs().max()) <= 2e-2 * float(b.abs().max()) + 1e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_preprocess_u8_matches_reference_formula(dtype):
+    """csrc/pool.cu preprocess_u8_kernel == rcnn.py:223-234 ((x - mean) / std in fp32) + image_list.py zero padding."""
+    from u2seg_b200.modeling.ops import preprocess_u8
+    g = torch.Generator().manual_seed(2)
+    img = torch.randint(0, 256, (2, 3, 50, 70), generator=g, dtype=torch.uint8).cuda().contiguous(memory_format=torch.channels_last)
+    mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    got = preprocess_u8(img, mean, std, 32, dtype)
+    m = torch.tensor(mean, device="cuda").view(-1, 1, 1)
+    s = torch.tensor(std, device="cuda").view(-1, 1, 1)
+    want = torch.nn.functional.pad((img.float() - m) / s, (0, 96 - 70, 0, 64 - 50)).to(dtype)
+    assert got.shape == (2, 3, 64, 96) and got.dtype == dtype and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got, want)                      # bit-exact: same op order, IEEE division, one rounding

@@ -2,6 +2,7 @@
 set -u
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_fused_losses_gpu.py -m gpu -q > gpurun_out/r02e_fused_tests.log 2>&1; tail -6 gpurun_out/r02e_fused_tests.log | cut -c1-400
+timeout 300 python -m pytest tests/test_ops_gpu.py -m gpu -q -k "maxpool or fpn_lateral" 2>&1 | tail -4 | cut -c1-300
 timeout 900 python -m pytest tests/test_conv_gpu.py -m gpu -q -k "conv2 or wgrad2 or autograd" > gpurun_out/r02e_conv_tests.log 2>&1; tail -5 gpurun_out/r02e_conv_tests.log | cut -c1-300
 timeout 600 python -m pytest tests/test_baseline_config_gpu.py tests/test_model_gpu.py -m gpu -q -s > gpurun_out/r02e_model_tests.log 2>&1
 grep -E "worst loss|gradient-norm|vs float64|AssertionError|passed|failed" gpurun_out/r02e_model_tests.log | cut -c1-300
@@ -19,9 +20,10 @@ except Exception as e:
     print("bench failed", e)
 PY
 }
-run U2B_WGRAD2=0 U2B_FUSED_MASK_LOSS=0
-run U2B_WGRAD2=0 U2B_FUSED_MASK_LOSS=1
-run U2B_WGRAD2=1 U2B_FUSED_MASK_LOSS=1
+run U2B_WGRAD2=0 U2B_FUSED_MASK_LOSS=0 U2B_FUSED_FPN_SUM=0 U2B_MAXPOOL_KERNEL=0
+run U2B_WGRAD2=0 U2B_FUSED_MASK_LOSS=1 U2B_FUSED_FPN_SUM=0 U2B_MAXPOOL_KERNEL=0
+run U2B_WGRAD2=0 U2B_FUSED_MASK_LOSS=1 U2B_FUSED_FPN_SUM=1 U2B_MAXPOOL_KERNEL=1
+run U2B_WGRAD2=1 U2B_FUSED_MASK_LOSS=1 U2B_FUSED_FPN_SUM=1 U2B_MAXPOOL_KERNEL=1
 for shp in res2_conv3 fpn_output2; do
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv2_kernel -s 2 -c 1 -o gpurun_out/r02e_ncu_conv2_$shp -f python tools/ncu_conv2.py $shp 2>&1 | tail -1
 done

@@ -88,6 +88,9 @@ SIGNATURES = {
     "u2b_conv2_dgrad_supported": (c_int, [c_int] * 6),
     "u2b_conv2_nhwc_dgrad": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p]),
+    "u2b_deconv2x2_supported": (c_int, [c_int, c_int]),
+    "u2b_deconv2x2_nhwc_fwd": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
+                                       c_void_p, c_void_p]),
     "u2b_conv_wgrad2_supported": (c_int, [c_int] * 6),
     "u2b_conv_wgrad2_workspace_floats": (c_int64, [c_int] * 9),
     "u2b_conv_wgrad2": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -97,6 +100,12 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p]),
     "u2b_mask_loss_bwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "u2b_maxpool3x3s2_fwd": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "u2b_maxpool3x3s2_bwd": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "u2b_sum2x2_nhwc": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "u2b_bn_apply_resup": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "u2b_preprocess_u8_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_float),
+                                       ctypes.POINTER(c_float), c_int, c_void_p, c_void_p]),
     "u2b_bn_supported": (c_int, [c_int]),
     "u2b_bn_num_strips": (c_int, [c_int64, c_int]),
     "u2b_bn_stats": (c_int, [c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p]),

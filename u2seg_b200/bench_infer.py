@@ -6,7 +6,7 @@ import time
 import torch
 
 
-def run_infer(args, ClockSampler, load_peaks, dist_info):
+def run_infer(args, ClockSampler, load_peaks, dist_info, emit=True):
     from . import _lib
     from .config import get_u2seg_cfg
     from .modeling import build_model
@@ -65,4 +65,82 @@ def run_infer(args, ClockSampler, load_peaks, dist_info):
             "e2e": {"value": 1.0 / dt, "unit": "images/s", "h2d_bytes_per_step": 3 * 800 * 1333,
                     "d2h_bytes_per_step": 800 * 1333 * 4,
                     "what": "model([{image (pinned uint8 host), height, width}]) incl. H2D and D2H of the panoptic map"}}
+    peaks = load_peaks()
+    line["rooflines"] = infer_kernel_rooflines(peaks, dev)
+    line["roofline"] = line["rooflines"]["paste_masks_kernel"]
+    del model
+    torch.cuda.empty_cache()
+    if not emit:
+        return line
     print(json.dumps(line))
+
+
+def _size_law_boxes(n, W, H, g, lo=32.0, hi=512.0):
+    """centres uniform over the image, sides log-uniform lo..hi px, clipped to the image."""
+    import math
+    cx, cy = torch.rand(n, generator=g) * W, torch.rand(n, generator=g) * H
+    w = torch.exp(torch.rand(n, generator=g) * (math.log(hi) - math.log(lo)) + math.log(lo))
+    h = torch.exp(torch.rand(n, generator=g) * (math.log(hi) - math.log(lo)) + math.log(lo))
+    b = torch.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1)
+    b[:, 0::2] = b[:, 0::2].clamp(0, W)
+    b[:, 1::2] = b[:, 1::2].clamp(0, H)
+    return b
+
+
+def infer_kernel_rooflines(peaks, dev):
+    """The two HBM-bound kernels BASELINE.json configs[4] names, on the SURVEY 8(d) fixed-detections micro-benchmark:
+    paste_masks_in_image (100 masks of 28x28 -> 100 x 800 x 1333 bool; algorithmic bytes = N*H*W written + N*784*4 read)
+    and the multi-level ROIAlign (1000 boxes, 7x7, p2..p5 of an 800x1344 image, 256 channels bf16; algorithmic bytes =
+    output + rois + the feature-map area under the boxes, capped per level by the level itself). CUDA events on the launch
+    stream; a 256 MB buffer is written between launches (L2 flush). Peak = measured HBM copy bandwidth."""
+    from .layers import ROIPooler, paste_masks_in_image
+    from .structures import Boxes
+    g = torch.Generator().manual_seed(3)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timeit(fn, n=10):
+        for _ in range(3):
+            fn()
+        tot = 0.0
+        for _ in range(n):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / n
+
+    out = {}
+    Hh, Ww, N = 800, 1333, 100
+    masks = torch.rand(N, 28, 28, generator=g).to(dev)
+    boxes = _size_law_boxes(N, Ww, Hh, g).to(dev)
+    ms = timeit(lambda: paste_masks_in_image(masks, boxes, (Hh, Ww), 0.5))
+    nbytes = N * Hh * Ww + N * 784 * 4
+    out["paste_masks_kernel"] = {"bound": "hbm", "kernel": "paste_masks_kernel (100 x 28x28 -> 100 x 800 x 1333 bool)",
+                                 "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                                 "frac": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm"], "peak_source": peaks["src"] + " HBM copy",
+                                 "traffic": None, "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": ms}
+    K, C, P = 1000, 256, 7
+    strides = (4, 8, 16, 32)
+    feats = [torch.randn(1, C, 800 // s, 1344 // s, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+             for s in strides]
+    rb = _size_law_boxes(K, 1333, 800, g).to(dev)
+    pooler = ROIPooler(P, tuple(1.0 / s for s in strides), 0, "ROIAlignV2")
+    with torch.no_grad():
+        ms = timeit(lambda: pooler(feats, [Boxes(rb)]))
+    # feature bytes under the boxes at their assigned level (poolers.py:23-59), capped by the level's size
+    area = ((rb[:, 2] - rb[:, 0]) * (rb[:, 3] - rb[:, 1])).clamp(min=1e-6)
+    lvl = torch.floor(4 + torch.log2(torch.sqrt(area) / 224 + 1e-8)).clamp(2, 5).long() - 2
+    touched = 0.0
+    for li, s in enumerate(strides):
+        m = lvl == li
+        px = float((((rb[m, 2] - rb[m, 0]) / s + 2) * ((rb[m, 3] - rb[m, 1]) / s + 2)).sum())
+        touched += min(px, (800 // s) * (1344 // s)) * C * 2
+    nbytes = K * C * P * P * 2 + K * 20 + touched
+    out["roi_align_fwd_kernel"] = {"bound": "hbm", "kernel": "roi_align_fwd_kernel (1000 boxes, 7x7, 4 levels, 256 ch bf16)",
+                                   "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                                   "frac": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm"], "peak_source": peaks["src"] + " HBM copy",
+                                   "traffic": None, "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": ms}
+    return out

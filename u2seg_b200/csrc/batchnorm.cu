@@ -395,10 +395,12 @@ gn_bwd_coeff_kernel(const float* __restrict__ partials, int S, double m, int G, 
 }
 
 // total_vec vectors of 8 channels; (blockDim*gridDim) % (C/8) == 0 so a thread's channels never change
+// up_h/up_w > 0: `residual` is a (N, up_h/2, up_w/2, C) map added through a nearest-neighbour x2 upsampling (the FPN
+// top-down sum, backbone/fpn.py:153-156, folded into the lateral conv's SyncBN pass); x / y are (N, up_h, up_w, C).
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats, const T* __restrict__ residual, int relu,
-                T* __restrict__ y, long long total_vec, int C) {
+                T* __restrict__ y, long long total_vec, int C, int up_h = 0, int up_w = 0) {
   const int vecs = C / 8;
   const long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int c0 = static_cast<int>(i0 % vecs) * 8;
@@ -416,7 +418,16 @@ bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats, const 
     for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
     if (residual) {
       float r[8];
-      V8<T>::load(residual + i * 8, r);
+      long long ri = i;
+      if (up_w > 0) {
+        long long pix = i / vecs;
+        const int w = static_cast<int>(pix % up_w);
+        pix /= up_w;
+        const int h = static_cast<int>(pix % up_h);
+        const long long n = pix / up_h;
+        ri = ((n * (up_h / 2) + h / 2) * (up_w / 2) + w / 2) * vecs + (i % vecs);
+      }
+      V8<T>::load(residual + ri * 8, r);
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] += r[k];
     }
@@ -643,6 +654,20 @@ int u2b_bn_apply(int dtype, const void* x, const float* stats, const void* resid
       (bn_apply_kernel<float><<<ew_grid(tv), 256, 0, stream>>>((const float*)x, stats, (const float*)residual, relu, (float*)y, tv, C)),
       (bn_apply_kernel<__half><<<ew_grid(tv), 256, 0, stream>>>((const __half*)x, stats, (const __half*)residual, relu, (__half*)y, tv, C)),
       (bn_apply_kernel<__nv_bfloat16><<<ew_grid(tv), 256, 0, stream>>>((const __nv_bfloat16*)x, stats, (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)y, tv, C)))
+  U2B_LAUNCH_CHECK();
+  return 0;
+}
+
+// y = [relu](x * scale[c] + shift[c] + up2x(residual)): x, y (N,H,W,C); residual (N,H/2,W/2,C); H, W even
+int u2b_bn_apply_resup(int dtype, const void* x, const float* stats, const void* residual, int relu, void* y, int N, int H,
+                       int W, int C, cudaStream_t stream) {
+  U2B_CHECK_ARG(x && y && stats && residual && u2b_bn_supported(C) && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0,
+                "bn_apply_resup: bad arguments");
+  const long long tv = static_cast<long long>(N) * H * W * C / 8;
+  U2B_BN_DISPATCH(
+      (bn_apply_kernel<float><<<ew_grid(tv), 256, 0, stream>>>((const float*)x, stats, (const float*)residual, relu, (float*)y, tv, C, H, W)),
+      (bn_apply_kernel<__half><<<ew_grid(tv), 256, 0, stream>>>((const __half*)x, stats, (const __half*)residual, relu, (__half*)y, tv, C, H, W)),
+      (bn_apply_kernel<__nv_bfloat16><<<ew_grid(tv), 256, 0, stream>>>((const __nv_bfloat16*)x, stats, (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)y, tv, C, H, W)))
   U2B_LAUNCH_CHECK();
   return 0;
 }

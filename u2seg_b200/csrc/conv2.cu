@@ -533,6 +533,7 @@ extern "C" {
 // 1 if (shape) is handled by the 2-CTA tcgen05 kernel
 int u2b_conv2_supported(int Cin, int Cout, int R, int S, int stride, int pad) {
   if (Cin <= 0 || Cin % 64 != 0 || Cout <= 0 || Cout % 64 != 0) return 0;
+  if (R == 2 && S == 2) return pad == 0 && stride == 2;  // the input gradient of ConvTranspose2d(k=2, s=2) (mask_head.py:256)
   if (!((R == 1 && S == 1 && pad == 0) || (R == 3 && S == 3 && pad == 1))) return 0;
   if (stride != 1 && stride != 2) return 0;
   return 1;
@@ -584,6 +585,74 @@ int u2b_conv2_nhwc_dgrad(int dtype, const void* dy, int N, int H, int W, int Cou
     return U2B_ERR_UNSUPPORTED;
   }
   return conv2_run(dtype, dy, N, H, W, Cout, w, Cin, R, S, 1, R - 1 - pad, 1, nullptr, 0, dx, nullptr, stream);
+}
+
+// ConvTranspose2d(kernel 2, stride 2, pad 0) forward (roi_heads/mask_head.py:256 `deconv`), NHWC:
+//   y[n, 2h+i, 2w+j, co] = [relu](bias[co] + sum_ci x[n,h,w,ci] * Wt[ci,co,i,j])
+// as four 1x1 GEMMs on the 2-CTA kernel, one per output phase (i, j): the filter slice Wt[:, :, i, j] is read in place from
+// the channels_last weight (physical (Cin,2,2,Cout)) as an MN-major operand, and the TMA-store epilogue writes each
+// phase's rows straight into its interleaved positions of y (tensor map with doubled pixel / row strides).
+// (Its input gradient is u2b_conv2_nhwc_fwd with the same weight as a 2x2 / stride-2 filter, its weight gradient
+// u2b_conv_wgrad2 of that convolution.)
+int u2b_deconv2x2_supported(int Cin, int Cout) { return Cin > 0 && Cin % 64 == 0 && Cout > 0 && Cout % 128 == 0; }
+
+int u2b_deconv2x2_nhwc_fwd(int dtype, const void* x, int N, int H, int W, int Cin, const void* w, int Cout,
+                           const float* bias, int relu, void* y, cudaStream_t stream) {
+  U2B_CHECK_ARG(x && w && y && N > 0 && H > 0 && W > 0, "deconv2x2_nhwc_fwd: bad arguments");
+  U2B_CHECK_ARG(dtype == 1 || dtype == 2, "deconv2x2_nhwc_fwd: dtype must be fp16(1) or bf16(2)");
+  if (!u2b_deconv2x2_supported(Cin, Cout)) {
+    u2b_set_error("deconv2x2_nhwc_fwd: unsupported channels Cin=%d Cout=%d", Cin, Cout);
+    return U2B_ERR_UNSUPPORTED;
+  }
+  Conv2Params p;
+  conv2_geometry(p, N, H, W, Cin, Cout, 1, 1, 1, 0);
+  const int BN = conv2_pick_bn(p, 128);
+  if (BN == 0) return U2B_ERR_UNSUPPORTED;
+  p.tiles_n = Cout / BN;
+  p.num_work = ((p.tiles_m + 1) / 2) * p.tiles_n;
+  p.b_mn = 1;
+  p.relu = relu;
+  p.bias = bias;
+  p.stats = nullptr;
+  const CUtensorMapDataType tdt = dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap tx;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t box[4] = {BK, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+    int rc = u2b_encode_tmap(&tx, tdt, 4, x, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc) return rc;
+  }
+  const bool bf = dtype == 2;
+  for (int ph = 0; ph < 4; ++ph) {
+    const int i = ph >> 1, j = ph & 1;
+    CUtensorMap tw, ty;
+    {
+      // rows = Cin (GEMM-K), columns = Cout of phase (i, j): physical (Cin, 2, 2, Cout) -> row pitch 4*Cout elements
+      const uint16_t* wp = static_cast<const uint16_t*>(w) + static_cast<size_t>(ph) * Cout;
+      uint64_t dims[2] = {(uint64_t)Cout, (uint64_t)Cin};
+      uint64_t strides[1] = {(uint64_t)4 * Cout * 2};
+      uint32_t box[2] = {64, 64};
+      int rc = u2b_encode_tmap(&tw, tdt, 2, wp, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (rc) return rc;
+    }
+    {
+      uint16_t* yp = static_cast<uint16_t*>(y) + (static_cast<size_t>(i) * 2 * W + j) * Cout;
+      uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+      uint64_t strides[3] = {(uint64_t)2 * Cout * 2, (uint64_t)2 * (2 * W) * Cout * 2, (uint64_t)(2 * H) * (2 * W) * Cout * 2};
+      uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+      int rc = u2b_encode_tmap(&ty, tdt, 4, yp, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (rc) return rc;
+    }
+    int rc;
+    if (BN == 256) rc = bf ? launch_conv2<256, true>(tx, tw, ty, p, stream) : launch_conv2<256, false>(tx, tw, ty, p, stream);
+    else rc = bf ? launch_conv2<128, true>(tx, tw, ty, p, stream) : launch_conv2<128, false>(tx, tw, ty, p, stream);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 }  // extern "C"

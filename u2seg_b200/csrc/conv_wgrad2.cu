@@ -412,6 +412,7 @@ extern "C" {
 int u2b_conv_wgrad2_supported(int Cin, int Cout, int R, int S, int stride, int pad) {
   if (Cin <= 0 || Cout <= 0) return 0;
   if (!((Cout % 256 == 0 && Cin % 128 == 0) || (Cin % 256 == 0 && Cout % 128 == 0))) return 0;
+  if (R == 2 && S == 2) return pad == 0 && stride == 2;  // ConvTranspose2d(k=2, s=2) seen as the conv it is the gradient of
   if (!((R == 1 && S == 1 && pad == 0) || (R == 3 && S == 3 && pad == 1))) return 0;
   return stride == 1 || stride == 2;
 }

@@ -52,6 +52,15 @@ def _aligned(n, a=64):
     return (n + a - 1) // a * a
 
 
+def _all_reduce_avg(t, group=None):
+    """DDP's gradient averaging: SUM / world in one NCCL call (ReduceOp.AVG) - no separate division pass."""
+    try:
+        dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
+    except (RuntimeError, ValueError):      # backends without AVG (gloo)
+        dist.all_reduce(t, group=group)
+        t.div_(_world())
+
+
 class FlatGradients:
     """All gradients as views into one flat fp32 buffer -> the DDP-equivalent is ONE all-reduce per step.
     `tail` lists tensors whose fp32 gradients live at the end of the buffer without being attached as `.grad`
@@ -76,8 +85,7 @@ class FlatGradients:
 
     def all_reduce_mean(self, group=None):
         if _world() > 1:
-            dist.all_reduce(self.flat, group=group)
-            self.flat.div_(_world())
+            _all_reduce_avg(self.flat, group)
 
 
 class _BackboneTuple(torch.nn.Module):
@@ -388,6 +396,95 @@ class Trainer:
         for dsts, srcs in buckets.values():
             torch._foreach_copy_(dsts, srcs)
 
+    # ---- gradient all-reduce overlapped with the backward pass (data-parallel runs) ----
+    def _setup_overlap(self):
+        """The flat fp32 gradient buffer is cut into contiguous buckets (~U2B_BUCKET_MB each, whole parameters). A
+        post-accumulate-grad hook per parameter counts its bucket down; when the last gradient of a bucket has been
+        produced, the bucket is gathered into the flat buffer (widening bf16 weight gradients) and all-reduced (AVG) on
+        a communication stream while autograd keeps going on the compute streams. Parameters are laid out in forward
+        order, so the heads' buckets (half of all weights: the three 12544x1024 box-head FCs) finish first and their
+        NVLink traffic hides behind the backbone's backward. Equivalent to the reference's DDP buckets
+        (engine/defaults.py:60-79 create_ddp_model); captured into the step's CUDA graph like everything else."""
+        dst = self._upd_grads if self._upd_grads is not None else self._flat_views
+        base = self.grads.flat.data_ptr()
+        order = sorted(range(len(self.params)), key=lambda i: dst[i].data_ptr())
+        cap = int(float(os.environ.get("U2B_BUCKET_MB", "24")) * (1 << 20) / 4)
+        buckets, cur, cur_n = [], [], 0
+        for i in order:
+            n = _aligned(self.params[i].numel())
+            if cur and cur_n + n > cap:
+                buckets.append(cur)
+                cur, cur_n = [], 0
+            cur.append(i)
+            cur_n += n
+        if cur:
+            buckets.append(cur)
+        self._ov = {"buckets": buckets, "dst": dst, "bucket_of": {}, "range": [], "comm": torch.cuda.Stream(self.device)}
+        for b, idxs in enumerate(buckets):
+            lo = (dst[idxs[0]].data_ptr() - base) // 4
+            hi = (dst[idxs[-1]].data_ptr() - base) // 4 + _aligned(self.params[idxs[-1]].numel())
+            self._ov["range"].append((lo, hi))
+            for i in idxs:
+                self._ov["bucket_of"][i] = b
+        index_of = {id(p): i for i, p in enumerate(self.params)}
+
+        def hook(p):
+            ov = self._ov
+            if not ov.get("armed"):
+                return
+            i = index_of[id(p)]
+            b = ov["bucket_of"][i]
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))      # the stream this gradient was produced on
+            ov["events"][b].append(ev)
+            ov["pending"][b] -= 1
+            if ov["pending"][b] == 0:
+                self._reduce_bucket(b)
+
+        for p in self.params:
+            p.register_post_accumulate_grad_hook(hook)
+
+    @torch.no_grad()
+    def _reduce_bucket(self, b, on_comm_stream=True):
+        ov = self._ov
+        idxs = ov["buckets"][b]
+        lo, hi = ov["range"][b]
+        comm = ov["comm"] if on_comm_stream else torch.cuda.current_stream(self.device)
+        if on_comm_stream:
+            for ev in ov["events"][b]:
+                comm.wait_event(ev)
+        with torch.cuda.stream(comm):
+            have = [(ov["dst"][i], self.params[i].grad) for i in idxs if self.params[i].grad is not None]
+            if len(have) != len(idxs):
+                self.grads.flat[lo:hi].zero_()                     # parameters outside this step's graph: zero gradient
+            groups = {}
+            for d, g in have:
+                groups.setdefault((g.dtype, d.stride() == g.stride()), ([], []))
+                groups[(g.dtype, d.stride() == g.stride())][0].append(d)
+                groups[(g.dtype, d.stride() == g.stride())][1].append(g)
+            for dsts, srcs in groups.values():
+                torch._foreach_copy_(dsts, srcs)
+            _all_reduce_avg(self.grads.flat[lo:hi])
+        ov["done"][b] = True
+
+    def _arm_overlap(self):
+        ov = self._ov
+        n = len(ov["buckets"])
+        ov["pending"] = [len(b) for b in ov["buckets"]]
+        ov["events"] = [[] for _ in range(n)]
+        ov["done"] = [False] * n
+        ov["comm"].wait_stream(torch.cuda.current_stream(self.device))     # the flat buffer's previous consumers are done
+        ov["armed"] = True
+
+    def _finish_overlap(self):
+        ov = self._ov
+        ov["armed"] = False
+        main = torch.cuda.current_stream(self.device)
+        main.wait_stream(ov["comm"])
+        for b, done in enumerate(ov["done"]):                      # buckets with parameters that received no gradient
+            if not done:
+                self._reduce_bucket(b, on_comm_stream=False)
+
     def _static_step(self):
         from .modeling.static_train import forward_train_static
         # .grad = None: autograd hands over each gradient tensor instead of launching one `grad += g` kernel per
@@ -395,11 +492,19 @@ class Trainer:
         # fp32 buffer. Under graph capture the gradient tensors live in the graph's private pool.
         for p in self.params:
             p.grad = None
+        overlap = _world() > 1 and os.environ.get("U2B_OVERLAP_ALLREDUCE", "1") == "1"
+        if overlap and getattr(self, "_ov", None) is None:
+            self._setup_overlap()
         with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
             loss_dict, flag = forward_train_static(self.model, *self._static_in)
-        sum(loss_dict.values()).backward()
-        self._gather_grads()
-        self.grads.all_reduce_mean()          # one NCCL all-reduce of the flat gradient buffer (captured with the graph)
+        if overlap:
+            self._arm_overlap()
+            sum(loss_dict.values()).backward()
+            self._finish_overlap()
+        else:
+            sum(loss_dict.values()).backward()
+            self._gather_grads()
+            self.grads.all_reduce_mean()      # one NCCL all-reduce of the flat gradient buffer (captured with the graph)
         if self.lowp and os.environ.get("U2B_FUSED_OPT", "1") != "0":
             self._fused_clip_sgd()
         else:

@@ -101,7 +101,7 @@ class BasicStem(nn.Module):
 
     def forward(self, x):
         x = self.conv1(x)
-        return F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+        return ops.max_pool_3x3_s2(x)
 
 
 class BottleneckBlock(nn.Module):

@@ -289,7 +289,7 @@ def eligible(x, m):
     return bool(_lib.lib().u2b_conv2d_supported(m.in_channels, m.out_channels, R, S, m.stride[0], m.padding[0]))
 
 
-def try_conv(x, m, residual=None):
+def try_conv(x, m, residual=None, residual_up2x=False):
     """act(norm(conv(x)) [+ residual]) for a backbone.Conv2d module, or None when the shape is not covered."""
     from . import ops
     if not eligible(x, m):
@@ -303,7 +303,9 @@ def try_conv(x, m, residual=None):
             y, stats = _ConvTC.apply(x, m.weight, m.bias, m.stride[0], m.padding[0], False, True)
             if m.norm.num_batches_tracked is not None and not getattr(m.norm, "_counter_batched", False):
                 m.norm.num_batches_tracked.add_(1)
-            return fused_bn.bn_act(y, m.norm, residual, is_relu, partials=stats)
+            return fused_bn.bn_act(y, m.norm, residual, is_relu, partials=stats, residual_up2x=residual_up2x)
+    if residual_up2x:
+        return None
     y = _ConvTC.apply(x, m.weight, m.bias, m.stride[0], m.padding[0], fuse_relu)
     if fuse_relu:
         return y
@@ -357,6 +359,64 @@ class _LinearTC(torch.autograd.Function):
         if has_bias and ctx.needs_input_grad[2]:
             gb = gy.sum(0, dtype=torch.float32)
         return gx, gw, gb, None
+
+
+class _Deconv2x2(torch.autograd.Function):
+    """[relu](ConvTranspose2d(k=2, s=2)(x) + b) on the tcgen05 kernels (mask_head.py:256-262): forward = four interleaved
+    1x1 GEMMs (u2b_deconv2x2_nhwc_fwd); input gradient = the 2x2 / stride-2 convolution of dY with the same weight;
+    weight gradient = that convolution's wgrad. The channels_last weight (physical (Cin,2,2,Cout)) is used in place."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        L = _lib.lib()
+        dt = x.dtype
+        xc = _nhwc(x)
+        N, Cin, H, W = xc.shape
+        Cout = weight.shape[1]
+        w = weight.detach().to(dt).permute(0, 2, 3, 1).contiguous()             # (Cin, 2, 2, Cout)
+        b = bias.detach().float().contiguous() if bias is not None else None
+        y = torch.empty((N, 2 * H, 2 * W, Cout), dtype=dt, device=x.device).permute(0, 3, 1, 2)
+        if y.numel():
+            with _Timed("fwd", (N, H, W, Cin, 4 * Cout, 1, 1), 2.0 * N * H * W * Cin * 4 * Cout):
+                _lib.check(L.u2b_deconv2x2_nhwc_fwd(_CODE[dt], ctypes.c_void_p(xc.data_ptr()), N, H, W, Cin,
+                                                    ctypes.c_void_p(w.data_ptr()), Cout, _lib.ptr(b), int(relu),
+                                                    ctypes.c_void_p(y.data_ptr()), _lib.stream_ptr()), "u2b_deconv2x2_nhwc_fwd")
+            _lib.count_launches(4)
+        ctx.save_for_backward(xc, weight, y if relu else torch.empty(0))
+        ctx.meta = (relu, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xc, weight, y = ctx.saved_tensors
+        relu, has_bias = ctx.meta
+        dt = xc.dtype
+        if relu:
+            gy = torch.ops.aten.threshold_backward(gy, y, 0)
+        gy = _nhwc(gy.to(dt))
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            w = weight.detach().to(dt).permute(0, 2, 3, 1).contiguous()         # OHWI filter of the 2x2 / s2 conv: (Cin,2,2,Cout)
+            gx = conv2_nhwc(gy, w, 2, 0, None, False)
+        if ctx.needs_input_grad[1]:
+            if wgrad2_supported(gy, weight.shape[0], 2, 2, 2, 0):
+                gw = conv_wgrad2(gy, xc, 2, 2, 2, 0, weight.dtype)               # logical (Cin, Cout, 2, 2), channels_last storage
+            else:
+                gw = torch.ops.aten.convolution_backward(gy, xc, weight.detach().to(dt), None, [2, 2], [0, 0], [1, 1], True,
+                                                         [0, 0], 1, [False, True, False])[1].to(weight.dtype)
+        if has_bias and ctx.needs_input_grad[2]:
+            from .fused_bn import channel_sum
+            gb = channel_sum(gy)
+        return gx, gw, gb, None
+
+
+def deconv2x2(x, m, relu=False):
+    """nn.ConvTranspose2d(kernel 2, stride 2) module `m` (+ ReLU) on the tcgen05 kernels, or None if not covered."""
+    if not (USE_CONV2 and x.is_cuda and x.dim() == 4 and x.dtype in _CODE and m.kernel_size == (2, 2) and m.stride == (2, 2)
+            and m.padding == (0, 0) and m.output_padding == (0, 0) and m.groups == 1 and m.dilation == (1, 1)
+            and bool(_lib.lib().u2b_deconv2x2_supported(m.in_channels, m.out_channels))):
+        return None
+    return _Deconv2x2.apply(x, m.weight, m.bias, relu)
 
 
 def linear_eligible(x, weight):

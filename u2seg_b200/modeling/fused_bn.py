@@ -99,7 +99,8 @@ def channel_sum(x):
 
 class _BNAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, running_mean, running_var, eps, momentum, relu, partials=None):
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, eps, momentum, relu, partials=None,
+                residual_up2x=False):
         L = _lib.lib()
         s = _lib.stream_ptr()
         xc = _nhwc(x)
@@ -136,10 +137,14 @@ class _BNAct(torch.autograd.Function):
                                          _p(running_mean), _p(running_var), _p(stats), C, s), "u2b_bn_finalize")
         res = _nhwc(residual.to(xc.dtype)) if residual is not None else None
         y = torch.empty((N, H, W, C), dtype=xc.dtype, device=dev).permute(0, 3, 1, 2)
-        _lib.check(L.u2b_bn_apply(dt, _p(xc), _p(stats), _p(res), int(relu), _p(y), P, C, s), "u2b_bn_apply")
+        if residual_up2x:     # residual is the coarser pyramid level: added through a nearest x2 upsampling (fpn.py:153-156)
+            assert res is not None and tuple(res.shape) == (N, C, H // 2, W // 2) and H % 2 == 0 and W % 2 == 0
+            _lib.check(L.u2b_bn_apply_resup(dt, _p(xc), _p(stats), _p(res), int(relu), _p(y), N, H, W, C, s), "u2b_bn_apply_resup")
+        else:
+            _lib.check(L.u2b_bn_apply(dt, _p(xc), _p(stats), _p(res), int(relu), _p(y), P, C, s), "u2b_bn_apply")
         _lib.count_launches(3)
         ctx.save_for_backward(xc, y if relu else torch.empty(0), weight, stats)
-        ctx.meta = (relu, residual is not None, n_total, world)
+        ctx.meta = (relu, residual is not None, n_total, world, bool(residual_up2x))
         return y
 
     @staticmethod
@@ -147,7 +152,7 @@ class _BNAct(torch.autograd.Function):
         L = _lib.lib()
         s = _lib.stream_ptr()
         xc, y, weight, stats = ctx.saved_tensors
-        relu, has_res, n_total, world = ctx.meta
+        relu, has_res, n_total, world, res_up = ctx.meta
         N, C, H, W = xc.shape
         P = N * H * W
         dt = _CODE[xc.dtype]
@@ -176,17 +181,29 @@ class _BNAct(torch.autograd.Function):
         else:
             _lib.check(L.u2b_bn_bwd_coeff(_p(part), S, n_total, _p(stats), _p(weight), _p(coeff), _p(gwb), C, s), "u2b_bn_bwd_coeff")
         dx = torch.empty((N, H, W, C), dtype=xc.dtype, device=dev).permute(0, 3, 1, 2)
-        dres = torch.empty((N, H, W, C), dtype=xc.dtype, device=dev).permute(0, 3, 1, 2) if has_res else None
+        # without ReLU the residual's gradient IS the incoming gradient (no masked copy needed)
+        need_dres = has_res and (relu or not res_up)
+        dres = torch.empty((N, H, W, C), dtype=xc.dtype, device=dev).permute(0, 3, 1, 2) if need_dres else None
         _lib.check(L.u2b_bn_bwd_apply(dt, _p(g), _p(xc), _p(yy), _p(coeff), _p(dx), _p(dres), P, C, s), "u2b_bn_bwd_apply")
         _lib.count_launches(3)
-        return dx, gwb[:C].to(weight.dtype), gwb[C:].to(weight.dtype), dres, None, None, None, None, None, None
+        if has_res and res_up:      # gradient of the nearest x2 upsampling: fold every 2x2 block (csrc/pool.cu)
+            src = dres if dres is not None else g
+            if dt in (1, 2):
+                folded = torch.empty((N, H // 2, W // 2, C), dtype=xc.dtype, device=dev).permute(0, 3, 1, 2)
+                _lib.check(L.u2b_sum2x2_nhwc(dt, _p(src), N, H, W, C, _p(folded), s), "u2b_sum2x2_nhwc")
+                _lib.count_launches(1)
+            else:
+                folded = src.reshape(N, C, H // 2, 2, W // 2, 2).sum(dim=(3, 5))
+            dres = folded
+        return dx, gwb[:C].to(weight.dtype), gwb[C:].to(weight.dtype), dres, None, None, None, None, None, None, None
 
 
-def bn_act(x, bn, residual=None, relu=False, partials=None):
+def bn_act(x, bn, residual=None, relu=False, partials=None, residual_up2x=False):
     """relu(SyncBN_train(x) + residual) for a BatchNorm2d-like module `bn` in training mode. `partials`: optional
-    per-tile statistics of x computed by the kernel that produced it (skips the reduction pass)."""
+    per-tile statistics of x computed by the kernel that produced it (skips the reduction pass). residual_up2x: the
+    residual is the next-coarser map, added through a nearest-neighbour x2 upsampling (FPN top-down path)."""
     return _BNAct.apply(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, bn.eps,
-                        0.1 if bn.momentum is None else bn.momentum, relu, partials)
+                        0.1 if bn.momentum is None else bn.momentum, relu, partials, residual_up2x)
 
 
 # The fused multi-GPU path takes the group's element count as P * world, i.e. it assumes every rank holds the same

@@ -125,7 +125,87 @@ class Upsample(nn.Upsample):
                            align_corners=self.align_corners)
 
 
+FUSED_FPN_SUM = os.environ.get("U2B_FUSED_FPN_SUM", "1") == "1"
+MAXPOOL_KERNEL = os.environ.get("U2B_MAXPOOL_KERNEL", "1") == "1"
+
+
 def lateral_add_upsample(lateral, feat, prev):
-    """fpn.py:153-156: lateral(feat) + F.interpolate(prev, scale_factor=2, mode='nearest')."""
+    """fpn.py:153-156: lateral(feat) + F.interpolate(prev, scale_factor=2, mode='nearest'). With the tcgen05 conv +
+    fused SyncBN path the sum is folded into the norm's apply pass (the upsampled map is never materialised) and the
+    gradient of the upsampling is one 2x2 fold kernel."""
+    if (FUSED_FPN_SUM and _use_tc(feat, lateral) and lateral.activation is None
+            and prev.shape[2] * 2 == feat.shape[2] and prev.shape[3] * 2 == feat.shape[3]):
+        from . import conv_tc
+        y = conv_tc.try_conv(feat, lateral, prev, residual_up2x=True)
+        if y is not None:
+            return y
     td = interpolate(prev, scale_factor=2.0, mode="nearest")
     return lateral(feat) + td
+
+
+class _MaxPool3x3S2(torch.autograd.Function):
+    """F.max_pool2d(x, 3, 2, 1) on NHWC half tensors (resnet.py:358): csrc/pool.cu."""
+
+    @staticmethod
+    def forward(ctx, x):
+        import ctypes
+        from .. import _lib
+        L = _lib.lib()
+        xc = x if (x.is_contiguous(memory_format=torch.channels_last) and x.stride(1) == 1) else \
+            x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        N, C, H, W = xc.shape
+        OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((N, OH, OW, C), dtype=xc.dtype, device=xc.device).permute(0, 3, 1, 2)
+        idx = torch.empty((N, OH, OW, C), dtype=torch.uint8, device=xc.device)
+        code = 2 if xc.dtype == torch.bfloat16 else 1
+        _lib.check(L.u2b_maxpool3x3s2_fwd(code, ctypes.c_void_p(xc.data_ptr()), N, H, W, C, ctypes.c_void_p(y.data_ptr()),
+                                          ctypes.c_void_p(idx.data_ptr()), _lib.stream_ptr()), "u2b_maxpool3x3s2_fwd")
+        _lib.count_launches(1)
+        ctx.save_for_backward(idx)
+        ctx.meta = (N, C, H, W, code, xc.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        import ctypes
+        from .. import _lib
+        (idx,) = ctx.saved_tensors
+        N, C, H, W, code, dt = ctx.meta
+        g = gy.to(dt)
+        if not (g.is_contiguous(memory_format=torch.channels_last) and g.stride(1) == 1):
+            g = g.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        dx = torch.empty((N, H, W, C), dtype=dt, device=g.device).permute(0, 3, 1, 2)
+        _lib.check(_lib.lib().u2b_maxpool3x3s2_bwd(code, ctypes.c_void_p(g.data_ptr()), ctypes.c_void_p(idx.data_ptr()), N, H, W,
+                                                   C, ctypes.c_void_p(dx.data_ptr()), _lib.stream_ptr()), "u2b_maxpool3x3s2_bwd")
+        _lib.count_launches(1)
+        return dx
+
+
+def max_pool_3x3_s2(x):
+    """F.max_pool2d(x, kernel_size=3, stride=2, padding=1)."""
+    if MAXPOOL_KERNEL and x.is_cuda and x.dim() == 4 and x.dtype in (torch.float16, torch.bfloat16) and x.shape[1] % 8 == 0:
+        return _MaxPool3x3S2.apply(x)
+    return F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+
+
+PREPROCESS_KERNEL = os.environ.get("U2B_PREPROCESS_KERNEL", "1") == "1"
+
+
+def preprocess_u8(images_u8, mean, std, size_divisibility, out_dtype=torch.float32):
+    """rcnn.py:223-234 for a (N,3,H,W) uint8 batch stored channels_last: normalise, zero-pad to the backbone's size
+    divisibility, keep NHWC (csrc/pool.cu preprocess_u8_kernel). mean / std: sequences of 3 python floats."""
+    import ctypes
+    from .. import _lib
+    N, C, H, W = images_u8.shape
+    assert C == 3 and images_u8.dtype == torch.uint8 and images_u8.is_cuda
+    x = images_u8 if (images_u8.is_contiguous(memory_format=torch.channels_last) and images_u8.stride(1) == 1) else \
+        images_u8.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    s = size_divisibility
+    Hp, Wp = (H + s - 1) // s * s, (W + s - 1) // s * s
+    out = torch.empty((N, Hp, Wp, 3), dtype=out_dtype, device=x.device).permute(0, 3, 1, 2)
+    m3, s3 = (ctypes.c_float * 3)(*[float(v) for v in mean]), (ctypes.c_float * 3)(*[float(v) for v in std])
+    code = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}[out_dtype]
+    _lib.check(_lib.lib().u2b_preprocess_u8_nhwc(ctypes.c_void_p(x.data_ptr()), N, H, W, Hp, Wp, m3, s3, code,
+                                                 ctypes.c_void_p(out.data_ptr()), _lib.stream_ptr()), "u2b_preprocess_u8_nhwc")
+    _lib.count_launches(1)
+    return out

@@ -26,6 +26,9 @@ class PanopticFPN(nn.Module):
         self.sem_seg_head = build_sem_seg_head(cfg, shapes)
         self.register_buffer("pixel_mean", torch.tensor(cfg.MODEL.PIXEL_MEAN).view(-1, 1, 1), False)
         self.register_buffer("pixel_std", torch.tensor(cfg.MODEL.PIXEL_STD).view(-1, 1, 1), False)
+        # host copies (fp32-rounded like the buffers) for the fused preprocessing kernel's scalar arguments
+        self._pixel_mean_host = [float(torch.tensor(v, dtype=torch.float32)) for v in cfg.MODEL.PIXEL_MEAN]
+        self._pixel_std_host = [float(torch.tensor(v, dtype=torch.float32)) for v in cfg.MODEL.PIXEL_STD]
         c = cfg.MODEL.PANOPTIC_FPN.COMBINE
         self.combine_overlap_thresh = c.OVERLAP_THRESH
         self.combine_stuff_area_thresh = c.STUFF_AREA_LIMIT

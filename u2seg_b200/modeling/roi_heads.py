@@ -255,16 +255,33 @@ class MaskRCNNConvUpsampleHead(nn.Sequential):
         nn.init.normal_(self.predictor.weight, std=0.001)
         nn.init.constant_(self.predictor.bias, 0)
 
+    def features(self, x):
+        """everything before the predictor: mask_fcn1..n (+ReLU), deconv + ReLU (mask_head.py:242-262). Under CUDA
+        autocast with the tcgen05 policy the transposed convolution runs on the 2-CTA kernel, ReLU fused."""
+        from . import conv_tc, ops
+        skip_relu = False
+        for layer in self:
+            if layer is self.predictor:
+                break
+            if skip_relu and isinstance(layer, nn.ReLU):
+                skip_relu = False
+                continue
+            if (layer is self.deconv and x.is_cuda and ops.USE_TCGEN05_CONV and ops.TCGEN05_CONV_POLICY == "all"
+                    and x.dtype in (torch.float16, torch.bfloat16)):
+                y = conv_tc.deconv2x2(x, layer, relu=True)
+                if y is not None:
+                    x, skip_relu = y, True
+                    continue
+            x = layer(x)
+        return x
+
     def forward_selected(self, x, classes):
         """Logits of ONE class per ROI, (R, S, S): exactly the entries that mask_head.py:95-97 (training, gt class)
         and mask_head.py:141-143 (inference, predicted class) read from the (R, num_classes, S, S) predictor output.
         With 800 pseudo-classes that output is 800x larger than what is used (321 MB per step at 256 ROIs), so the
         1x1 predictor runs as a per-ROI dot product with the selected filter instead; unselected filters get a zero
         gradient either way."""
-        for layer in self:
-            if layer is self.predictor:
-                break
-            x = layer(x)
+        x = self.features(x)
         R, C, S, _ = x.shape
         w = self.predictor.weight.view(-1, C)
         if w.shape[0] == 1:

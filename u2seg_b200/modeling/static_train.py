@@ -318,11 +318,7 @@ def _mask_branch_static(rh, feats, tap, boxes0, cls0, fg0, gidx0, gt_masks, K, R
     if FUSED_MASK_LOSS:
         from .fused_losses import mask_loss_selected, mask_loss_supported
         head = rh.mask_head
-        xf = xm
-        for layer in head:                                       # mask_fcn1..4, deconv, ReLU; the predictor is fused below
-            if layer is head.predictor:
-                break
-            xf = layer(xf)
+        xf = head.features(xm)                                   # mask_fcn1..4, deconv + ReLU; the predictor is fused below
         if mask_loss_supported(xf) and head.predictor.weight.shape[0] > 1:
             side = xf.shape[-1]
             with torch.no_grad():
@@ -356,13 +352,21 @@ def forward_train_static(model, images_u8, gt_boxes, gt_classes, gt_valid, gt_ma
     """PanopticFPN.forward (training) on padded tensors. images_u8: (N,3,H,W) uint8 on the device. Returns
     (dict of the 10 losses in the reference's key order, nonfinite flag tensor)."""
     N, _, H, W = images_u8.shape
-    x = ((images_u8.float() - model.pixel_mean) / model.pixel_std)
     s = model.backbone.size_divisibility
     Hp, Wp = (H + s - 1) // s * s, (W + s - 1) // s * s
+    from . import ops
+    if ops.PREPROCESS_KERNEL and images_u8.is_cuda and images_u8.dtype == torch.uint8:
+        # normalise + pad + layout in one kernel; under autocast straight to the stem's input dtype (same single rounding
+        # autocast's cast would apply to the fp32 tensor)
+        odt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float32
+        x = ops.preprocess_u8(images_u8, model._pixel_mean_host, model._pixel_std_host, s, odt)
+    else:
+        x = ((images_u8.float() - model.pixel_mean) / model.pixel_std)
+        if (Hp, Wp) != (H, W):
+            x = F.pad(x, (0, Wp - W, 0, Hp - H))
+        x = x.contiguous(memory_format=torch.channels_last)
     if (Hp, Wp) != (H, W):
-        x = F.pad(x, (0, Wp - W, 0, Hp - H))
         sem_seg = F.pad(sem_seg, (0, Wp - W, 0, Hp - H), value=model.sem_seg_head.ignore_value)
-    x = x.contiguous(memory_format=torch.channels_last)
     if model._bn_counters:
         torch._foreach_add_(model._bn_counters, 1)
     features = model.backbone(x)
