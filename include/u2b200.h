@@ -220,10 +220,11 @@ int u2b_conv_wgrad2(int dtype, const void* x, const void* dy, int N, int H, int 
  * the class gather and binary_cross_entropy_with_logits of detectron2/modeling/roi_heads/mask_head.py:33-112 (and their
  * backward) for fixed-capacity ROI slots. x (R, P, C): ROI features after the deconv+ReLU, NHWC rows, fp16 (1) / bf16 (2);
  * w (K, C) in x's dtype, bias (K) fp32; classes (R) int64; target (R, P) bool; ok (R) bool (dead slots contribute 0).
- * fwd: loss_per_roi[r] = sum_p bce(z[r,p], t[r,p]) * ok[r], g[r,p] = (sigmoid(z) - t) * ok[r].
+ * fwd: sum_j loss_per_roi[r][j] = sum_p bce(z[r,p], t[r,p]) * ok[r], g[r,p] = (sigmoid(z) - t) * ok[r].
  * bwd: upstream = device scalar d/d(loss sum); dx (R, P, C); dw (K, C), db (K) fp32 zero-filled by the caller;
  *      workspace R * (C + 1) floats. Deterministic (no atomics). C % 256 == 0, C <= 1024. */
 int u2b_mask_loss_supported(int C);
+int u2b_mask_loss_num_partials(void);   /* loss_per_roi is (R, this many) partial sums */
 int u2b_mask_loss_fwd(int dtype, const void* x, const void* w, const float* bias, const int64_t* classes,
                       const uint8_t* target, const uint8_t* ok, int64_t R, int P, int C, float* g, float* loss_per_roi,
                       u2b_stream_t stream);

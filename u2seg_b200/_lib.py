@@ -96,6 +96,7 @@ SIGNATURES = {
     "u2b_conv_wgrad2": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_void_p, c_int, c_void_p, c_void_p]),
     "u2b_mask_loss_supported": (c_int, [c_int]),
+    "u2b_mask_loss_num_partials": (c_int, []),
     "u2b_mask_loss_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                   c_void_p, c_void_p, c_void_p]),
     "u2b_mask_loss_bwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,

@@ -193,13 +193,16 @@ def in_step_conv_roofline(trainer, batch, peaks, ms_step):
     snap = trainer._snapshot_training_state()
     trainer._load_static_inputs(batch)
     torch.cuda.synchronize()
+    from .modeling import static_train
     conv_tc.TIMING = []
+    static_train.FORCE_SINGLE_STREAM = True     # no concurrent branch kernels: the events bracket each kernel alone
     try:
         trainer._static_step()
         torch.cuda.synchronize()
         recs = conv_tc.TIMING
     finally:
         conv_tc.TIMING = None
+        static_train.FORCE_SINGLE_STREAM = False
     trainer._restore_training_state(snap)
     groups = {}
     for kind, key, flop, e0, e1 in recs:
@@ -229,7 +232,9 @@ def in_step_conv_roofline(trainer, batch, peaks, ms_step):
                                      "frac": tot_flop / (tot_ms * 1e-3) / 1e12 / peaks["tf_sus"],
                                      "share_of_step_time": tot_ms / ms_step,
                                      "share_of_step_flop": tot_flop / (FLOP_PER_IMAGE * IMS_PER_GPU)},
-            "method": "CUDA events on the launching stream around each launch of one eager execution of the static step"}
+            "method": "CUDA events on the launching stream around each launch of one eager, single-stream execution of the "
+                      "static step (the graph replays overlap independent branches on side streams, which would stretch "
+                      "per-kernel durations)"}
 
 
 def conv_tc_roofline(peaks):

@@ -68,8 +68,11 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t cta_addr, uint32_t rank) 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(cta_addr), "r"(rank));
   return out;
 }
+// relaxed: the only data this arrive publishes are completed TMEM reads, ordered by tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync; a release.cluster arrive compiles to MEMBAR.ALL + ERRBAR and stalls every
+// epilogue warp for hundreds of cycles per tile (ncu source page, round 2)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

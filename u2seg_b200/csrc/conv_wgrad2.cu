@@ -305,7 +305,7 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0)
-        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(t_empty_leader) : "memory");
+        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(t_empty_leader) : "memory");
     }
   }
   ptx::tc_fence_before();

@@ -59,14 +59,21 @@ __device__ __forceinline__ uint4 pack8<__half>(const float (&v)[8]) {
   return r;
 }
 
+// grid (R, ML_SPLIT): CTA (r, s) takes pixels [s*chunk, (s+1)*chunk) of ROI r. A warp walks 32 pixels at a time: the 32
+// dot products are reduced one after the other (independent loads, pipelined), lane j keeps pixel j's logit, then all
+// lanes evaluate the loss / gradient of their pixel together (no single-lane transcendental chain) and store g coalesced.
+constexpr int ML_SPLIT = 4;
+
 template <typename T, int G>
 __global__ void __launch_bounds__(ML_THREADS)
 mask_loss_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
                      const int64_t* __restrict__ classes, const uint8_t* __restrict__ target,
-                     const uint8_t* __restrict__ ok, int P, float* __restrict__ g, float* __restrict__ loss_per_roi) {
+                     const uint8_t* __restrict__ ok, int P, float* __restrict__ g, float* __restrict__ loss_part) {
   constexpr int C = 256 * G;
   __shared__ float red[ML_THREADS / 32];
   const int r = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = (P + ML_SPLIT - 1) / ML_SPLIT;
+  const int p_begin = blockIdx.y * chunk, p_end = min(P, p_begin + chunk);
   const int64_t cls = classes[r];
   const float live = ok[r] ? 1.f : 0.f;
   float wr[G][8];
@@ -76,31 +83,40 @@ mask_loss_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w, const flo
   const float b = bias ? bias[cls] : 0.f;
   const T* xr = x + static_cast<size_t>(r) * P * C;
   float acc = 0.f;
-  for (int p = warp; p < P; p += ML_THREADS / 32) {
-    float d = 0.f;
+  for (int p0 = p_begin + warp * 32; p0 < p_end; p0 += (ML_THREADS / 32) * 32) {
+    float z = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+      const int p = p0 + j;
+      if (p >= p_end) break;            // warp-uniform
+      float d = 0.f;
 #pragma unroll
-    for (int gI = 0; gI < G; ++gI) {
-      float v[8];
-      unpack8<T>(*reinterpret_cast<const uint4*>(xr + static_cast<size_t>(p) * C + gI * 256 + lane * 8), v);
+      for (int gI = 0; gI < G; ++gI) {
+        float v[8];
+        unpack8<T>(*reinterpret_cast<const uint4*>(xr + static_cast<size_t>(p) * C + gI * 256 + lane * 8), v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d = fmaf(v[i], wr[gI][i], d);
+        for (int i = 0; i < 8; ++i) d = fmaf(v[i], wr[gI][i], d);
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+      if (lane == j) z = d + b;
     }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-    if (lane == 0) {
-      const float z = d + b;
+    const int p = p0 + lane;
+    if (p < p_end) {
       const float t = target[static_cast<size_t>(r) * P + p] ? 1.f : 0.f;
       // binary_cross_entropy_with_logits (ATen): max(z,0) - z*t + log1p(exp(-|z|))
       acc += fmaxf(z, 0.f) - z * t + log1pf(expf(-fabsf(z)));
       g[static_cast<size_t>(r) * P + p] = (1.f / (1.f + expf(-z)) - t) * live;
     }
   }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
   if (lane == 0) red[warp] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int i = 0; i < ML_THREADS / 32; ++i) s += red[i];
-    loss_per_roi[r] = s * live;
+    loss_part[static_cast<size_t>(r) * ML_SPLIT + blockIdx.y] = s * live;
   }
 }
 
@@ -155,18 +171,29 @@ mask_loss_bwd_kernel(const T* __restrict__ x, const T* __restrict__ w, const int
 }
 
 // dW[k,:] = sum over ROIs r with classes[r] == k (index order) of dw_roi[r,:]; same for db. One CTA per ROI: the first
-// ROI of each class owns the sum. dW / db must be zero-filled by the caller (classes without an ROI).
+// ROI of each class owns the sum (the others exit after one block-wide vote). dW / db must be zero-filled by the caller
+// (classes without an ROI). Deterministic.
 __global__ void __launch_bounds__(256)
 mask_loss_scatter_kernel(const int64_t* __restrict__ classes, const float* __restrict__ dw_roi,
                          const float* __restrict__ db_roi, int R, int C, float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ int same[1024];
+  __shared__ int n_same;
   const int r = blockIdx.x;
   const int64_t cls = classes[r];
-  for (int j = 0; j < r; ++j)
-    if (classes[j] == cls) return;  // an earlier ROI owns this class
+  bool earlier = false;
+  for (int j = threadIdx.x; j < r; j += blockDim.x) earlier |= classes[j] == cls;
+  if (__syncthreads_or(earlier)) return;   // an earlier ROI owns this class
+  if (threadIdx.x == 0) {                  // the (few) later ROIs of the same class, in index order
+    int n = 0;
+    for (int j = r; j < R && n < 1024; ++j)
+      if (classes[j] == cls) same[n++] = j;
+    n_same = n;
+  }
+  __syncthreads();
+  const int n = n_same;
   for (int c = threadIdx.x; c <= C; c += blockDim.x) {
     float t = 0.f;
-    for (int j = r; j < R; ++j)
-      if (classes[j] == cls) t += (c < C) ? dw_roi[static_cast<size_t>(j) * C + c] : db_roi[j];
+    for (int k = 0; k < n; ++k) t += (c < C) ? dw_roi[static_cast<size_t>(same[k]) * C + c] : db_roi[same[k]];
     if (c < C) dw[cls * C + c] = t;
     else db[cls] = t;
   }
@@ -177,17 +204,19 @@ mask_loss_scatter_kernel(const int64_t* __restrict__ classes, const float* __res
 extern "C" {
 
 int u2b_mask_loss_supported(int C) { return C > 0 && C % 256 == 0 && C <= 256 * ML_MAXG; }
+int u2b_mask_loss_num_partials(void) { return ML_SPLIT; }
 
 // dtype 1 = fp16, 2 = bf16. x (R, P, C) pooled-and-convolved ROI features (NHWC rows, P = S*S); w (K, C) predictor filter
 // in x's dtype; bias (K) fp32 or NULL; classes (R) int64 in [0, K); target (R, P) bool; ok (R) bool (fixed-capacity
-// slots: dead ROIs contribute nothing). Outputs: g (R, P) fp32 = d loss_sum / d logit, loss_per_roi (R) fp32.
+// slots: dead ROIs contribute nothing). Outputs: g (R, P) fp32 = d loss_sum / d logit, loss_per_roi (R, 4) fp32 partial
+// sums (u2b_mask_loss_num_partials() per ROI; the caller adds them up).
 int u2b_mask_loss_fwd(int dtype, const void* x, const void* w, const float* bias, const int64_t* classes,
                       const uint8_t* target, const uint8_t* ok, int64_t R, int P, int C, float* g, float* loss_per_roi,
                       cudaStream_t stream) {
   if (R == 0) return 0;
   U2B_CHECK_ARG(x && w && classes && target && ok && g && loss_per_roi && P > 0, "mask_loss_fwd: bad arguments");
   U2B_CHECK_ARG(u2b_mask_loss_supported(C) && (dtype == 1 || dtype == 2), "mask_loss_fwd: C=%d dtype=%d unsupported", C, dtype);
-  const unsigned grid = static_cast<unsigned>(R);
+  const dim3 grid(static_cast<unsigned>(R), ML_SPLIT);
 #define U2B_ML_FWD(T, G)                                                                                              \
   mask_loss_fwd_kernel<T, G><<<grid, ML_THREADS, 0, stream>>>(static_cast<const T*>(x), static_cast<const T*>(w), bias, \
                                                               classes, target, ok, P, g, loss_per_roi)

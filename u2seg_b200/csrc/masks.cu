@@ -15,12 +15,14 @@ namespace {
 
 constexpr int PASTE_MAX_M = 56;  // mask side staged in smem (28 in the reference configs)
 
-// One block = one instance x PASTE_ROWS output rows. The x-dependent part of the bilinear sample (source column,
-// the two column weights) is identical for every row, so it is computed once per block into shared-memory column
-// tables (structure of arrays: conflict-free 16-byte reads); each thread then produces 4 consecutive pixels of a
-// row (a warp writes 128 contiguous bytes) from the tables, the mask in shared memory and the row's two y weights.
-// Rows / groups outside the mask's support are written as zeros directly (there every bilinear corner is out of
-// bounds and grid_sample yields exactly 0).
+// One block = one instance x PASTE_ROWS output rows = one contiguous span of the output. ~98 % of an instance's image
+// lies outside its box, where every bilinear corner is out of bounds and grid_sample yields exactly 0, so the block
+// first FILLS its span with the constant (0 >= threshold) using 16-byte stores (memset speed), then - only if some of
+// its rows reach into the mask's support - builds the x-dependent half of the bilinear sample once (source column and
+// the two column weights per output column: identical for every row; structure of arrays, conflict-free 16-byte reads)
+// and recomputes the pixels of the support rectangle, 4 consecutive pixels per thread from the tables, the mask in shared
+// memory and the row's two y weights. Degenerate boxes (x1 <= x0 or y1 <= y0: NaN / inf coordinates) take the per-pixel
+// path for the whole span, as the reference's formula would.
 constexpr int PASTE_ROWS = 32;
 constexpr int PASTE_MAX_W = 4096;
 
@@ -28,15 +30,54 @@ __global__ void __launch_bounds__(256)
 paste_masks_kernel(const float* __restrict__ masks, const float* __restrict__ boxes, int N, int M,
                    int H, int W, int Wpad, float threshold, uint8_t* __restrict__ out) {
   __shared__ float sm[PASTE_MAX_M * PASTE_MAX_M];
+  __shared__ int s_xlo, s_xhi;
   extern __shared__ __align__(16) uint8_t col_raw[];
   float* cwx0 = reinterpret_cast<float*>(col_raw);  // [Wpad]
   float* cwx1 = cwx0 + Wpad;                        // [Wpad]
   int* cxi0 = reinterpret_cast<int*>(cwx1 + Wpad);  // [Wpad]
   const int n = blockIdx.y;
-  const float* mk = masks + static_cast<size_t>(n) * M * M;
-  for (int i = threadIdx.x; i < M * M; i += blockDim.x) sm[i] = mk[i];
+  const int row0 = blockIdx.x * PASTE_ROWS;
+  const int rows = min(PASTE_ROWS, H - row0);
   const float x0 = boxes[n * 4 + 0], y0 = boxes[n * 4 + 1], x1 = boxes[n * 4 + 2], y1 = boxes[n * 4 + 3];
   const float fM = static_cast<float>(M);
+  const bool regular = (x1 > x0) && (y1 > y0);
+  const uint8_t fill = (0.f >= threshold) ? 1 : 0;
+
+  // rows of this block inside the mask's vertical support (same arithmetic as the sampling code below)
+  bool row_in = false;
+  if (threadIdx.x < rows) {
+    const int y = row0 + threadIdx.x;
+    const float gy = ((static_cast<float>(y) + 0.5f) - y0) / (y1 - y0) * 2.f - 1.f;
+    const float iy = ((gy + 1.f) * fM - 1.f) / 2.f;
+    const float iy_nw = floorf(iy);
+    row_in = iy_nw >= -1.f && iy_nw <= fM - 1.f;   // yi0 or yi0 + 1 inside [0, M)
+  }
+  const bool any_row = __syncthreads_or(row_in || !regular);
+
+  if (regular) {   // constant fill of the whole span
+    uint8_t* p = out + (static_cast<size_t>(n) * H + row0) * W;
+    const size_t len = static_cast<size_t>(rows) * W;
+    size_t head = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
+    if (head > len) head = len;
+    const size_t body = (len - head) / 16;
+    const uint32_t w32 = fill * 0x01010101u;
+    const uint4 v = make_uint4(w32, w32, w32, w32);
+    for (size_t i = threadIdx.x; i < head; i += blockDim.x) p[i] = fill;
+    uint4* pb = reinterpret_cast<uint4*>(p + head);
+    for (size_t i = threadIdx.x; i < body; i += blockDim.x) pb[i] = v;
+    const size_t tail0 = head + body * 16;
+    for (size_t i = tail0 + threadIdx.x; i < len; i += blockDim.x) p[i] = fill;
+    if (!any_row) return;
+  }
+
+  const float* mk = masks + static_cast<size_t>(n) * M * M;
+  for (int i = threadIdx.x; i < M * M; i += blockDim.x) sm[i] = mk[i];
+  if (threadIdx.x == 0) {
+    s_xlo = Wpad;
+    s_xhi = -1;
+  }
+  __syncthreads();   // also orders the fill before the recomputation below (same block, same addresses)
+  int my_lo = Wpad, my_hi = -1;
   for (int x = threadIdx.x; x < Wpad; x += blockDim.x) {
     // mask_ops.py:51-54: img_x = (arange + 0.5 - x0) / (x1 - x0) * 2 - 1; grid_sample unnormalize
     // (align_corners=False): ((g + 1) * size - 1) / 2
@@ -45,17 +86,30 @@ paste_masks_kernel(const float* __restrict__ masks, const float* __restrict__ bo
     const float ix_nw = floorf(ix);
     // out-of-range coordinates are clamped to sentinels whose two corners are both invalid:
     // left of the mask -> -2, right of it -> M + 1, NaN (degenerate box) -> -3
-    cxi0[x] = (ix_nw != ix_nw) ? -3 : (ix_nw < -1.f ? -2 : (ix_nw > fM ? M + 1 : static_cast<int>(ix_nw)));
+    const int xi = (ix_nw != ix_nw) ? -3 : (ix_nw < -1.f ? -2 : (ix_nw > fM ? M + 1 : static_cast<int>(ix_nw)));
+    cxi0[x] = xi;
     cwx1[x] = ix - ix_nw;
     cwx0[x] = (ix_nw + 1.f) - ix;
+    if (xi >= -1 && xi < M) {   // a valid corner exists
+      my_lo = min(my_lo, x);
+      my_hi = max(my_hi, x);
+    }
+  }
+  if (my_hi >= 0) {
+    atomicMin(&s_xlo, my_lo);
+    atomicMax(&s_xhi, my_hi);
   }
   __syncthreads();
-  const int groups_per_row = Wpad / 4;
-  const int row0 = blockIdx.x * PASTE_ROWS;
-  for (int t = threadIdx.x; t < PASTE_ROWS * groups_per_row; t += blockDim.x) {
-    const int y = row0 + t / groups_per_row;
-    if (y >= H) break;
-    const int xg = (t % groups_per_row) * 4;
+  int g_lo = 0, g_hi = Wpad / 4;                     // 4-pixel groups to recompute: [g_lo, g_hi)
+  if (regular) {
+    if (s_xhi < 0) return;                           // no column touches the mask
+    g_lo = s_xlo / 4;
+    g_hi = s_xhi / 4 + 1;
+  }
+  const int ng = g_hi - g_lo;
+  for (int t = threadIdx.x; t < rows * ng; t += blockDim.x) {
+    const int y = row0 + t / ng;
+    const int xg = (g_lo + t % ng) * 4;
     const float gy = ((static_cast<float>(y) + 0.5f) - y0) / (y1 - y0) * 2.f - 1.f;
     const float iy = ((gy + 1.f) * fM - 1.f) / 2.f;
     const float iy_nw = floorf(iy);
@@ -63,28 +117,25 @@ paste_masks_kernel(const float* __restrict__ masks, const float* __restrict__ bo
     const int yi1 = yi0 + 1;
     const float wy1 = iy - iy_nw, wy0 = (iy_nw + 1.f) - iy;
     const bool y0ok = yi0 >= 0 && yi0 < M, y1ok = yi1 >= 0 && yi1 < M;
+    if (regular && !(y0ok || y1ok)) continue;        // the fill already wrote this row
     const int4 xi = *reinterpret_cast<const int4*>(cxi0 + xg);
-    // ix is monotone in x for x1 > x0: first column already right of the mask, or last one still left of it
-    const bool grp_out = (x1 > x0) && (xi.x >= M || xi.w <= -2);
-    uint8_t res[4] = {0, 0, 0, 0};
-    if (!((!(y0ok || y1ok) || grp_out) && 0.f < threshold)) {
-      const float4 w0 = *reinterpret_cast<const float4*>(cwx0 + xg);
-      const float4 w1 = *reinterpret_cast<const float4*>(cwx1 + xg);
-      const int xis[4] = {xi.x, xi.y, xi.z, xi.w};
-      const float w0s[4] = {w0.x, w0.y, w0.z, w0.w}, w1s[4] = {w1.x, w1.y, w1.z, w1.w};
+    const float4 w0 = *reinterpret_cast<const float4*>(cwx0 + xg);
+    const float4 w1 = *reinterpret_cast<const float4*>(cwx1 + xg);
+    const int xis[4] = {xi.x, xi.y, xi.z, xi.w};
+    const float w0s[4] = {w0.x, w0.y, w0.z, w0.w}, w1s[4] = {w1.x, w1.y, w1.z, w1.w};
+    uint8_t res[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int xi0 = xis[j], xi1 = xis[j] + 1;
-        const bool x0ok = xi0 >= 0 && xi0 < M, x1ok = xi1 >= 0 && xi1 < M;
-        float v = 0.f;
-        // ATen grid_sampler_2d bilinear: nw*(ix_se-ix)*(iy_se-iy) + ne*(ix-ix_sw)*(iy_sw-iy) + sw*... + se*...
-        if (y0ok && x0ok) v += sm[yi0 * M + xi0] * (w0s[j] * wy0);
-        if (y0ok && x1ok) v += sm[yi0 * M + xi1] * (w1s[j] * wy0);
-        if (y1ok && x0ok) v += sm[yi1 * M + xi0] * (w0s[j] * wy1);
-        if (y1ok && x1ok) v += sm[yi1 * M + xi1] * (w1s[j] * wy1);
-        // NaN (degenerate box: 0/0) compares false, as `img >= threshold` does in the reference
-        res[j] = (v >= threshold) ? 1 : 0;
-      }
+    for (int j = 0; j < 4; ++j) {
+      const int xi0 = xis[j], xi1 = xis[j] + 1;
+      const bool x0ok = xi0 >= 0 && xi0 < M, x1ok = xi1 >= 0 && xi1 < M;
+      float v = 0.f;
+      // ATen grid_sampler_2d bilinear: nw*(ix_se-ix)*(iy_se-iy) + ne*(ix-ix_sw)*(iy_sw-iy) + sw*... + se*...
+      if (y0ok && x0ok) v += sm[yi0 * M + xi0] * (w0s[j] * wy0);
+      if (y0ok && x1ok) v += sm[yi0 * M + xi1] * (w1s[j] * wy0);
+      if (y1ok && x0ok) v += sm[yi1 * M + xi0] * (w0s[j] * wy1);
+      if (y1ok && x1ok) v += sm[yi1 * M + xi1] * (w1s[j] * wy1);
+      // NaN (degenerate box: 0/0) compares false, as `img >= threshold` does in the reference
+      res[j] = (v >= threshold) ? 1 : 0;
     }
     uint8_t* o = out + (static_cast<size_t>(n) * H + y) * W + xg;
     if (xg + 4 <= W && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {

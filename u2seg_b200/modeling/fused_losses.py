@@ -215,7 +215,7 @@ class _MaskLossSelected(torch.autograd.Function):
         tg = target.reshape(R, P).to(torch.uint8).contiguous()
         okb = ok.to(torch.uint8).contiguous()
         g = torch.empty((R, P), dtype=torch.float32, device=x.device)
-        per = torch.empty((R,), dtype=torch.float32, device=x.device)
+        per = torch.empty((R, int(L.u2b_mask_loss_num_partials())), dtype=torch.float32, device=x.device)
         _lib.check(L.u2b_mask_loss_fwd(_CODE[x.dtype], _p(xr), _p(w), _p(b), _p(cls), _p(tg), _p(okb), R, P, C, _p(g), _p(per),
                                        _lib.stream_ptr()), "u2b_mask_loss_fwd")
         _lib.count_launches(1)

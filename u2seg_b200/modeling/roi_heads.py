@@ -136,6 +136,20 @@ class FastRCNNOutputLayers(nn.Module):
     def forward(self, x):
         if x.dim() > 2:
             x = torch.flatten(x, start_dim=1)
+        if x.is_cuda and torch.is_autocast_enabled("cuda") and x.shape[0] > 0:
+            from . import conv_tc, ops
+            dt = torch.get_autocast_dtype("cuda")
+            if ops.TCGEN05_CONV_POLICY == "all" and ops.USE_TCGEN05_CONV and conv_tc.USE_CONV2 and x.shape[1] % 128 == 0:
+                # fast_rcnn.py:236-239 as ONE tcgen05 GEMM: the (K+1)-way classifier and the box regressor share their
+                # input, so their filters are stacked and zero-padded to a multiple of 64 rows (801 + 4 -> 832); the library
+                # would run the 801-wide GEMM on its unaligned legacy path
+                nc, nb = self.cls_score.weight.shape[0], self.bbox_pred.weight.shape[0]
+                pad = (-(nc + nb)) % 64
+                w = torch.cat([self.cls_score.weight, self.bbox_pred.weight,
+                               self.cls_score.weight.new_zeros((pad, x.shape[1]))])
+                b = torch.cat([self.cls_score.bias, self.bbox_pred.bias, self.cls_score.bias.new_zeros((pad,))])
+                y = conv_tc.linear(x.to(dt), w, b, relu=False)
+                return y[:, :nc], y[:, nc:nc + nb]
         return self.cls_score(x), self.bbox_pred(x)
 
     def losses(self, predictions, proposals):

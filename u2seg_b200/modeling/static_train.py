@@ -37,6 +37,7 @@ _rand_keys = lambda mask: torch.rand(mask.shape, dtype=torch.float32, device=mas
 # per-image NMS with its single-CTA scan) next to the RPN losses, the mask branch next to cascade stages 0-2, the
 # semantic head next to everything. Most of these kernels fill a few SMs only.
 MULTI_STREAM = os.environ.get("U2B_MULTI_STREAM", "1") == "1"
+FORCE_SINGLE_STREAM = False    # bench.py's in-step kernel timing: one stream, so a kernel's events bracket that kernel alone
 _streams = {}
 
 
@@ -53,7 +54,7 @@ class _Fork:
     .join() makes the current stream wait for it. Tensors that cross are kept alive by the caller until the join."""
 
     def __init__(self, name, enabled=True):
-        self.enabled = enabled and MULTI_STREAM and torch.cuda.is_available()
+        self.enabled = enabled and MULTI_STREAM and not FORCE_SINGLE_STREAM and torch.cuda.is_available()
         self.name = name
 
     def __enter__(self):
@@ -371,7 +372,7 @@ def forward_train_static(model, images_u8, gt_boxes, gt_classes, gt_valid, gt_ma
         torch._foreach_add_(model._bn_counters, 1)
     features = model.backbone(x)
     sem_fork = _Fork("sem_seg_head", enabled=True)
-    sem_fork.enabled = torch.cuda.is_available()      # always forked (round-1 behaviour), also with U2B_MULTI_STREAM=0
+    sem_fork.enabled = torch.cuda.is_available() and not FORCE_SINGLE_STREAM   # forked also with U2B_MULTI_STREAM=0 (round 1)
     with sem_fork:
         _, sem_losses = model.sem_seg_head(features, sem_seg)
     flags = []
