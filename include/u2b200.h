@@ -58,6 +58,10 @@ int u2b_kmeans_assign(const void* x16, int64_t N, int64_t D, int64_t K, const vo
 
 /* thread-block cluster size of the E-step kernel (1, 2 or 4): centroid tiles are TMA-multicast across the cluster */
 int u2b_kmeans_set_cluster(int cluster);
+/* M-step implementation: 1 (default) = rows counting-sorted by label, then atomics-free segment sums (X read once, at
+ * whole-row granularity); 0 = round-1 shared-memory accumulators (fp32 shared atomics). Same results up to fp32
+ * summation order. */
+int u2b_kmeans_set_mstep(int sort_by_label);
 
 /* M-step part 1, nn_utils.py:359-363: sums[k, 0:D] = sum of rows with label k, sums[k, D] =
  * count (fp32). (K, D+1) fp32 — the buffer a row-sharded job all-reduces across ranks. */

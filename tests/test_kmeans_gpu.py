@@ -123,3 +123,29 @@ def test_full_size_properties():
     st.finalize(c)
     lab2 = st.assign(c).long()
     assert objective(c, lab2) <= before * (1 + 1e-6)
+
+
+@pytest.mark.parametrize("N,D,K", [(50000, 384, 800), (4097, 128, 37), (20000, 256, 300)])
+def test_mstep_sort_by_label_equals_shared_accumulators(N, D, K):
+    """The two M-step implementations (csrc/kmeans.cu: counting sort + segment sums vs shared-memory accumulators) agree:
+    counts exactly, sums to fp32 summation-order accuracy; also against a float64 scatter-add of the same fp16 data."""
+    from u2seg_b200 import _lib
+    from u2seg_b200.clustering import KMeansState
+    g = torch.Generator().manual_seed(N)
+    x16 = torch.randn(N, D, generator=g).half().cuda()
+    st = KMeansState(x16, K)
+    st.labels.copy_(torch.randint(0, K, (N,), generator=g).int().cuda())
+    st.labels[:100] = 3                                   # one long run + some empty clusters possible
+    outs = []
+    for mode in (1, 0):
+        _lib.check(_lib.lib().u2b_kmeans_set_mstep(mode), "u2b_kmeans_set_mstep")
+        try:
+            outs.append(st.accumulate().clone())
+        finally:
+            _lib.lib().u2b_kmeans_set_mstep(1)
+    a, b = outs
+    assert torch.equal(a[:, D], b[:, D])                  # counts
+    want = torch.zeros(K, D, dtype=torch.float64, device="cuda").index_add_(0, st.labels.long(), x16.double())
+    for got in (a, b):
+        assert float((got[:, :D].double() - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max()))
+    assert torch.equal(a[:, D].double(), torch.bincount(st.labels.long(), minlength=K).double())

@@ -27,6 +27,7 @@ SIGNATURES = {
     "u2b_kmeans_assign": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "u2b_kmeans_set_cluster": (c_int, [c_int]),
+    "u2b_kmeans_set_mstep": (c_int, [c_int]),
     "u2b_kmeans_accumulate": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                       c_size_t, c_void_p]),
     "u2b_kmeans_finalize": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),

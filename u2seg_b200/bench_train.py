@@ -232,6 +232,9 @@ def in_step_conv_roofline(trainer, batch, peaks, ms_step):
                                      "frac": tot_flop / (tot_ms * 1e-3) / 1e12 / peaks["tf_sus"],
                                      "share_of_step_time": tot_ms / ms_step,
                                      "share_of_step_flop": tot_flop / (FLOP_PER_IMAGE * IMS_PER_GPU)},
+            "groups": [{"kind": k[0], "shape_N_H_W_Cin_Cout_k_stride": list(k[1]), "launches": v[0], "ms": round(v[1], 4),
+                        "tflops": round(v[2] / (v[1] * 1e-3) / 1e12, 1)}
+                       for k, v in sorted(groups.items(), key=lambda kv: -kv[1][1])[:40]],
             "method": "CUDA events on the launching stream around each launch of one eager, single-stream execution of the "
                       "static step (the graph replays overlap independent branches on side streams, which would stretch "
                       "per-kernel durations)"}

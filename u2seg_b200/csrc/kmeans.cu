@@ -278,6 +278,7 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap tmap_x,
 }
 
 int g_kmeans_cluster = 2;
+int g_kmeans_mstep_sort = 1;   // 1: sort-by-label M-step (u2b_kmeans_set_mstep), 0: shared-memory accumulators
 
 template <int CL>
 int launch_assign(const CUtensorMap& tx, const CUtensorMap& tc, const float* cnorm, const float* xmax,
@@ -521,6 +522,150 @@ kmeans_accum_kernel(const __half* __restrict__ x, const int32_t* __restrict__ la
       out[static_cast<size_t>(i) * (D + 1) + D] = static_cast<float>(scnt[i]);
 }
 
+// ---- M-step, second generation: rows grouped by label (counting sort), then segment sums without shared atomics ----
+// fp32 atomicAdd on shared memory is a compare-and-swap loop (ATOMS.CAST.SPIN): the accumulator kernel above spends its
+// time there (28 % of the HBM roofline). Here the labels are counting-sorted into a row-index list (native integer
+// shared atomics only: ATOMS.POPC.INC / ATOMS.ADD), and every warp then walks 64 consecutive list entries - rows of at
+// most a few different labels, nondecreasing - summing whole 768-byte rows into registers (coalesced 8-byte loads, no
+// atomics) and flushing one partial per label run with global fp32 reductions (RED.ADD.F32, ~20k per iteration).
+// X is read exactly once, at gather granularity of a full row.
+constexpr int SORT_THREADS = 1024;
+
+__global__ void __launch_bounds__(SORT_THREADS)
+kmeans_label_count_kernel(const int32_t* __restrict__ labels, long long N, int K, int* __restrict__ count) {
+  extern __shared__ int sh[];
+  for (int i = threadIdx.x; i < K; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const long long per = (N + gridDim.x - 1) / gridDim.x;
+  const long long r0 = blockIdx.x * per, r1 = min(N, r0 + per);
+  for (long long i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+    const int l = labels[i];
+    if (l >= 0 && l < K) atomicAdd(&sh[l], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K; i += blockDim.x)
+    if (sh[i]) atomicAdd(&count[i], sh[i]);
+}
+
+// start[k] = exclusive prefix sum of count[]; cursor[k] = start[k]; sums[k][D] = count[k] (the count column)
+__global__ void __launch_bounds__(1024)
+kmeans_label_scan_kernel(const int* __restrict__ count, int K, int D, int* __restrict__ start, int* __restrict__ cursor,
+                         float* __restrict__ sums) {
+  __shared__ int sh[1024];
+  int carry = 0;
+  for (int base = 0; base < K; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < K ? count[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      const int t = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    const int incl = sh[threadIdx.x];
+    if (i < K) {
+      start[i] = carry + incl - v;
+      cursor[i] = carry + incl - v;
+      sums[static_cast<size_t>(i) * (D + 1) + D] = static_cast<float>(v);
+    }
+    const int total = sh[1023];
+    __syncthreads();
+    carry += total;
+  }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+kmeans_label_scatter_kernel(const int32_t* __restrict__ labels, long long N, int K, int* __restrict__ cursor,
+                            int32_t* __restrict__ sorted_rows, int32_t* __restrict__ sorted_labels) {
+  extern __shared__ int sh[];   // [K] counts of this chunk, then reused as this chunk's write cursors
+  for (int i = threadIdx.x; i < K; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const long long per = (N + gridDim.x - 1) / gridDim.x;
+  const long long r0 = blockIdx.x * per, r1 = min(N, r0 + per);
+  for (long long i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+    const int l = labels[i];
+    if (l >= 0 && l < K) atomicAdd(&sh[l], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const int c = sh[i];
+    sh[i] = c ? atomicAdd(&cursor[i], c) : 0;   // reserve this chunk's range of label i's segment
+  }
+  __syncthreads();
+  for (long long i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+    const int l = labels[i];
+    if (l >= 0 && l < K) {
+      const int pos = atomicAdd(&sh[l], 1);
+      sorted_rows[pos] = static_cast<int32_t>(i);
+      sorted_labels[pos] = l;
+    }
+  }
+}
+
+// one warp per run of SEG consecutive entries of the sorted list; NP = D / 128 eight-byte pieces per lane
+template <int NP>
+__global__ void __launch_bounds__(256)
+kmeans_gather_sum_kernel(const __half* __restrict__ x, const int32_t* __restrict__ sorted_rows,
+                         const int32_t* __restrict__ sorted_labels, const int* __restrict__ start,
+                         const int* __restrict__ count, int K, int D, float* __restrict__ sums) {
+  constexpr int SEG = 64;
+  const int lane = threadIdx.x & 31;
+  const long long M = static_cast<long long>(start[K - 1]) + count[K - 1];   // rows with a label in [0, K)
+  const long long w = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long e0 = w * SEG, e1 = min(M, e0 + SEG);
+  if (e0 >= M) return;
+  float acc[NP][4];
+#pragma unroll
+  for (int j = 0; j < NP; ++j)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[j][k] = 0.f;
+  int cur = sorted_labels[e0];
+  auto flush = [&](int label) {
+    float* dst = sums + static_cast<size_t>(label) * (D + 1);
+#pragma unroll
+    for (int j = 0; j < NP; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        atomicAdd(dst + j * 128 + lane * 4 + k, acc[j][k]);
+        acc[j][k] = 0.f;
+      }
+  };
+  for (long long e = e0; e < e1; e += 4) {
+    // 4 rows in flight per step: labels / row ids first (uniform across the warp), then the loads, then the adds
+    int lab[4];
+    long long row[4];
+    uint2 v[4][NP];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long ee = e + u < e1 ? e + u : e1 - 1;
+      lab[u] = sorted_labels[ee];
+      row[u] = sorted_rows[ee];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < NP; ++j)
+        v[u][j] = *reinterpret_cast<const uint2*>(x + row[u] * D + j * 128 + lane * 4);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (e + u >= e1) break;
+      if (lab[u] != cur) {
+        flush(cur);
+        cur = lab[u];
+      }
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v[u][j].x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v[u][j].y));
+        acc[j][0] += a.x; acc[j][1] += a.y; acc[j][2] += b.x; acc[j][3] += b.y;
+      }
+    }
+  }
+  flush(cur);
+}
+
 __global__ void kmeans_reduce_partials_kernel(const float* __restrict__ partial,
                                               float* __restrict__ sums, int R, long long KD1) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -668,6 +813,11 @@ int u2b_kmeans_set_cluster(int cluster) {
   return 0;
 }
 
+int u2b_kmeans_set_mstep(int sort_by_label) {
+  g_kmeans_mstep_sort = sort_by_label ? 1 : 0;
+  return 0;
+}
+
 int u2b_kmeans_accumulate(const void* x16, const int32_t* labels, int64_t N, int64_t D, int64_t K,
                           float* sums, void* workspace, size_t workspace_bytes,
                           cudaStream_t stream) {
@@ -677,6 +827,36 @@ int u2b_kmeans_accumulate(const void* x16, const int32_t* labels, int64_t N, int
     u2b_set_error("kmeans_accumulate: K=%lld D=%lld does not fit the shared-memory accumulators",
                   (long long)K, (long long)D);
     return U2B_ERR_UNSUPPORTED;
+  }
+  if (g_kmeans_mstep_sort && D % 128 == 0 && D <= 512 && N < (1LL << 31) && K <= 54000 &&
+      workspace_bytes >= static_cast<size_t>(N) * 8 + static_cast<size_t>(K) * 12 + 64) {
+    // sort-by-label M-step: workspace = sorted_rows[N] | sorted_labels[N] | count[K] | start[K] | cursor[K]
+    int32_t* sorted_rows = static_cast<int32_t*>(workspace);
+    int32_t* sorted_labels = sorted_rows + N;
+    int* count = reinterpret_cast<int*>(sorted_labels + N);
+    int* start = count + K;
+    int* cursor = start + K;
+    U2B_CUDA(cudaMemsetAsync(count, 0, static_cast<size_t>(K) * 4, stream));
+    U2B_CUDA(cudaMemsetAsync(sums, 0, static_cast<size_t>(K) * (D + 1) * 4, stream));
+    const int chunks = u2b_num_sms() * 2;
+    const size_t sh = static_cast<size_t>(K) * 4;
+    kmeans_label_count_kernel<<<chunks, SORT_THREADS, sh, stream>>>(labels, N, static_cast<int>(K), count);
+    U2B_LAUNCH_CHECK();
+    kmeans_label_scan_kernel<<<1, 1024, 0, stream>>>(count, static_cast<int>(K), static_cast<int>(D), start, cursor, sums);
+    U2B_LAUNCH_CHECK();
+    kmeans_label_scatter_kernel<<<chunks, SORT_THREADS, sh, stream>>>(labels, N, static_cast<int>(K), cursor, sorted_rows,
+                                                                     sorted_labels);
+    U2B_LAUNCH_CHECK();
+    // the list holds the rows with a label in [0, K) (all of them after u2b_kmeans_assign); its length is read on the device
+    const long long warps = (N + 63) / 64;
+    const unsigned grid = static_cast<unsigned>((warps + 7) / 8);
+    const __half* xh = static_cast<const __half*>(x16);
+    if (D == 128) kmeans_gather_sum_kernel<1><<<grid, 256, 0, stream>>>(xh, sorted_rows, sorted_labels, start, count, (int)K, (int)D, sums);
+    else if (D == 256) kmeans_gather_sum_kernel<2><<<grid, 256, 0, stream>>>(xh, sorted_rows, sorted_labels, start, count, (int)K, (int)D, sums);
+    else if (D == 384) kmeans_gather_sum_kernel<3><<<grid, 256, 0, stream>>>(xh, sorted_rows, sorted_labels, start, count, (int)K, (int)D, sums);
+    else kmeans_gather_sum_kernel<4><<<grid, 256, 0, stream>>>(xh, sorted_rows, sorted_labels, start, count, (int)K, (int)D, sums);
+    U2B_LAUNCH_CHECK();
+    return 0;
   }
   const size_t need = static_cast<size_t>(p.R) * K * (D + 1) * 4;
   U2B_CHECK_ARG(workspace_bytes >= need, "kmeans_accumulate: workspace too small");
