@@ -8,6 +8,7 @@ Workloads (BASELINE.json `metric`: "u2seg_R50_800 train images/sec ...; k-means 
           once the detector step is available in this build, else kmeans
   kmeans  Lloyd iterations, N=1.28M, D=384, K=800 (configs[3]); rows sharded over ranks
   infer   u2seg_R50_300 panoptic inference, synthetic 800x1333, batch 1 (configs[4])
+  knn     exact self-kNN (K=20) over the same 1.28M x 384 embeddings, explicit workload only
 
 One JSON line on rank 0. `value` = device-resident throughput (CUDA events, max over ranks);
 `e2e` = same metric through the public API with host buffers (H2D/D2H inside the timed region);
@@ -279,13 +280,90 @@ def run_kmeans(args, emit=True):
         os._exit(0)
 
 
+# --------------------------------------------------------------------------------------
+# B200 arm, kNN (nn_utils.py:203-299, the density-peak selection's neighbour search)
+# --------------------------------------------------------------------------------------
+def run_knn(args, emit=True):
+    import torch
+    from u2seg_b200 import _lib
+    from u2seg_b200.clustering import _knn_prepare, kNN
+
+    rank, world, local = dist_info()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    peaks = load_peaks()
+    N, D, K = KM_N, KM_D, 20
+    n_q = N // world                                       # query rows sharded over ranks; every rank holds the train set
+    g = torch.Generator(device=dev).manual_seed(1234)
+    centres = torch.randn(1000, D, generator=g, device=dev)
+    x = torch.empty((N, D), dtype=torch.float32, device=dev)
+    for s in range(0, N, 160000):
+        e = min(N, s + 160000)
+        which = torch.randint(0, 1000, (e - s,), generator=g, device=dev)
+        x[s:e] = torch.nn.functional.normalize(torch.randn(e - s, D, generator=g, device=dev) + centres[which], dim=1)
+    xq = x[rank * n_q:(rank + 1) * n_q]
+    kNN(x[:20000], x[:4096], K=K)                          # lazy initialisation (function attributes, allocator)
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ind, d, stats = kNN(x, xq, K=K, return_stats=True)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count - l0
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    # the candidate pass alone (dominant kernel), timed live on a 131,072-query chunk
+    y16, yn, _ = _knn_prepare(x)
+    nc = int(_lib.lib().u2b_knn_candidates_per_row())
+    n1 = 131072
+    cand = torch.empty((n1, nc), dtype=torch.int32, device=dev)
+    thr = torch.empty((n1, 2), dtype=torch.float32, device=dev)
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    _lib.check(_lib.lib().u2b_knn_candidates(_lib.ptr(y16), n1, _lib.ptr(y16), _lib.ptr(yn), N, D, _lib.ptr(cand), _lib.ptr(thr),
+                                             _lib.stream_ptr()), "u2b_knn_candidates")
+    eb.record()
+    torch.cuda.synchronize()
+    ms_c = ea.elapsed_time(eb)
+    flops = 2.0 * n1 * N * D
+    ach = flops / (ms_c * 1e-3) / 1e12
+    line = {"metric": "knn_queries_per_sec", "value": n_q * world / (ms * 1e-3), "unit": "queries/s", "n_gpus": world,
+            "steps": 1, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f16 candidate pass (f32 accumulate) + f32 exact pass", "data": "synthetic",
+            "config": {"workload": "exact self-kNN, K=20, N=1.28M L2-normalised embeddings, D=384 (nn_utils.partitioned_kNN), "
+                                   "query rows sharded over ranks", "N": N, "D": D, "K": K,
+                       "uncertified_rows_recomputed": stats["uncertified_rows"],
+                       "l2_note": "train set (983 MB fp16 + 1.97 GB fp32) exceeds the 126 MB L2"},
+            "clocks": clocks, "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "knn_candidates_kernel (tcgen05, 131072 queries x 1.28M train rows)",
+                         "achieved": ach, "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sus"],
+                         "peak_source": peaks["src"] + " bf16 sustained", "traffic": None,
+                         "algorithmic_flops_per_launch": flops, "ms_per_launch": ms_c},
+            "e2e": {"value": n_q * world / (ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0, "what": "device-resident embeddings in, device-resident (ind, dist) out"}}
+    del x, y16, cand
+    torch.cuda.empty_cache()
+    if not emit:
+        return line
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=None, choices=["train", "kmeans", "infer"])
+    ap.add_argument("--workload", default=None, choices=["train", "kmeans", "infer", "knn"])
     args = ap.parse_args()
     if args.workload is None:
         args.workload = "train" if os.path.exists(os.path.join(ROOT, "u2seg_b200", "bench_train.py")) else "kmeans"
@@ -293,6 +371,8 @@ def main():
         return run_reference(args)
     if args.workload == "kmeans":
         return run_kmeans(args)
+    if args.workload == "knn":
+        return run_knn(args)
     if args.workload == "infer":
         from u2seg_b200.bench_infer import run_infer
         return run_infer(args, ClockSampler, load_peaks, dist_info)

@@ -73,6 +73,23 @@ int u2b_kmeans_accumulate(const void* x16, const int32_t* labels, int64_t N, int
 int u2b_kmeans_finalize(const float* sums, int64_t K, int64_t D, float* c32, u2b_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Exact k-nearest neighbours (squared L2) - u2seg/Instance_Clustering/shared/utils/nn_utils.py:203-224 kNN()
+ * (KeOps Kmin_argKmin over ((x_i - y_j)^2).sum(-1)) and :227-299 partitioned_kNN(). csrc/knn.cu.
+ * Candidate pass on tcgen05 (fp16 operands, fp32 accumulate) keeping 48 candidates per query, then an exact fp32 pass
+ * that returns the K smallest distances (ascending; ties: lower index) and certifies them against the rounding bound
+ * `eps` of the candidate pass; rows that cannot be certified are listed in `flagged` for exhaustive recomputation.
+ * x16 / y16: fp16 rows, ynorm = |y|^2 (+inf beyond N2): u2b_kmeans_prepare() produces them (kpad = u2b_knn_npad).
+ * ------------------------------------------------------------------------------------------ */
+int u2b_knn_candidates_per_row(void);
+int64_t u2b_knn_npad(int64_t N2);
+int u2b_knn_set_cluster(int cluster);
+int u2b_knn_candidates(const void* x16, int64_t N1, const void* y16, const float* ynorm, int64_t N2, int64_t D,
+                       int32_t* cand_idx, float* cand_thr, u2b_stream_t stream);
+int u2b_knn_refine(const float* x, const float* y, const int32_t* cand_idx, const float* cand_thr, const float* xnorm,
+                   int64_t N1, int64_t D, int K, float eps, float* d_out, int64_t* i_out, int32_t* flagged,
+                   int32_t* n_flagged, u2b_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Detector ops. Feature maps are NHWC ("channels_last"); dtype codes: 0 = fp32, 1 = fp16, 2 = bf16.
  * rois5: (K, 5) fp32 rows (batch_index, x0, y0, x1, y1) — detectron2/modeling/poolers.py:72-98.
  * ------------------------------------------------------------------------------------------ */
@@ -277,6 +294,14 @@ int u2b_bn_apply(int dtype, const void* x, const float* stats, const void* resid
  * folded into the lateral conv's SyncBN pass. x, y (N,H,W,C); residual (N,H/2,W/2,C); H, W even. */
 int u2b_bn_apply_resup(int dtype, const void* x, const float* stats, const void* residual, int relu, void* y, int N, int H,
                        int W, int C, u2b_stream_t stream);
+
+/* Backward of y = relu(bn(x)) WITHOUT residual, ReLU mask recomputed from x (y is not read: one tensor read less in each
+ * of the two passes): dz = dy * (stored(x * scale + shift) > 0) with scale / shift = stats[2C:4C] and `stored` = rounding
+ * to the activation dtype, i.e. exactly the mask y > 0. Otherwise as u2b_bn_bwd_reduce / u2b_bn_bwd_apply. */
+int u2b_bn_bwd_reduce_relu_x(int dtype, const void* dy, const void* x, const float* stats, int64_t P, int C,
+                             float* partials, u2b_stream_t stream);
+int u2b_bn_bwd_apply_relu_x(int dtype, const void* dy, const void* x, const float* stats, const float* coeff, void* dx,
+                            int64_t P, int C, u2b_stream_t stream);
 
 /* partials[s] = (sum dz | sum dz*xhat), dz = dy * (y > 0) when y != NULL (fused ReLU backward) */
 int u2b_bn_bwd_reduce(int dtype, const void* dy, const void* x, const void* y, const float* stats, int64_t P, int C,

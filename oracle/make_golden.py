@@ -48,6 +48,28 @@ def _kmeans_child():
         print("wrote", name)
 
 
+def _knn_child():
+    """Runs inside selective_labeling/ (like _kmeans_child): the unmodified nn_utils.kNN through the dense pykeops stub."""
+    sys.path.insert(0, STUBS)
+    sys.path.insert(0, ".")
+    import utils
+    from oracle.kmeans_oracle import make_mixture
+    cases = [("knn_n3000_d128_k20", 3000, 1200, 128, 20, 7), ("knn_self_n2500_d384_k20", 2500, 2500, 384, 20, 8)]
+    for name, n_train, n_test, D, K, seed in cases:
+        xt = make_mixture(n_train, D, 60, seed=seed, spread=1.0).float()
+        xq = xt if n_test == n_train else make_mixture(n_test, D, 60, seed=seed + 100, spread=1.0).float()
+        ind, d = utils.kNN(xt, xq, K=K)          # (ind_knn, d_knn): nn_utils.py:224 returns (d_knn, ind_knn) from KeOps swapped
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), ind=ind.numpy().astype(np.int64), dist=d.numpy(),
+                            meta=np.array([n_train, n_test, D, K, seed], dtype=np.int64))
+        print("wrote", name, tuple(ind.shape), float(d[:, 0].max()))
+
+
+def gen_knn():
+    env = dict(os.environ, USL_MODE="USL", PYTHONPATH=ROOT)
+    cwd = os.path.join(REF, "u2seg", "Instance_Clustering", "selective_labeling")
+    subprocess.check_call([sys.executable, os.path.abspath(__file__), "_knn_child"], cwd=cwd, env=env)
+
+
 def gen_kmeans():
     env = dict(os.environ, USL_MODE="USL", PYTHONPATH=ROOT)
     cwd = os.path.join(REF, "u2seg", "Instance_Clustering", "selective_labeling")
@@ -60,8 +82,13 @@ if __name__ == "__main__":
     if "_kmeans_child" in what:
         _kmeans_child()
         sys.exit(0)
+    if "_knn_child" in what:
+        _knn_child()
+        sys.exit(0)
     if "kmeans" in what:
         gen_kmeans()
+    if "knn" in what:
+        gen_knn()
     if {"ops", "model", "baseline", "baseline64"} & set(what):
         sys.path.insert(0, STUBS)
         sys.path.insert(0, REF)

@@ -28,6 +28,12 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "u2b_kmeans_set_cluster": (c_int, [c_int]),
     "u2b_kmeans_set_mstep": (c_int, [c_int]),
+    "u2b_knn_candidates_per_row": (c_int, []),
+    "u2b_knn_npad": (c_int64, [c_int64]),
+    "u2b_knn_set_cluster": (c_int, [c_int]),
+    "u2b_knn_candidates": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "u2b_knn_refine": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p]),
     "u2b_kmeans_accumulate": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                       c_size_t, c_void_p]),
     "u2b_kmeans_finalize": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
@@ -116,6 +122,8 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_int, c_void_p]),
     "u2b_bn_apply": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p]),
     "u2b_bn_bwd_reduce": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "u2b_bn_bwd_reduce_relu_x": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "u2b_bn_bwd_apply_relu_x": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "u2b_bn_bwd_coeff": (c_int, [c_void_p, c_int, ctypes.c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p]),
     "u2b_bn_xchg_buffer_bytes": (c_size_t, [c_int, c_int]),

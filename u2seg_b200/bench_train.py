@@ -194,14 +194,31 @@ def in_step_conv_roofline(trainer, batch, peaks, ms_step):
     trainer._load_static_inputs(batch)
     torch.cuda.synchronize()
     from .modeling import static_train
-    conv_tc.TIMING = []
     static_train.FORCE_SINGLE_STREAM = True     # no concurrent branch kernels: the events bracket each kernel alone
+    how = "graph"
     try:
-        trainer._static_step()
-        torch.cuda.synchronize()
-        recs = conv_tc.TIMING
+        try:
+            # the step captured ONCE MORE as a single-stream CUDA graph whose tcgen05 launches are bracketed by external
+            # event-record nodes: replayed, the events time each kernel on the device with no host launch gap in between
+            conv_tc.TIMING, conv_tc.TIMING_EXTERNAL = [], True
+            mg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(mg):
+                trainer._static_step()
+            recs = conv_tc.TIMING
+            conv_tc.TIMING = None
+            for _ in range(2):
+                mg.replay()
+            torch.cuda.synchronize()
+            _ = recs[0][3].elapsed_time(recs[0][4])
+        except Exception as e:      # external events unavailable: eager step behind a long device-side sleep
+            how = "eager (%s)" % type(e).__name__
+            conv_tc.TIMING, conv_tc.TIMING_EXTERNAL = [], False
+            torch.cuda._sleep(int(2e8))
+            trainer._static_step()
+            torch.cuda.synchronize()
+            recs = conv_tc.TIMING
     finally:
-        conv_tc.TIMING = None
+        conv_tc.TIMING, conv_tc.TIMING_EXTERNAL = None, False
         static_train.FORCE_SINGLE_STREAM = False
     trainer._restore_training_state(snap)
     groups = {}
@@ -235,9 +252,10 @@ def in_step_conv_roofline(trainer, batch, peaks, ms_step):
             "groups": [{"kind": k[0], "shape_N_H_W_Cin_Cout_k_stride": list(k[1]), "launches": v[0], "ms": round(v[1], 4),
                         "tflops": round(v[2] / (v[1] * 1e-3) / 1e12, 1)}
                        for k, v in sorted(groups.items(), key=lambda kv: -kv[1][1])[:40]],
-            "method": "CUDA events on the launching stream around each launch of one eager, single-stream execution of the "
-                      "static step (the graph replays overlap independent branches on side streams, which would stretch "
-                      "per-kernel durations)"}
+            "method": "CUDA events on the launching stream around each tcgen05 launch of a single-stream execution of the "
+                      "static step (%s): the production graph overlaps independent branches on side streams, which would "
+                      "stretch per-kernel durations" % ("captured as a second CUDA graph with external event-record nodes, "
+                      "replayed" if how == "graph" else how)}
 
 
 def conv_tc_roofline(peaks):

@@ -171,3 +171,114 @@ def run_kMeans(feats_list, num_centroids, final_sample_num=None, train_memory_da
                 cluster_labels.numpy())
         np.save(os.path.join(save_dir, "centroids_{}{}.npy".format(final_sample_num, sfx)), centroids.numpy())
     return cluster_labels, centroids
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# k-nearest neighbours (nn_utils.py:203-299): exact, tensor-core candidate pass + fp32 certification (csrc/knn.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+def _knn_prepare(x32):
+    """fp32 (N, D) CUDA rows -> (fp16 rows padded to the train-tile multiple, |x|^2 fp32 (+inf in the padding), max |x|^2)."""
+    import ctypes
+    L = _lib.lib()
+    N, D = x32.shape
+    npad = int(L.u2b_knn_npad(N))
+    x16 = torch.empty((npad, D), dtype=torch.float16, device=x32.device)
+    xn = torch.empty((npad,), dtype=torch.float32, device=x32.device)
+    xmax2 = torch.zeros((1,), dtype=torch.float32, device=x32.device)
+    # u2b_kmeans_prepare pads to ITS tile multiple (same 160-row tile as the kNN kernel): kpad == npad
+    assert int(L.u2b_kmeans_kpad(N)) == npad
+    _lib.check(L.u2b_kmeans_prepare(_lib.ptr(x32), N, D, _lib.ptr(x16), _lib.ptr(xn), _lib.ptr(xmax2), _lib.stream_ptr()),
+               "u2b_kmeans_prepare")
+    _lib.count_launches(1)
+    return x16, xn, xmax2
+
+
+def _knn_exhaustive(xq, y, K, chunk=65536):
+    """exact fp32 kNN of a FEW query rows by the reference's dense formula (rows the fast path could not certify)."""
+    best_d = torch.full((xq.shape[0], K), float("inf"), device=xq.device)
+    best_i = torch.zeros((xq.shape[0], K), dtype=torch.int64, device=xq.device)
+    for s in range(0, y.shape[0], chunk):
+        d = ((xq[:, None, :] - y[None, s:s + chunk, :]) ** 2).sum(-1)
+        dd = torch.cat([best_d, d], 1)
+        ii = torch.cat([best_i, torch.arange(s, s + d.shape[1], device=xq.device).expand(xq.shape[0], -1)], 1)
+        # stable sort by (distance, index): indices ascend within each block and blocks arrive in order
+        vals, order = torch.sort(dd, dim=1, stable=True)
+        best_d, best_i = vals[:, :K], torch.gather(ii, 1, order[:, :K])
+    return best_d, best_i
+
+
+def kNN(x_train, x_test, K=20, query_chunk=262144, return_stats=False):
+    """nn_utils.py:203-224: (ind_knn int64 (N_test, K), d_knn fp32 (N_test, K)) = the K smallest squared L2 distances of
+    every test row to the train rows, ascending, with the train indices. Exact fp32 results (sum_d (x-y)^2 evaluated in
+    fp32 for the returned pairs); equal distances are ordered by index. x_*: (N, D) float tensors, D in {128, 256, 384}."""
+    import ctypes
+    L = _lib.lib()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    y = x_train.to(dev, torch.float32).contiguous()
+    xt = x_test.to(dev, torch.float32).contiguous()
+    assert y.dim() == 2 and xt.dim() == 2 and y.shape[1] == xt.shape[1]
+    N2, D = y.shape
+    assert N2 >= K, "kNN: fewer train rows than K"
+    y16, yn, ymax2 = _knn_prepare(y)
+    same = x_train is x_test or (xt.data_ptr() == y.data_ptr() and xt.shape == y.shape)
+    NC = int(L.u2b_knn_candidates_per_row())
+    ind = torch.empty((xt.shape[0], K), dtype=torch.int64, device=dev)
+    dist = torch.empty((xt.shape[0], K), dtype=torch.float32, device=dev)
+    n_flag_total = 0
+    for s in range(0, xt.shape[0], query_chunk):
+        xq = xt[s:s + query_chunk]
+        n1 = xq.shape[0]
+        if same:
+            x16, xn, xmax2 = y16[s:s + n1], yn[s:s + n1], ymax2
+        else:
+            x16, xn, xmax2 = _knn_prepare(xq)
+        cand = torch.empty((n1, NC), dtype=torch.int32, device=dev)
+        thr = torch.empty((n1, 2), dtype=torch.float32, device=dev)
+        _lib.check(L.u2b_knn_candidates(_lib.ptr(x16), n1, _lib.ptr(y16), _lib.ptr(yn), N2, D, _lib.ptr(cand), _lib.ptr(thr),
+                                        _lib.stream_ptr()), "u2b_knn_candidates")
+        # rounding bound of the fp16 candidate pass: 2 |x.y - x16.y16| <= 2^-9 |x| |y| (+ fp32 accumulation), with margin
+        eps = 1.25 * 2.0 ** -9 * float(torch.sqrt(xmax2 * ymax2))
+        flagged = torch.empty((n1,), dtype=torch.int32, device=dev)
+        nflag = torch.zeros((1,), dtype=torch.int32, device=dev)
+        _lib.check(L.u2b_knn_refine(_lib.ptr(xq), _lib.ptr(y), _lib.ptr(cand), _lib.ptr(thr), _lib.ptr(xn), n1, D, int(K),
+                                    ctypes.c_float(eps), _lib.ptr(dist[s:s + n1]), _lib.ptr(ind[s:s + n1]), _lib.ptr(flagged),
+                                    _lib.ptr(nflag), _lib.stream_ptr()), "u2b_knn_refine")
+        _lib.count_launches(2)
+        nf = int(nflag)
+        if nf:        # not certifiable from 48 candidates (dense ties around the K-th neighbour): exhaustive, exact
+            rows = flagged[:nf].long()
+            for b in range(0, nf, 512):
+                rr = rows[b:b + 512]
+                d_e, i_e = _knn_exhaustive(xq[rr], y, K)
+                dist[s + rr] = d_e
+                ind[s + rr] = i_e
+            n_flag_total += nf
+    if return_stats:
+        return ind, dist, {"uncertified_rows": n_flag_total}
+    return ind, dist
+
+
+def partitioned_kNN(feats_list, K=20, recompute=True, partitions_size=130000, verify=False, save_dir=None):
+    """nn_utils.py:227-299: self-kNN of `feats_list` -> (d_knns (N,K) fp32, ind_knns (N,K) int64). The reference
+    partitions train and test rows to bound KeOps' memory and merges the per-partition lists; the kernel here streams
+    the whole train set past every query tile, so partitions_size only bounds the per-launch query chunk. With
+    recompute=False the saved .npy files are loaded, as in the reference."""
+    import os
+
+    import numpy as np
+    suffix = "" if K == 20 else "_{}".format(K)
+    if not recompute:
+        assert save_dir is not None, "recompute=False needs save_dir (where d_knns / ind_knns .npy live)"
+        return (torch.tensor(np.load(os.path.join(save_dir, "d_knns{}.npy".format(suffix)))),
+                torch.tensor(np.load(os.path.join(save_dir, "ind_knns{}.npy".format(suffix)))))
+    ind, d = kNN(feats_list, feats_list, K=K, query_chunk=max(int(partitions_size), 1024))
+    if verify:        # the reference's own check: distances of the selected neighbours are the true ones
+        g = torch.Generator().manual_seed(0)
+        rows = torch.randperm(feats_list.shape[0], generator=g)[:256].to(ind.device)
+        d_e, _ = _knn_exhaustive(feats_list.to(ind.device, torch.float32)[rows], feats_list.to(ind.device, torch.float32), K)
+        assert torch.allclose(d[rows], d_e, rtol=1e-5, atol=1e-6)
+    d, ind = d.cpu(), ind.cpu()
+    if save_dir is not None:
+        np.save(os.path.join(save_dir, "d_knns{}.npy".format(suffix)), d.numpy())
+        np.save(os.path.join(save_dir, "ind_knns{}.npy".format(suffix)), ind.numpy())
+    return d, ind

@@ -104,6 +104,16 @@ struct V8<__nv_bfloat16> {
   }
 };
 
+// x * scale + shift as the forward pass STORED it (rounded to T): the ReLU mask y > 0 recomputed without reading y
+template <typename T>
+__device__ __forceinline__ float as_stored(float z);
+template <>
+__device__ __forceinline__ float as_stored<float>(float z) { return z; }
+template <>
+__device__ __forceinline__ float as_stored<__half>(float z) { return __half2float(__float2half_rn(z)); }
+template <>
+__device__ __forceinline__ float as_stored<__nv_bfloat16>(float z) { return __bfloat162float(__float2bfloat16_rn(z)); }
+
 constexpr int BN_THREADS = 256;
 #ifndef BN_STRIPS_PER_SM
 #define BN_STRIPS_PER_SM 4
@@ -127,7 +137,7 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(BN_THREADS, (MODE == 0 ? 4 : 2))
 bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ x, const T* __restrict__ y,
                  const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int C,
-                 int vpb, float* __restrict__ partials) {
+                 int vpb, float* __restrict__ partials, const float* __restrict__ relu_scale_shift = nullptr) {
   __shared__ float red[BN_THREADS * 16];
   const int lanes = BN_THREADS / vpb;
   const int tv = threadIdx.x % vpb, tp = threadIdx.x / vpb;
@@ -137,11 +147,14 @@ bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ x, const T* __re
   float s0[8], s1[8], m[8], is[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s0[i] = s1[i] = 0.f;
+  float rsc[8], rsh[8];   // relu_scale_shift != NULL: mask = (stored(x * scale + shift) > 0), y is not read
   if (MODE == 1 && active) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       m[i] = mean[c0 + i];
       is[i] = invstd[c0 + i];
+      rsc[i] = relu_scale_shift ? relu_scale_shift[c0 + i] : 0.f;
+      rsh[i] = relu_scale_shift ? relu_scale_shift[C + c0 + i] : 0.f;
     }
   }
   const long long strip = (P + gridDim.x - 1) / gridDim.x;
@@ -184,6 +197,9 @@ bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ x, const T* __re
             V8<T>::unpack(ry[u], vy);
 #pragma unroll
             for (int i = 0; i < 8; ++i) va[i] = vy[i] > 0.f ? va[i] : 0.f;
+          } else if (relu_scale_shift) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) va[i] = as_stored<T>(fmaf(vx[i], rsc[i], rsh[i])) > 0.f ? va[i] : 0.f;
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -443,16 +459,18 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                     const float* __restrict__ coeff, T* __restrict__ dx, T* __restrict__ dres,
-                    long long total_vec, int C) {
+                    long long total_vec, int C, const float* __restrict__ relu_scale_shift = nullptr) {
   const int vecs = C / 8;
   const long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int c0 = static_cast<int>(i0 % vecs) * 8;
-  float A[8], B[8], K[8];
+  float A[8], B[8], K[8], rsc[8], rsh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     A[k] = coeff[c0 + k];
     B[k] = coeff[C + c0 + k];
     K[k] = coeff[2 * C + c0 + k];
+    rsc[k] = relu_scale_shift ? relu_scale_shift[c0 + k] : 0.f;
+    rsh[k] = relu_scale_shift ? relu_scale_shift[C + c0 + k] : 0.f;
   }
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = i0; i < total_vec; i += stride) {
@@ -464,6 +482,9 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
       V8<T>::load(y + i * 8, vy);
 #pragma unroll
       for (int k = 0; k < 8; ++k) g[k] = vy[k] > 0.f ? g[k] : 0.f;
+    } else if (relu_scale_shift) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = as_stored<T>(fmaf(vx[k], rsc[k], rsh[k])) > 0.f ? g[k] : 0.f;
     }
     if (dres) V8<T>::store(dres + i * 8, g);
     float o[8];
@@ -586,11 +607,11 @@ bn_xchg_bwd_coeff_kernel(const float* __restrict__ sums, const unsigned long lon
 
 template <typename T, int MODE>
 int launch_reduce(const void* a, const void* x, const void* y, const float* mean, const float* invstd,
-                  long long P, int C, float* partials, cudaStream_t stream) {
+                  long long P, int C, float* partials, cudaStream_t stream, const float* relu_scale_shift = nullptr) {
   dim3 grid(num_strips(P, C), channel_groups(C));
   bn_reduce_kernel<T, MODE><<<grid, BN_THREADS, 0, stream>>>(static_cast<const T*>(a), static_cast<const T*>(x),
                                                              static_cast<const T*>(y), mean, invstd, P, C,
-                                                             vecs_per_block(C), partials);
+                                                             vecs_per_block(C), partials, relu_scale_shift);
   U2B_LAUNCH_CHECK();
   return 0;
 }
@@ -681,6 +702,16 @@ int u2b_bn_bwd_reduce(int dtype, const void* dy, const void* x, const void* y, c
                   return (launch_reduce<__nv_bfloat16, 1>(dy, x, y, stats, stats + C, P, C, partials, stream)))
 }
 
+// same with the ReLU mask recomputed from x: dz = dy * (stored(x * scale + shift) > 0), scale / shift = stats[2C:4C]. Valid
+// when the forward was y = relu(bn(x)) WITHOUT a residual; saves the read of y (one of three tensors).
+int u2b_bn_bwd_reduce_relu_x(int dtype, const void* dy, const void* x, const float* stats, int64_t P, int C,
+                             float* partials, cudaStream_t stream) {
+  U2B_CHECK_ARG(dy && x && stats && partials && P > 0 && u2b_bn_supported(C), "bn_bwd_reduce_relu_x: bad arguments");
+  U2B_BN_DISPATCH(return (launch_reduce<float, 1>(dy, x, nullptr, stats, stats + C, P, C, partials, stream, stats + 2 * C)),
+                  return (launch_reduce<__half, 1>(dy, x, nullptr, stats, stats + C, P, C, partials, stream, stats + 2 * C)),
+                  return (launch_reduce<__nv_bfloat16, 1>(dy, x, nullptr, stats, stats + C, P, C, partials, stream, stats + 2 * C)))
+}
+
 // coefficients of dx = A*dz + B*x + K from S partial rows (S = 1: all-reduced sums); gw_gb (2C, nullable) receives
 // dgamma | dbeta = the sums themselves (meaningful when the rows are this rank's local sums)
 int u2b_bn_bwd_coeff(const float* partials, int S, double n_total, const float* stats, const float* w, float* coeff,
@@ -757,6 +788,21 @@ int u2b_bn_bwd_apply(int dtype, const void* dy, const void* x, const void* y, co
       (bn_bwd_apply_kernel<float><<<ew_grid(tv), 256, 0, stream>>>((const float*)dy, (const float*)x, (const float*)y, coeff, (float*)dx, (float*)dres, tv, C)),
       (bn_bwd_apply_kernel<__half><<<ew_grid(tv), 256, 0, stream>>>((const __half*)dy, (const __half*)x, (const __half*)y, coeff, (__half*)dx, (__half*)dres, tv, C)),
       (bn_bwd_apply_kernel<__nv_bfloat16><<<ew_grid(tv), 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, coeff, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, tv, C)))
+  U2B_LAUNCH_CHECK();
+  return 0;
+}
+
+// dx = A*dz + B*x + K with dz = dy * (stored(x * scale + shift) > 0): the companion of u2b_bn_bwd_reduce_relu_x
+int u2b_bn_bwd_apply_relu_x(int dtype, const void* dy, const void* x, const float* stats, const float* coeff, void* dx,
+                            int64_t P, int C, cudaStream_t stream) {
+  if (P == 0) return 0;
+  U2B_CHECK_ARG(dy && x && dx && coeff && stats && u2b_bn_supported(C), "bn_bwd_apply_relu_x: bad arguments");
+  const long long tv = static_cast<long long>(P) * C / 8;
+  const float* rs = stats + 2 * C;
+  U2B_BN_DISPATCH(
+      (bn_bwd_apply_kernel<float><<<ew_grid(tv), 256, 0, stream>>>((const float*)dy, (const float*)x, nullptr, coeff, (float*)dx, nullptr, tv, C, rs)),
+      (bn_bwd_apply_kernel<__half><<<ew_grid(tv), 256, 0, stream>>>((const __half*)dy, (const __half*)x, nullptr, coeff, (__half*)dx, nullptr, tv, C, rs)),
+      (bn_bwd_apply_kernel<__nv_bfloat16><<<ew_grid(tv), 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, nullptr, coeff, (__nv_bfloat16*)dx, nullptr, tv, C, rs)))
   U2B_LAUNCH_CHECK();
   return 0;
 }

@@ -31,13 +31,15 @@ def conv2d_nhwc(x, w_ohwi, stride, pad, bias=None, residual=None, relu=False):
 # bench.py's in-step roofline: when TIMING is a list, every tcgen05 launch below is bracketed by CUDA events on the
 # launching stream and recorded as (kind, shape key, flop, start event, end event)
 TIMING = None
+TIMING_EXTERNAL = False    # True while the measurement step is being captured into a CUDA graph (event record NODES)
 
 
 class _Timed:
     def __init__(self, kind, key, flop):
         self.on = TIMING is not None
         if self.on:
-            self.rec = (kind, key, float(flop), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.rec = (kind, key, float(flop), torch.cuda.Event(enable_timing=True, external=TIMING_EXTERNAL),
+                        torch.cuda.Event(enable_timing=True, external=TIMING_EXTERNAL))
 
     def __enter__(self):
         if self.on:
@@ -131,9 +133,20 @@ USE_WGRAD2 = __import__("os").environ.get("U2B_WGRAD2", "1") == "1"   # 2-CTA tc
 _OUT_CODE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 
 
-def wgrad2_supported(x, Cout, R, S, stride, pad):
-    return (USE_WGRAD2 and x.is_cuda and x.dtype in _CODE
-            and bool(_lib.lib().u2b_conv_wgrad2_supported(int(x.shape[1]), int(Cout), R, S, stride, pad)))
+# The 2-CTA weight-gradient kernel wins where the GEMM-K (pixel) axis is long: 1.17x the library on the 154.6 GFLOP FPN /
+# RPN layers, about level at 40-80 GFLOP, behind it on the small late-stage layers whose K is a few thousand pixels (two
+# launches and a split-K partial round trip against ~15 us of work). Below this size the library kernel is used.
+WGRAD2_MIN_GFLOP = float(__import__("os").environ.get("U2B_WGRAD2_MIN_GF", "35"))
+
+
+def wgrad2_supported(x, Cout, R, S, stride, pad, gy_hw=None):
+    if not (USE_WGRAD2 and x.is_cuda and x.dtype in _CODE
+            and bool(_lib.lib().u2b_conv_wgrad2_supported(int(x.shape[1]), int(Cout), R, S, stride, pad))):
+        return False
+    if gy_hw is not None:
+        gf = 2.0 * x.shape[0] * gy_hw[0] * gy_hw[1] * Cout * x.shape[1] * R * S / 1e9
+        return gf >= WGRAD2_MIN_GFLOP
+    return True
 
 
 def conv_wgrad2(x, gy, R, S, stride, pad, out_dtype=torch.float32):
@@ -218,7 +231,7 @@ class _ConvTC(torch.autograd.Function):
                     weight.detach().to(dt).permute(1, 2, 3, 0).contiguous()           # (Cin,R,S,Cout)
                 gx = _conv_fwd(gy, wt, 1, R - 1 - pad, None, False)
         need_gx_lib = ctx.needs_input_grad[0] and gx is None
-        if ctx.needs_input_grad[1] and wgrad2_supported(xc, weight.shape[0], R, weight.shape[3], stride, pad):
+        if ctx.needs_input_grad[1] and wgrad2_supported(xc, weight.shape[0], R, weight.shape[3], stride, pad, gy.shape[2:]):
             gw = conv_wgrad2(xc, gy, R, weight.shape[3], stride, pad, weight.dtype)
         elif TC_WGRAD and ctx.needs_input_grad[1] and wgrad_supported(xc, weight, stride, pad):
             gw = conv2d_nhwc_wgrad(xc, gy, weight.shape[2], weight.shape[3], stride, pad).to(weight.dtype)   # 1-CTA draft
@@ -352,7 +365,7 @@ class _LinearTC(torch.autograd.Function):
             gx = g.permute(0, 2, 3, 1).reshape(M, K)
         if ctx.needs_input_grad[1]:
             x4 = x2.view(1, 1, M, K).permute(0, 3, 1, 2)
-            if wgrad2_supported(x4, Nout, 1, 1, 1, 0):       # dW = dY^T X with the rows as the GEMM-K (pixel) axis
+            if wgrad2_supported(x4, Nout, 1, 1, 1, 0, (1, M)):   # dW = dY^T X with the rows as the GEMM-K (pixel) axis
                 gw = conv_wgrad2(x4, gy.view(1, 1, M, Nout).permute(0, 3, 1, 2), 1, 1, 1, 0, weight.dtype).reshape(Nout, K)
             else:
                 gw = torch.mm(gy.t(), x2).to(weight.dtype)
@@ -399,7 +412,7 @@ class _Deconv2x2(torch.autograd.Function):
             w = weight.detach().to(dt).permute(0, 2, 3, 1).contiguous()         # OHWI filter of the 2x2 / s2 conv: (Cin,2,2,Cout)
             gx = conv2_nhwc(gy, w, 2, 0, None, False)
         if ctx.needs_input_grad[1]:
-            if wgrad2_supported(gy, weight.shape[0], 2, 2, 2, 0):
+            if wgrad2_supported(gy, weight.shape[0], 2, 2, 2, 0, xc.shape[2:]):
                 gw = conv_wgrad2(gy, xc, 2, 2, 2, 0, weight.dtype)               # logical (Cin, Cout, 2, 2), channels_last storage
             else:
                 gw = torch.ops.aten.convolution_backward(gy, xc, weight.detach().to(dt), None, [2, 2], [0, 0], [1, 1], True,

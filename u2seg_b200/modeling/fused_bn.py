@@ -143,8 +143,11 @@ class _BNAct(torch.autograd.Function):
         else:
             _lib.check(L.u2b_bn_apply(dt, _p(xc), _p(stats), _p(res), int(relu), _p(y), P, C, s), "u2b_bn_apply")
         _lib.count_launches(3)
-        ctx.save_for_backward(xc, y if relu else torch.empty(0), weight, stats)
-        ctx.meta = (relu, residual is not None, n_total, world, bool(residual_up2x))
+        # y = relu(bn(x)) without residual: the backward recomputes the mask from x and the saved scale / shift (exactly
+        # y > 0) instead of reading y - one of three tensor reads less in both backward passes
+        mask_from_x = relu and residual is None and RELU_MASK_FROM_X
+        ctx.save_for_backward(xc, y if (relu and not mask_from_x) else torch.empty(0), weight, stats)
+        ctx.meta = (relu, residual is not None, n_total, world, bool(residual_up2x), mask_from_x)
         return y
 
     @staticmethod
@@ -152,16 +155,19 @@ class _BNAct(torch.autograd.Function):
         L = _lib.lib()
         s = _lib.stream_ptr()
         xc, y, weight, stats = ctx.saved_tensors
-        relu, has_res, n_total, world, res_up = ctx.meta
+        relu, has_res, n_total, world, res_up, mask_from_x = ctx.meta
         N, C, H, W = xc.shape
         P = N * H * W
         dt = _CODE[xc.dtype]
         dev = xc.device
         g = _nhwc(gy.to(xc.dtype))
-        yy = y if relu else None
+        yy = y if (relu and not mask_from_x) else None
         S = int(L.u2b_bn_num_strips(P, C))
         part = _partials(S, C, dev)
-        _lib.check(L.u2b_bn_bwd_reduce(dt, _p(g), _p(xc), _p(yy), _p(stats), P, C, _p(part), s), "u2b_bn_bwd_reduce")
+        if mask_from_x:
+            _lib.check(L.u2b_bn_bwd_reduce_relu_x(dt, _p(g), _p(xc), _p(stats), P, C, _p(part), s), "u2b_bn_bwd_reduce_relu_x")
+        else:
+            _lib.check(L.u2b_bn_bwd_reduce(dt, _p(g), _p(xc), _p(yy), _p(stats), P, C, _p(part), s), "u2b_bn_bwd_reduce")
         coeff = torch.empty((3 * C,), dtype=torch.float32, device=dev)
         gwb = torch.empty((2 * C,), dtype=torch.float32, device=dev)      # dgamma | dbeta (LOCAL sums: DDP reduces them)
         if world > 1:
@@ -184,7 +190,10 @@ class _BNAct(torch.autograd.Function):
         # without ReLU the residual's gradient IS the incoming gradient (no masked copy needed)
         need_dres = has_res and (relu or not res_up)
         dres = torch.empty((N, H, W, C), dtype=xc.dtype, device=dev).permute(0, 3, 1, 2) if need_dres else None
-        _lib.check(L.u2b_bn_bwd_apply(dt, _p(g), _p(xc), _p(yy), _p(coeff), _p(dx), _p(dres), P, C, s), "u2b_bn_bwd_apply")
+        if mask_from_x:
+            _lib.check(L.u2b_bn_bwd_apply_relu_x(dt, _p(g), _p(xc), _p(stats), _p(coeff), _p(dx), P, C, s), "u2b_bn_bwd_apply_relu_x")
+        else:
+            _lib.check(L.u2b_bn_bwd_apply(dt, _p(g), _p(xc), _p(yy), _p(coeff), _p(dx), _p(dres), P, C, s), "u2b_bn_bwd_apply")
         _lib.count_launches(3)
         if has_res and res_up:      # gradient of the nearest x2 upsampling: fold every 2x2 block (csrc/pool.cu)
             src = dres if dres is not None else g
@@ -211,6 +220,7 @@ def bn_act(x, bn, residual=None, relu=False, partials=None, residual_up2x=False)
 # reference-shaped eager step pads each rank's multi-scale batch on its own (MIN_SIZE_TRAIN 240..1024), so there the
 # model falls back to nn.SyncBatchNorm's own function, which all-gathers the per-rank counts (ops.batch_norm).
 EQUAL_SHAPES_ACROSS_RANKS = False
+RELU_MASK_FROM_X = __import__("os").environ.get("U2B_BN_MASK_FROM_X", "1") == "1"
 
 
 def supported(x, bn):
