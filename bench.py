@@ -325,11 +325,12 @@ def run_knn(args, emit=True):
     nc = int(_lib.lib().u2b_knn_candidates_per_row())
     n1 = 131072
     cand = torch.empty((n1, nc), dtype=torch.int32, device=dev)
+    cval = torch.empty((n1, nc), dtype=torch.float32, device=dev)
     thr = torch.empty((n1, 2), dtype=torch.float32, device=dev)
     ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ea.record()
-    _lib.check(_lib.lib().u2b_knn_candidates(_lib.ptr(y16), n1, _lib.ptr(y16), _lib.ptr(yn), N, D, _lib.ptr(cand), _lib.ptr(thr),
-                                             _lib.stream_ptr()), "u2b_knn_candidates")
+    _lib.check(_lib.lib().u2b_knn_candidates(_lib.ptr(y16), n1, _lib.ptr(y16), _lib.ptr(yn), N, D, _lib.ptr(cand), _lib.ptr(cval),
+                                             _lib.ptr(thr), _lib.stream_ptr()), "u2b_knn_candidates")
     eb.record()
     torch.cuda.synchronize()
     ms_c = ea.elapsed_time(eb)

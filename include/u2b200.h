@@ -84,10 +84,10 @@ int u2b_knn_candidates_per_row(void);
 int64_t u2b_knn_npad(int64_t N2);
 int u2b_knn_set_cluster(int cluster);
 int u2b_knn_candidates(const void* x16, int64_t N1, const void* y16, const float* ynorm, int64_t N2, int64_t D,
-                       int32_t* cand_idx, float* cand_thr, u2b_stream_t stream);
-int u2b_knn_refine(const float* x, const float* y, const int32_t* cand_idx, const float* cand_thr, const float* xnorm,
-                   int64_t N1, int64_t D, int K, float eps, float* d_out, int64_t* i_out, int32_t* flagged,
-                   int32_t* n_flagged, u2b_stream_t stream);
+                       int32_t* cand_idx, float* cand_val, float* cand_thr, u2b_stream_t stream);
+int u2b_knn_refine(const float* x, const float* y, const int32_t* cand_idx, const float* cand_val, const float* cand_thr,
+                   const float* xnorm, int64_t N1, int64_t D, int K, float eps, float* d_out, int64_t* i_out,
+                   int32_t* flagged, int32_t* n_flagged, u2b_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Detector ops. Feature maps are NHWC ("channels_last"); dtype codes: 0 = fp32, 1 = fp16, 2 = bf16.

@@ -87,3 +87,41 @@ def test_static_graph_trainer_ranks_stay_in_sync():
     dist.all_gather(other, losses)
     assert not torch.equal(other[0], other[1])          # ranks really worked on different data
     dist.barrier()
+
+
+@pytest.mark.skipif(not _MULTI, reason="needs torchrun with WORLD_SIZE > 1")
+def test_overlapped_bucketed_allreduce_equals_single_allreduce(monkeypatch):
+    """engine.Trainer: gradient buckets all-reduced on a side stream while backward runs (post-accumulate-grad hooks) give
+    the same averaged flat gradient buffer as the single all-reduce issued after backward."""
+    from u2seg_b200.config import get_u2seg_cfg
+    from u2seg_b200.data_synth import synthetic_batch
+    from u2seg_b200.engine import Trainer
+    from u2seg_b200.modeling import rpn, static_train
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    monkeypatch.setattr(rpn, "_randperm", lambda n, device=None: torch.arange(n, device=device))
+    monkeypatch.setattr(static_train, "_rand_keys",
+                        lambda mask: torch.arange(mask.numel(), device=mask.device, dtype=torch.float32).view(mask.shape) / (mask.numel() + 1))
+    batch = synthetic_batch(2, 256, 320, 800, 28, seed=70 + rank, G=6, min_size=24, max_size=160)
+    flats = []
+    for overlap in ("1", "0"):
+        monkeypatch.setenv("U2B_OVERLAP_ALLREDUCE", overlap)
+        cfg = get_u2seg_cfg(800)
+        cfg.SOLVER.BASE_LR = 0.0
+        torch.manual_seed(0)
+        tr = Trainer(cfg, amp_dtype=torch.bfloat16, static_graph=True)
+        tr.broadcast_parameters(0)
+        tr.run_step(batch)
+        torch.cuda.synchronize()
+        flats.append(tr.grads.flat.clone())
+        assert (overlap == "1") == (getattr(tr, "_ov", None) is not None)
+        del tr
+    a, b = flats
+    assert float(a.abs().max()) > 0
+    assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), float((a - b).abs().max())
+    ga = [torch.zeros_like(a[:1000]) for _ in range(world)]
+    dist.all_gather(ga, a[-1000:].contiguous())
+    assert torch.equal(ga[0], ga[1])                                    # every rank holds the same averaged gradients
+    dist.barrier()

@@ -31,9 +31,10 @@ SIGNATURES = {
     "u2b_knn_candidates_per_row": (c_int, []),
     "u2b_knn_npad": (c_int64, [c_int64]),
     "u2b_knn_set_cluster": (c_int, [c_int]),
-    "u2b_knn_candidates": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
-    "u2b_knn_refine": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p,
-                               c_void_p, c_void_p, c_void_p, c_void_p]),
+    "u2b_knn_candidates": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                   c_void_p]),
+    "u2b_knn_refine": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "u2b_kmeans_accumulate": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                       c_size_t, c_void_p]),
     "u2b_kmeans_finalize": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),

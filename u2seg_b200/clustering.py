@@ -233,14 +233,15 @@ def kNN(x_train, x_test, K=20, query_chunk=262144, return_stats=False):
         else:
             x16, xn, xmax2 = _knn_prepare(xq)
         cand = torch.empty((n1, NC), dtype=torch.int32, device=dev)
+        cval = torch.empty((n1, NC), dtype=torch.float32, device=dev)
         thr = torch.empty((n1, 2), dtype=torch.float32, device=dev)
-        _lib.check(L.u2b_knn_candidates(_lib.ptr(x16), n1, _lib.ptr(y16), _lib.ptr(yn), N2, D, _lib.ptr(cand), _lib.ptr(thr),
-                                        _lib.stream_ptr()), "u2b_knn_candidates")
+        _lib.check(L.u2b_knn_candidates(_lib.ptr(x16), n1, _lib.ptr(y16), _lib.ptr(yn), N2, D, _lib.ptr(cand), _lib.ptr(cval),
+                                        _lib.ptr(thr), _lib.stream_ptr()), "u2b_knn_candidates")
         # rounding bound of the fp16 candidate pass: 2 |x.y - x16.y16| <= 2^-9 |x| |y| (+ fp32 accumulation), with margin
         eps = 1.25 * 2.0 ** -9 * float(torch.sqrt(xmax2 * ymax2))
         flagged = torch.empty((n1,), dtype=torch.int32, device=dev)
         nflag = torch.zeros((1,), dtype=torch.int32, device=dev)
-        _lib.check(L.u2b_knn_refine(_lib.ptr(xq), _lib.ptr(y), _lib.ptr(cand), _lib.ptr(thr), _lib.ptr(xn), n1, D, int(K),
+        _lib.check(L.u2b_knn_refine(_lib.ptr(xq), _lib.ptr(y), _lib.ptr(cand), _lib.ptr(cval), _lib.ptr(thr), _lib.ptr(xn), n1, D, int(K),
                                     ctypes.c_float(eps), _lib.ptr(dist[s:s + n1]), _lib.ptr(ind[s:s + n1]), _lib.ptr(flagged),
                                     _lib.ptr(nflag), _lib.stream_ptr()), "u2b_knn_refine")
         _lib.count_launches(2)

@@ -52,8 +52,8 @@ struct KnnSmem {
 template <int CL>
 __global__ void __launch_bounds__(KNN_THREADS, 1)
 knn_candidates_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
-                      const float* __restrict__ ynorm, int32_t* __restrict__ cand_idx, float* __restrict__ cand_thr,
-                      int N1, int ntiles_n, int kblocks, int num_tiles) {
+                      const float* __restrict__ ynorm, int32_t* __restrict__ cand_idx, float* __restrict__ cand_val,
+                      float* __restrict__ cand_thr, int N1, int ntiles_n, int kblocks, int num_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem + KnnSmem::A_OFF;
@@ -223,8 +223,12 @@ knn_candidates_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       const long long row = static_cast<long long>(tile) * BM + row_in_tile;
       if (tile < num_tiles && row < N1) {
         int32_t* ci = cand_idx + row * (2 * KC) + half * KC;
+        float* cv = cand_val + row * (2 * KC) + half * KC;
 #pragma unroll
-        for (int k = 0; k < KC; ++k) ci[k] = sIdx[k * EPI_T + te];
+        for (int k = 0; k < KC; ++k) {
+          ci[k] = sIdx[k * EPI_T + te];
+          cv[k] = sVal[k * EPI_T + te];
+        }
         cand_thr[row * 2 + half] = thr;
       }
     }
@@ -239,7 +243,8 @@ knn_candidates_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 template <int NP>   // D = 128 * NP
 __global__ void __launch_bounds__(256)
 knn_refine_kernel(const float* __restrict__ x, const float* __restrict__ y, const int32_t* __restrict__ cand_idx,
-                  const float* __restrict__ cand_thr, const float* __restrict__ xnorm, long long N1, int K, float eps,
+                  const float* __restrict__ cand_val, const float* __restrict__ cand_thr,
+                  const float* __restrict__ xnorm, long long N1, int K, float eps,
                   float* __restrict__ d_out, int64_t* __restrict__ i_out, int32_t* __restrict__ flagged,
                   int* __restrict__ n_flagged) {
   constexpr int D = 128 * NP;
@@ -250,11 +255,33 @@ knn_refine_kernel(const float* __restrict__ x, const float* __restrict__ y, cons
 #pragma unroll
   for (int j = 0; j < NP; ++j) xv[j] = *reinterpret_cast<const float4*>(x + row * D + j * 128 + lane * 4);
   const int32_t* ci = cand_idx + row * (2 * KC);
+  // Only candidates that can still belong to the answer are re-evaluated exactly: with |approx - true| <= eps for every
+  // pair, a candidate whose approximate value exceeds the K-th smallest approximate value by more than 2 eps is farther
+  // than the true K-th neighbour. (Typically ~K + a few of the 48 survive: the exact pass is a random 1.5 KB gather per
+  // surviving candidate and would otherwise dominate the search.)
+  float va = lane < 2 * KC ? cand_val[row * (2 * KC) + lane] : __int_as_float(0x7f800000);
+  float vb = lane + 32 < 2 * KC ? cand_val[row * (2 * KC) + lane + 32] : __int_as_float(0x7f800000);
+  const float keep_a = va, keep_b = vb;
+  float vK = __int_as_float(0x7f800000);
+  for (int k = 0; k < K; ++k) {   // K-th smallest approximate value: K rounds of warp-min with removal
+    const float m = fminf(va, vb);
+    float best = m;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, off));
+    const unsigned who = __ballot_sync(0xffffffffu, m == best);
+    if (lane == __ffs(who) - 1) {   // one holder retires one entry
+      if (va == best) va = __int_as_float(0x7f800000);
+      else vb = __int_as_float(0x7f800000);
+    }
+    vK = best;
+  }
+  const float tau = vK + 2.f * eps;
   float myd[2] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000)};
   int myi[2] = {0x7fffffff, 0x7fffffff};
 #pragma unroll 4
   for (int c = 0; c < 2 * KC; ++c) {
-    const int j = ci[c];
+    const float vc = __shfl_sync(0xffffffffu, (c < 32) ? keep_a : keep_b, c & 31);
+    const int j = (vc <= tau) ? ci[c] : -1;
     float d = __int_as_float(0x7f800000);
     if (j >= 0) {   // warp-uniform
       float s = 0.f;
@@ -306,8 +333,8 @@ knn_refine_kernel(const float* __restrict__ x, const float* __restrict__ y, cons
 int g_knn_cluster = 2;
 
 template <int CL>
-int launch_knn(const CUtensorMap& tx, const CUtensorMap& ty, const float* ynorm, int32_t* cand_idx, float* cand_thr,
-               int N1, int ntiles_n, int kblocks, int num_tiles, cudaStream_t stream) {
+int launch_knn(const CUtensorMap& tx, const CUtensorMap& ty, const float* ynorm, int32_t* cand_idx, float* cand_val,
+               float* cand_thr, int N1, int ntiles_n, int kblocks, int num_tiles, cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
     U2B_CUDA(cudaFuncSetAttribute(knn_candidates_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, KnnSmem::BYTES));
@@ -328,8 +355,8 @@ int launch_knn(const CUtensorMap& tx, const CUtensorMap& ty, const float* ynorm,
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  U2B_CUDA(cudaLaunchKernelEx(&cfg, knn_candidates_kernel<CL>, tx, ty, ynorm, cand_idx, cand_thr, N1, ntiles_n, kblocks,
-                              num_tiles));
+  U2B_CUDA(cudaLaunchKernelEx(&cfg, knn_candidates_kernel<CL>, tx, ty, ynorm, cand_idx, cand_val, cand_thr, N1, ntiles_n,
+                              kblocks, num_tiles));
   return 0;
 }
 
@@ -342,10 +369,11 @@ int64_t u2b_knn_npad(int64_t N2) { return ceil_div64(N2, NT) * NT; }
 
 // Candidate pass. x16 (N1, D) / y16 (npad(N2), D) fp16 row-major (rows beyond N2 zero), ynorm (npad(N2)) fp32 = |y|^2 of
 // the fp32 rows, +inf beyond N2 (u2b_kmeans_prepare produces both). D % 64 == 0, D <= 384.
-// cand_idx (N1, 48) int32 (-1 = empty slot), cand_thr (N1, 2) fp32 = worst kept value of each list (|y|^2 - 2 x.y space).
+// cand_idx (N1, 48) int32 (-1 = empty slot), cand_val (N1, 48) fp32 = their values in |y|^2 - 2 x.y space (+inf = empty),
+// cand_thr (N1, 2) fp32 = worst kept value of each of the two lists.
 int u2b_knn_candidates(const void* x16, int64_t N1, const void* y16, const float* ynorm, int64_t N2, int64_t D,
-                       int32_t* cand_idx, float* cand_thr, cudaStream_t stream) {
-  U2B_CHECK_ARG(x16 && y16 && ynorm && cand_idx && cand_thr && N1 > 0 && N2 > 0, "knn_candidates: bad arguments");
+                       int32_t* cand_idx, float* cand_val, float* cand_thr, cudaStream_t stream) {
+  U2B_CHECK_ARG(x16 && y16 && ynorm && cand_idx && cand_val && cand_thr && N1 > 0 && N2 > 0, "knn_candidates: bad arguments");
   U2B_CHECK_ARG(N1 < (1LL << 31) && N2 < (1LL << 31), "knn_candidates: more than 2^31 rows");
   if (D % BK != 0 || D / BK > MAXKB) {
     u2b_set_error("knn_candidates: D=%lld unsupported (need D %% 64 == 0 and D <= %d)", (long long)D, MAXKB * BK);
@@ -373,24 +401,24 @@ int u2b_knn_candidates(const void* x16, int64_t N1, const void* y16, const float
     if (rc) return rc;
   }
   const int ntn = static_cast<int>(npad / NT), kb = static_cast<int>(D / BK);
-  if (CL == 4) return launch_knn<4>(tx, ty, ynorm, cand_idx, cand_thr, (int)N1, ntn, kb, num_tiles, stream);
-  if (CL == 2) return launch_knn<2>(tx, ty, ynorm, cand_idx, cand_thr, (int)N1, ntn, kb, num_tiles, stream);
-  return launch_knn<1>(tx, ty, ynorm, cand_idx, cand_thr, (int)N1, ntn, kb, num_tiles, stream);
+  if (CL == 4) return launch_knn<4>(tx, ty, ynorm, cand_idx, cand_val, cand_thr, (int)N1, ntn, kb, num_tiles, stream);
+  if (CL == 2) return launch_knn<2>(tx, ty, ynorm, cand_idx, cand_val, cand_thr, (int)N1, ntn, kb, num_tiles, stream);
+  return launch_knn<1>(tx, ty, ynorm, cand_idx, cand_val, cand_thr, (int)N1, ntn, kb, num_tiles, stream);
 }
 
 // Exact pass. x (N1, D), y (N2, D) fp32; xnorm (N1) fp32; eps = rounding bound of the candidate pass in distance units.
 // d_out (N1, K) fp32 ascending, i_out (N1, K) int64; flagged (N1) int32 + n_flagged (device int, zeroed by the caller)
 // list the rows whose result could not be certified. D in {128, 256, 384}; K <= 2*KC.
-int u2b_knn_refine(const float* x, const float* y, const int32_t* cand_idx, const float* cand_thr, const float* xnorm,
-                   int64_t N1, int64_t D, int K, float eps, float* d_out, int64_t* i_out, int32_t* flagged,
-                   int32_t* n_flagged, cudaStream_t stream) {
-  U2B_CHECK_ARG(x && y && cand_idx && cand_thr && xnorm && d_out && i_out && flagged && n_flagged && N1 > 0,
+int u2b_knn_refine(const float* x, const float* y, const int32_t* cand_idx, const float* cand_val, const float* cand_thr,
+                   const float* xnorm, int64_t N1, int64_t D, int K, float eps, float* d_out, int64_t* i_out,
+                   int32_t* flagged, int32_t* n_flagged, cudaStream_t stream) {
+  U2B_CHECK_ARG(x && y && cand_idx && cand_val && cand_thr && xnorm && d_out && i_out && flagged && n_flagged && N1 > 0,
                 "knn_refine: bad arguments");
   U2B_CHECK_ARG(K > 0 && K <= 2 * KC, "knn_refine: K=%d outside 1..%d", K, 2 * KC);
   const unsigned grid = static_cast<unsigned>((N1 + 7) / 8);
-  if (D == 128) knn_refine_kernel<1><<<grid, 256, 0, stream>>>(x, y, cand_idx, cand_thr, xnorm, N1, K, eps, d_out, i_out, flagged, n_flagged);
-  else if (D == 256) knn_refine_kernel<2><<<grid, 256, 0, stream>>>(x, y, cand_idx, cand_thr, xnorm, N1, K, eps, d_out, i_out, flagged, n_flagged);
-  else if (D == 384) knn_refine_kernel<3><<<grid, 256, 0, stream>>>(x, y, cand_idx, cand_thr, xnorm, N1, K, eps, d_out, i_out, flagged, n_flagged);
+  if (D == 128) knn_refine_kernel<1><<<grid, 256, 0, stream>>>(x, y, cand_idx, cand_val, cand_thr, xnorm, N1, K, eps, d_out, i_out, flagged, n_flagged);
+  else if (D == 256) knn_refine_kernel<2><<<grid, 256, 0, stream>>>(x, y, cand_idx, cand_val, cand_thr, xnorm, N1, K, eps, d_out, i_out, flagged, n_flagged);
+  else if (D == 384) knn_refine_kernel<3><<<grid, 256, 0, stream>>>(x, y, cand_idx, cand_val, cand_thr, xnorm, N1, K, eps, d_out, i_out, flagged, n_flagged);
   else {
     u2b_set_error("knn_refine: D=%lld unsupported (128, 256 or 384)", (long long)D);
     return U2B_ERR_UNSUPPORTED;
