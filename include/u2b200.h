@@ -331,6 +331,17 @@ int u2b_bn_xchg_finalize(const float* sums, const void* peers, int world, int ra
 int u2b_bn_xchg_bwd_coeff(const float* sums, const void* peers, int world, int rank, uint32_t* epoch_ctr, int slot_floats,
                           double n_total, const float* stats, const float* w, float* coeff, float* gw_gb, int C,
                           u2b_stream_t stream);
+/* Multi-CTA variants (one CTA per 32 channels) that take the (S, 2C) partial rows directly: partial-row summation, NVLink
+ * exchange and the statistics / coefficients in ONE launch per BN direction. epoch_ctrs: device uint32[u2b_bn_xchg2_max_ctas()],
+ * zero-initialised once. Same symmetric buffers (u2b_bn_xchg_buffer_bytes covers both flag areas). Reference:
+ * detectron2/layers/batch_norm.py:187-229 (NaiveSyncBatchNorm: all-reduce of [mean, meansqr] / of the backward sums). */
+int u2b_bn_xchg2_max_ctas(void);
+int u2b_bn_xchg2_finalize(const float* partials, int S, const void* peers, int world, int rank, uint32_t* epoch_ctrs,
+                          int slot_floats, double n_total, const float* w, const float* b, float eps, float momentum,
+                          float* running_mean, float* running_var, float* stats, int C, cudaStream_t stream);
+int u2b_bn_xchg2_bwd_coeff(const float* partials, int S, const void* peers, int world, int rank, uint32_t* epoch_ctrs,
+                           int slot_floats, double n_total, const float* stats, const float* w, float* coeff, float* gw_gb,
+                           int C, cudaStream_t stream);
 /* dx = A*dz + B*x + K; dres = dz when dres != NULL */
 int u2b_bn_bwd_apply(int dtype, const void* dy, const void* x, const void* y, const float* coeff, void* dx,
                      void* dres, int64_t P, int C, u2b_stream_t stream);

@@ -51,6 +51,34 @@ def test_assign_bit_exact_vs_oracle(N, D, K, cluster):
         assert bad.numel() <= max(1, N // 100000), "too many near-tie differences: %d" % bad.numel()
 
 
+def test_assign_full_baseline_size_sampled_rows_vs_oracle():
+    """BASELINE config 4 itself (N=1.28 M, D=384, K=800): the E-step over ALL rows, then 65,536 sampled rows against the chunked
+    oracle (nn_utils.py:342-355 dense branch). Same acceptance as the small cases: identical labels except fp32-rounding ties,
+    each checked in float64."""
+    from u2seg_b200.clustering import KMeansState, set_cluster
+    set_cluster(2)
+    N, D, K, S = 1_280_000, 384, 800, 65_536
+    x16 = make_mixture(N, D, 1000, seed=3, spread=1.0)
+    g = torch.Generator().manual_seed(9)
+    c = x16.float()[torch.randint(0, N, (K,), generator=g)] + 0.01 * torch.randn(K, D, generator=g)
+    st = KMeansState(x16.cuda(), K)
+    got_all = st.assign(c.cuda().contiguous()).cpu().long()
+    assert got_all.shape == (N,) and int(got_all.min()) >= 0 and int(got_all.max()) < K
+    rows = torch.randperm(N, generator=g)[:S]
+    rows = torch.cat([rows, torch.tensor([0, 127, 128, N - 129, N - 128, N - 1])])   # tile edges of the first / last CTA
+    want = assign_oracle(x16[rows].float(), c, chunk=512)
+    got = got_all[rows]
+    bad = (got != want).nonzero().flatten()
+    print("full-size E-step: %d of %d sampled rows differ from the oracle (rounding ties)" % (bad.numel(), rows.numel()))
+    if bad.numel():
+        xd, cd = x16[rows].double(), c.double()
+        for i in bad.tolist():
+            dg = ((xd[i] - cd[got[i]]) ** 2).sum()
+            dw = ((xd[i] - cd[want[i]]) ** 2).sum()
+            assert abs(dg - dw) <= 2e-6 * max(1.0, float(dw)), (i, float(dg), float(dw))
+    assert bad.numel() <= 2
+
+
 def test_assign_duplicate_centroids_first_minimum():
     from u2seg_b200.clustering import KMeansState
     x16 = make_mixture(1000, 64, 10, seed=1, spread=1.0)

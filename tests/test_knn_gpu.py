@@ -65,8 +65,26 @@ def test_knn_uncertifiable_rows_fall_back_to_exhaustive_search():
     xq = base + 1e-4 * torch.randn(64, D, generator=g)
     want_ind, want_d = knn_oracle(xt, xq, K)
     ind, d, stats = kNN(xt.cuda(), xq.cuda(), K=K, return_stats=True)
-    assert stats["uncertified_rows"] > 0
+    assert stats["uncertified_rows"] > 0 and stats["exhaustive_rows"] > 0
     assert torch.allclose(d.cpu(), want_d, rtol=1e-4, atol=1e-9)
+
+
+def test_knn_dense_neighbourhood_certified_by_second_pass():
+    """100 train rows within the fp16 rounding bound of each other: the 48-candidate lists cannot be certified, the fp32 second
+    pass (128 candidates, bound 4 D 2^-24 |x||y|) can; no exhaustive search, exact answer."""
+    from u2seg_b200.clustering import kNN
+    g = torch.Generator().manual_seed(11)
+    D, K = 128, 20
+    base = torch.nn.functional.normalize(torch.randn(1, D, generator=g), dim=1)
+    xt = torch.cat([base + 2e-3 * torch.randn(100, D, generator=g),
+                    torch.nn.functional.normalize(torch.randn(3000, D, generator=g), dim=1)])
+    xq = base + 2e-3 * torch.randn(64, D, generator=g)
+    want_ind, want_d = knn_oracle(xt, xq, K)
+    ind, d, stats = kNN(xt.cuda(), xq.cuda(), K=K, return_stats=True)
+    print("dense neighbourhood:", stats)
+    assert stats["uncertified_rows"] > 0 and stats["exhaustive_rows"] == 0
+    assert torch.allclose(d.cpu(), want_d, rtol=1e-4, atol=1e-9)
+    assert float((ind.cpu() != want_ind).float().mean()) < 0.02      # fp32 summation-order ties only
 
 
 def test_partitioned_knn_self_search_properties():

@@ -78,7 +78,7 @@ def test_training_gradients_match_oracle(monkeypatch):
     K, S, seed = 800, 28, 5
     cfg = do.DetCfg(K, S)
     params = do.init_params(cfg, 0)
-    data = do.synthetic_batch(1, 128, 160, K, S, seed=seed, G=4, min_size=16, max_size=80)
+    data = do.synthetic_batch(2, 256, 256, K, S, seed=seed, G=6, min_size=16, max_size=120)   # 2 images: BN batches are not degenerate
     names = ["backbone.fpn_output2.weight", "backbone.bottom_up.res3.0.conv2.weight", "roi_heads.box_head.1.fc1.weight",
              "roi_heads.mask_head.mask_fcn2.weight", "proposal_generator.rpn_head.conv.weight", "sem_seg_head.p4.2.weight",
              "backbone.bottom_up.stem.conv1.norm.weight"]
@@ -92,10 +92,12 @@ def test_training_gradients_match_oracle(monkeypatch):
     named = dict(model.named_parameters())
     bad = []
     for k in names:
-        a, b = named[k].grad.float().cpu(), op[k].grad
-        denom = float(b.abs().max()) + 1e-12
-        if float((a - b).abs().max()) / denom > (0.1 if "roi_heads" in k else 5e-2):   # cuDNN-vs-CPU fp32 summation order through 53 BN layers on a tiny batch
-            bad.append((k, float((a - b).abs().max()), denom))
+        a, b = named[k].grad.double().cpu(), op[k].grad.double()
+        l2 = float((a - b).norm() / (b.norm() + 1e-30))
+        mx = float((a - b).abs().max() / (b.abs().max() + 1e-30))
+        print("   %-45s relative L2 error %.2e, max error / max entry %.2e" % (k, l2, mx))
+        if l2 > 1e-2 or mx > 2e-2:     # fp32 on both sides; what is left is summation order through 53 BN layers
+            bad.append((k, l2, mx))
     assert not bad, bad
 
 

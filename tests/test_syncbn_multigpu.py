@@ -105,8 +105,10 @@ def test_overlapped_bucketed_allreduce_equals_single_allreduce(monkeypatch):
     monkeypatch.setattr(static_train, "_rand_keys",
                         lambda mask: torch.arange(mask.numel(), device=mask.device, dtype=torch.float32).view(mask.shape) / (mask.numel() + 1))
     batch = synthetic_batch(2, 256, 320, 800, 28, seed=70 + rank, G=6, min_size=24, max_size=160)
-    flats = []
-    for overlap in ("1", "0"):
+    flats, ranges = {}, None
+    # Two runs of the SAME configuration are not bit-identical (fp32 atomics in the ROI-align / upsampling backward, then bf16
+    # roundings downstream): the single-all-reduce path runs twice and its own run-to-run difference is the yardstick.
+    for name, overlap in (("overlap", "1"), ("single", "0"), ("single_again", "0")):
         monkeypatch.setenv("U2B_OVERLAP_ALLREDUCE", overlap)
         cfg = get_u2seg_cfg(800)
         cfg.SOLVER.BASE_LR = 0.0
@@ -115,12 +117,23 @@ def test_overlapped_bucketed_allreduce_equals_single_allreduce(monkeypatch):
         tr.broadcast_parameters(0)
         tr.run_step(batch)
         torch.cuda.synchronize()
-        flats.append(tr.grads.flat.clone())
+        flats[name] = tr.grads.flat.clone()
         assert (overlap == "1") == (getattr(tr, "_ov", None) is not None)
+        if overlap == "1":
+            ranges = list(tr._ov["range"])
+            assert len(ranges) >= 4 and ranges[0][0] == 0 and ranges[-1][1] == tr.grads.flat.numel()
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))            # buckets tile the whole buffer
         del tr
-    a, b = flats
+    a, b, c = flats["overlap"], flats["single"], flats["single_again"]
     assert float(a.abs().max()) > 0
-    assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), float((a - b).abs().max())
+
+    def rel(u, v):
+        return float((u - v).double().norm() / (v.double().norm() + 1e-30))
+
+    print("overlap vs single %.2e; single vs single (run-to-run) %.2e" % (rel(a, b), rel(c, b)))
+    assert rel(a, b) <= 3 * rel(c, b) + 1e-6
+    for lo, hi in ranges:                # a bucket reduced too early / twice / never would stand out on its own
+        assert rel(a[lo:hi], b[lo:hi]) <= 5 * rel(c[lo:hi], b[lo:hi]) + 1e-5, (lo, hi, rel(a[lo:hi], b[lo:hi]), rel(c[lo:hi], b[lo:hi]))
     ga = [torch.zeros_like(a[:1000]) for _ in range(world)]
     dist.all_gather(ga, a[-1000:].contiguous())
     assert torch.equal(ga[0], ga[1])                                    # every rank holds the same averaged gradients

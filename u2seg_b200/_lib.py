@@ -132,6 +132,11 @@ SIGNATURES = {
                                      c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "u2b_bn_xchg_bwd_coeff": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, ctypes.c_double, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "u2b_bn_xchg2_max_ctas": (c_int, []),
+    "u2b_bn_xchg2_finalize": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, ctypes.c_double, c_void_p,
+                                      c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "u2b_bn_xchg2_bwd_coeff": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, ctypes.c_double, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "u2b_bn_bwd_apply": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                  c_void_p]),
     "u2b_nms_workspace_bytes": (c_size_t, [c_int64]),

@@ -177,7 +177,8 @@ def run_kMeans(feats_list, num_centroids, final_sample_num=None, train_memory_da
 # k-nearest neighbours (nn_utils.py:203-299): exact, tensor-core candidate pass + fp32 certification (csrc/knn.cu)
 # ---------------------------------------------------------------------------------------------------------------------
 def _knn_prepare(x32):
-    """fp32 (N, D) CUDA rows -> (fp16 rows padded to the train-tile multiple, |x|^2 fp32 (+inf in the padding), max |x|^2)."""
+    """fp32 (N, D) CUDA rows -> (fp16 rows padded to the train-tile multiple, |x|^2 fp32 (+inf in the padding), max |x|^2).
+    Use _knn_rounding(x32, x16) for the rows' fp16 rounding-error norm."""
     import ctypes
     L = _lib.lib()
     N, D = x32.shape
@@ -191,6 +192,54 @@ def _knn_prepare(x32):
                "u2b_kmeans_prepare")
     _lib.count_launches(1)
     return x16, xn, xmax2
+
+
+def _knn_rounding(x32, x16, chunk=262144):
+    """max_i |x_i - fp16(x_i)|_2 (the MEASURED rounding error of the candidate pass's operands), as a 0-d tensor."""
+    worst = torch.zeros((), dtype=torch.float32, device=x32.device)
+    for s in range(0, x32.shape[0], chunk):
+        worst = torch.maximum(worst, (x32[s:s + chunk] - x16[s:s + chunk].float()).norm(dim=1).max())
+    return worst
+
+
+def _knn_eps(xmax2, ymax2, ex, ey, D):
+    """Bound on |candidate-pass value - (|y|^2 - 2 x.y)| for every pair: with x~, y~ the fp16 operands,
+    |x.y - x~.y~| <= |x| |y - y~| + |x - x~| |y~|  (Cauchy-Schwarz; the rounding-error norms are measured, not the 2^-11
+    worst case), plus the fp32 accumulation of D products and of |y|^2."""
+    xm, ym = float(torch.sqrt(xmax2)), float(torch.sqrt(ymax2))
+    ex, ey = float(ex), float(ey)
+    return 2.0 * (xm * ey + ex * (ym + ey)) + 4.0 * D * 2.0 ** -24 * max(xm, ym) ** 2
+
+
+def _knn_second_pass(xq, xnq, y, yn, K, M=128, rows_per_chunk=1024):
+    """Rows the 48-candidate lists could not certify (dense neighbourhoods: more than ~48 train rows within the fp16
+    rounding bound of the K-th distance). Values |y|^2 - 2 x.y for ALL train rows from an fp32 library GEMM (no fp16
+    rounding, error <= eps2 = 4 D 2^-24 |x| |y|), the M smallest re-evaluated exactly, the same certificate with eps2.
+    Returns (d (r,K), i (r,K), certified (r,) bool)."""
+    N2, D = y.shape
+    eps2 = 4.0 * D * 2.0 ** -24 * float(torch.sqrt(xnq.max() * yn[:N2].max()))
+    d_out = torch.empty((xq.shape[0], K), dtype=torch.float32, device=xq.device)
+    i_out = torch.empty((xq.shape[0], K), dtype=torch.int64, device=xq.device)
+    ok = torch.empty((xq.shape[0],), dtype=torch.bool, device=xq.device)
+    M = min(M, N2)
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for s in range(0, xq.shape[0], rows_per_chunk):
+            q = xq[s:s + rows_per_chunk]
+            v = torch.addmm(yn[None, :N2].expand(q.shape[0], -1), q, y.t(), alpha=-2.0)
+            vals, idx = torch.topk(v, M, dim=1, largest=False, sorted=True)
+            del v
+            idx, order = torch.sort(idx, dim=1)                       # by train index, so that the stable sort breaks ties by index
+            d = ((q[:, None, :] - y[idx]) ** 2).sum(-1)
+            d, o2 = torch.sort(d, dim=1, stable=True)
+            d_out[s:s + q.shape[0]] = d[:, :K]
+            i_out[s:s + q.shape[0]] = torch.gather(idx, 1, o2[:, :K])
+            # every discarded row has value >= vals[:, M-1], i.e. true distance >= vals[:, M-1] + |x|^2 - eps2
+            ok[s:s + q.shape[0]] = (d[:, K - 1] + eps2 < vals[:, M - 1] + xnq[s:s + q.shape[0]] - eps2) if M < N2 else True
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    return d_out, i_out, ok
 
 
 def _knn_exhaustive(xq, y, K, chunk=65536):
@@ -220,25 +269,26 @@ def kNN(x_train, x_test, K=20, query_chunk=262144, return_stats=False):
     N2, D = y.shape
     assert N2 >= K, "kNN: fewer train rows than K"
     y16, yn, ymax2 = _knn_prepare(y)
+    ey = _knn_rounding(y, y16)
     same = x_train is x_test or (xt.data_ptr() == y.data_ptr() and xt.shape == y.shape)
     NC = int(L.u2b_knn_candidates_per_row())
     ind = torch.empty((xt.shape[0], K), dtype=torch.int64, device=dev)
     dist = torch.empty((xt.shape[0], K), dtype=torch.float32, device=dev)
-    n_flag_total = 0
+    n_flag_total = n_exhaustive = 0
     for s in range(0, xt.shape[0], query_chunk):
         xq = xt[s:s + query_chunk]
         n1 = xq.shape[0]
         if same:
-            x16, xn, xmax2 = y16[s:s + n1], yn[s:s + n1], ymax2
+            x16, xn, xmax2, ex = y16[s:s + n1], yn[s:s + n1], ymax2, ey
         else:
             x16, xn, xmax2 = _knn_prepare(xq)
+            ex = _knn_rounding(xq, x16)
         cand = torch.empty((n1, NC), dtype=torch.int32, device=dev)
         cval = torch.empty((n1, NC), dtype=torch.float32, device=dev)
         thr = torch.empty((n1, 2), dtype=torch.float32, device=dev)
         _lib.check(L.u2b_knn_candidates(_lib.ptr(x16), n1, _lib.ptr(y16), _lib.ptr(yn), N2, D, _lib.ptr(cand), _lib.ptr(cval),
                                         _lib.ptr(thr), _lib.stream_ptr()), "u2b_knn_candidates")
-        # rounding bound of the fp16 candidate pass: 2 |x.y - x16.y16| <= 2^-9 |x| |y| (+ fp32 accumulation), with margin
-        eps = 1.25 * 2.0 ** -9 * float(torch.sqrt(xmax2 * ymax2))
+        eps = _knn_eps(xmax2, ymax2, ex, ey, D)
         flagged = torch.empty((n1,), dtype=torch.int32, device=dev)
         nflag = torch.zeros((1,), dtype=torch.int32, device=dev)
         _lib.check(L.u2b_knn_refine(_lib.ptr(xq), _lib.ptr(y), _lib.ptr(cand), _lib.ptr(cval), _lib.ptr(thr), _lib.ptr(xn), n1, D, int(K),
@@ -246,16 +296,21 @@ def kNN(x_train, x_test, K=20, query_chunk=262144, return_stats=False):
                                     _lib.ptr(nflag), _lib.stream_ptr()), "u2b_knn_refine")
         _lib.count_launches(2)
         nf = int(nflag)
-        if nf:        # not certifiable from 48 candidates (dense ties around the K-th neighbour): exhaustive, exact
+        if nf:        # not certifiable from 48 candidates (dense neighbourhood of the K-th neighbour)
             rows = flagged[:nf].long()
-            for b in range(0, nf, 512):
-                rr = rows[b:b + 512]
+            d2, i2, ok = _knn_second_pass(xq[rows], xn[rows], y, yn, K)
+            dist[s + rows] = d2
+            ind[s + rows] = i2
+            bad = rows[~ok]
+            for b in range(0, bad.numel(), 512):     # exact ties beyond the second pass's 128 candidates: exhaustive
+                rr = bad[b:b + 512]
                 d_e, i_e = _knn_exhaustive(xq[rr], y, K)
                 dist[s + rr] = d_e
                 ind[s + rr] = i_e
             n_flag_total += nf
+            n_exhaustive += int(bad.numel())
     if return_stats:
-        return ind, dist, {"uncertified_rows": n_flag_total}
+        return ind, dist, {"uncertified_rows": n_flag_total, "exhaustive_rows": n_exhaustive, "eps": eps}
     return ind, dist
 
 

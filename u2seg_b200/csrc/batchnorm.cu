@@ -605,6 +605,125 @@ bn_xchg_bwd_coeff_kernel(const float* __restrict__ sums, const unsigned long lon
   }
 }
 
+// ---- multi-CTA exchange: partial rows -> sums -> NVLink exchange -> statistics, ONE kernel per BN direction ----------
+// One CTA per 32 channels (<= 64 CTAs). Each CTA sums its 64 columns of the (S, 2C) partial rows (8 warps stride the rows,
+// 128-byte coalesced reads, fixed combination order), exchanges those 64 floats with every peer through its own flag
+// (flag[src rank][cta], epoch sequence per cta index: every rank runs the same layer sequence, so the per-cta sequences
+// agree across ranks), and finishes its 32 channels. Replaces bn_sum_partials_kernel + the single-CTA exchange kernel.
+constexpr int X2_CH = 32;
+constexpr int X2_MAXCTAS = 64;
+constexpr size_t X2_FLAG_SKIP = 256;   // the single-CTA kernels' flags (world <= 32 words) live in front of ours
+
+__device__ __forceinline__ void xchg2_reduce(const float* __restrict__ partials, int S, int C,
+                                             const unsigned long long* __restrict__ peers, int world, int rank,
+                                             unsigned int* __restrict__ epoch_ctrs, int slot_floats,
+                                             float* __restrict__ local /*smem[64]*/, float* __restrict__ tot /*smem[64]*/) {
+  __shared__ float red[8][2 * X2_CH];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, t = threadIdx.x;
+  const int c0 = blockIdx.x * X2_CH;
+  const bool live = c0 + l < C;
+  float s1 = 0.f, s2 = 0.f;
+  if (live)
+    for (int row = w; row < S; row += 8) {
+      s1 += partials[static_cast<size_t>(row) * 2 * C + c0 + l];
+      s2 += partials[static_cast<size_t>(row) * 2 * C + C + c0 + l];
+    }
+  red[w][l] = s1;
+  red[w][X2_CH + l] = s2;
+  const unsigned int epoch = epoch_ctrs[blockIdx.x] + 1u;
+  __syncthreads();
+  if (t == 0) epoch_ctrs[blockIdx.x] = epoch;
+  const int slot = epoch & 1;
+  const int col = (t < X2_CH) ? c0 + t : C + c0 + (t - X2_CH);
+  const bool col_live = t < 2 * X2_CH && (c0 + (t & (X2_CH - 1))) < C;
+  if (t < 2 * X2_CH) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += red[q][t];
+    local[t] = v;
+    if (col_live)
+      for (int p = 0; p < world; ++p)
+        reinterpret_cast<float*>(peers[p])[(static_cast<size_t>(slot) * world + rank) * slot_floats + col] = v;
+  }
+  __syncthreads();
+  const size_t flag_off = static_cast<size_t>(2) * world * slot_floats * sizeof(float) + X2_FLAG_SKIP;
+  if (t < world) {
+    unsigned int* f = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(peers[t]) + flag_off) + rank * X2_MAXCTAS + blockIdx.x;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+    const unsigned int* g = reinterpret_cast<const unsigned int*>(reinterpret_cast<const char*>(peers[rank]) + flag_off) +
+                            t * X2_MAXCTAS + blockIdx.x;
+    const long long t0 = clock64();
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(g) : "memory");
+      if (static_cast<int>(v - epoch) >= 0) break;
+      if (clock64() - t0 > U2B_XCHG_TIMEOUT_CYCLES) {
+        printf("u2b: SyncBN peer exchange timeout rank %d cta %d waiting for rank %d epoch %u (have %u)\n", rank,
+               static_cast<int>(blockIdx.x), t, epoch, v);
+        __trap();
+      }
+    } while (true);
+  }
+  __syncthreads();
+  if (t < 2 * X2_CH) {
+    float acc = 0.f;
+    if (col_live) {
+      const float* mine = reinterpret_cast<const float*>(peers[rank]) + static_cast<size_t>(slot) * world * slot_floats + col;
+      for (int q = 0; q < world; ++q) acc += __ldcv(mine + static_cast<size_t>(q) * slot_floats);
+    }
+    tot[t] = acc;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+bn_xchg2_finalize_kernel(const float* __restrict__ partials, int S, const unsigned long long* __restrict__ peers, int world,
+                         int rank, unsigned int* __restrict__ epoch_ctrs, int slot_floats, double n_total,
+                         const float* __restrict__ w, const float* __restrict__ b, float eps, float momentum,
+                         float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ stats,
+                         int C) {
+  __shared__ float local[2 * X2_CH], tot[2 * X2_CH];
+  xchg2_reduce(partials, S, C, peers, world, rank, epoch_ctrs, slot_floats, local, tot);
+  const int c = blockIdx.x * X2_CH + threadIdx.x;
+  if (threadIdx.x >= X2_CH || c >= C) return;
+  const double mu = static_cast<double>(tot[threadIdx.x]) / n_total;
+  double var = static_cast<double>(tot[X2_CH + threadIdx.x]) / n_total - mu * mu;
+  if (var < 0.0) var = 0.0;
+  const float is = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float sc = (w ? w[c] : 1.f) * is;
+  stats[c] = static_cast<float>(mu);
+  stats[C + c] = is;
+  stats[2 * C + c] = sc;
+  stats[3 * C + c] = (b ? b[c] : 0.f) - static_cast<float>(mu) * sc;
+  if (running_mean) {
+    const double unbiased = n_total > 1.0 ? var * n_total / (n_total - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mu);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_xchg2_bwd_coeff_kernel(const float* __restrict__ partials, int S, const unsigned long long* __restrict__ peers, int world,
+                          int rank, unsigned int* __restrict__ epoch_ctrs, int slot_floats, double n_total,
+                          const float* __restrict__ stats, const float* __restrict__ w, float* __restrict__ coeff,
+                          float* __restrict__ gw_gb, int C) {
+  __shared__ float local[2 * X2_CH], tot[2 * X2_CH];
+  xchg2_reduce(partials, S, C, peers, world, rank, epoch_ctrs, slot_floats, local, tot);
+  const int c = blockIdx.x * X2_CH + threadIdx.x;
+  if (threadIdx.x >= X2_CH || c >= C) return;
+  if (gw_gb) {   // LOCAL sums: the gradient all-reduce averages them like every other parameter gradient
+    gw_gb[c] = local[X2_CH + threadIdx.x];
+    gw_gb[C + c] = local[threadIdx.x];
+  }
+  const float inv_n = static_cast<float>(1.0 / n_total);
+  const float mu = stats[c], is = stats[C + c];
+  const float A = (w ? w[c] : 1.f) * is;
+  const float B = -A * is * tot[X2_CH + threadIdx.x] * inv_n;
+  coeff[c] = A;
+  coeff[C + c] = B;
+  coeff[2 * C + c] = -A * tot[threadIdx.x] * inv_n - B * mu;
+}
+
 template <typename T, int MODE>
 int launch_reduce(const void* a, const void* x, const void* y, const float* mean, const float* invstd,
                   long long P, int C, float* partials, cudaStream_t stream, const float* relu_scale_shift = nullptr) {
@@ -749,7 +868,38 @@ int u2b_gn_bwd_coeff(const float* partials, int S, int64_t HW, int G, const floa
 // epoch_ctr: device uint32 (start 0), advanced by one per exchange inside the kernel; every rank performs the same
 // sequence of exchanges, so the counters stay identical (and a CUDA-graph replay keeps working). slot_floats >= 2C.
 size_t u2b_bn_xchg_buffer_bytes(int world, int slot_floats) {
-  return static_cast<size_t>(2) * world * slot_floats * sizeof(float) + static_cast<size_t>(world) * 4 + 64;
+  return static_cast<size_t>(2) * world * slot_floats * sizeof(float) + X2_FLAG_SKIP +
+         static_cast<size_t>(world) * X2_MAXCTAS * 4 + 64;
+}
+
+int u2b_bn_xchg2_max_ctas(void) { return X2_MAXCTAS; }
+
+// Multi-CTA variants taking the (S, 2C) partial rows directly (no separate u2b_bn_sum_partials launch). epoch_ctrs: device
+// uint32[u2b_bn_xchg2_max_ctas()], zero-initialised once, advanced inside the kernels.
+int u2b_bn_xchg2_finalize(const float* partials, int S, const void* peers, int world, int rank, uint32_t* epoch_ctrs,
+                          int slot_floats, double n_total, const float* w, const float* b, float eps, float momentum,
+                          float* running_mean, float* running_var, float* stats, int C, cudaStream_t stream) {
+  U2B_CHECK_ARG(partials && S > 0 && peers && stats && epoch_ctrs && world > 0 && world <= 32 && rank >= 0 && rank < world &&
+                    2 * C <= slot_floats && C <= X2_CH * X2_MAXCTAS,
+                "bn_xchg2_finalize: bad arguments");
+  bn_xchg2_finalize_kernel<<<(C + X2_CH - 1) / X2_CH, 256, 0, stream>>>(
+      partials, S, static_cast<const unsigned long long*>(peers), world, rank, epoch_ctrs, slot_floats, n_total, w, b, eps,
+      momentum, running_mean, running_var, stats, C);
+  U2B_LAUNCH_CHECK();
+  return 0;
+}
+
+int u2b_bn_xchg2_bwd_coeff(const float* partials, int S, const void* peers, int world, int rank, uint32_t* epoch_ctrs,
+                           int slot_floats, double n_total, const float* stats, const float* w, float* coeff, float* gw_gb,
+                           int C, cudaStream_t stream) {
+  U2B_CHECK_ARG(partials && S > 0 && peers && stats && coeff && epoch_ctrs && world > 0 && world <= 32 && rank >= 0 &&
+                    rank < world && 2 * C <= slot_floats && C <= X2_CH * X2_MAXCTAS,
+                "bn_xchg2_bwd_coeff: bad arguments");
+  bn_xchg2_bwd_coeff_kernel<<<(C + X2_CH - 1) / X2_CH, 256, 0, stream>>>(
+      partials, S, static_cast<const unsigned long long*>(peers), world, rank, epoch_ctrs, slot_floats, n_total, stats, w,
+      coeff, gw_gb, C);
+  U2B_LAUNCH_CHECK();
+  return 0;
 }
 
 int u2b_bn_xchg_finalize(const float* sums, const void* peers, int world, int rank, uint32_t* epoch_ctr, int slot_floats,

@@ -45,6 +45,7 @@ class _PeerExchange:
         self.hdl = symm.rendezvous(self.buf, dist.group.WORLD.group_name)
         self.peers = torch.tensor([int(p) for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=device)
         self.epoch_ctr = torch.zeros((1,), dtype=torch.int32, device=device)   # advanced inside the kernels
+        self.epoch_ctrs = torch.zeros((int(L.u2b_bn_xchg2_max_ctas()),), dtype=torch.int32, device=device)   # per-CTA sequences
         dist.barrier()
 
 
@@ -120,16 +121,17 @@ class _BNAct(torch.autograd.Function):
         n_total = float(P) * world
         done = False
         if world > 1:
-            sums = torch.empty((2 * C,), dtype=torch.float32, device=dev)
-            _lib.check(L.u2b_bn_sum_partials(_p(part), S, 2 * C, _p(sums), s), "u2b_bn_sum_partials")
             px = peer_exchange(dev)
             if px is not None and 2 * C <= px.SLOT_FLOATS:
-                _lib.check(L.u2b_bn_xchg_finalize(_p(sums), _p(px.peers), px.world, px.rank, _p(px.epoch_ctr),
-                                                  px.SLOT_FLOATS, n_total, _p(weight), _p(bias), float(eps),
-                                                  float(momentum), _p(running_mean), _p(running_var), _p(stats), C, s),
-                           "u2b_bn_xchg_finalize")
+                # partial rows -> sums -> NVLink exchange -> statistics in ONE launch (one CTA per 32 channels)
+                _lib.check(L.u2b_bn_xchg2_finalize(_p(part), S, _p(px.peers), px.world, px.rank, _p(px.epoch_ctrs),
+                                                   px.SLOT_FLOATS, n_total, _p(weight), _p(bias), float(eps),
+                                                   float(momentum), _p(running_mean), _p(running_var), _p(stats), C, s),
+                           "u2b_bn_xchg2_finalize")
                 done = True
             else:
+                sums = torch.empty((2 * C,), dtype=torch.float32, device=dev)
+                _lib.check(L.u2b_bn_sum_partials(_p(part), S, 2 * C, _p(sums), s), "u2b_bn_sum_partials")
                 dist.all_reduce(sums)
                 part, S = sums, 1
         if not done:
@@ -171,14 +173,14 @@ class _BNAct(torch.autograd.Function):
         coeff = torch.empty((3 * C,), dtype=torch.float32, device=dev)
         gwb = torch.empty((2 * C,), dtype=torch.float32, device=dev)      # dgamma | dbeta (LOCAL sums: DDP reduces them)
         if world > 1:
-            sums = torch.empty((2 * C,), dtype=torch.float32, device=dev)
-            _lib.check(L.u2b_bn_sum_partials(_p(part), S, 2 * C, _p(sums), s), "u2b_bn_sum_partials")
             px = peer_exchange(dev)
             if px is not None and 2 * C <= px.SLOT_FLOATS:
-                _lib.check(L.u2b_bn_xchg_bwd_coeff(_p(sums), _p(px.peers), px.world, px.rank, _p(px.epoch_ctr),
-                                                   px.SLOT_FLOATS, n_total, _p(stats), _p(weight), _p(coeff), _p(gwb),
-                                                   C, s), "u2b_bn_xchg_bwd_coeff")
+                _lib.check(L.u2b_bn_xchg2_bwd_coeff(_p(part), S, _p(px.peers), px.world, px.rank, _p(px.epoch_ctrs),
+                                                    px.SLOT_FLOATS, n_total, _p(stats), _p(weight), _p(coeff), _p(gwb),
+                                                    C, s), "u2b_bn_xchg2_bwd_coeff")
             else:
+                sums = torch.empty((2 * C,), dtype=torch.float32, device=dev)
+                _lib.check(L.u2b_bn_sum_partials(_p(part), S, 2 * C, _p(sums), s), "u2b_bn_sum_partials")
                 gwb[:C].copy_(sums[C:])
                 gwb[C:].copy_(sums[:C])
                 dist.all_reduce(sums)
