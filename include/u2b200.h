@@ -114,6 +114,10 @@ int u2b_roi_align_bwd(int dtype, int num_levels, float* const* grad_feats, const
                       const int32_t* ws, const float* scales, int64_t C, const float* rois5,
                       const int32_t* levels, int64_t K, int P, const void* grad_out, float grad_scale,
                       u2b_stream_t stream);
+/* Implementation switch for u2b_roi_align_fwd / _bwd: 1 (default) = one CTA per ROI, separable weight tables in shared
+ * memory (forward gathers (g+1)^2 pixels per bin, backward issues one vector atomic per footprint pixel); 0 = one warp per
+ * output bin (torchvision's per-sample order). Same results up to fp32 summation order. */
+int u2b_roi_align_set_impl(int impl);
 
 /* Channel-major variants (round-2 draft): out / grad_out are (K, C, P, P) contiguous, the layout torch.flatten(x, 1)
  * of the box head reads (box_head.py:99-106), so no transposing copy is needed on either side of the FC layers. */

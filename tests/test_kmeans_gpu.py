@@ -177,3 +177,23 @@ def test_mstep_sort_by_label_equals_shared_accumulators(N, D, K):
     for got in (a, b):
         assert float((got[:, :D].double() - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max()))
     assert torch.equal(a[:, D].double(), torch.bincount(st.labels.long(), minlength=K).double())
+
+
+def test_run_kmeans_save_load_and_decode_json(tmp_path):
+    """nn_utils.py:382-405: recompute=True saves labels / centroids (never overwriting), recompute=False loads them back,
+    cluster_labels_decode.json maps the last two path components of every image to its cluster id."""
+    import json
+    from types import SimpleNamespace
+    from u2seg_b200.clustering import run_kMeans
+    x = make_mixture(3000, 64, 12, seed=2, spread=1.0)
+    ds = SimpleNamespace(imgs=[("/data/imagenet/train/n%04d/img_%05d.JPEG" % (i % 7, i), 0) for i in range(3000)])
+    cl, c = run_kMeans(x, 10, 400, ds, Niter=5, recompute=True, seed=3, save=True, save_dir=str(tmp_path))
+    assert (tmp_path / "cluster_labels_400_3.npy").exists() and (tmp_path / "centroids_400_3.npy").exists()
+    cl2, c2 = run_kMeans(None, 10, 400, ds, Niter=5, seed=3, save_dir=str(tmp_path))        # reference default: recompute=False
+    assert torch.equal(cl, cl2) and torch.equal(c, c2)
+    dec = json.load(open(tmp_path / "cluster_labels_decode.json"))
+    assert len(dec) == 3000 and dec["n0003/img_00003.JPEG"] == int(cl[3])
+    with pytest.raises(ValueError):
+        run_kMeans(None, 10, 400, None, Niter=5, seed=3)                                   # nothing to load from
+    with pytest.raises(ValueError):
+        run_kMeans(x.float() * 1e6, 10, 401, None, Niter=2, recompute=True, seed=3)      # beyond fp16: refused, not inf

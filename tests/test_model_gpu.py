@@ -73,22 +73,34 @@ def test_training_losses_match_reference(golden_dir, monkeypatch):
 
 
 def test_training_gradients_match_oracle(monkeypatch):
-    """Backward parity: d(sum of losses)/d(params) vs autograd through the CPU oracle."""
+    """Backward parity: d(sum of losses)/d(params) vs autograd through the CPU oracle, 2 images of 256x256 (BN batches are not
+    degenerate). Both sides sample "the first k candidates in index order" (randperm -> arange, as in the BASELINE-size
+    fixtures): with random draws one borderline candidate changes the length of a permutation and with it every later
+    sample, which shows up as a few per cent in the gradients and says nothing about the arithmetic."""
     from u2seg_b200.modeling import rpn
     K, S, seed = 800, 28, 5
     cfg = do.DetCfg(K, S)
     params = do.init_params(cfg, 0)
-    data = do.synthetic_batch(2, 256, 256, K, S, seed=seed, G=6, min_size=16, max_size=120)   # 2 images: BN batches are not degenerate
+    data = do.synthetic_batch(2, 256, 256, K, S, seed=seed, G=6, min_size=16, max_size=120)
     names = ["backbone.fpn_output2.weight", "backbone.bottom_up.res3.0.conv2.weight", "roi_heads.box_head.1.fc1.weight",
              "roi_heads.mask_head.mask_fcn2.weight", "proposal_generator.rpn_head.conv.weight", "sem_seg_head.p4.2.weight",
              "backbone.bottom_up.stem.conv1.norm.weight"]
     op = {k: v.clone().requires_grad_(k in names) for k, v in params.items()}
-    torch.manual_seed(seed)
-    sum(do.forward_train(op, cfg, *data).values()).backward()
+
+    def first(n, device=None, **kw):
+        return torch.arange(n, device=device)
+
+    with monkeypatch.context() as m:
+        m.setattr(torch, "randperm", first)
+        want_losses = do.forward_train(op, cfg, *data)
+        sum(want_losses.values()).backward()
     model = _build(K, params, True)
-    monkeypatch.setattr(rpn, "_randperm", _cpu_randperm)
-    torch.manual_seed(seed)
-    sum(model(_make_batch(data)).values()).backward()
+    monkeypatch.setattr(rpn, "_randperm", first)
+    got_losses = model(_make_batch(data))
+    sum(got_losses.values()).backward()
+    worst = max(abs(float(got_losses[k]) - float(want_losses[k])) / max(abs(float(want_losses[k])), 1e-3) for k in want_losses)
+    print("   worst loss error %.2e" % worst)
+    assert worst < 1e-4
     named = dict(model.named_parameters())
     bad = []
     for k in names:
@@ -96,7 +108,7 @@ def test_training_gradients_match_oracle(monkeypatch):
         l2 = float((a - b).norm() / (b.norm() + 1e-30))
         mx = float((a - b).abs().max() / (b.abs().max() + 1e-30))
         print("   %-45s relative L2 error %.2e, max error / max entry %.2e" % (k, l2, mx))
-        if l2 > 1e-2 or mx > 2e-2:     # fp32 on both sides; what is left is summation order through 53 BN layers
+        if l2 > 1e-2 or mx > 1e-2:     # fp32 on both sides; what is left is summation order through 53 BN layers
             bad.append((k, l2, mx))
     assert not bad, bad
 

@@ -82,6 +82,40 @@ def test_pooler_hot_path_shapes_fwd_bwd(dtype, tol):
         assert float((a.grad.float().cpu() - b.grad).abs().max()) <= max(tol * 8 * scale, 1e-4)
 
 
+@pytest.mark.parametrize("P", [7, 14])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_roi_align_per_roi_kernels_equal_per_bin_kernels(P, dtype):
+    """csrc/roi_align.cu: the per-ROI factorised kernels (separable weight tables, one atomic per footprint pixel) against the
+    per-sample kernels (torchvision's order) - same values up to fp32 summation order. Boxes: ordinary, tiny (bins < 1 px),
+    elongated beyond the 64-pixel table (fallback inside the launch), partly / fully outside the image, degenerate."""
+    from u2seg_b200 import _lib
+    from u2seg_b200.layers import ROIPooler
+    g = torch.Generator().manual_seed(5)
+    feats = [cl(torch.randn(2, 64, 256 // s, 256 // s, generator=g).to(dtype).cuda()) for s in (4, 8, 16, 32)]
+    c = torch.rand(150, 2, generator=g) * 256
+    wh = torch.exp(torch.rand(150, 2, generator=g) * 5.5)
+    b = torch.cat([c - wh / 2, c + wh / 2], 1)
+    special = torch.tensor([[0, 0, 256, 256.0], [-40, -30, 20, 25], [250, 240, 300, 290], [400, 400, 420, 430], [10, 10, 10, 10],
+                            [3, 100, 253, 104], [100, 2, 103, 255], [5.2, 7.9, 6.1, 8.3]])
+    boxes = [torch.cat([b[:75], special]).cuda(), b[75:].cuda()]
+    res = []
+    for impl in (0, 1):
+        _lib.check(_lib.lib().u2b_roi_align_set_impl(impl), "set_impl")
+        try:
+            fs = [f.clone().requires_grad_(True) for f in feats]
+            out = ROIPooler(P, (0.25, 0.125, 0.0625, 0.03125), 0, "ROIAlignV2")(fs, boxes)
+            gout = torch.randn(out.shape, generator=torch.Generator().manual_seed(1)).to(dtype).cuda()
+            out.backward(gout)
+            res.append((out.detach().float(), [f.grad.float() for f in fs]))
+        finally:
+            _lib.check(_lib.lib().u2b_roi_align_set_impl(1), "set_impl")
+    (o0, g0), (o1, g1) = res
+    tol = 1e-5 if dtype == torch.float32 else 8e-3          # bf16: the OUTPUT rounding of a value that differs in the last fp32 bits
+    assert torch.allclose(o1, o0, rtol=tol, atol=tol), float((o1 - o0).abs().max())
+    for a, bb in zip(g1, g0):
+        assert float((a - bb).abs().max()) <= (2e-5 if dtype == torch.float32 else 1e-2) * max(1.0, float(bb.abs().max()))
+
+
 def test_feature_tap_shared_backward_equals_separate_calls():
     """4 pooling calls through one FeatureTap (one zero-fill + one cast per step) == 4 independent calls."""
     from u2seg_b200.layers import FeatureTap, ROIPooler

@@ -5,7 +5,8 @@ n=${1:-2}
 mkdir -p gpurun_out
 timeout 420 bash tools/run_multigpu_tests.sh "$n" > gpurun_out/r02_multi_tests_n$n.log 2>&1; tail -6 gpurun_out/r02_multi_tests_n$n.log | cut -c1-300
 for ov in 1 0; do
-  U2B_OVERLAP_ALLREDUCE=$ov U2B_BENCH_SKIP_CPU=1 U2B_BENCH_SKIP_INFER=1 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 \
+  skipkm=0; [ "$ov" = 0 ] && skipkm=1
+  U2B_OVERLAP_ALLREDUCE=$ov U2B_BENCH_SKIP_KMEANS=$skipkm U2B_BENCH_SKIP_CPU=1 U2B_BENCH_SKIP_INFER=1 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 \
       --master-port 29511 bench.py --gpus "$n" --steps 20 --warmup 3 > "gpurun_out/r02_bench_n${n}_ov$ov.json" 2> "gpurun_out/r02_bench_n${n}_ov$ov.err"
   echo "bench n=$n overlap=$ov rc=$?"; tail -c 300 "gpurun_out/r02_bench_n${n}_ov$ov.err"
   python - "gpurun_out/r02_bench_n${n}_ov$ov.json" <<'PY'

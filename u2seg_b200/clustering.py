@@ -86,7 +86,14 @@ def to_device_fp16(x, device=None):
     if not torch.cuda.is_available():
         raise RuntimeError("u2seg_b200.clustering needs a CUDA device (no CPU fallback)")
     device = device or torch.device("cuda", torch.cuda.current_device())
-    return x.to(device=device, dtype=torch.float16, non_blocking=True).contiguous()
+    x16 = x.to(device=device, dtype=torch.float16, non_blocking=True).contiguous()
+    # The reference keeps fp32 (nn_utils.py:304); here distances AND centroid means are taken over the fp16-rounded rows
+    # (relative rounding 2^-11 per component; DINO embeddings are L2-normalised). Values beyond fp16's range would turn
+    # into inf silently - refuse them instead.
+    if x.dtype != torch.float16 and not bool(torch.isfinite(x16).all()):
+        raise ValueError("u2seg_b200.clustering: embeddings exceed the fp16 range (|x| > 65504) or are not finite; "
+                         "rescale them (k-means labels are invariant to a common scale)")
+    return x16
 
 
 def init_centroids_sharded(x_local, r, row_offset, group=None):
@@ -156,20 +163,51 @@ def KMeans(x, seed, K=10, Niter=10, init_inds=None, verbose=True, force_no_lazy_
     return cl, c
 
 
-def run_kMeans(feats_list, num_centroids, final_sample_num=None, train_memory_dataset=None, Niter=100,
-               recompute=True, use_cuda=True, seed=None, force_no_lazy_tensor=False, save=False,
-               save_dir=None):
-    """Mirror of nn_utils.py:382 `run_kMeans` (recompute branch; optional .npy dump)."""
-    cluster_labels, centroids = KMeans(feats_list, seed=seed, K=num_centroids, Niter=Niter, verbose=False)
-    cluster_labels, centroids = cluster_labels.cpu(), centroids.cpu()
-    if save and save_dir is not None:
-        import os
+def run_kMeans(feats_list, num_centroids, final_sample_num, train_memory_dataset=None, Niter=100, recompute=False,
+               use_cuda=True, seed=None, force_no_lazy_tensor=False, save=True, save_dir=None):
+    """nn_utils.py:382-405 `run_kMeans`, same arguments and defaults. recompute=True: k-means, then (save=True) the labels /
+    centroids go to cluster_labels_{n}{_seed}.npy / centroids_{n}{_seed}.npy; recompute=False (the reference's default):
+    those files are loaded. Either way cluster_labels_decode.json ({image path: cluster id}) is written when
+    `train_memory_dataset` (an object with `.imgs`, as in the reference) is given. Existing files are never overwritten
+    (nn_utils.py:75-107). `save_dir` stands in for the reference's global cfg.RUN_DIR; without it nothing touches the disk
+    (= cfg.SKIP_SAVE) and recompute=False is an error. use_cuda / force_no_lazy_tensor: accepted, there is one device path."""
+    import json
+    import os
 
-        import numpy as np
-        sfx = "_{}".format(seed) if seed is not None else ""
-        np.save(os.path.join(save_dir, "cluster_labels_{}{}.npy".format(final_sample_num, sfx)),
-                cluster_labels.numpy())
-        np.save(os.path.join(save_dir, "centroids_{}{}.npy".format(final_sample_num, sfx)), centroids.numpy())
+    import numpy as np
+    sfx = "_{}".format(seed) if seed is not None else ""
+    names = ("cluster_labels_{}{}.npy".format(final_sample_num, sfx), "centroids_{}{}.npy".format(final_sample_num, sfx))
+
+    def save_once(name, writer):
+        path = os.path.join(save_dir, name)
+        if os.path.exists(path):
+            print("File exists: {}. Not overwriting (if the file is stale, please save manually).".format(path))
+        else:
+            writer(path)
+            print("File saved to: {}".format(path))
+
+    if recompute:
+        cluster_labels, centroids = KMeans(feats_list, seed=seed, K=num_centroids, Niter=Niter, verbose=True,
+                                           force_no_lazy_tensor=force_no_lazy_tensor)
+        cluster_labels, centroids = cluster_labels.cpu(), centroids.cpu()
+        inds, cnts = torch.unique(cluster_labels, return_counts=True)
+        print("Num of clusters: {} min: {} max: {}".format(len(inds), cnts.min().item(), cnts.max().item()))
+        if save and save_dir is not None:
+            save_once(names[0], lambda path: np.save(path, cluster_labels.numpy()))
+            save_once(names[1], lambda path: np.save(path, centroids.numpy()))
+    else:
+        if save_dir is None:
+            raise ValueError("run_kMeans(recompute=False) loads {} / {} from save_dir (the reference's cfg.RUN_DIR): "
+                             "pass save_dir, or recompute=True".format(*names))
+        cluster_labels = torch.tensor(np.load(os.path.join(save_dir, names[0])))
+        centroids = torch.tensor(np.load(os.path.join(save_dir, names[1])))
+    if train_memory_dataset is not None and save_dir is not None:
+        def image_key(entry):            # nn_utils.py:87-91: the last two path components of the image file
+            parts = entry[0].split("/")
+            return "/".join(parts[-2:])
+
+        decode = {image_key(train_memory_dataset.imgs[i]): int(cid) for i, cid in enumerate(cluster_labels.tolist())}
+        save_once("cluster_labels_decode.json", lambda path: json.dump(decode, open(path, "w")))
     return cluster_labels, centroids
 
 
@@ -197,8 +235,10 @@ def _knn_prepare(x32):
 def _knn_rounding(x32, x16, chunk=262144):
     """max_i |x_i - fp16(x_i)|_2 (the MEASURED rounding error of the candidate pass's operands), as a 0-d tensor."""
     worst = torch.zeros((), dtype=torch.float32, device=x32.device)
-    for s in range(0, x32.shape[0], chunk):
-        worst = torch.maximum(worst, (x32[s:s + chunk] - x16[s:s + chunk].float()).norm(dim=1).max())
+    n = x32.shape[0]                  # x16 may carry zero padding rows beyond n
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        worst = torch.maximum(worst, (x32[s:e] - x16[s:e].float()).norm(dim=1).max())
     return worst
 
 

@@ -636,40 +636,42 @@ __device__ __forceinline__ void xchg2_reduce(const float* __restrict__ partials,
   const int slot = epoch & 1;
   const int col = (t < X2_CH) ? c0 + t : C + c0 + (t - X2_CH);
   const bool col_live = t < 2 * X2_CH && (c0 + (t & (X2_CH - 1))) < C;
+  // Low-latency exchange (the "LL" idea of NCCL's small-message protocol): every value travels as ONE 8-byte store
+  // {float bits, epoch}; 8-byte scalar stores are single-copy atomic, so the reader polls the value words themselves and
+  // needs neither a separate flag nor a release fence (which would cost a second NVLink round trip per exchange).
+  const size_t ll_off = static_cast<size_t>(2) * world * slot_floats * sizeof(float) + X2_FLAG_SKIP +
+                        static_cast<size_t>(world) * X2_MAXCTAS * 4 + 64;
   if (t < 2 * X2_CH) {
     float v = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; ++q) v += red[q][t];
     local[t] = v;
-    if (col_live)
-      for (int p = 0; p < world; ++p)
-        reinterpret_cast<float*>(peers[p])[(static_cast<size_t>(slot) * world + rank) * slot_floats + col] = v;
-  }
-  __syncthreads();
-  const size_t flag_off = static_cast<size_t>(2) * world * slot_floats * sizeof(float) + X2_FLAG_SKIP;
-  if (t < world) {
-    unsigned int* f = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(peers[t]) + flag_off) + rank * X2_MAXCTAS + blockIdx.x;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
-    const unsigned int* g = reinterpret_cast<const unsigned int*>(reinterpret_cast<const char*>(peers[rank]) + flag_off) +
-                            t * X2_MAXCTAS + blockIdx.x;
-    const long long t0 = clock64();
-    unsigned int v;
-    do {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(g) : "memory");
-      if (static_cast<int>(v - epoch) >= 0) break;
-      if (clock64() - t0 > U2B_XCHG_TIMEOUT_CYCLES) {
-        printf("u2b: SyncBN peer exchange timeout rank %d cta %d waiting for rank %d epoch %u (have %u)\n", rank,
-               static_cast<int>(blockIdx.x), t, epoch, v);
-        __trap();
+    if (col_live) {
+      const unsigned long long word = (static_cast<unsigned long long>(epoch) << 32) | __float_as_uint(v);
+      const size_t idx = (static_cast<size_t>(slot) * world + rank) * slot_floats + col;
+      for (int p = 0; p < world; ++p) {
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peers[p]) + ll_off) + idx;
+        asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
       }
-    } while (true);
-  }
-  __syncthreads();
-  if (t < 2 * X2_CH) {
+    }
     float acc = 0.f;
     if (col_live) {
-      const float* mine = reinterpret_cast<const float*>(peers[rank]) + static_cast<size_t>(slot) * world * slot_floats + col;
-      for (int q = 0; q < world; ++q) acc += __ldcv(mine + static_cast<size_t>(q) * slot_floats);
+      const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(peers[rank]) + ll_off) +
+                                       static_cast<size_t>(slot) * world * slot_floats + col;
+      const long long t0 = clock64();
+      for (int q = 0; q < world; ++q) {        // fixed order: every rank adds the same values in the same order
+        unsigned long long w64;
+        do {
+          asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(w64) : "l"(mine + static_cast<size_t>(q) * slot_floats) : "memory");
+          if (static_cast<unsigned int>(w64 >> 32) == epoch) break;
+          if (clock64() - t0 > U2B_XCHG_TIMEOUT_CYCLES) {
+            printf("u2b: SyncBN peer exchange timeout rank %d cta %d column %d waiting for rank %d epoch %u (have %u)\n", rank,
+                   static_cast<int>(blockIdx.x), col, q, epoch, static_cast<unsigned int>(w64 >> 32));
+            __trap();
+          }
+        } while (true);
+        acc += __uint_as_float(static_cast<unsigned int>(w64));
+      }
     }
     tot[t] = acc;
   }
@@ -868,8 +870,10 @@ int u2b_gn_bwd_coeff(const float* partials, int S, int64_t HW, int G, const floa
 // epoch_ctr: device uint32 (start 0), advanced by one per exchange inside the kernel; every rank performs the same
 // sequence of exchanges, so the counters stay identical (and a CUDA-graph replay keeps working). slot_floats >= 2C.
 size_t u2b_bn_xchg_buffer_bytes(int world, int slot_floats) {
+  // [2 slots x world x slot_floats fp32 | flags of the single-CTA kernels | (unused) | 2 slots x world x slot_floats 8-byte
+  // {value, epoch} words of the multi-CTA kernels]
   return static_cast<size_t>(2) * world * slot_floats * sizeof(float) + X2_FLAG_SKIP +
-         static_cast<size_t>(world) * X2_MAXCTAS * 4 + 64;
+         static_cast<size_t>(world) * X2_MAXCTAS * 4 + 64 + static_cast<size_t>(2) * world * slot_floats * 8 + 64;
 }
 
 int u2b_bn_xchg2_max_ctas(void) { return X2_MAXCTAS; }

@@ -332,6 +332,211 @@ roi_align_bwd_kernel(Pyramid pyr, int C, const float* __restrict__ rois,
                   [&](int c0, float (&gv)[Vec<T>::N]) { Vec<T>::load(go + c0, gv); });
 }
 
+// ---- per-ROI factorised kernels (round 2) -----------------------------------------------------------------------------
+// A sample's bilinear weight is wy * wx and a bin's samples form a product grid, so the whole ROI pooling is a separable
+// linear map:   Y[ph][pw] = 1/count * sum_py sum_px AY[py][ph] * BX[px][pw] * X[py][px],
+// AY[py][ph] = total y-weight the sample rows of bin row ph give pixel row py (BX likewise; invalid samples - outside
+// [-1, size] - contribute nothing, and validity is per axis, roi_align_kernel.cu bilinear_interpolate). One CTA per ROI
+// builds the two small tables in shared memory once; then
+//   forward : a warp per output bin gathers the (rows x cols) pixels its samples touch - (g+1)^2 loads for a g x g sample
+//             grid instead of 4 g^2, no per-sample index arithmetic;
+//   backward: a warp per FOOTPRINT PIXEL gathers the <= 2 x 2 bins that touch it and issues ONE vector atomic per pixel
+//             and 4 channels - (P g + 1)^2 per ROI instead of P^2 (g + 1)^2 (bins share their border pixels): 2x fewer
+//             for g = 2. Results equal the per-sample kernels up to fp32 summation order.
+// ROIs whose footprint exceeds RA_FMAX pixels on an axis (not produced by the level assignment for boxes inside the image)
+// are handled by the per-bin routines inside the same launch.
+constexpr int RA_FMAX = 64;
+constexpr int RA_PMAX = 14;
+
+struct RoiTables {
+  float ay[RA_FMAX][RA_PMAX];
+  float bx[RA_FMAX][RA_PMAX];
+  int lo[2][RA_PMAX], hi[2][RA_PMAX];      // per bin row / column: first and last touched pixel (absolute), hi < lo = none
+  int bin_lo[2][RA_FMAX], bin_hi[2][RA_FMAX];   // per footprint row / column: first and last bin with a non-zero weight
+  int org[2], ext[2];
+};
+
+// returns false when the footprint does not fit the tables (caller falls back); all threads of the CTA must call it
+__device__ __forceinline__ bool roi_build_tables(RoiTables& t, const BinGeom& g, int P, int H, int W) {
+  const int tid = threadIdx.x;
+  if (tid < 2 * P) {
+    const int axis = tid / P, p = tid % P;          // axis 0: y, 1: x
+    const float start = axis ? g.start_w : g.start_h, bin = axis ? g.bin_w : g.bin_h;
+    const int grid = axis ? g.grid_w : g.grid_h, size = axis ? W : H;
+    int lo = 0x7fffffff, hi = -1;
+    for (int i = 0; i < grid; ++i) {
+      const AxisSample a = axis_sample(start + p * bin + (i + 0.5f) * bin / static_cast<float>(grid), size);
+      if (a.valid) {
+        lo = min(lo, a.lo);
+        hi = max(hi, a.hi);
+      }
+    }
+    t.lo[axis][p] = lo;
+    t.hi[axis][p] = hi;
+  }
+  __syncthreads();
+  if (tid < 2) {
+    int lo = 0x7fffffff, hi = -1;
+    for (int p = 0; p < P; ++p)
+      if (t.hi[tid][p] >= t.lo[tid][p]) {
+        lo = min(lo, t.lo[tid][p]);
+        hi = max(hi, t.hi[tid][p]);
+      }
+    t.org[tid] = lo;
+    t.ext[tid] = hi >= lo ? hi - lo + 1 : 0;
+  }
+  for (int i = tid; i < RA_FMAX * RA_PMAX; i += blockDim.x) {
+    (&t.ay[0][0])[i] = 0.f;
+    (&t.bx[0][0])[i] = 0.f;
+  }
+  __syncthreads();
+  if (t.ext[0] > RA_FMAX || t.ext[1] > RA_FMAX) return false;
+  if (tid < 2 * P) {      // bin p only writes column p of its axis' table: no conflicts
+    const int axis = tid / P, p = tid % P;
+    const float start = axis ? g.start_w : g.start_h, bin = axis ? g.bin_w : g.bin_h;
+    const int grid = axis ? g.grid_w : g.grid_h, size = axis ? W : H;
+    float (*tab)[RA_PMAX] = axis ? t.bx : t.ay;
+    const int org = t.org[axis];
+    for (int i = 0; i < grid; ++i) {
+      const AxisSample a = axis_sample(start + p * bin + (i + 0.5f) * bin / static_cast<float>(grid), size);
+      if (a.valid) {
+        tab[a.lo - org][p] += a.wlo;
+        tab[a.hi - org][p] += a.whi;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * RA_FMAX; i += blockDim.x) {
+    const int axis = i / RA_FMAX, r = i % RA_FMAX;
+    int lo = P, hi = -1;
+    if (r < t.ext[axis]) {
+      const float (*tab)[RA_PMAX] = axis ? t.bx : t.ay;
+      for (int p = 0; p < P; ++p)
+        if (tab[r][p] != 0.f) {
+          lo = min(lo, p);
+          hi = p;
+        }
+    }
+    t.bin_lo[axis][r] = lo;
+    t.bin_hi[axis][r] = hi;
+  }
+  __syncthreads();
+  return true;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+roi_align_fwd2_kernel(Pyramid pyr, int C, const float* __restrict__ rois, const int32_t* __restrict__ levels, int K, int P,
+                      T* __restrict__ out) {
+  constexpr int VN = Vec<T>::N;
+  __shared__ RoiTables t;
+  const int k = blockIdx.x, lane = threadIdx.x & 31;
+  const int nwarps = (blockDim.x >> 5) * gridDim.y, warp = (threadIdx.x >> 5) * gridDim.y + blockIdx.y;   // work items are strided over the ROI's CTAs
+  const float* r = rois + static_cast<size_t>(k) * 5;
+  const int lvl = levels ? levels[k] : 0;
+  const int H = pyr.H[lvl], W = pyr.W[lvl];
+  const T* feat = static_cast<const T*>(pyr.feat[lvl]) + static_cast<size_t>(static_cast<int>(r[0])) * H * W * C;
+  const BinGeom g = bin_geometry(r, pyr.scale[lvl], P);
+  T* o = out + static_cast<size_t>(k) * P * P * C;
+  if (!roi_build_tables(t, g, P, H, W)) {
+    for (int bin = warp; bin < P * P; bin += nwarps)
+      for (int c0 = lane * VN; c0 < C; c0 += 32 * VN) {
+        float acc[VN];
+        bin_forward<T>(feat, H, W, C, g, bin / P, bin % P, c0, acc);
+        Vec<T>::store(o + static_cast<size_t>(bin) * C + c0, acc);
+      }
+    return;
+  }
+  const float inv_count = 1.f / g.count;
+  const int oy = t.org[0], ox = t.org[1];
+  for (int bin = warp; bin < P * P; bin += nwarps) {
+    const int ph = bin / P, pw = bin % P;
+    const int y0 = t.lo[0][ph], y1 = t.hi[0][ph], x0 = t.lo[1][pw], x1 = t.hi[1][pw];
+    for (int c0 = lane * VN; c0 < C; c0 += 32 * VN) {
+      float acc[VN];
+#pragma unroll
+      for (int i = 0; i < VN; ++i) acc[i] = 0.f;
+      for (int py = y0; py <= y1; ++py) {
+        const float wy = t.ay[py - oy][ph];
+        if (wy == 0.f) continue;
+        const T* row = feat + (static_cast<size_t>(py) * W) * C + c0;
+        for (int px = x0; px <= x1; ++px) {
+          const float w = wy * t.bx[px - ox][pw];
+          if (w == 0.f) continue;
+          float v[VN];
+          Vec<T>::load(row + static_cast<size_t>(px) * C, v);
+#pragma unroll
+          for (int i = 0; i < VN; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VN; ++i) acc[i] *= inv_count;
+      Vec<T>::store(o + static_cast<size_t>(bin) * C + c0, acc);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+roi_align_bwd2_kernel(Pyramid pyr, int C, const float* __restrict__ rois, const int32_t* __restrict__ levels, int K, int P,
+                      const T* __restrict__ gout, float grad_scale) {
+  constexpr int VN = Vec<T>::N;
+  __shared__ RoiTables t;
+  const int k = blockIdx.x, lane = threadIdx.x & 31;
+  const int nwarps = (blockDim.x >> 5) * gridDim.y, warp = (threadIdx.x >> 5) * gridDim.y + blockIdx.y;   // work items are strided over the ROI's CTAs
+  const float* r = rois + static_cast<size_t>(k) * 5;
+  const int lvl = levels ? levels[k] : 0;
+  const int H = pyr.H[lvl], W = pyr.W[lvl];
+  float* gfeat = pyr.grad[lvl] + static_cast<size_t>(static_cast<int>(r[0])) * H * W * C;
+  const BinGeom g = bin_geometry(r, pyr.scale[lvl], P);
+  const T* go = gout + static_cast<size_t>(k) * P * P * C;
+  if (!roi_build_tables(t, g, P, H, W)) {
+    for (int bin = warp; bin < P * P; bin += nwarps) {
+      const T* gb = go + static_cast<size_t>(bin) * C;
+      bin_backward<T>(gfeat, H, W, C, g, bin / P, bin % P, lane, grad_scale,
+                      [&](int c0, float (&gv)[Vec<T>::N]) { Vec<T>::load(gb + c0, gv); });
+    }
+    return;
+  }
+  const float scale = grad_scale / g.count;
+  const int oy = t.org[0], ox = t.org[1], eh = t.ext[0], ew = t.ext[1];
+  for (int pix = warp; pix < eh * ew; pix += nwarps) {
+    const int ry = pix / ew, rx = pix % ew;
+    const int ph0 = t.bin_lo[0][ry], ph1 = t.bin_hi[0][ry], pw0 = t.bin_lo[1][rx], pw1 = t.bin_hi[1][rx];
+    if (ph1 < ph0 || pw1 < pw0) continue;
+    float* dst = gfeat + (static_cast<size_t>(oy + ry) * W + ox + rx) * C;
+    for (int c0 = lane * VN; c0 < C; c0 += 32 * VN) {
+      float acc[VN];
+#pragma unroll
+      for (int i = 0; i < VN; ++i) acc[i] = 0.f;
+      for (int ph = ph0; ph <= ph1; ++ph) {
+        const float wy = t.ay[ry][ph];
+        if (wy == 0.f) continue;
+        for (int pw = pw0; pw <= pw1; ++pw) {
+          const float w = wy * t.bx[rx][pw];
+          if (w == 0.f) continue;
+          float v[VN];
+          Vec<T>::load(go + static_cast<size_t>(ph * P + pw) * C + c0, v);
+#pragma unroll
+          for (int i = 0; i < VN; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VN; i += 4)
+        atomicAdd(reinterpret_cast<float4*>(dst + c0 + i),
+                  make_float4(scale * acc[i], scale * acc[i + 1], scale * acc[i + 2], scale * acc[i + 3]));
+    }
+  }
+}
+
+// CTAs per ROI: few ROIs (inference mask head: 100) would leave most SMs idle with one CTA each
+inline unsigned roi2_splits(long long K) {
+  const long long want = (4LL * u2b_num_sms() + K - 1) / K;
+  return static_cast<unsigned>(want < 1 ? 1 : (want > 4 ? 4 : want));
+}
+
+int g_roi_align_impl = 1;   // 1: per-ROI factorised kernels, 0: one warp per output bin (round 1)
+
 // ---- channel-major ("CHW") output layout: out (K, C, P, P) contiguous, i.e. what torch.flatten(x, 1) of the box head
 // (box_head.py:99-106) wants. One CTA per ROI: the P*P bins are computed by the 8 warps into a shared-memory tile
 // [bin][C + 1] (fp32), which is then written out as C*P*P contiguous elements (and read back the same way in backward),
@@ -445,6 +650,14 @@ int u2b_roi_align_fwd(int dtype, int num_levels, const void* const* feats, const
   U2B_CHECK_ARG(C > 0 && C % vn == 0, "roi_align_fwd: C=%lld must be a multiple of %d", (long long)C, vn);
   const long long bins = static_cast<long long>(K) * P * P;
   const unsigned grid = static_cast<unsigned>((bins + 7) / 8);
+  if (g_roi_align_impl == 1 && P <= RA_PMAX && (dtype == 0 || dtype == 1 || dtype == 2)) {
+    const dim3 g2(static_cast<unsigned>(K), roi2_splits(K));
+    if (dtype == 0) roi_align_fwd2_kernel<float><<<g2, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (float*)out);
+    else if (dtype == 1) roi_align_fwd2_kernel<__half><<<g2, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (__half*)out);
+    else roi_align_fwd2_kernel<__nv_bfloat16><<<g2, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (__nv_bfloat16*)out);
+    U2B_LAUNCH_CHECK();
+    return 0;
+  }
   if (dtype == 0)
     roi_align_fwd_kernel<float><<<grid, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (float*)out);
   else if (dtype == 1)
@@ -475,6 +688,14 @@ int u2b_roi_align_bwd(int dtype, int num_levels, float* const* grad_feats, const
   U2B_CHECK_ARG(C > 0 && C % vn == 0, "roi_align_bwd: C must be a multiple of %d", vn);
   const long long bins = static_cast<long long>(K) * P * P;
   const unsigned grid = static_cast<unsigned>((bins + 7) / 8);
+  if (g_roi_align_impl == 1 && P <= RA_PMAX && (dtype == 0 || dtype == 1 || dtype == 2)) {
+    const dim3 g2(static_cast<unsigned>(K), roi2_splits(K));
+    if (dtype == 0) roi_align_bwd2_kernel<float><<<g2, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (const float*)grad_out, grad_scale);
+    else if (dtype == 1) roi_align_bwd2_kernel<__half><<<g2, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (const __half*)grad_out, grad_scale);
+    else roi_align_bwd2_kernel<__nv_bfloat16><<<g2, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (const __nv_bfloat16*)grad_out, grad_scale);
+    U2B_LAUNCH_CHECK();
+    return 0;
+  }
   if (dtype == 0)
     roi_align_bwd_kernel<float><<<grid, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (const float*)grad_out, grad_scale);
   else if (dtype == 1)
@@ -490,6 +711,13 @@ int u2b_roi_align_bwd(int dtype, int num_levels, float* const* grad_feats, const
   return 0;
 }
 
+
+// 1 (default): per-ROI factorised kernels; 0: one warp per output bin. Both produce the same values up to fp32 summation order.
+int u2b_roi_align_set_impl(int impl) {
+  U2B_CHECK_ARG(impl == 0 || impl == 1, "roi_align_set_impl: 0 or 1");
+  g_roi_align_impl = impl;
+  return 0;
+}
 
 // ---- channel-major layout (round-2 draft): out / grad_out are (K, C, P, P) contiguous ----
 int u2b_roi_align_chw_supported(int64_t C, int P) {
