@@ -19,3 +19,4 @@ except Exception as e:
     print("parse failed", e)
 PY
 done
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29517 tools/timeline_static.py "gpurun_out/r02_timeline_static_n$n.txt" 70 2>&1 | tail -14 | cut -c1-170

@@ -14,9 +14,16 @@ from u2seg_b200.engine import Trainer
 out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/timeline_static.txt"
 top_n = int(sys.argv[2]) if len(sys.argv) > 2 else 60
 torch.manual_seed(0)
-tr = Trainer(get_u2seg_cfg(800), amp_dtype=torch.bfloat16, static_graph=True, g_max=20)
-dev = torch.device("cuda", 0)
-pool = [_to_device(synthetic_batch(2, 1024, 1024, 800, 28, seed=1234 + i), dev) for i in range(2)]
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:        # torchrun: the data-parallel step (SyncBN exchanges + overlapped gradient all-reduce); rank 0 reports
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+tr = Trainer(get_u2seg_cfg(800), amp_dtype=torch.bfloat16, device=dev, static_graph=True, g_max=20)
+if world > 1:
+    tr.broadcast_parameters(0)
+pool = [_to_device(synthetic_batch(2, 1024, 1024, 800, 28, seed=1234 + 97 * rank + i), dev) for i in range(2)]
 for i in range(4):
     tr.run_step(pool[i % 2])
 torch.cuda.synchronize()
@@ -54,5 +61,9 @@ small = sum(1 for s, e, _ in last if e - s < 5.0)
 lines.append("kernels shorter than 5 us: %d (%.3f ms)" % (small, sum(e - s for s, e, _ in last if e - s < 5.0) / 1e3))
 for n, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top_n]:
     lines.append("%9.1f us %5d x %7.1f us  %s" % (v, c, v / c, n))
-open(out, "w").write("\n".join(lines) + "\n")
-print("\n".join(lines[:12]))
+if rank == 0:
+    open(out, "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines[:12]))
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()

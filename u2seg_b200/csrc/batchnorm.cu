@@ -634,8 +634,10 @@ __device__ __forceinline__ void xchg2_reduce(const float* __restrict__ partials,
   __syncthreads();
   if (t == 0) epoch_ctrs[blockIdx.x] = epoch;
   const int slot = epoch & 1;
-  const int col = (t < X2_CH) ? c0 + t : C + c0 + (t - X2_CH);
   const bool col_live = t < 2 * X2_CH && (c0 + (t & (X2_CH - 1))) < C;
+  // A word's location is (cta, t), not the channel column: every location is then written by ONE cta index only, whose epoch
+  // sequence it follows (a column-indexed layout lets a stale word of another layer's cta carry the awaited epoch).
+  const int cell = static_cast<int>(blockIdx.x) * 2 * X2_CH + t;
   // Low-latency exchange (the "LL" idea of NCCL's small-message protocol): every value travels as ONE 8-byte store
   // {float bits, epoch}; 8-byte scalar stores are single-copy atomic, so the reader polls the value words themselves and
   // needs neither a separate flag nor a release fence (which would cost a second NVLink round trip per exchange).
@@ -648,7 +650,7 @@ __device__ __forceinline__ void xchg2_reduce(const float* __restrict__ partials,
     local[t] = v;
     if (col_live) {
       const unsigned long long word = (static_cast<unsigned long long>(epoch) << 32) | __float_as_uint(v);
-      const size_t idx = (static_cast<size_t>(slot) * world + rank) * slot_floats + col;
+      const size_t idx = (static_cast<size_t>(slot) * world + rank) * slot_floats + cell;
       for (int p = 0; p < world; ++p) {
         unsigned long long* dst = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peers[p]) + ll_off) + idx;
         asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
@@ -657,7 +659,7 @@ __device__ __forceinline__ void xchg2_reduce(const float* __restrict__ partials,
     float acc = 0.f;
     if (col_live) {
       const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(peers[rank]) + ll_off) +
-                                       static_cast<size_t>(slot) * world * slot_floats + col;
+                                       static_cast<size_t>(slot) * world * slot_floats + cell;
       const long long t0 = clock64();
       for (int q = 0; q < world; ++q) {        // fixed order: every rank adds the same values in the same order
         unsigned long long w64;
@@ -665,8 +667,8 @@ __device__ __forceinline__ void xchg2_reduce(const float* __restrict__ partials,
           asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(w64) : "l"(mine + static_cast<size_t>(q) * slot_floats) : "memory");
           if (static_cast<unsigned int>(w64 >> 32) == epoch) break;
           if (clock64() - t0 > U2B_XCHG_TIMEOUT_CYCLES) {
-            printf("u2b: SyncBN peer exchange timeout rank %d cta %d column %d waiting for rank %d epoch %u (have %u)\n", rank,
-                   static_cast<int>(blockIdx.x), col, q, epoch, static_cast<unsigned int>(w64 >> 32));
+            printf("u2b: SyncBN peer exchange timeout rank %d cta %d cell %d waiting for rank %d epoch %u (have %u)\n", rank,
+                   static_cast<int>(blockIdx.x), cell, q, epoch, static_cast<unsigned int>(w64 >> 32));
             __trap();
           }
         } while (true);
@@ -884,7 +886,7 @@ int u2b_bn_xchg2_finalize(const float* partials, int S, const void* peers, int w
                           int slot_floats, double n_total, const float* w, const float* b, float eps, float momentum,
                           float* running_mean, float* running_var, float* stats, int C, cudaStream_t stream) {
   U2B_CHECK_ARG(partials && S > 0 && peers && stats && epoch_ctrs && world > 0 && world <= 32 && rank >= 0 && rank < world &&
-                    2 * C <= slot_floats && C <= X2_CH * X2_MAXCTAS,
+                    2 * C <= slot_floats && C <= X2_CH * X2_MAXCTAS && slot_floats >= 2 * X2_CH * ((C + X2_CH - 1) / X2_CH),
                 "bn_xchg2_finalize: bad arguments");
   bn_xchg2_finalize_kernel<<<(C + X2_CH - 1) / X2_CH, 256, 0, stream>>>(
       partials, S, static_cast<const unsigned long long*>(peers), world, rank, epoch_ctrs, slot_floats, n_total, w, b, eps,
@@ -897,7 +899,7 @@ int u2b_bn_xchg2_bwd_coeff(const float* partials, int S, const void* peers, int 
                            int slot_floats, double n_total, const float* stats, const float* w, float* coeff, float* gw_gb,
                            int C, cudaStream_t stream) {
   U2B_CHECK_ARG(partials && S > 0 && peers && stats && coeff && epoch_ctrs && world > 0 && world <= 32 && rank >= 0 &&
-                    rank < world && 2 * C <= slot_floats && C <= X2_CH * X2_MAXCTAS,
+                    rank < world && 2 * C <= slot_floats && C <= X2_CH * X2_MAXCTAS && slot_floats >= 2 * X2_CH * ((C + X2_CH - 1) / X2_CH),
                 "bn_xchg2_bwd_coeff: bad arguments");
   bn_xchg2_bwd_coeff_kernel<<<(C + X2_CH - 1) / X2_CH, 256, 0, stream>>>(
       partials, S, static_cast<const unsigned long long*>(peers), world, rank, epoch_ctrs, slot_floats, n_total, stats, w,

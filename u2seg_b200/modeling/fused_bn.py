@@ -49,6 +49,9 @@ class _PeerExchange:
         dist.barrier()
 
 
+# 1: one launch per BN direction (multi-CTA, 8-byte {value, epoch} words); 0: round 1's bn_sum_partials + single-CTA exchange
+XCHG_MULTI_CTA = __import__("os").environ.get("U2B_SYNCBN_XCHG2", "1") != "0"
+
 _xchg = {"obj": None, "failed": False}
 
 
@@ -122,7 +125,15 @@ class _BNAct(torch.autograd.Function):
         done = False
         if world > 1:
             px = peer_exchange(dev)
-            if px is not None and 2 * C <= px.SLOT_FLOATS:
+            if px is not None and 2 * C <= px.SLOT_FLOATS and not XCHG_MULTI_CTA:
+                sums = torch.empty((2 * C,), dtype=torch.float32, device=dev)
+                _lib.check(L.u2b_bn_sum_partials(_p(part), S, 2 * C, _p(sums), s), "u2b_bn_sum_partials")
+                _lib.check(L.u2b_bn_xchg_finalize(_p(sums), _p(px.peers), px.world, px.rank, _p(px.epoch_ctr),
+                                                  px.SLOT_FLOATS, n_total, _p(weight), _p(bias), float(eps),
+                                                  float(momentum), _p(running_mean), _p(running_var), _p(stats), C, s),
+                           "u2b_bn_xchg_finalize")
+                done = True
+            elif px is not None and 2 * C <= px.SLOT_FLOATS:
                 # partial rows -> sums -> NVLink exchange -> statistics in ONE launch (one CTA per 32 channels)
                 _lib.check(L.u2b_bn_xchg2_finalize(_p(part), S, _p(px.peers), px.world, px.rank, _p(px.epoch_ctrs),
                                                    px.SLOT_FLOATS, n_total, _p(weight), _p(bias), float(eps),
@@ -174,7 +185,13 @@ class _BNAct(torch.autograd.Function):
         gwb = torch.empty((2 * C,), dtype=torch.float32, device=dev)      # dgamma | dbeta (LOCAL sums: DDP reduces them)
         if world > 1:
             px = peer_exchange(dev)
-            if px is not None and 2 * C <= px.SLOT_FLOATS:
+            if px is not None and 2 * C <= px.SLOT_FLOATS and not XCHG_MULTI_CTA:
+                sums = torch.empty((2 * C,), dtype=torch.float32, device=dev)
+                _lib.check(L.u2b_bn_sum_partials(_p(part), S, 2 * C, _p(sums), s), "u2b_bn_sum_partials")
+                _lib.check(L.u2b_bn_xchg_bwd_coeff(_p(sums), _p(px.peers), px.world, px.rank, _p(px.epoch_ctr),
+                                                   px.SLOT_FLOATS, n_total, _p(stats), _p(weight), _p(coeff), _p(gwb),
+                                                   C, s), "u2b_bn_xchg_bwd_coeff")
+            elif px is not None and 2 * C <= px.SLOT_FLOATS:
                 _lib.check(L.u2b_bn_xchg2_bwd_coeff(_p(part), S, _p(px.peers), px.world, px.rank, _p(px.epoch_ctrs),
                                                     px.SLOT_FLOATS, n_total, _p(stats), _p(weight), _p(coeff), _p(gwb),
                                                     C, s), "u2b_bn_xchg2_bwd_coeff")
