@@ -114,9 +114,9 @@ int u2b_roi_align_bwd(int dtype, int num_levels, float* const* grad_feats, const
                       const int32_t* ws, const float* scales, int64_t C, const float* rois5,
                       const int32_t* levels, int64_t K, int P, const void* grad_out, float grad_scale,
                       u2b_stream_t stream);
-/* Implementation switch for u2b_roi_align_fwd / _bwd: 1 (default) = one CTA per ROI, separable weight tables in shared
- * memory (forward gathers (g+1)^2 pixels per bin, backward issues one vector atomic per footprint pixel); 0 = one warp per
- * output bin (torchvision's per-sample order). Same results up to fp32 summation order. */
+/* Implementation switch for u2b_roi_align_fwd (bit 0) / _bwd (bit 1): bit set = one CTA per ROI, separable weight tables in
+ * shared memory (forward gathers (g+1)^2 pixels per bin, backward issues one vector atomic per footprint pixel); clear = one
+ * warp per output bin (torchvision's per-sample order). Default 2 (backward only). Same results up to fp32 summation order. */
 int u2b_roi_align_set_impl(int impl);
 
 /* Channel-major variants (round-2 draft): out / grad_out are (K, C, P, P) contiguous, the layout torch.flatten(x, 1)
@@ -211,6 +211,9 @@ int u2b_conv2d_nhwc_fwd(int dtype, const void* x, int N, int H, int W, int Cin, 
 int u2b_conv2_supported(int Cin, int Cout, int R, int S, int stride, int pad);
 int64_t u2b_conv2_stats_rows(int N, int H, int W, int R, int S, int stride, int pad);
 /* 0 = choose the tile width per problem (default); 64 / 128 / 256 force it (benchmarking) */
+/* SMs the persistent tcgen05 kernels (conv2, conv_wgrad2) size their grids for; 0 = all. Data-parallel training sets it
+ * below the SM count during the backward pass so that NCCL's resident all-reduce CTAs do not force a second wave. */
+int u2b_set_sm_budget(int sms);
 int u2b_conv2_set_tile_n(int bn);
 int u2b_conv2_nhwc_fwd(int dtype, const void* x, int N, int H, int W, int Cin, const void* w, int Cout, int R, int S,
                        int stride, int pad, const float* bias, int relu, void* out, float* stats,

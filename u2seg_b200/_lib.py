@@ -133,6 +133,7 @@ SIGNATURES = {
     "u2b_bn_xchg_bwd_coeff": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, ctypes.c_double, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "u2b_roi_align_set_impl": (c_int, [c_int]),
+    "u2b_set_sm_budget": (c_int, [c_int]),
     "u2b_bn_xchg2_max_ctas": (c_int, []),
     "u2b_bn_xchg2_finalize": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, ctypes.c_double, c_void_p,
                                       c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

@@ -161,7 +161,7 @@ def infer_kernel_rooflines(peaks, dev):
         px = float((((rb[m, 2] - rb[m, 0]) / s + 2) * ((rb[m, 3] - rb[m, 1]) / s + 2)).sum())
         touched += min(px, (800 // s) * (1344 // s)) * C * 2
     nbytes = K * C * P * P * 2 + K * 20 + touched
-    out["roi_align_fwd_kernel"] = {"bound": "hbm", "kernel": "roi_align_fwd2_kernel (1000 boxes, 7x7, 4 levels, 256 ch bf16; one launch through u2b_roi_align_fwd)",
+    out["roi_align_fwd_kernel"] = {"bound": "hbm", "kernel": "roi_align_fwd_kernel (1000 boxes, 7x7, 4 levels, 256 ch bf16; one launch through u2b_roi_align_fwd)",
                                    "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                                    "frac": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm"], "peak_source": peaks["src"] + " HBM copy",
                                    "traffic": None, "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": ms}

@@ -27,6 +27,23 @@ int u2b_num_sms() {
   return cached[dev];
 }
 
+// Persistent kernels (conv2, conv_wgrad2) assign tiles statically to one cluster per SM pair. When another kernel holds SMs
+// for the whole duration (NCCL's all-reduce CTAs during the overlapped backward pass), clusters that cannot be co-resident
+// run as a second wave and double the kernel's time; a budget below the SM count leaves room for them.
+static int g_sm_budget = 0;
+int u2b_persistent_sms() {
+  const int n = u2b_num_sms();
+  return (g_sm_budget > 0 && g_sm_budget < n) ? g_sm_budget : n;
+}
+extern "C" int u2b_set_sm_budget(int sms) {
+  if (sms < 0 || (sms > 0 && sms < 2)) {
+    u2b_set_error("set_sm_budget: %d (0 = all SMs, otherwise >= 2)", sms);
+    return U2B_ERR_BAD_ARG;
+  }
+  g_sm_budget = sms & ~1;
+  return 0;
+}
+
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                         const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                         const cuuint32_t*, CUtensorMapInterleave,

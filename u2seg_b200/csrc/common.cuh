@@ -14,6 +14,7 @@
 
 void u2b_set_error(const char* fmt, ...);
 int u2b_num_sms();
+int u2b_persistent_sms();   // SMs the persistent tcgen05 kernels size their grids for (u2b_set_sm_budget)
 
 #define U2B_CHECK_ARG(cond, ...)            \
   do {                                      \

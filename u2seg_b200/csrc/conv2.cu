@@ -418,7 +418,7 @@ int launch_conv2(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap
                                   Cfg::SMEM_BYTES));
     attr = true;
   }
-  int clusters = u2b_num_sms() / 2;
+  int clusters = u2b_persistent_sms() / 2;
   if (clusters > p.num_work) clusters = p.num_work;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * 2);
@@ -462,7 +462,7 @@ void conv2_geometry(Conv2Params& p, int N, int H, int W, int Cin, int Cout, int 
 
 int conv2_pick_bn(const Conv2Params& p, int min_bn) {
   if (g_conv2_bn >= min_bn && p.Cout % g_conv2_bn == 0) return g_conv2_bn;
-  const int pairs = (p.tiles_m + 1) / 2, want = u2b_num_sms() / 2;
+  const int pairs = (p.tiles_m + 1) / 2, want = u2b_persistent_sms() / 2;
   // widest tile that still gives every SM pair a work item; otherwise the narrowest (most parallelism)
   for (int bn = 256; bn >= min_bn; bn >>= 1)
     if (p.Cout % bn == 0 && pairs * (p.Cout / bn) >= want) return bn;

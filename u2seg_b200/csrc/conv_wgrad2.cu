@@ -347,7 +347,7 @@ int launch_wgrad2(const CUtensorMap& ta, const CUtensorMap& tb, const Wg2Params&
     attr = true;
   }
   cudaLaunchConfig_t cfg = {};
-  int clusters = u2b_num_sms() / 2;
+  int clusters = u2b_persistent_sms() / 2;
   if (clusters > p.num_work) clusters = p.num_work;
   cfg.gridDim = dim3(clusters * 2);
   cfg.blockDim = dim3(W2_THREADS);
@@ -393,7 +393,7 @@ int wgrad2_plan(Wg2Params& p, int N, int H, int W, int Cin, int Cout, int R, int
   p.m_tiles = p.Ca / 256;
   p.n_tiles = p.Cb / BN;
   const int base = p.m_tiles * p.n_tiles * R * S;
-  const int pairs = u2b_num_sms() / 2;
+  const int pairs = u2b_persistent_sms() / 2;
   // one wave of work items over the SM pairs when the tile count allows it (a second, mostly empty wave would double
   // the time), at least 8 pixel blocks (512 pixels) per split; more tiles than pairs: no split, the kernel is persistent
   int ks = base >= pairs ? 1 : pairs / base;

@@ -535,7 +535,10 @@ inline unsigned roi2_splits(long long K) {
   return static_cast<unsigned>(want < 1 ? 1 : (want > 4 ? 4 : want));
 }
 
-int g_roi_align_impl = 1;   // 1: per-ROI factorised kernels, 0: one warp per output bin (round 1)
+// bit 0: forward, bit 1: backward use the per-ROI factorised kernel. Measured in the training step (1024 ROIs, 7x7, 256 ch,
+// bf16): backward 213 -> 174 us (half the atomics); forward 86 -> 98 us (its 49 bins do not amortise the table set-up), so the
+// forward stays on the warp-per-bin kernel by default.
+int g_roi_align_impl = 2;
 
 // ---- channel-major ("CHW") output layout: out (K, C, P, P) contiguous, i.e. what torch.flatten(x, 1) of the box head
 // (box_head.py:99-106) wants. One CTA per ROI: the P*P bins are computed by the 8 warps into a shared-memory tile
@@ -650,7 +653,7 @@ int u2b_roi_align_fwd(int dtype, int num_levels, const void* const* feats, const
   U2B_CHECK_ARG(C > 0 && C % vn == 0, "roi_align_fwd: C=%lld must be a multiple of %d", (long long)C, vn);
   const long long bins = static_cast<long long>(K) * P * P;
   const unsigned grid = static_cast<unsigned>((bins + 7) / 8);
-  if (g_roi_align_impl == 1 && P <= RA_PMAX && (dtype == 0 || dtype == 1 || dtype == 2)) {
+  if ((g_roi_align_impl & 1) && P <= RA_PMAX && (dtype == 0 || dtype == 1 || dtype == 2)) {
     const dim3 g2(static_cast<unsigned>(K), roi2_splits(K));
     if (dtype == 0) roi_align_fwd2_kernel<float><<<g2, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (float*)out);
     else if (dtype == 1) roi_align_fwd2_kernel<__half><<<g2, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (__half*)out);
@@ -688,7 +691,7 @@ int u2b_roi_align_bwd(int dtype, int num_levels, float* const* grad_feats, const
   U2B_CHECK_ARG(C > 0 && C % vn == 0, "roi_align_bwd: C must be a multiple of %d", vn);
   const long long bins = static_cast<long long>(K) * P * P;
   const unsigned grid = static_cast<unsigned>((bins + 7) / 8);
-  if (g_roi_align_impl == 1 && P <= RA_PMAX && (dtype == 0 || dtype == 1 || dtype == 2)) {
+  if ((g_roi_align_impl & 2) && P <= RA_PMAX && (dtype == 0 || dtype == 1 || dtype == 2)) {
     const dim3 g2(static_cast<unsigned>(K), roi2_splits(K));
     if (dtype == 0) roi_align_bwd2_kernel<float><<<g2, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (const float*)grad_out, grad_scale);
     else if (dtype == 1) roi_align_bwd2_kernel<__half><<<g2, 256, 0, stream>>>(p, (int)C, rois5, levels, (int)K, P, (const __half*)grad_out, grad_scale);
@@ -712,9 +715,10 @@ int u2b_roi_align_bwd(int dtype, int num_levels, float* const* grad_feats, const
 }
 
 
-// 1 (default): per-ROI factorised kernels; 0: one warp per output bin. Both produce the same values up to fp32 summation order.
+// bit 0: forward, bit 1: backward through the per-ROI factorised kernels (default 2); 0 = one warp per output bin for both.
+// Both produce the same values up to fp32 summation order.
 int u2b_roi_align_set_impl(int impl) {
-  U2B_CHECK_ARG(impl == 0 || impl == 1, "roi_align_set_impl: 0 or 1");
+  U2B_CHECK_ARG(impl >= 0 && impl <= 3, "roi_align_set_impl: 0..3");
   g_roi_align_impl = impl;
   return 0;
 }

@@ -475,10 +475,19 @@ class Trainer:
         ov["done"] = [False] * n
         ov["comm"].wait_stream(torch.cuda.current_stream(self.device))     # the flat buffer's previous consumers are done
         ov["armed"] = True
+        # NCCL's all-reduce CTAs stay resident while backward runs: the persistent conv kernels leave them room (their grids
+        # are fixed at capture time), otherwise the clusters that find no free SM pair run as a second wave
+        budget = int(os.environ.get("U2B_OVERLAP_SM_BUDGET", "0"))
+        if budget:
+            from . import _lib
+            _lib.check(_lib.lib().u2b_set_sm_budget(budget), "u2b_set_sm_budget")
 
     def _finish_overlap(self):
         ov = self._ov
         ov["armed"] = False
+        if int(os.environ.get("U2B_OVERLAP_SM_BUDGET", "0")):
+            from . import _lib
+            _lib.check(_lib.lib().u2b_set_sm_budget(0), "u2b_set_sm_budget")
         main = torch.cuda.current_stream(self.device)
         main.wait_stream(ov["comm"])
         for b, done in enumerate(ov["done"]):                      # buckets with parameters that received no gradient
