@@ -30,16 +30,3 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
-
-
-@pytest.fixture(scope="session", autouse=True)
-def _destroy_process_group_at_exit():
-    """torchrun-launched test sessions (tools/run_multigpu_tests.sh): tear NCCL down explicitly, otherwise a failing run can
-    sit in the communicator's destructor until the launcher's timeout."""
-    yield
-    try:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            dist.destroy_process_group()
-    except Exception:
-        pass

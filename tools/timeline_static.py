@@ -66,4 +66,5 @@ if rank == 0:
     print("\n".join(lines[:12]))
 if world > 1:
     dist.barrier()
-    dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)       # see tools/pytest_then_exit.py: interpreter shutdown with captured NCCL graphs can block

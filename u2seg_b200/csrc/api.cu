@@ -44,6 +44,13 @@ extern "C" int u2b_set_sm_budget(int sms) {
   return 0;
 }
 
+static int g_pdl = 1;
+int u2b_pdl_enabled() { return g_pdl; }
+extern "C" int u2b_set_pdl(int on) {
+  g_pdl = on ? 1 : 0;
+  return 0;
+}
+
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                         const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                         const cuuint32_t*, CUtensorMapInterleave,

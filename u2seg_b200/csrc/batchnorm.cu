@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(BN_THREADS, (MODE == 0 ? 4 : 2))
 bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ x, const T* __restrict__ y,
                  const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int C,
                  int vpb, float* __restrict__ partials, const float* __restrict__ relu_scale_shift = nullptr) {
+  ptx_free::pdl_prologue();
   __shared__ float red[BN_THREADS * 16];
   const int lanes = BN_THREADS / vpb;
   const int tv = threadIdx.x % vpb, tp = threadIdx.x / vpb;
@@ -238,6 +239,7 @@ bn_reduce_kernel(const T* __restrict__ a, const T* __restrict__ x, const T* __re
 // combined in a fixed order, instead of one thread walking all S rows serially.
 __global__ void __launch_bounds__(256)
 bn_sum_partials_kernel(const float* __restrict__ partials, int S, int C2, float* __restrict__ sums) {
+  ptx_free::pdl_prologue();
   __shared__ float sh[32][8];
   const int cl = threadIdx.x & 7, sl = threadIdx.x >> 3;
   const int c = blockIdx.x * 8 + cl;
@@ -255,6 +257,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int S, do
                                    const float* __restrict__ w, const float* __restrict__ b, float eps,
                                    float momentum, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float* __restrict__ stats, int C) {
+  ptx_free::pdl_prologue();
   // block = 8 channels x 32 strip lanes; lanes sum strided partial rows, then combine through shared memory
   __shared__ double sh[2][32][8];
   const int cl = threadIdx.x & 7, sl = threadIdx.x >> 3;
@@ -292,6 +295,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int S, do
 __global__ void bn_bwd_coeff_kernel(const float* __restrict__ partials, int S, double n_total,
                                     const float* __restrict__ stats, const float* __restrict__ w,
                                     float* __restrict__ coeff, float* __restrict__ gw_gb, int C) {
+  ptx_free::pdl_prologue();
   __shared__ float sh[2][32][8];
   const int cl = threadIdx.x & 7, sl = threadIdx.x >> 3;
   const int c = blockIdx.x * 8 + cl;
@@ -417,6 +421,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats, const T* __restrict__ residual, int relu,
                 T* __restrict__ y, long long total_vec, int C, int up_h = 0, int up_w = 0) {
+  ptx_free::pdl_prologue();
   const int vecs = C / 8;
   const long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int c0 = static_cast<int>(i0 % vecs) * 8;
@@ -460,6 +465,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                     const float* __restrict__ coeff, T* __restrict__ dx, T* __restrict__ dres,
                     long long total_vec, int C, const float* __restrict__ relu_scale_shift = nullptr) {
+  ptx_free::pdl_prologue();
   const int vecs = C / 8;
   const long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int c0 = static_cast<int>(i0 % vecs) * 8;
@@ -612,22 +618,27 @@ bn_xchg_bwd_coeff_kernel(const float* __restrict__ sums, const unsigned long lon
 // agree across ranks), and finishes its 32 channels. Replaces bn_sum_partials_kernel + the single-CTA exchange kernel.
 constexpr int X2_CH = 32;
 constexpr int X2_MAXCTAS = 64;
+constexpr int X2_WARPS = 32;   // 1024 threads per CTA
 constexpr size_t X2_FLAG_SKIP = 256;   // the single-CTA kernels' flags (world <= 32 words) live in front of ours
 
 __device__ __forceinline__ void xchg2_reduce(const float* __restrict__ partials, int S, int C,
                                              const unsigned long long* __restrict__ peers, int world, int rank,
                                              unsigned int* __restrict__ epoch_ctrs, int slot_floats,
                                              float* __restrict__ local /*smem[64]*/, float* __restrict__ tot /*smem[64]*/) {
-  __shared__ float red[8][2 * X2_CH];
+  // X2_WARPS warps stride the partial rows (up to 1024 of them after a res2 convolution): the row loop is a chain of
+  // L2 latencies, so its length - not bandwidth - sets the kernel's duration
+  __shared__ float red[X2_WARPS][2 * X2_CH];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31, t = threadIdx.x;
   const int c0 = blockIdx.x * X2_CH;
   const bool live = c0 + l < C;
   float s1 = 0.f, s2 = 0.f;
-  if (live)
-    for (int row = w; row < S; row += 8) {
+  if (live) {
+#pragma unroll 4
+    for (int row = w; row < S; row += X2_WARPS) {
       s1 += partials[static_cast<size_t>(row) * 2 * C + c0 + l];
       s2 += partials[static_cast<size_t>(row) * 2 * C + C + c0 + l];
     }
+  }
   red[w][l] = s1;
   red[w][X2_CH + l] = s2;
   const unsigned int epoch = epoch_ctrs[blockIdx.x] + 1u;
@@ -646,7 +657,7 @@ __device__ __forceinline__ void xchg2_reduce(const float* __restrict__ partials,
   if (t < 2 * X2_CH) {
     float v = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v += red[q][t];
+    for (int q = 0; q < X2_WARPS; ++q) v += red[q][t];
     local[t] = v;
     if (col_live) {
       const unsigned long long word = (static_cast<unsigned long long>(epoch) << 32) | __float_as_uint(v);
@@ -680,12 +691,13 @@ __device__ __forceinline__ void xchg2_reduce(const float* __restrict__ partials,
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(X2_WARPS * 32)
 bn_xchg2_finalize_kernel(const float* __restrict__ partials, int S, const unsigned long long* __restrict__ peers, int world,
                          int rank, unsigned int* __restrict__ epoch_ctrs, int slot_floats, double n_total,
                          const float* __restrict__ w, const float* __restrict__ b, float eps, float momentum,
                          float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ stats,
                          int C) {
+  ptx_free::pdl_prologue();
   __shared__ float local[2 * X2_CH], tot[2 * X2_CH];
   xchg2_reduce(partials, S, C, peers, world, rank, epoch_ctrs, slot_floats, local, tot);
   const int c = blockIdx.x * X2_CH + threadIdx.x;
@@ -706,11 +718,12 @@ bn_xchg2_finalize_kernel(const float* __restrict__ partials, int S, const unsign
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(X2_WARPS * 32)
 bn_xchg2_bwd_coeff_kernel(const float* __restrict__ partials, int S, const unsigned long long* __restrict__ peers, int world,
                           int rank, unsigned int* __restrict__ epoch_ctrs, int slot_floats, double n_total,
                           const float* __restrict__ stats, const float* __restrict__ w, float* __restrict__ coeff,
                           float* __restrict__ gw_gb, int C) {
+  ptx_free::pdl_prologue();
   __shared__ float local[2 * X2_CH], tot[2 * X2_CH];
   xchg2_reduce(partials, S, C, peers, world, rank, epoch_ctrs, slot_floats, local, tot);
   const int c = blockIdx.x * X2_CH + threadIdx.x;
@@ -732,7 +745,7 @@ template <typename T, int MODE>
 int launch_reduce(const void* a, const void* x, const void* y, const float* mean, const float* invstd,
                   long long P, int C, float* partials, cudaStream_t stream, const float* relu_scale_shift = nullptr) {
   dim3 grid(num_strips(P, C), channel_groups(C));
-  bn_reduce_kernel<T, MODE><<<grid, BN_THREADS, 0, stream>>>(static_cast<const T*>(a), static_cast<const T*>(x),
+  u2b_launch_pdl(bn_reduce_kernel<T, MODE>, dim3(grid), dim3(BN_THREADS), 0, stream, static_cast<const T*>(a), static_cast<const T*>(x),
                                                              static_cast<const T*>(y), mean, invstd, P, C,
                                                              vecs_per_block(C), partials, relu_scale_shift);
   U2B_LAUNCH_CHECK();
@@ -771,7 +784,7 @@ int u2b_bn_stats(int dtype, const void* x, int64_t P, int C, float* partials, cu
 // sums[0:C2] = sum over the S partial rows (used when the sums are all-reduced across ranks before finalize/coeff)
 int u2b_bn_sum_partials(const float* partials, int S, int C2, float* sums, cudaStream_t stream) {
   U2B_CHECK_ARG(partials && sums && S > 0 && C2 > 0, "bn_sum_partials: bad arguments");
-  bn_sum_partials_kernel<<<(C2 + 7) / 8, 256, 0, stream>>>(partials, S, C2, sums);
+  u2b_launch_pdl(bn_sum_partials_kernel, dim3((C2 + 7) / 8), dim3(256), 0, stream, partials, S, C2, sums);
   U2B_LAUNCH_CHECK();
   return 0;
 }
@@ -782,7 +795,7 @@ int u2b_bn_finalize(const float* partials, int S, double n_total, const float* w
                     float momentum, float* running_mean, float* running_var, float* stats, int C,
                     cudaStream_t stream) {
   U2B_CHECK_ARG(partials && stats && S > 0 && C > 0 && n_total > 0, "bn_finalize: bad arguments");
-  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, stream>>>(partials, S, n_total, w, b, eps, momentum, running_mean,
+  u2b_launch_pdl(bn_finalize_kernel, dim3((C + 7) / 8), dim3(256), 0, stream, partials, S, n_total, w, b, eps, momentum, running_mean,
                                                           running_var, stats, C);
   U2B_LAUNCH_CHECK();
   return 0;
@@ -795,9 +808,9 @@ int u2b_bn_apply(int dtype, const void* x, const float* stats, const void* resid
   U2B_CHECK_ARG(x && y && stats && u2b_bn_supported(C), "bn_apply: bad arguments");
   const long long tv = static_cast<long long>(P) * C / 8;
   U2B_BN_DISPATCH(
-      (bn_apply_kernel<float><<<ew_grid(tv), 256, 0, stream>>>((const float*)x, stats, (const float*)residual, relu, (float*)y, tv, C)),
-      (bn_apply_kernel<__half><<<ew_grid(tv), 256, 0, stream>>>((const __half*)x, stats, (const __half*)residual, relu, (__half*)y, tv, C)),
-      (bn_apply_kernel<__nv_bfloat16><<<ew_grid(tv), 256, 0, stream>>>((const __nv_bfloat16*)x, stats, (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)y, tv, C)))
+      (u2b_launch_pdl(bn_apply_kernel<float>, dim3(ew_grid(tv)), dim3(256), 0, stream, (const float*)x, stats, (const float*)residual, relu, (float*)y, tv, C, 0, 0)),
+      (u2b_launch_pdl(bn_apply_kernel<__half>, dim3(ew_grid(tv)), dim3(256), 0, stream, (const __half*)x, stats, (const __half*)residual, relu, (__half*)y, tv, C, 0, 0)),
+      (u2b_launch_pdl(bn_apply_kernel<__nv_bfloat16>, dim3(ew_grid(tv)), dim3(256), 0, stream, (const __nv_bfloat16*)x, stats, (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)y, tv, C, 0, 0)))
   U2B_LAUNCH_CHECK();
   return 0;
 }
@@ -809,9 +822,9 @@ int u2b_bn_apply_resup(int dtype, const void* x, const float* stats, const void*
                 "bn_apply_resup: bad arguments");
   const long long tv = static_cast<long long>(N) * H * W * C / 8;
   U2B_BN_DISPATCH(
-      (bn_apply_kernel<float><<<ew_grid(tv), 256, 0, stream>>>((const float*)x, stats, (const float*)residual, relu, (float*)y, tv, C, H, W)),
-      (bn_apply_kernel<__half><<<ew_grid(tv), 256, 0, stream>>>((const __half*)x, stats, (const __half*)residual, relu, (__half*)y, tv, C, H, W)),
-      (bn_apply_kernel<__nv_bfloat16><<<ew_grid(tv), 256, 0, stream>>>((const __nv_bfloat16*)x, stats, (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)y, tv, C, H, W)))
+      (u2b_launch_pdl(bn_apply_kernel<float>, dim3(ew_grid(tv)), dim3(256), 0, stream, (const float*)x, stats, (const float*)residual, relu, (float*)y, tv, C, H, W)),
+      (u2b_launch_pdl(bn_apply_kernel<__half>, dim3(ew_grid(tv)), dim3(256), 0, stream, (const __half*)x, stats, (const __half*)residual, relu, (__half*)y, tv, C, H, W)),
+      (u2b_launch_pdl(bn_apply_kernel<__nv_bfloat16>, dim3(ew_grid(tv)), dim3(256), 0, stream, (const __nv_bfloat16*)x, stats, (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)y, tv, C, H, W)))
   U2B_LAUNCH_CHECK();
   return 0;
 }
@@ -840,7 +853,7 @@ int u2b_bn_bwd_reduce_relu_x(int dtype, const void* dy, const void* x, const flo
 int u2b_bn_bwd_coeff(const float* partials, int S, double n_total, const float* stats, const float* w, float* coeff,
                      float* gw_gb, int C, cudaStream_t stream) {
   U2B_CHECK_ARG(partials && stats && coeff && S > 0 && C > 0 && n_total > 0, "bn_bwd_coeff: bad arguments");
-  bn_bwd_coeff_kernel<<<(C + 7) / 8, 256, 0, stream>>>(partials, S, n_total, stats, w, coeff, gw_gb, C);
+  u2b_launch_pdl(bn_bwd_coeff_kernel, dim3((C + 7) / 8), dim3(256), 0, stream, partials, S, n_total, stats, w, coeff, gw_gb, C);
   U2B_LAUNCH_CHECK();
   return 0;
 }
@@ -888,7 +901,7 @@ int u2b_bn_xchg2_finalize(const float* partials, int S, const void* peers, int w
   U2B_CHECK_ARG(partials && S > 0 && peers && stats && epoch_ctrs && world > 0 && world <= 32 && rank >= 0 && rank < world &&
                     2 * C <= slot_floats && C <= X2_CH * X2_MAXCTAS && slot_floats >= 2 * X2_CH * ((C + X2_CH - 1) / X2_CH),
                 "bn_xchg2_finalize: bad arguments");
-  bn_xchg2_finalize_kernel<<<(C + X2_CH - 1) / X2_CH, 256, 0, stream>>>(
+  u2b_launch_pdl(bn_xchg2_finalize_kernel, dim3((C + X2_CH - 1) / X2_CH), dim3(X2_WARPS * 32), 0, stream, 
       partials, S, static_cast<const unsigned long long*>(peers), world, rank, epoch_ctrs, slot_floats, n_total, w, b, eps,
       momentum, running_mean, running_var, stats, C);
   U2B_LAUNCH_CHECK();
@@ -901,7 +914,7 @@ int u2b_bn_xchg2_bwd_coeff(const float* partials, int S, const void* peers, int 
   U2B_CHECK_ARG(partials && S > 0 && peers && stats && coeff && epoch_ctrs && world > 0 && world <= 32 && rank >= 0 &&
                     rank < world && 2 * C <= slot_floats && C <= X2_CH * X2_MAXCTAS && slot_floats >= 2 * X2_CH * ((C + X2_CH - 1) / X2_CH),
                 "bn_xchg2_bwd_coeff: bad arguments");
-  bn_xchg2_bwd_coeff_kernel<<<(C + X2_CH - 1) / X2_CH, 256, 0, stream>>>(
+  u2b_launch_pdl(bn_xchg2_bwd_coeff_kernel, dim3((C + X2_CH - 1) / X2_CH), dim3(X2_WARPS * 32), 0, stream, 
       partials, S, static_cast<const unsigned long long*>(peers), world, rank, epoch_ctrs, slot_floats, n_total, stats, w,
       coeff, gw_gb, C);
   U2B_LAUNCH_CHECK();
@@ -941,9 +954,9 @@ int u2b_bn_bwd_apply(int dtype, const void* dy, const void* x, const void* y, co
   U2B_CHECK_ARG(dy && x && dx && coeff && u2b_bn_supported(C), "bn_bwd_apply: bad arguments");
   const long long tv = static_cast<long long>(P) * C / 8;
   U2B_BN_DISPATCH(
-      (bn_bwd_apply_kernel<float><<<ew_grid(tv), 256, 0, stream>>>((const float*)dy, (const float*)x, (const float*)y, coeff, (float*)dx, (float*)dres, tv, C)),
-      (bn_bwd_apply_kernel<__half><<<ew_grid(tv), 256, 0, stream>>>((const __half*)dy, (const __half*)x, (const __half*)y, coeff, (__half*)dx, (__half*)dres, tv, C)),
-      (bn_bwd_apply_kernel<__nv_bfloat16><<<ew_grid(tv), 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, coeff, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, tv, C)))
+      (u2b_launch_pdl(bn_bwd_apply_kernel<float>, dim3(ew_grid(tv)), dim3(256), 0, stream, (const float*)dy, (const float*)x, (const float*)y, coeff, (float*)dx, (float*)dres, tv, C, nullptr)),
+      (u2b_launch_pdl(bn_bwd_apply_kernel<__half>, dim3(ew_grid(tv)), dim3(256), 0, stream, (const __half*)dy, (const __half*)x, (const __half*)y, coeff, (__half*)dx, (__half*)dres, tv, C, nullptr)),
+      (u2b_launch_pdl(bn_bwd_apply_kernel<__nv_bfloat16>, dim3(ew_grid(tv)), dim3(256), 0, stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, coeff, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, tv, C, nullptr)))
   U2B_LAUNCH_CHECK();
   return 0;
 }
@@ -956,9 +969,9 @@ int u2b_bn_bwd_apply_relu_x(int dtype, const void* dy, const void* x, const floa
   const long long tv = static_cast<long long>(P) * C / 8;
   const float* rs = stats + 2 * C;
   U2B_BN_DISPATCH(
-      (bn_bwd_apply_kernel<float><<<ew_grid(tv), 256, 0, stream>>>((const float*)dy, (const float*)x, nullptr, coeff, (float*)dx, nullptr, tv, C, rs)),
-      (bn_bwd_apply_kernel<__half><<<ew_grid(tv), 256, 0, stream>>>((const __half*)dy, (const __half*)x, nullptr, coeff, (__half*)dx, nullptr, tv, C, rs)),
-      (bn_bwd_apply_kernel<__nv_bfloat16><<<ew_grid(tv), 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, nullptr, coeff, (__nv_bfloat16*)dx, nullptr, tv, C, rs)))
+      (u2b_launch_pdl(bn_bwd_apply_kernel<float>, dim3(ew_grid(tv)), dim3(256), 0, stream, (const float*)dy, (const float*)x, nullptr, coeff, (float*)dx, nullptr, tv, C, rs)),
+      (u2b_launch_pdl(bn_bwd_apply_kernel<__half>, dim3(ew_grid(tv)), dim3(256), 0, stream, (const __half*)dy, (const __half*)x, nullptr, coeff, (__half*)dx, nullptr, tv, C, rs)),
+      (u2b_launch_pdl(bn_bwd_apply_kernel<__nv_bfloat16>, dim3(ew_grid(tv)), dim3(256), 0, stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, nullptr, coeff, (__nv_bfloat16*)dx, nullptr, tv, C, rs)))
   U2B_LAUNCH_CHECK();
   return 0;
 }

@@ -45,6 +45,42 @@ int u2b_encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const
                     const uint32_t* elem_strides, CUtensorMapSwizzle swizzle,
                     CUtensorMapFloatOOBfill oob);
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------------
+// The training step is a chain of ~1700 mostly short kernels; between two dependent kernels on a stream the GPU drains, then
+// pays the next launch's set-up. A kernel launched with the programmatic-stream-serialization attribute may become resident
+// while its predecessor is still running IF the predecessor executed griddepcontrol.launch_dependents; it then blocks in
+// griddepcontrol.wait until the predecessor's grid has completed and its writes are visible. Every kernel launched through
+// u2b_launch_pdl calls pdl_prologue() as its first statement (nothing touches global memory before it); kernels of other
+// libraries in between never trigger, so they keep ordinary stream semantics. u2b_set_pdl(0) switches the attribute off.
+int u2b_pdl_enabled();
+
+#ifdef __CUDACC__
+namespace ptx_free {
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+}  // namespace ptx_free
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t u2b_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                         Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = u2b_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 #ifdef __CUDACC__
 namespace ptx_free {
 // structures/boxes.py:310-358 pairwise_iou, same op order: inter>0 ? inter/(area1+area2-inter) : 0.

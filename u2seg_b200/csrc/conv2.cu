@@ -205,6 +205,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
+  ptx_free::pdl_launch_dependents();   // the next kernel of the stream may set itself up while this one runs (common.cuh)
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_x);
     ptx::prefetch_tmap(&tmap_w);
@@ -229,6 +230,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
   __syncthreads();
   ptx::cluster_sync_all();  // the peer's barriers exist before any remote arrive / complete_tx
   ptx::tc_fence_after();
+  ptx_free::pdl_wait();     // barriers, TMEM and descriptor prefetch above overlap the predecessor's tail; its data is read below
   const uint32_t tmem_base = *tmem_ptr;
   const int kblocks = p.R * p.S * p.kblocks_c;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -425,13 +427,15 @@ int launch_conv2(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap
   cfg.blockDim = dim3(C2_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = u2b_pdl_enabled() ? 2 : 1;
   U2B_CUDA(cudaLaunchKernelEx(&cfg, conv2_kernel<BN, BF16>, tx, tw, ty, p));
   return 0;
 }

@@ -130,6 +130,7 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
+  ptx_free::pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
@@ -153,6 +154,7 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   __syncthreads();
   ptx::cluster_sync_all();
   ptx::tc_fence_after();
+  ptx_free::pdl_wait();
   const uint32_t tmem_base = *tmem_ptr;
 
   // persistent: cluster c takes work items c, c + #clusters, ...; work = (m tile, n tile, tap, k split)
@@ -322,6 +324,7 @@ template <typename OutT>
 __global__ void __launch_bounds__(256)
 wgrad2_reduce_kernel(const float* __restrict__ partials, int ksplit, int taps, int Ca, int Cb, int a_is_dy,
                      OutT* __restrict__ dw, long long total) {
+  ptx_free::pdl_prologue();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   // i indexes dW in OHWI order: co, tap, ci
@@ -353,13 +356,15 @@ int launch_wgrad2(const CUtensorMap& ta, const CUtensorMap& tb, const Wg2Params&
   cfg.blockDim = dim3(W2_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = u2b_pdl_enabled() ? 2 : 1;
   U2B_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad2_kernel<BN, BF16>, ta, tb, p));
   return 0;
 }
@@ -470,13 +475,13 @@ int u2b_conv_wgrad2(int dtype, const void* x, const void* dy, int N, int H, int 
   const long long total = static_cast<long long>(Cout) * R * S * Cin;
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
   if (out_dtype == 0)
-    wgrad2_reduce_kernel<float><<<grid, 256, 0, stream>>>(workspace, p.ksplit, R * S, p.Ca, p.Cb, p.a_is_dy,
+    u2b_launch_pdl(wgrad2_reduce_kernel<float>, dim3(grid), dim3(256), 0, stream, workspace, p.ksplit, R * S, p.Ca, p.Cb, p.a_is_dy,
                                                           static_cast<float*>(dw), total);
   else if (out_dtype == 1)
-    wgrad2_reduce_kernel<__half><<<grid, 256, 0, stream>>>(workspace, p.ksplit, R * S, p.Ca, p.Cb, p.a_is_dy,
+    u2b_launch_pdl(wgrad2_reduce_kernel<__half>, dim3(grid), dim3(256), 0, stream, workspace, p.ksplit, R * S, p.Ca, p.Cb, p.a_is_dy,
                                                            static_cast<__half*>(dw), total);
   else
-    wgrad2_reduce_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(workspace, p.ksplit, R * S, p.Ca, p.Cb, p.a_is_dy,
+    u2b_launch_pdl(wgrad2_reduce_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, workspace, p.ksplit, R * S, p.Ca, p.Cb, p.a_is_dy,
                                                                   static_cast<__nv_bfloat16*>(dw), total);
   U2B_LAUNCH_CHECK();
   return 0;
