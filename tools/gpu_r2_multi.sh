@@ -3,7 +3,7 @@
 set -u
 n=${1:-2}
 mkdir -p gpurun_out
-timeout 420 bash tools/run_multigpu_tests.sh "$n" > gpurun_out/r02_multi_tests_n$n.log 2>&1; tail -6 gpurun_out/r02_multi_tests_n$n.log | cut -c1-300
+timeout 300 bash tools/run_multigpu_tests.sh "$n" > gpurun_out/r02_multi_tests_n$n.log 2>&1; tail -6 gpurun_out/r02_multi_tests_n$n.log | cut -c1-300
 runb() {   # label, env...
   label=$1; shift
   env "$@" U2B_BENCH_SKIP_KMEANS=1 U2B_BENCH_SKIP_CPU=1 U2B_BENCH_SKIP_INFER=1 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 \
@@ -17,10 +17,7 @@ except Exception as e:
     print(sys.argv[2], "parse failed", e)
 PY
 }
-runb ov1 U2B_OVERLAP_ALLREDUCE=1
-runb ov0 U2B_OVERLAP_ALLREDUCE=0
-runb ov1_ctas8 U2B_OVERLAP_ALLREDUCE=1 NCCL_MAX_CTAS=8
-runb ov1_budget132 U2B_OVERLAP_ALLREDUCE=1 U2B_OVERLAP_SM_BUDGET=132
-runb ov1_ctas8_budget140 U2B_OVERLAP_ALLREDUCE=1 NCCL_MAX_CTAS=8 U2B_OVERLAP_SM_BUDGET=140
-runb ov1_xchg1 U2B_OVERLAP_ALLREDUCE=1 U2B_SYNCBN_XCHG2=0
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29517 tools/timeline_static.py "gpurun_out/r02_timeline_static_n$n.txt" 70 2>&1 | tail -14 | cut -c1-170
+runb xchg2 U2B_SYNCBN_XCHG2=1
+runb xchg1 U2B_SYNCBN_XCHG2=0
+runb xchg2_again U2B_SYNCBN_XCHG2=1
+timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29517 tools/timeline_static.py "gpurun_out/r02_timeline_static_n$n.txt" 70 2>&1 | tail -14 | cut -c1-170
