@@ -33,6 +33,7 @@ def test_syncbn_peer_exchange_matches_reference():
         yr = F.relu(F.batch_norm(xr, rm, rv, wr, br, True, 0.1, 1e-5))
         yr.backward(torch.cat(gys).cuda())
         outs = {}
+        dist.barrier()                # the reference pass above loads library kernels lazily: ranks drift apart by seconds
         for mode in ("1", "0"):       # peer exchange, then NCCL
             os.environ["U2B_SYNCBN_XCHG"] = mode
             bn = SyncBatchNorm(C).cuda().train()

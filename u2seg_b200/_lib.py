@@ -135,6 +135,7 @@ SIGNATURES = {
     "u2b_roi_align_set_impl": (c_int, [c_int]),
     "u2b_set_sm_budget": (c_int, [c_int]),
     "u2b_set_pdl": (c_int, [c_int]),
+    "u2b_conv2_set_staging": (c_int, [c_int]),
     "u2b_bn_xchg2_max_ctas": (c_int, []),
     "u2b_bn_xchg2_finalize": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, ctypes.c_double, c_void_p,
                                       c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
@@ -160,6 +161,8 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
+        if os.environ.get("U2B_CONV2_STAGING", "1") == "0":   # csrc/conv2.cu conv2_pick_pipeline (A/B timing)
+            L.u2b_conv2_set_staging(0)
         if os.environ.get("U2B_PDL", "1") == "0":      # programmatic dependent launch between libu2b200 kernels (common.cuh)
             L.u2b_set_pdl(0)
         _lib = L

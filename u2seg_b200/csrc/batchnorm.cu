@@ -509,7 +509,8 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
 // fixed order (all ranks get bit-identical sums). A rank can be at most one call ahead of a peer (it needs the
 // peer's flag of the previous call to proceed), so two slots are enough.
 #ifndef U2B_XCHG_TIMEOUT_CYCLES
-#define U2B_XCHG_TIMEOUT_CYCLES (40000000000LL)  // ~20 s: ranks may enter their first step seconds apart (lazy inits)
+#define U2B_XCHG_TIMEOUT_CYCLES (240000000000LL)  // ~2 min: with 8 processes loading kernels from a cold file system, ranks were seen
+                                                     // to reach an exchange more than 20 s apart (lazy module loading); a dead peer still traps
 #endif
 
 __device__ __forceinline__ void xchg_all_reduce(float* __restrict__ vals /*smem [n]*/, int n,

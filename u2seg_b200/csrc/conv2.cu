@@ -47,6 +47,8 @@ struct Conv2Params {
   int relu;
   const float* bias;
   float* stats;  // (tiles_m, 2*Cout) fp32 partial sums [sum | sum of squares] or NULL
+  int stages;    // operand ring depth actually used (<= Cfg2::STAGES)
+  int nstg;      // epilogue staging chunks per epilogue half (1..3): shared memory not used by the ring
 };
 
 template <int BN>
@@ -193,7 +195,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* stg = smem + Cfg::STG_OFF;
+  uint8_t* stg = smem + p.stages * Cfg::STAGE_BYTES;   // staging chunks follow the ring actually used
   float* sstat = reinterpret_cast<float*>(smem + Cfg::STAT_OFF);  // [4 quadrants][2*BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
   uint64_t* full = bars;
@@ -264,7 +266,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
                 for (int j = 0; j < BN / 128; ++j)
                   tma_load_2d_2sm(sa + A_BYTES + j * (64 * 128), &tmap_w, full_leader, col0 + j * 64, cb * BK);
               }
-              if (++stage == Cfg::STAGES) {
+              if (++stage == static_cast<uint32_t>(p.stages)) {
                 stage = 0;
                 phase ^= 1;
               }
@@ -292,7 +294,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
           for (int k = 0; k < BK / 16; ++k)
             umma_f16_2sm(tmem_d, a_desc + 2 * k, b_desc + b_step * k, idesc, (kb | k) != 0);
           umma_commit_2sm(&empty[stage]);
-          if (++stage == Cfg::STAGES) {
+          if (++stage == static_cast<uint32_t>(p.stages)) {
             stage = 0;
             phase ^= 1;
           }
@@ -307,8 +309,9 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     const int epi_tid = threadIdx.x - 128;     // 0..255
     const int half_tid = epi_tid & 127;
     const uint32_t sw = static_cast<uint32_t>(row & 7);
-    uint8_t* sbuf = stg + half * STG_BYTES;
-    const uint32_t srow = ptx::smem_u32(sbuf) + static_cast<uint32_t>(row) * 128u;
+    // p.nstg staging chunks per half, used round-robin: the TMA store of chunk i drains while chunks i+1.. are produced
+    // (one chunk per half made every 16 KB store a ~2 us round trip on the memory-bound 1x1 layers)
+    uint32_t sc = 0;
     const uint32_t t_empty_leader = mapa_rank(ptx::smem_u32(&T_empty[0]), 0);
     uint32_t acc_it = 0;
     for (int work = cluster_id; work < p.num_work; work += num_clusters, ++acc_it) {
@@ -347,8 +350,15 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 16; ++j) pk[h * 16 + j] = pack2<BF16>(f[2 * j], f[2 * j + 1]);
         }
-        // this half's previous TMA store must have finished reading the staging chunk before it is overwritten
-        if (half_tid == 0) bulk_wait_group_read<0>();
+        uint8_t* sbuf = stg + (half * p.nstg + static_cast<int>(sc % static_cast<uint32_t>(p.nstg))) * STG_BYTES;
+        const uint32_t srow = ptx::smem_u32(sbuf) + static_cast<uint32_t>(row) * 128u;
+        ++sc;
+        // the store that last used this chunk (nstg chunks ago) must have finished reading it before it is overwritten
+        if (half_tid == 0) {
+          if (p.nstg == 1) bulk_wait_group_read<0>();
+          else if (p.nstg == 2) bulk_wait_group_read<1>();
+          else bulk_wait_group_read<2>();
+        }
         ptx::named_bar_sync(1 + half, 128);
 #pragma unroll
         for (uint32_t j = 0; j < 8; ++j)
@@ -410,10 +420,35 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
   if (warp == 2) tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
 }
 
+int g_conv2_staging = 1;   // 1: trade ring stages for epilogue staging chunks on short-K layers, 0: full ring + one chunk
+
+// Short reductions (1x1 convolutions with K <= 256: 1-4 k-blocks per tile) are bound by the epilogue - 64 KB of output per
+// CTA and tile against 16-64 KB of operands - and a deep operand ring is of no use to them; the shared memory goes to
+// staging chunks instead so that several TMA stores are in flight per epilogue half.
+template <int BN>
+void conv2_pick_pipeline(Conv2Params& p) {
+  using Cfg = Cfg2<BN>;
+  const int kblocks = p.R * p.S * p.kblocks_c;
+  p.stages = Cfg::STAGES;
+  p.nstg = 1;
+  if (!g_conv2_staging) return;
+  if (kblocks <= 4) {
+    p.stages = 3;
+    p.nstg = 3;
+  } else if (kblocks <= 12) {
+    p.stages = 4;
+    p.nstg = 2;
+  }
+  // staging chunks live between the ring actually used and the fixed statistics / barrier area
+  while (p.nstg > 1 && p.stages * Cfg::STAGE_BYTES + 2 * p.nstg * STG_BYTES > Cfg::STAT_OFF) --p.nstg;
+}
+
 template <int BN, bool BF16>
-int launch_conv2(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const Conv2Params& p,
+int launch_conv2(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const Conv2Params& p_in,
                  cudaStream_t stream) {
   using Cfg = Cfg2<BN>;
+  Conv2Params p = p_in;
+  conv2_pick_pipeline<BN>(p);
   static bool attr = false;
   if (!attr) {
     U2B_CUDA(cudaFuncSetAttribute(conv2_kernel<BN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -551,6 +586,11 @@ int64_t u2b_conv2_stats_rows(int N, int H, int W, int R, int S, int stride, int 
   Conv2Params p;
   conv2_geometry(p, N, H, W, 64, 64, R, S, stride, pad);
   return p.tiles_m;
+}
+
+int u2b_conv2_set_staging(int on) {
+  g_conv2_staging = on ? 1 : 0;
+  return 0;
 }
 
 int u2b_conv2_set_tile_n(int bn) {
