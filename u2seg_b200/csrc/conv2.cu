@@ -367,9 +367,9 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
                        : "memory");
         ptx::fence_proxy_async();
         ptx::named_bar_sync(1 + half, 128);
-        if (half_tid == 0 && store_tile) {
-          tma_store_4d(&tmap_y, sbuf, tn * BN + c * 64, owb * p.BW, ohb * p.BH, n);
-          bulk_commit_group();
+        if (half_tid == 0) {
+          if (store_tile) tma_store_4d(&tmap_y, sbuf, tn * BN + c * 64, owb * p.BW, ohb * p.BH, n);
+          bulk_commit_group();     // also for the padding tile (an empty group): wait_group counts groups, one per chunk
         }
         if (p.stats) {
           // per-channel sum / sum of squares of the staged (rounded) chunk: this warp takes rows q*32..q*32+31, lane l
