@@ -218,8 +218,8 @@ int u2b_set_pdl(int on);
  * below the SM count during the backward pass so that NCCL's resident all-reduce CTAs do not force a second wave. */
 int u2b_set_sm_budget(int sms);
 int u2b_conv2_set_tile_n(int bn);
-/* 1 (default): short-K layers (<= 12 k-blocks of 64) run a shorter operand ring and 2-3 epilogue staging chunks per half (several
- * TMA stores in flight); 0: full ring, one chunk. Developer switch for A/B timing. */
+/* 1: short-K layers (<= 12 k-blocks of 64) run a shorter operand ring and 2-3 epilogue staging chunks per half (several TMA
+ * stores in flight); 0 (default: measured no faster): full ring, one chunk. Developer switch for A/B timing. */
 int u2b_conv2_set_staging(int on);
 int u2b_conv2_nhwc_fwd(int dtype, const void* x, int N, int H, int W, int Cin, const void* w, int Cout, int R, int S,
                        int stride, int pad, const float* bias, int relu, void* out, float* stats,

@@ -161,8 +161,8 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if os.environ.get("U2B_CONV2_STAGING", "1") == "0":   # csrc/conv2.cu conv2_pick_pipeline (A/B timing)
-            L.u2b_conv2_set_staging(0)
+        if os.environ.get("U2B_CONV2_STAGING", "0") == "1":   # csrc/conv2.cu conv2_pick_pipeline (A/B timing; default off)
+            L.u2b_conv2_set_staging(1)
         if os.environ.get("U2B_PDL", "1") == "0":      # programmatic dependent launch between libu2b200 kernels (common.cuh)
             L.u2b_set_pdl(0)
         _lib = L

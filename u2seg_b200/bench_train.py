@@ -199,9 +199,10 @@ def _conv_policy_text():
     from .modeling import conv_tc, ops
     if ops.TCGEN05_CONV_POLICY == "all":
         return ("tcgen05 2-CTA kernels (csrc/conv2.cu, conv_wgrad2.cu) for every conv with Cin,Cout %% 64 == 0 (1x1 and 3x3, "
-                "stride 1 and 2: forward; stride-1 input gradient; weight gradient when Cout or Cin %% 256 == 0) and the box-head "
-                "Linear layers; library (cuDNN/cuBLAS) for the rest (Cout 3/4/12/28/801 heads, 64-channel wgrads, stride-2 dgrads); "
-                "conv2=%s wgrad2=%s" % (conv_tc.USE_CONV2, conv_tc.USE_WGRAD2))
+                "stride 1 and 2: forward; stride-1 input gradient; weight gradient when Cout or Cin %% 256 == 0 and the layer has "
+                ">= %g GFLOP), the box-head Linear layers (forward, input gradient) and the mask head's 2x2 transposed convolution; "
+                "library (cuDNN/cuBLAS) for the rest (Cout 3/12/28 heads, smaller weight gradients, stride-2 input gradients, "
+                "FC weight gradients); conv2=%s wgrad2=%s" % (conv_tc.WGRAD2_MIN_GFLOP, conv_tc.USE_CONV2, conv_tc.USE_WGRAD2))
     return "policy %s (conv2=%s wgrad2=%s)" % (ops.TCGEN05_CONV_POLICY, conv_tc.USE_CONV2, conv_tc.USE_WGRAD2)
 
 
@@ -258,6 +259,11 @@ def in_step_conv_roofline(trainer, batch, peaks, ms_step):
     tot_flop = sum(v[2] for v in groups.values())
     (kind, key), (cnt, ms, flop) = max(groups.items(), key=lambda kv: kv[1][1])
     N, Hh, Ww, Cin, Cout, R, stride = key
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (cold L2)
+    ncu = {("wgrad", (256, 14, 14, 256, 256, 3, 1)): (51.45e6 + 2.90e6, "profiles/r02_ncu_wgrad2_mask_head_summary.txt"),
+           ("fwd", (2, 256, 256, 256, 256, 3, 1)): (68.0e6 + 31.0e6, "profiles/r02_ncu_conv2_fpn_output2_summary.txt")}
+    traffic, traffic_src = ncu.get((kind, tuple(key)), (None, None))
+    alg_bytes = 2.0 * (N * Hh * Ww * Cin + N * (Hh // stride) * (Ww // stride) * Cout + R * R * Cin * Cout)
     ach = flop / (ms * 1e-3) / 1e12
     name = {"fwd": "conv2_kernel (tcgen05 cta_group::2 implicit GEMM, forward)",
             "dgrad": "conv2_kernel (tcgen05 cta_group::2, input gradient, filter read MN-major)",
@@ -266,7 +272,9 @@ def in_step_conv_roofline(trainer, batch, peaks, ms_step):
                                          % (name, R, R, Cin, Cout, stride, N, Hh, Ww, cnt),
             "in_step": True, "achieved": ach, "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sus"],
             "peak_source": peaks["src"] + " bf16 sustained (kernel timed inside the step)",
-            "traffic": None, "algorithmic_flops_per_launch": flop / cnt, "ms_per_launch": ms / cnt,
+            "traffic": traffic, "traffic_unit": "bytes/launch", "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": alg_bytes,
+            "algorithmic_flops_per_launch": flop / cnt, "ms_per_launch": ms / cnt,
             "share_of_step_time": ms / ms_step,
             "all_tcgen05_launches": {"launches_per_step": len(recs), "flop_per_step": tot_flop, "ms_per_step": tot_ms,
                                      "achieved": tot_flop / (tot_ms * 1e-3) / 1e12, "unit": "TFLOP/s",

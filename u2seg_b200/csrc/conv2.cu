@@ -420,10 +420,13 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
   if (warp == 2) tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
 }
 
-int g_conv2_staging = 1;   // 1: trade ring stages for epilogue staging chunks on short-K layers, 0: full ring + one chunk
+// 1: trade ring stages for epilogue staging chunks on short-K layers; 0 (default): full ring + one chunk per half. Measured in
+// the training step (A/B, twice each): 15.60 ms off vs 15.65 ms on - the memory-bound 1x1 layers are not limited by the number
+// of TMA stores in flight, so the experiment stays behind u2b_conv2_set_staging / U2B_CONV2_STAGING=1.
+int g_conv2_staging = 0;
 
-// Short reductions (1x1 convolutions with K <= 256: 1-4 k-blocks per tile) are bound by the epilogue - 64 KB of output per
-// CTA and tile against 16-64 KB of operands - and a deep operand ring is of no use to them; the shared memory goes to
+// Experiment (see g_conv2_staging): short reductions (1x1 convolutions with K <= 256: 1-4 k-blocks per tile) move 64 KB of
+// output per CTA and tile against 16-64 KB of operands and do not need a deep operand ring; the shared memory can go to
 // staging chunks instead so that several TMA stores are in flight per epilogue half.
 template <int BN>
 void conv2_pick_pipeline(Conv2Params& p) {
