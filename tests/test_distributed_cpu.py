@@ -166,3 +166,51 @@ def test_static_trainer_broadcast_and_flat_allreduce_two_ranks():
     assert a0 == a1 == b0 and s0 == s1                # ... identical (rank 0's) after the broadcast
     assert w0 and w1 and v0 and v1
     assert torch.allclose(m0, (g0 + g1) / 2, rtol=1e-6, atol=1e-7) and torch.equal(m0, m1)
+
+
+def _overlap_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), U2B_BUCKET_MB="24")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from u2seg_b200.config import get_u2seg_cfg
+    from u2seg_b200.engine import Trainer
+    cfg = get_u2seg_cfg(800)
+    cfg.defrost()
+    cfg.MODEL.DEVICE = "cpu"
+    torch.manual_seed(0)
+    tr = Trainer(cfg, amp_dtype=torch.bfloat16, device=torch.device("cpu"), static_graph=True)
+    tr._setup_overlap()
+    ranges = list(tr._ov["range"])
+    for p in tr.params:
+        p.grad = None
+    g = torch.Generator().manual_seed(500 + rank)
+    # a backward pass whose gradient for every parameter is a known random tensor (d/dp sum(p * r) = r); a few parameters are
+    # left out of the graph on purpose: their buckets must still be reduced (zero gradient) by _finish_overlap
+    left_out = {3, len(tr.params) // 2, len(tr.params) - 1}
+    rs = [torch.randn(p.shape, generator=g) for p in tr.params]
+    tr._arm_overlap()
+    sum((p.float() * r).sum() for i, (p, r) in enumerate(zip(tr.params, rs)) if i not in left_out).backward()
+    fired = sum(1 for d in tr._ov["done"] if d)
+    tr._finish_overlap()
+    overlap = tr.grads.flat.clone()
+    tr._gather_grads()                      # the same local gradients through the single-all-reduce path
+    tr.grads.all_reduce_mean()
+    single = tr.grads.flat.clone()
+    dst = tr._upd_grads
+    lo_views = [dst[i].clone() for i in sorted(left_out)]
+    q.put((rank, len(ranges), ranges[0][0], ranges[-1][1], tr.grads.flat.numel(), fired, torch.equal(overlap, single),
+           float(overlap.abs().max()), [float(v.abs().max()) for v in lo_views], overlap[:2048].clone()))
+    dist.destroy_process_group()
+
+
+def test_overlapped_bucketed_allreduce_equals_single_allreduce_two_ranks():
+    """engine.Trainer's data-parallel gradient path on 2 gloo ranks: buckets of whole parameters tile the flat buffer; the
+    post-accumulate-grad hooks reduce a bucket as soon as its last gradient exists, _finish_overlap reduces the buckets that
+    contain parameters without a gradient (zero-filled); the result is identical to gathering everything and issuing one
+    all-reduce, and identical on both ranks."""
+    out = sorted(_run_ranks(_overlap_worker, 2, 400), key=lambda t: t[0])
+    for rank, nb, lo0, hi_last, n, fired, same, mx, left, head in out:
+        assert nb >= 8 and lo0 == 0 and hi_last == n
+        assert 0 < fired < nb            # some buckets went out during backward, the ones with left-out parameters afterwards
+        assert same and mx > 0
+        assert all(v == 0.0 for v in left)
+    assert torch.equal(out[0][-1], out[1][-1])

@@ -419,7 +419,9 @@ class Trainer:
             cur_n += n
         if cur:
             buckets.append(cur)
-        self._ov = {"buckets": buckets, "dst": dst, "bucket_of": {}, "range": [], "comm": torch.cuda.Stream(self.device)}
+        on_gpu = self.device.type == "cuda"      # on the CPU (gloo tests of this logic) there are no streams: every bucket is
+        self._ov = {"buckets": buckets, "dst": dst, "bucket_of": {}, "range": [],     # reduced in place when it completes
+                    "comm": torch.cuda.Stream(self.device) if on_gpu else None}
         for b, idxs in enumerate(buckets):
             lo = (dst[idxs[0]].data_ptr() - base) // 4
             hi = (dst[idxs[-1]].data_ptr() - base) // 4 + _aligned(self.params[idxs[-1]].numel())
@@ -434,9 +436,10 @@ class Trainer:
                 return
             i = index_of[id(p)]
             b = ov["bucket_of"][i]
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(self.device))      # the stream this gradient was produced on
-            ov["events"][b].append(ev)
+            if ov["comm"] is not None:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))      # the stream this gradient was produced on
+                ov["events"][b].append(ev)
             ov["pending"][b] -= 1
             if ov["pending"][b] == 0:
                 self._reduce_bucket(b)
@@ -449,11 +452,16 @@ class Trainer:
         ov = self._ov
         idxs = ov["buckets"][b]
         lo, hi = ov["range"][b]
-        comm = ov["comm"] if on_comm_stream else torch.cuda.current_stream(self.device)
-        if on_comm_stream:
-            for ev in ov["events"][b]:
-                comm.wait_event(ev)
-        with torch.cuda.stream(comm):
+        import contextlib
+        if ov["comm"] is None:
+            ctx = contextlib.nullcontext()
+        else:
+            comm = ov["comm"] if on_comm_stream else torch.cuda.current_stream(self.device)
+            if on_comm_stream:
+                for ev in ov["events"][b]:
+                    comm.wait_event(ev)
+            ctx = torch.cuda.stream(comm)
+        with ctx:
             have = [(ov["dst"][i], self.params[i].grad) for i in idxs if self.params[i].grad is not None]
             if len(have) != len(idxs):
                 self.grads.flat[lo:hi].zero_()                     # parameters outside this step's graph: zero gradient
@@ -473,7 +481,8 @@ class Trainer:
         ov["pending"] = [len(b) for b in ov["buckets"]]
         ov["events"] = [[] for _ in range(n)]
         ov["done"] = [False] * n
-        ov["comm"].wait_stream(torch.cuda.current_stream(self.device))     # the flat buffer's previous consumers are done
+        if ov["comm"] is not None:
+            ov["comm"].wait_stream(torch.cuda.current_stream(self.device))     # the flat buffer's previous consumers are done
         ov["armed"] = True
         # NCCL's all-reduce CTAs stay resident while backward runs: the persistent conv kernels leave them room (their grids
         # are fixed at capture time), otherwise the clusters that find no free SM pair run as a second wave
@@ -488,8 +497,8 @@ class Trainer:
         if int(os.environ.get("U2B_OVERLAP_SM_BUDGET", "0")):
             from . import _lib
             _lib.check(_lib.lib().u2b_set_sm_budget(0), "u2b_set_sm_budget")
-        main = torch.cuda.current_stream(self.device)
-        main.wait_stream(ov["comm"])
+        if ov["comm"] is not None:
+            torch.cuda.current_stream(self.device).wait_stream(ov["comm"])
         for b, done in enumerate(ov["done"]):                      # buckets with parameters that received no gradient
             if not done:
                 self._reduce_bucket(b, on_comm_stream=False)
