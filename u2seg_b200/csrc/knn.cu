@@ -10,12 +10,14 @@
 //      TMA ring (multicast across a cluster), two accumulators so the epilogue overlaps the next tile's MMAs. The
 //      epilogue forms |y|^2 - 2 acc and keeps, per (row, column half), the KC = 24 smallest values and their indices in
 //      sorted shared-memory lists (insertion only when a value beats the list's worst: ~K ln(N2/K) times per row);
-//   2. exact pass: one warp per query recomputes sum_d (x-y)^2 in fp32 (the reference's formula) for its 2*KC
-//      candidates, selects the K smallest (ties: lower index), and certifies the result: the fp16 rounding of the
-//      candidate pass perturbs a distance by at most eps = 1.25 * 2^-9 |x|max |y|max, so if the exact K-th distance +
-//      eps is below every list's worst kept value (in distance space, minus eps) no discarded train row can belong
-//      to the answer. Rows that cannot be certified are flagged and re-done by exhaustive exact search (host side:
-//      u2seg_b200/clustering.py), so the result is always the exact fp32 answer.
+//   2. exact pass: one warp per query takes the K-th smallest candidate value, recomputes sum_d (x-y)^2 in fp32 (the
+//      reference's formula) for the candidates within 2 eps of it, selects the K smallest (ties: lower index), and
+//      certifies the result: the fp16 rounding of the candidate pass perturbs a value by at most eps - computed on the host
+//      from the MEASURED rounding-error norms of the operands, |x.y - x~.y~| <= |x| |y - y~| + |x - x~| |y~| - so if the
+//      exact K-th distance + eps is below every list's worst kept value (in distance space, minus eps) no discarded train
+//      row can belong to the answer. Rows that cannot be certified are flagged; the host (u2seg_b200/clustering.py) gives
+//      them an fp32 pass over all train rows (128 candidates, bound 4 D 2^-24 |x||y|) and, for exact ties beyond that, an
+//      exhaustive search, so the result is always the exact fp32 answer.
 #include <cuda_fp16.h>
 
 #include "../../include/u2b200.h"

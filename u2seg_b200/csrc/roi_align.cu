@@ -4,10 +4,12 @@
 // poolers.py:23-59 (assign_boxes_to_levels), detectron2/layers/roi_align.py:49-65 ->
 // torchvision.ops.roi_align (CUDA kernel roi_align_forward_kernel_impl / bilinear_interpolate).
 //
-// HBM/L2-bound: one warp owns one output bin (roi, ph, pw) and sweeps the channel vector with
-// 16-byte loads (NHWC makes the 4 bilinear corners 4 contiguous channel vectors); fp32 accumulation;
-// one 16-byte store per lane. Backward scatters with vectorised fp32 atomics (red.v4.f32) into
-// per-level fp32 gradient maps.
+// HBM/L2-bound. Forward (roi_align_fwd_kernel): one warp owns one output bin (roi, ph, pw) and sweeps the channel
+// vector with 16-byte loads (NHWC makes the 4 bilinear corners 4 contiguous channel vectors); fp32 accumulation;
+// one 16-byte store per lane. Backward (roi_align_bwd2_kernel): one CTA per ROI factorises the pooling into two small
+// per-axis weight tables and issues ONE vectorised fp32 atomic (red.v4.f32) per footprint pixel and 4 channels into
+// per-level fp32 gradient maps; roi_align_bwd_kernel (one warp per bin) and roi_align_fwd2_kernel are the alternative
+// implementations selected by u2b_roi_align_set_impl.
 #include <cuda_bf16.h>
 
 #include <type_traits>
