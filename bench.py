@@ -358,13 +358,110 @@ def run_knn(args, emit=True):
         print(json.dumps(line), flush=True)
 
 
+def run_dino(args, emit=True):
+    """DINO ViT-S/8 feature extraction (u2seg_b200/dino.py) at 480x480 (3601 tokens), 8 images per step."""
+    import torch
+    from u2seg_b200 import _lib
+    from u2seg_b200.dino import vit_small
+    from u2seg_b200.modeling import conv_tc
+
+    rank, world, local = dist_info()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    peaks = load_peaks()
+    B, HW, P = 8, 480, 8
+    torch.manual_seed(0)
+    model = vit_small(patch_size=P, num_classes=0).to(dev).eval()
+    g = torch.Generator().manual_seed(1234 + rank)
+    host = [torch.randn(B, 3, HW, HW, generator=g).pin_memory() for _ in range(3)]
+    pool = [h.to(dev) for h in host]
+    N = (HW // P) ** 2 + 1
+    D, depth, hid = 384, 12, 1536
+    gemm_flop = 2.0 * B * N * (3 * P * P * D / N * (N - 1) + depth * (3 * D * D + D * D + 2 * D * hid))
+    attn_flop = depth * 4.0 * B * N * N * D
+    warm = max(3, args.warmup)
+    with torch.no_grad():
+        for i in range(warm):
+            model(pool[i % 3])
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        sampler.start()
+        l0 = _lib.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            feats = model(pool[i % 3])
+        e1.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        launches = _lib.launch_count - l0
+        ms = e0.elapsed_time(e1) / args.steps
+        # end to end: pinned host images in (H2D every step), features read back every step
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            host_feats = model(host[i % 3].to(dev, non_blocking=True)).cpu()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+        # the tensor-core GEMMs alone: CUDA events around every conv2 launch of one forward
+        conv_tc.TIMING = []
+        model(pool[0])
+        torch.cuda.synchronize()
+        recs, conv_tc.TIMING = conv_tc.TIMING, None
+    gemm_ms = sum(r[3].elapsed_time(r[4]) for r in recs)
+    gemm_f = sum(r[2] for r in recs)
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=dev)
+        t = torch.tensor([ms, dt * 1e3], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, dt = float(t[0]), float(t[1]) * 1e-3
+    line = {"metric": "dino_vits8_480_images_per_sec", "value": B * world / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 GEMM operands (fp32 accumulate, fp32 residual stream and LayerNorm)",
+            "data": "synthetic",
+            "config": {"workload": "DINO ViT-S/8 feature extraction (selective_labeling/dino.py ViTFeat.forward), 480x480 -> 3601 "
+                                   "tokens, 8 images per step per GPU, random weights", "tokens": N, "batch_per_gpu": B,
+                       "flop_per_step": gemm_flop + attn_flop, "l2_note": "inputs rotate over 3 batches (66 MB); activations "
+                                                                           "of one step (~0.5 GB) exceed the 126 MB L2"},
+            "clocks": clocks, "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "conv2_kernel as the ViT's Linear layers (%d launches per forward)" % len(recs),
+                         "achieved": gemm_f / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None, "peak": peaks["tf_sus"],
+                         "unit": "TFLOP/s", "frac": gemm_f / (gemm_ms * 1e-3) / 1e12 / peaks["tf_sus"] if gemm_ms else None,
+                         "peak_source": peaks["src"] + " bf16 sustained", "traffic": None,
+                         "ms_per_forward_in_gemms": gemm_ms, "gemm_flop_per_forward": gemm_f,
+                         "whole_forward_tflops": (gemm_flop + attn_flop) / (ms * 1e-3) / 1e12,
+                         "note": "attention (scaled_dot_product_attention), LayerNorm and GELU are library calls in this "
+                                 "version of the row; the GEMMs are 99 % of the non-attention flop"},
+            "e2e": {"value": B * world / dt, "unit": "images/s", "h2d_bytes_per_step": B * 3 * HW * HW * 4,
+                    "d2h_bytes_per_step": int(host_feats.numel() * 4)}}
+    if rank == 0 and world == 1 and not os.environ.get("U2B_BENCH_SKIP_CPU"):
+        from oracle import dino_oracle as vo
+        from u2seg_b200.bench_train import cpu_threads
+        cfg = vo.ViTCfg(patch_size=P, embed_dim=D, depth=depth, num_heads=6)
+        sd = vo.init_params(cfg, 0)
+        x1 = vo.synthetic_images(1, HW, HW, 1)
+        torch.set_num_threads(cpu_threads())
+        with torch.no_grad():
+            vo.forward_features(sd, cfg, x1[:, :, :96, :96])
+            t0 = time.perf_counter()
+            vo.forward_features(sd, cfg, x1)
+            tc = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 1.0 / tc, "unit": "images/s", "cores": cpu_threads(), "kind": "port",
+                                "sample": "1 image of 480x480 through the oracle port of the reference ViT-S/8 (fp32, torch CPU)"}
+    if not emit:
+        return line
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=None, choices=["train", "kmeans", "infer", "knn"])
+    ap.add_argument("--workload", default=None, choices=["train", "kmeans", "infer", "knn", "dino"])
     args = ap.parse_args()
     if args.workload is None:
         args.workload = "train" if os.path.exists(os.path.join(ROOT, "u2seg_b200", "bench_train.py")) else "kmeans"
@@ -374,6 +471,8 @@ def main():
         return run_kmeans(args)
     if args.workload == "knn":
         return run_knn(args)
+    if args.workload == "dino":
+        return run_dino(args)
     if args.workload == "infer":
         from u2seg_b200.bench_infer import run_infer
         return run_infer(args, ClockSampler, load_peaks, dist_info)

@@ -1,7 +1,7 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) in this
 container through the dependency stubs in oracle/ref_stubs (test infrastructure only).
 
-    python oracle/make_golden.py [kmeans] [ops] [model] [baseline] ...
+    python oracle/make_golden.py [kmeans] [knn] [dino] [ops] [model] [baseline] ...
 
 The fixtures travel to the GPU box; /root/reference does not. Each fixture stores the inputs
 (or the seed that regenerates them) and the reference's outputs.
@@ -76,6 +76,41 @@ def gen_kmeans():
     subprocess.check_call([sys.executable, os.path.abspath(__file__), "_kmeans_child"], cwd=cwd, env=env)
 
 
+DINO_CASES = [
+    # name, (patch, embed_dim, depth, heads), param seed, (B, H, W), image seed
+    ("dino_vits8_d3_64x96", (8, 384, 3, 6), 11, (2, 64, 96), 21),        # non-square: position table resized to 8 x 12
+    ("dino_vits16_d2_224", (16, 384, 2, 6), 12, (1, 224, 224), 22),       # native grid: position table used as it is
+    ("dino_vitb8_d2_72", (8, 768, 2, 12), 13, (2, 72, 72), 23),           # ViT-B widths (K = 768 / 3072)
+]
+
+
+def gen_dino():
+    """The UNMODIFIED reference VisionTransformer (selective_labeling/dino.py) with oracle.dino_oracle.init_params loaded
+    through its own load_state_dict(strict=True); outputs: CLS features (its forward) and the normalised tokens of the
+    last layer (get_intermediate_layers(n=1))."""
+    import importlib.util
+    from functools import partial
+    from oracle import dino_oracle as vo
+    spec = importlib.util.spec_from_file_location("ref_dino", os.path.join(REF, "u2seg", "Instance_Clustering", "selective_labeling", "dino.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    for name, (p, D, depth, heads), pseed, (B, H, W), iseed in DINO_CASES:
+        cfg = vo.ViTCfg(patch_size=p, embed_dim=D, depth=depth, num_heads=heads)
+        torch.manual_seed(0)
+        model = ref.VisionTransformer(patch_size=p, embed_dim=D, depth=depth, num_heads=heads, mlp_ratio=4, qkv_bias=True,
+                                      norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_classes=0).eval()
+        sd = vo.init_params(cfg, pseed)
+        model.load_state_dict(sd, strict=True)
+        x = vo.synthetic_images(B, H, W, iseed)
+        with torch.no_grad():
+            feats = model(x)
+            tokens = model.get_intermediate_layers(x, n=1)[0]
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), feats=feats.numpy(), tokens_head=tokens[:, :5].numpy(),
+                            tokens_abs_sum=np.array([float(tokens.double().abs().sum())]),
+                            meta=np.array([p, D, depth, heads, pseed, B, H, W, iseed], dtype=np.int64))
+        print("wrote", name, tuple(feats.shape), float(feats.abs().mean()))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     what = sys.argv[1:] or ["kmeans", "ops", "model"]
@@ -89,6 +124,8 @@ if __name__ == "__main__":
         gen_kmeans()
     if "knn" in what:
         gen_knn()
+    if "dino" in what:
+        gen_dino()
     if {"ops", "model", "baseline", "baseline64"} & set(what):
         sys.path.insert(0, STUBS)
         sys.path.insert(0, REF)
