@@ -210,13 +210,13 @@ int u2b_conv2d_nhwc_fwd(int dtype, const void* x, int N, int H, int W, int Cin, 
  * (layers/batch_norm.py:187 via layers/wrappers.py:127-134) without re-reading the activation. */
 int u2b_conv2_supported(int Cin, int Cout, int R, int S, int stride, int pad);
 int64_t u2b_conv2_stats_rows(int N, int H, int W, int R, int S, int stride, int pad);
-/* 0 = choose the tile width per problem (default); 64 / 128 / 256 force it (benchmarking) */
 /* Programmatic dependent launch between consecutive libu2b200 kernels of a stream (batch-norm and convolution kernels):
  * 1 (default) lets a kernel become resident and run its set-up while its predecessor drains; 0 = plain stream order. */
 int u2b_set_pdl(int on);
 /* SMs the persistent tcgen05 kernels (conv2, conv_wgrad2) size their grids for; 0 = all. Data-parallel training sets it
  * below the SM count during the backward pass so that NCCL's resident all-reduce CTAs do not force a second wave. */
 int u2b_set_sm_budget(int sms);
+/* 0 = choose the tile width per problem (default); 64 / 128 / 256 force it (benchmarking) */
 int u2b_conv2_set_tile_n(int bn);
 /* 1: short-K layers (<= 12 k-blocks of 64) run a shorter operand ring and 2-3 epilogue staging chunks per half (several TMA
  * stores in flight); 0 (default: measured no faster): full ring, one chunk. Developer switch for A/B timing. */
